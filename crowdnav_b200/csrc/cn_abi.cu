@@ -1,0 +1,230 @@
+/*
+ * cn_abi.cu -- the extern "C" boundary declared in include/crowdnav.h.
+ * Host-side only: argument checking, one device arena per handle, kernel
+ * parameter packing.  All device work goes to the caller's stream.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "cn_kernel.h"
+
+struct cn_handle {
+    cn_config cfg;
+    cn_derived d;
+    int device;
+    void* arena;            /* one cudaMalloc: [cn_config][robot][ped_a][ped_b] */
+    size_t arena_bytes;
+    cn_config* cfg_dev;
+    uint32_t* robot;
+    uint32_t* ped_a;
+    uint32_t* ped_b;
+    float* dbg_ranges;
+    uint8_t* dbg_hid;
+    int64_t launches;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+    return code;
+}
+#define CN_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) return fail(CN_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+const char* cn_last_error(void) { return g_err; }
+int cn_abi_version(void) { return CN_ABI_VERSION; }
+
+int cn_config_default(cn_config* c) {
+    if (!c) return fail(CN_ERR_INVALID, "cn_config_default: null config%s", NULL);
+    memset(c, 0, sizeof(*c));
+    c->struct_size = sizeof(cn_config);
+    c->n_envs = 1; c->n_peds = 14; c->n_samples = 360; c->k_obstacles = 8; c->max_steps = 1000;
+    c->seed = 1234;
+    c->dt = 0.15f;
+    c->room_xmin = -1.411074f; c->room_xmax = 1.398926f; c->room_ymin = -1.394624f; c->room_ymax = 1.405376f;
+    c->start_x = 1.0f; c->start_y = -1.0f; c->start_yaw = 3.14f;
+    c->goal_x = -1.0f; c->goal_y = 1.0f;
+    c->heading_off_x = 0.75f; c->heading_off_y = -0.75f;
+    c->max_range = 0.6f; c->collision_range = 0.12f; c->sensor_min_range = 0.08f;
+    c->sensor_sweep = 6.28f; c->mount_x = -0.032f; c->hit_angle_inc_deg = 1.0f;
+    c->ped_radius = 0.0505f; c->robot_radius = 0.105f; c->cp_radius = 0.178f;
+    c->waypoint_radius = 0.3f; c->goal_box = 0.20f;
+    c->rep_strength = 0.5f; c->rep_range = 0.05f; c->rep_cutoff = 0.05f; c->layout_jitter = 0.0f;
+    c->n_behaviors = 1;
+    c->behavior_kind[0] = CN_BEHAVIOR_RANDOM; c->behavior_speed[0] = 0.2f;
+    c->behavior_period_ticks[0] = 30; c->behavior_stagger_ticks[0] = 2;
+    static const float first6[6][2] = {{-0.01f, -1.0f}, {-1.15f, -0.3f}, {-0.32f, -0.12f},
+                                       {-0.85f, 0.92f}, {0.94f, 0.99f}, {0.65f, 0.2f}};
+    static const float ring[8][2] = {{1.0f, 0.0f}, {0.70710678f, 0.70710678f}, {0.0f, 1.0f}, {-0.70710678f, 0.70710678f},
+                                     {-1.0f, 0.0f}, {-0.70710678f, -0.70710678f}, {0.0f, -1.0f}, {0.70710678f, -0.70710678f}};
+    for (int i = 0; i < 6; ++i) { c->ped_layout[i][0] = first6[i][0]; c->ped_layout[i][1] = first6[i][1]; }
+    for (int i = 0; i < 8; ++i) { c->ped_layout[6 + i][0] = 0.22f + 0.16f * ring[i][0]; c->ped_layout[6 + i][1] = 0.54f + 0.16f * ring[i][1]; }
+    return CN_OK;
+}
+
+int cn_obs_dim(const cn_config* c) {
+    if (!c) return fail(CN_ERR_INVALID, "cn_obs_dim: null config%s", NULL);
+    return (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
+}
+
+size_t cn_blob_bytes(const cn_config* c) {
+    if (!c) return 0;
+    return cn_blob_words(c) * 4;
+}
+
+int cn_create(const cn_config* cfg, int device, cn_handle** out) {
+    if (!cfg || !out) return fail(CN_ERR_INVALID, "cn_create: null argument%s", NULL);
+    *out = NULL;
+    if (cfg->struct_size != sizeof(cn_config))
+        return fail(CN_ERR_INVALID, "cn_create: cn_config.struct_size mismatch (ABI)%s", NULL);
+    cn_derived d;
+    if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_create: config out of range%s", NULL);
+    int ndev = 0;
+    CN_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CN_ERR_INVALID, "cn_create: no such device%s", NULL);
+    CN_CUDA(cudaSetDevice(device));
+    int max_smem = 0;
+    CN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const size_t smem = cn_kernel_smem_bytes(cfg->n_peds, cfg->n_samples, d.obs_dim);
+    if (smem > (size_t)max_smem)
+        return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
+
+    cn_handle* h = new (std::nothrow) cn_handle();
+    if (!h) return fail(CN_ERR_NOMEM, "cn_create: host allocation failed%s", NULL);
+    h->cfg = *cfg; h->d = d; h->device = device; h->launches = 0;
+    h->dbg_ranges = NULL; h->dbg_hid = NULL;
+    const size_t cfg_b = align_up(sizeof(cn_config), 256);
+    const size_t rob_b = align_up(cn_robot_words(cfg) * 4, 256);
+    const size_t ped_b = align_up(cn_ped_plane_words(cfg) * 4 + 16, 256);
+    h->arena_bytes = cfg_b + rob_b + 2 * ped_b;
+    cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+    if (e != cudaSuccess) { delete h; return fail(CN_ERR_NOMEM, "cn_create: cudaMalloc: %s", cudaGetErrorString(e)); }
+    uint8_t* p = (uint8_t*)h->arena;
+    h->cfg_dev = (cn_config*)p; p += cfg_b;
+    h->robot = (uint32_t*)p; p += rob_b;
+    h->ped_a = (uint32_t*)p; p += ped_b;
+    h->ped_b = (uint32_t*)p;
+    e = cudaMemset(h->arena, 0, h->arena_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(h->cfg_dev, cfg, sizeof(cn_config), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->arena); delete h; return fail(CN_ERR_CUDA, "cn_create: init: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return CN_OK;
+}
+
+int cn_destroy(cn_handle* h) {
+    if (!h) return CN_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->arena);
+    delete h;
+    return CN_OK;
+}
+
+static void pack(const cn_handle* h, cn_kparams* P) {
+    const cn_config* c = &h->cfg;
+    memset(P, 0, sizeof(*P));
+    P->robot = h->robot; P->ped_a = h->ped_a; P->ped_b = h->ped_b;
+    P->dbg_ranges = h->dbg_ranges; P->dbg_hid = h->dbg_hid;
+    P->cfg = h->cfg_dev; P->d = h->d;
+    P->n_envs = c->n_envs; P->n_peds = c->n_peds; P->n_samples = c->n_samples; P->k_obstacles = c->k_obstacles;
+    P->max_steps = c->max_steps; P->env_id_offset = c->env_id_offset; P->n_behaviors = c->n_behaviors;
+    P->flags = c->flags; P->dt = c->dt;
+    P->room_xmin = c->room_xmin; P->room_xmax = c->room_xmax; P->room_ymin = c->room_ymin; P->room_ymax = c->room_ymax;
+    P->goal_x = c->goal_x; P->goal_y = c->goal_y; P->heading_off_x = c->heading_off_x; P->heading_off_y = c->heading_off_y;
+    P->max_range = c->max_range; P->collision_range = c->collision_range; P->sensor_min_range = c->sensor_min_range;
+    P->mount_x = c->mount_x; P->ped_radius = c->ped_radius; P->robot_radius = c->robot_radius; P->goal_box = c->goal_box;
+    P->rep_strength = c->rep_strength; P->rep_range = c->rep_range; P->rep_cutoff = c->rep_cutoff;
+    P->layout_jitter = c->layout_jitter;
+}
+
+int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    if (!h || !obs_dev) return fail(CN_ERR_INVALID, "cn_reset: null argument%s", NULL);
+    cn_kparams P; pack(h, &P);
+    P.mask = mask_dev; P.obs = obs_dev; P.obs_bulk_ok = 0;
+    CN_CUDA(cn_launch_env_kernel(P, 1, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_step: null argument%s", NULL);
+    cn_kparams P; pack(h, &P);
+    P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
+    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0 && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;
+    CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(CN_ERR_INVALID, "cn_get_counters: null argument%s", NULL);
+    if (((uintptr_t)out_dev) & 15u) return fail(CN_ERR_INVALID, "cn_get_counters: out_dev must be 16-byte aligned%s", NULL);
+    CN_CUDA(cn_launch_counters(h->robot, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_clear_done(cn_handle* h, const uint8_t* mask_dev, void* stream) {
+    if (!h) return fail(CN_ERR_INVALID, "cn_clear_done: null handle%s", NULL);
+    CN_CUDA(cn_launch_clear_done(h->robot, mask_dev, h->cfg.n_envs, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_get_blob(cn_handle* h, void* host, size_t bytes, void* stream) {
+    if (!h || !host) return fail(CN_ERR_INVALID, "cn_get_blob: null argument%s", NULL);
+    if (bytes != cn_blob_words(&h->cfg) * 4) return fail(CN_ERR_INVALID, "cn_get_blob: size mismatch%s", NULL);
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* w = (uint32_t*)host;
+    memset(w, 0, CN_BLOB_HEADER_WORDS * 4);
+    w[0] = CN_BLOB_MAGIC; w[1] = CN_ABI_VERSION;
+    w[2] = (uint32_t)h->cfg.n_envs; w[3] = (uint32_t)h->cfg.n_peds;
+    w[4] = (uint32_t)h->cfg.n_samples; w[5] = (uint32_t)h->cfg.k_obstacles;
+    w += CN_BLOB_HEADER_WORDS;
+    const size_t rw = cn_robot_words(&h->cfg), pw = cn_ped_plane_words(&h->cfg);
+    CN_CUDA(cudaMemcpyAsync(w, h->robot, rw * 4, cudaMemcpyDeviceToHost, s));
+    if (pw) {
+        CN_CUDA(cudaMemcpyAsync(w + rw, h->ped_a, pw * 4, cudaMemcpyDeviceToHost, s));
+        CN_CUDA(cudaMemcpyAsync(w + rw + pw, h->ped_b, pw * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CN_CUDA(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
+int cn_set_blob(cn_handle* h, const void* host, size_t bytes, void* stream) {
+    if (!h || !host) return fail(CN_ERR_INVALID, "cn_set_blob: null argument%s", NULL);
+    if (bytes != cn_blob_words(&h->cfg) * 4) return fail(CN_ERR_INVALID, "cn_set_blob: size mismatch%s", NULL);
+    const uint32_t* w = (const uint32_t*)host;
+    if (w[0] != CN_BLOB_MAGIC || w[2] != (uint32_t)h->cfg.n_envs || w[3] != (uint32_t)h->cfg.n_peds)
+        return fail(CN_ERR_INVALID, "cn_set_blob: blob does not match this handle%s", NULL);
+    cudaStream_t s = (cudaStream_t)stream;
+    w += CN_BLOB_HEADER_WORDS;
+    const size_t rw = cn_robot_words(&h->cfg), pw = cn_ped_plane_words(&h->cfg);
+    CN_CUDA(cudaMemcpyAsync(h->robot, w, rw * 4, cudaMemcpyHostToDevice, s));
+    if (pw) {
+        CN_CUDA(cudaMemcpyAsync(h->ped_a, w + rw, pw * 4, cudaMemcpyHostToDevice, s));
+        CN_CUDA(cudaMemcpyAsync(h->ped_b, w + rw + pw, pw * 4, cudaMemcpyHostToDevice, s));
+    }
+    CN_CUDA(cudaStreamSynchronize(s));
+    return CN_OK;
+}
+
+int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev) {
+    if (!h) return fail(CN_ERR_INVALID, "cn_set_debug_taps: null handle%s", NULL);
+    h->dbg_ranges = ranges_dev; h->dbg_hid = hit_ids_dev;
+    return CN_OK;
+}
+
+int64_t cn_launch_count(const cn_handle* h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */

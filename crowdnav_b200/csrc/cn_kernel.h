@@ -1,0 +1,41 @@
+/* cn_kernel.h -- launch interface between the C ABI (cn_abi.cu) and the kernels (cn_step.cu). */
+#ifndef CN_KERNEL_H
+#define CN_KERNEL_H
+
+#include <cuda_runtime.h>
+#include "cn_state.h"
+
+#define CN_TILE 16   /* worlds (= warps) per CTA */
+
+/* Everything the step kernel needs, passed by value (constant bank); the
+ * per-behaviour tables and the layout stay in the device copy of cn_config. */
+struct cn_kparams {
+    uint32_t* robot;
+    uint32_t* ped_a;
+    uint32_t* ped_b;
+    const float* action;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    const uint8_t* mask;
+    float* dbg_ranges;
+    uint8_t* dbg_hid;
+    const cn_config* cfg;       /* device copy */
+    cn_derived d;
+    int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors;
+    uint32_t flags;
+    int obs_bulk_ok;            /* obs base is 16-B aligned: tile rows may leave by bulk store */
+    float dt;
+    float room_xmin, room_xmax, room_ymin, room_ymax;
+    float goal_x, goal_y, heading_off_x, heading_off_y;
+    float max_range, collision_range, sensor_min_range, mount_x;
+    float ped_radius, robot_radius, goal_box;
+    float rep_strength, rep_range, rep_cutoff, layout_jitter;
+};
+
+size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim);
+cudaError_t cn_launch_env_kernel(const cn_kparams& P, int mode /*0 step, 1 reset*/, cudaStream_t stream);
+cudaError_t cn_launch_clear_done(uint32_t* robot, const uint8_t* mask, int E, cudaStream_t stream);
+cudaError_t cn_launch_counters(const uint32_t* robot, int32_t* out, int E, cudaStream_t stream);
+
+#endif

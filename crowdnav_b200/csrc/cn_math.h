@@ -1,0 +1,203 @@
+/*
+ * cn_math.h -- the numeric specification of the crowd-navigation step.
+ *
+ * Every floating-point primitive the env-step uses is defined here ONCE, in
+ * plain C, out of operations that IEEE-754 rounds identically on an x86 host
+ * and on an sm_100a device: + - * / sqrtf fmaf, int<->float conversions and
+ * 32/64-bit integer arithmetic.  No libm / libdevice transcendental is ever
+ * called, so `gcc -ffp-contract=off` and `nvcc -fmad=false` give the same
+ * bits; that is what makes "poses bit-exact on the integer grid" (and in
+ * practice the whole observation) true by construction, not by tolerance.
+ *
+ * The header is compiled three ways:
+ *   - nvcc (device)  : the CUDA step kernel (crowdnav_b200/csrc/cn_step.cu)
+ *   - gcc  (host)    : the CPU oracle (oracle/cn_oracle.c) -- test-only
+ *   - g++  (host)    : CPU unit tests of the primitives against libm
+ *
+ * Only PRIMITIVES live here.  The algorithms (LiDAR cast, waypoint logic,
+ * risk block, reward) are written independently in the kernel and in the
+ * oracle; the oracle restates the reference line by line, the kernel is a
+ * warp-parallel design.
+ *
+ * Accuracy (checked in tests/test_math_primitives.py against float64 libm):
+ *   cn_sincos_bin  <= 1.2e-7 abs      cn_atan2 <= 4e-7 abs
+ *   cn_exp         <= 3e-7 rel on [-8, 8]
+ */
+#ifndef CN_MATH_H
+#define CN_MATH_H
+
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define CN_HD __host__ __device__ __forceinline__
+#else
+#define CN_HD static inline
+#endif
+
+/* ---- fixed-point grid ---------------------------------------------------
+ * positions: int32 in units of 2^-24 m  (range +-128 m, resolution 6e-8 m)
+ * angles   : uint32 binary angle, 2*pi / 2^32 rad per unit (wrap is free)
+ */
+#define CN_GRID        5.9604644775390625e-08f /* 2^-24 */
+#define CN_INV_GRID    16777216.0f             /* 2^24  */
+#define CN_BIN2RAD     1.4629180792671596e-09f /* 2*pi / 2^32 */
+#define CN_RAD2BIN     683565275.57643158f     /* 2^32 / (2*pi) */
+#define CN_PI          3.14159265358979323846f
+#define CN_PIO2        1.57079632679489661923f
+#define CN_PIO4        0.78539816339744830962f
+#define CN_TWO_PI      6.28318530717958647692f
+#define CN_INV_TWO_PI  0.15915494309189533577f
+
+/* ---- bit casts and float->int with one definition of rounding ---------- */
+CN_HD uint32_t cn_f2bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+CN_HD float cn_bits2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+/* round-to-nearest-even float -> int32 (caller guarantees |x| < 2^31) */
+CN_HD int32_t cn_f2i(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rn(x);
+#else
+    return (int32_t)lrintf(x);
+#endif
+}
+/* round-to-nearest-even float -> int64 */
+CN_HD int64_t cn_f2ll(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2ll_rn(x);
+#else
+    return (int64_t)llrintf(x);
+#endif
+}
+
+/* ---- rounding helpers ---------------------------------------------------
+ * cn_round_he : numpy.around's rint (half to even)
+ * cn_round_ha : Python-2 round() (half away from zero)
+ */
+CN_HD float cn_round_he(float x) { return rintf(x); }
+CN_HD float cn_round_ha(float x) {
+    float t = truncf(x);
+    float d = x - t;                       /* exact */
+    if (fabsf(d) >= 0.5f) t += (x < 0.0f) ? -1.0f : 1.0f;
+    return t;
+}
+/* np.around(x, 3) as numpy does it: rint(x * 1000) / 1000 */
+CN_HD float cn_np_round3(float x) { return cn_round_he(x * 1000.0f) / 1000.0f; }
+/* Python-2 round(x, 3) / round(x, 2) */
+CN_HD float cn_py_round3(float x) { return cn_round_ha(x * 1000.0f) / 1000.0f; }
+CN_HD float cn_py_round2(float x) { return cn_round_ha(x * 100.0f) / 100.0f; }
+
+/* ---- trigonometry on binary angles --------------------------------------
+ * Range reduction is exact integer arithmetic (quadrant = top 2 bits after a
+ * 45-degree bias); the polynomials are the classic single-precision minimax
+ * kernels on [-pi/4, pi/4].
+ */
+CN_HD void cn_sincos_bin(uint32_t a, float* s_out, float* c_out) {
+    uint32_t q = (a + 0x20000000u) >> 30;
+    int32_t  r = (int32_t)(a - (q << 30));          /* [-2^29, 2^29) */
+    float x = (float)r * CN_BIN2RAD;
+    float z = x * x;
+    float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    float s = fmaf(ps * z, x, x);
+    float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    float c = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
+    switch (q & 3u) {
+        case 0:  *s_out =  s; *c_out =  c; break;
+        case 1:  *s_out =  c; *c_out = -s; break;
+        case 2:  *s_out = -s; *c_out = -c; break;
+        default: *s_out = -c; *c_out =  s; break;
+    }
+}
+
+/* radians -> binary angle, any finite |x| < 2^31 / RAD2BIN handled by int64 wrap */
+CN_HD uint32_t cn_rad2bin(float x) {
+    return (uint32_t)(uint64_t)cn_f2ll(x * CN_RAD2BIN);
+}
+/* binary angle -> radians in [-pi, pi) */
+CN_HD float cn_bin2rad(uint32_t a) { return (float)(int32_t)a * CN_BIN2RAD; }
+
+/* sin/cos of a float radian argument (|x| up to a few hundred) */
+CN_HD void cn_sincos_rad(float x, float* s_out, float* c_out) {
+    float k = rintf(x * CN_INV_TWO_PI);
+    float r = fmaf(-k, 6.28318548202514648f, x);        /* hi part of 2*pi (float) */
+    r = fmaf(-k, -1.74845553146951715e-07f, r);         /* 2*pi - hi */
+    cn_sincos_bin(cn_rad2bin(r), s_out, c_out);
+}
+
+/* atan on x >= 0, two-step reduction + degree-9 odd polynomial */
+CN_HD float cn_atan_pos(float x) {
+    float y0, t;
+    if (x > 2.414213562373095f)       { y0 = CN_PIO2; t = -1.0f / x; }
+    else if (x > 0.4142135623730950f) { y0 = CN_PIO4; t = (x - 1.0f) / (x + 1.0f); }
+    else                              { y0 = 0.0f;    t = x; }
+    float z = t * t;
+    float p = fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z,
+                        1.99777106478e-1f), z, -3.33329491539e-1f);
+    return y0 + fmaf(p * z, t, t);
+}
+/* atan2(y, x) in [-pi, pi]; atan2(0, 0) = 0 */
+CN_HD float cn_atan2(float y, float x) {
+    if (x == 0.0f) {
+        if (y > 0.0f) return CN_PIO2;
+        if (y < 0.0f) return -CN_PIO2;
+        return 0.0f;
+    }
+    float t = cn_atan_pos(fabsf(y / x));
+    if (x < 0.0f) t = CN_PI - t;
+    return (y < 0.0f) ? -t : t;
+}
+
+/* exp(x) for |x| <= 80: Cody-Waite reduction + degree-6 Taylor on |r| <= ln2/2 */
+CN_HD float cn_exp(float x) {
+    float n = rintf(x * 1.44269504088896341f);
+    float r = fmaf(-n, 0.693145751953125f, x);
+    r = fmaf(-n, 1.42860682030941723e-06f, r);
+    float p = fmaf(1.3888889e-3f, r, 8.3333333e-3f);
+    p = fmaf(p, r, 4.1666668e-2f);
+    p = fmaf(p, r, 1.6666667e-1f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    int32_t e = cn_f2i(n);
+    return cn_bits2f(cn_f2bits(p) + ((uint32_t)e << 23));
+}
+
+/* ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011) ---------------
+ * Stateless: the stream position is (env, episode, step, pedestrian), so a
+ * world's random numbers do not depend on how envs are sharded over GPUs.
+ */
+typedef struct { uint32_t v[4]; } cn_u32x4;
+
+CN_HD cn_u32x4 cn_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                             uint32_t k0, uint32_t k1) {
+    for (int i = 0; i < 10; ++i) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    cn_u32x4 r; r.v[0] = c0; r.v[1] = c1; r.v[2] = c2; r.v[3] = c3;
+    return r;
+}
+/* uniform in [0, 1) from the top 24 bits */
+CN_HD float cn_u01(uint32_t bits) { return (float)(bits >> 8) * 5.9604644775390625e-08f; }
+/* uniform in [-amp, amp) */
+CN_HD float cn_usym(uint32_t bits, float amp) { return fmaf(cn_u01(bits), 2.0f, -1.0f) * amp; }
+
+#endif /* CN_MATH_H */

@@ -1,0 +1,118 @@
+/*
+ * cn_state.h -- HBM state layout of a batch of worlds, and the constants
+ * derived once per config on the host.  Shared by the CUDA library and by the
+ * CPU oracle so a state blob can be moved between them bit for bit.
+ *
+ * Three planes, each an array of per-env records that are contiguous in
+ * memory (env-major), so a CTA that owns a tile of consecutive envs moves each
+ * plane's tile with ONE 1-D bulk (TMA) copy and a warp that owns one env reads
+ * its record with fully used 128-B lines:
+ *
+ *   robot  [E][16] words   64 B / env
+ *   ped_a  [E][N][4] words 16 B / pedestrian: x, y (int32 grid), vx, vy (f32)
+ *   ped_b  [E][N][4] words 16 B / pedestrian: last hit point x, y (f32, 3 dp),
+ *                                             resample timer (int32 ticks), flags
+ *
+ * Blob = 16-word header, then the three planes back to back.
+ */
+#ifndef CN_STATE_H
+#define CN_STATE_H
+
+#include "../../include/crowdnav.h"
+#include "cn_math.h"
+
+/* robot / episode record, word indices */
+enum {
+    CN_R_X = 0,      /* int32 grid */
+    CN_R_Y = 1,      /* int32 grid */
+    CN_R_TH = 2,     /* uint32 binary angle */
+    CN_R_V = 3,      /* f32 achieved linear velocity  (odom twist.linear.x) */
+    CN_R_W = 4,      /* f32 achieved angular velocity (odom twist.angular.z) */
+    CN_R_WPX = 5,    /* f32 waypoint (ENV:80-83,252-265) */
+    CN_R_WPY = 6,
+    CN_R_PDIST = 7,  /* f32 previous_distance (ENV:1133,1243) */
+    CN_R_PHEAD = 8,  /* f32 previous_heading  (ENV:1134,1244) */
+    CN_R_PPX = 9,    /* f32 agent_pose_deque[0], rounded 3 dp (ENV:294,1208) */
+    CN_R_PPY = 10,
+    CN_R_STEP = 11,  /* int32 steps taken this episode */
+    CN_R_EPISODE = 12, /* uint32 episodes started */
+    CN_R_FLAGS = 13,
+    CN_R_CNT0 = 14,  /* ego violations | social violations << 16 (ENV:998-1005) */
+    CN_R_CNT1 = 15   /* obstacle-present steps | sanitised actions << 16 */
+};
+#define CN_RF_DONE     1u
+#define CN_RF_SUCCESS  2u
+#define CN_RF_FAILURE  4u
+
+/* ped_b flags */
+#define CN_PF_TRACKED  1u   /* last hit point valid (object was confirmed last step) */
+
+/* hit ids */
+#define CN_HIT_NONE 0xFFu
+#define CN_HIT_WALL 0xFEu
+
+#define CN_BLOB_MAGIC 0x56414E43u /* "CNAV" */
+#define CN_BLOB_HEADER_WORDS 16
+
+/* action sanitising bounds (agents emit v in [0, 0.22], w in [-2, 2]) */
+#define CN_ACT_V_LIMIT 1.0f
+#define CN_ACT_W_LIMIT 6.0f
+#define CN_WHEEL_SEP   0.160f   /* XACRO:68 */
+#define CN_TICKS_PER_STEP 3
+
+typedef struct cn_derived {
+    uint32_t inc_bin;        /* binary angle between adjacent LiDAR samples */
+    uint32_t hit_inc_bin;    /* UTL:113-123 angle increment as binary angle */
+    uint32_t start_th;
+    int32_t  start_xi, start_yi;
+    int32_t  ped_xmin, ped_xmax, ped_ymin, ped_ymax; /* centre clamp, grid units */
+    float    ped_r2;         /* ped_radius^2 */
+    float    cp_r2;          /* cp_radius^2 */
+    float    apothem;        /* waypoint_radius * cos(pi/64): shapely 64-gon (UTL:301-302) */
+    float    cand_d2;        /* (max_range + ped_radius + 1e-3)^2 : LiDAR candidate cull */
+    float    goal_lo_x, goal_hi_x, goal_lo_y, goal_hi_y; /* ENV:1303-1319 */
+    float    inv_inc_bin;    /* 1 / inc_bin (span rasterisation only) */
+    int32_t  obs_dim;
+    uint32_t seed_lo, seed_hi;
+} cn_derived;
+
+static inline int cn_derive(const cn_config* c, cn_derived* d) {
+    if (c->n_envs < 1 || c->n_peds < 0 || c->n_peds > CN_MAX_PEDS) return -1;
+    if (c->n_samples < 3 || c->n_samples > 4096) return -1;
+    if (c->k_obstacles < 0 || c->k_obstacles > CN_MAX_PEDS) return -1;
+    if (c->n_behaviors < 1 || c->n_behaviors > CN_MAX_BEHAVIORS) return -1;
+    if (!(c->dt > 0.0f) || !(c->max_range > 0.0f)) return -1;
+    const double two_pi = 6.283185307179586476925286766559;
+    double inc = (double)c->sensor_sweep / (double)(c->n_samples - 1);
+    d->inc_bin = (uint32_t)llrint(inc / two_pi * 4294967296.0);
+    d->hit_inc_bin = (uint32_t)llrint((double)c->hit_angle_inc_deg / 360.0 * 4294967296.0);
+    d->start_th = (uint32_t)(int64_t)llrint((double)c->start_yaw / two_pi * 4294967296.0);
+    d->start_xi = (int32_t)llrint((double)c->start_x * 16777216.0);
+    d->start_yi = (int32_t)llrint((double)c->start_y * 16777216.0);
+    d->ped_xmin = (int32_t)llrint(((double)c->room_xmin + c->ped_radius) * 16777216.0);
+    d->ped_xmax = (int32_t)llrint(((double)c->room_xmax - c->ped_radius) * 16777216.0);
+    d->ped_ymin = (int32_t)llrint(((double)c->room_ymin + c->ped_radius) * 16777216.0);
+    d->ped_ymax = (int32_t)llrint(((double)c->room_ymax - c->ped_radius) * 16777216.0);
+    d->ped_r2 = c->ped_radius * c->ped_radius;
+    d->cp_r2 = c->cp_radius * c->cp_radius;
+    d->apothem = (float)((double)c->waypoint_radius * cos(two_pi / 128.0));
+    float cd = c->max_range + c->ped_radius + 1e-3f;
+    d->cand_d2 = cd * cd;
+    d->goal_lo_x = c->goal_x - c->goal_box;
+    d->goal_hi_x = c->goal_x + c->goal_box;
+    d->goal_lo_y = c->goal_y - c->goal_box;
+    d->goal_hi_y = c->goal_y + c->goal_box;
+    d->inv_inc_bin = (float)(1.0 / (double)d->inc_bin);
+    d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
+    d->seed_lo = (uint32_t)(c->seed & 0xFFFFFFFFu);
+    d->seed_hi = (uint32_t)(c->seed >> 32);
+    return 0;
+}
+
+static inline size_t cn_robot_words(const cn_config* c) { return (size_t)c->n_envs * CN_ROBOT_WORDS; }
+static inline size_t cn_ped_plane_words(const cn_config* c) { return (size_t)c->n_envs * (size_t)c->n_peds * 4; }
+static inline size_t cn_blob_words(const cn_config* c) {
+    return CN_BLOB_HEADER_WORDS + cn_robot_words(c) + 2 * cn_ped_plane_words(c);
+}
+
+#endif /* CN_STATE_H */

@@ -1,0 +1,163 @@
+/*
+ * crowdnav.h -- C ABI of libcrowdnav.so, the B200 batched crowd-navigation
+ * environment step.
+ *
+ * The reference (ailabspace/drl-based-mapless-crowd-navigation-with-perceived-risk)
+ * has no FFI of its own: its boundary is the Python duck-type `Env`
+ * (turtlebot3_rl_sim/src/environment_stage_1_nobonus.py:42-43,1164,1227,
+ * 1265-1283) called by the training drivers (start_td3_training.py:106-148).
+ * This header is the interface a maintainer binds underneath that class
+ * (ctypes stub in INTEGRATION.md).  Each entry point cites what it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer suffixed _dev is a CUDA
+ *     device pointer on the handle's device, _host is host memory.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*); no hidden synchronisation, graph-capturable.
+ *   - return 0 on success, a negative cn_status otherwise; message via
+ *     cn_last_error().  No C++ exception crosses the boundary.
+ *   - a handle is bound to one device; calls on one handle are not re-entrant.
+ */
+#ifndef CROWDNAV_H
+#define CROWDNAV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CN_MAX_PEDS       64
+#define CN_MAX_BEHAVIORS  8
+#define CN_ABI_VERSION    1
+
+/* words (4 B) per env in the three state planes */
+#define CN_ROBOT_WORDS    16
+#define CN_PED_WORDS      8   /* 4 in plane A (x, y, vx, vy) + 4 in plane B */
+
+typedef enum cn_status {
+    CN_OK = 0,
+    CN_ERR_INVALID = -1,     /* bad argument / config */
+    CN_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    CN_ERR_NOMEM = -3,
+    CN_ERR_UNSUPPORTED = -4  /* config outside compiled limits */
+} cn_status;
+
+/* cn_config.flags */
+#define CN_FLAG_AUTO_RESET      1u  /* done envs re-seed themselves inside cn_step */
+#define CN_FLAG_TOPK_HIGHEST    2u  /* keep the K highest-CP objects instead of the
+                                       reference's `[-K:]` (= K lowest), ENV:883 */
+
+/* behaviour kinds (crowd_behaviors/simulate_*.py, SURVEY table P') */
+#define CN_BEHAVIOR_RANDOM 0   /* U(-speed, speed)^2 redrawn every period */
+#define CN_BEHAVIOR_TABLE  1   /* fixed per-pedestrian direction table * speed */
+
+/*
+ * World + sensor + episode configuration.  One struct, plain data; the Python
+ * side mirrors it with ctypes.Structure.  Defaults (cn_config_default) are the
+ * reference's constants, each cited in DESIGN.md "constants".
+ */
+typedef struct cn_config {
+    uint32_t struct_size;        /* = sizeof(cn_config), ABI check */
+    uint32_t flags;
+    int32_t  n_envs;             /* E: worlds stepped per call */
+    int32_t  n_peds;             /* N <= CN_MAX_PEDS */
+    int32_t  n_samples;          /* R: LiDAR samples (scan_ranges, CFG:6); R-1 rays observed */
+    int32_t  k_obstacles;        /* K: slots in the perceived-risk block (ENV:55) */
+    int32_t  max_steps;          /* episode cap (td3.yaml:7) */
+    int32_t  env_id_offset;      /* global id of local env 0 (multi-GPU sharding) */
+    uint64_t seed;
+
+    float dt;                    /* control period, ENV:1201 */
+    float room_xmin, room_xmax, room_ymin, room_ymax;   /* inner wall faces */
+    float start_x, start_y, start_yaw;  /* put_robot_in_world_*.launch:3-8 */
+    float goal_x, goal_y;               /* desired_pose, CFG:10-13 */
+    float heading_off_x, heading_off_y; /* starting_pose added in ENV:223-224 */
+
+    float max_range;             /* max_scan_range, CFG:7 */
+    float collision_range;       /* min_scan_range, CFG:8 */
+    float sensor_min_range;      /* XACRO:164 */
+    float sensor_sweep;          /* 6.28 rad, XACRO:160 */
+    float mount_x;               /* scan frame offset, URDF:137 */
+    float hit_angle_inc_deg;     /* UTL:113 angle increment (Py2 int division) */
+
+    float ped_radius;            /* WORLD:109 */
+    float robot_radius;          /* pedestrian<->robot contact stand-in */
+    float cp_radius;             /* collision-cone circle, ENV:823 */
+    float waypoint_radius;       /* ENV:250 */
+    float goal_box;              /* ENV:1285,1303 */
+
+    float rep_strength;          /* contact stand-in: A  [m/s]   */
+    float rep_range;             /*                   B  [m]     */
+    float rep_cutoff;            /* extra gap beyond r_i + r_j where the term is 0 */
+    float layout_jitter;         /* U(-j, j) added to each pedestrian start pose */
+
+    int32_t n_behaviors;         /* env behaviour = global_env_id % n_behaviors */
+    int32_t behavior_kind[CN_MAX_BEHAVIORS];
+    float   behavior_speed[CN_MAX_BEHAVIORS];
+    int32_t behavior_period_ticks[CN_MAX_BEHAVIORS];  /* tick = dt / 3 */
+    int32_t behavior_stagger_ticks[CN_MAX_BEHAVIORS]; /* per-pedestrian offset */
+    float   behavior_table[CN_MAX_BEHAVIORS][CN_MAX_PEDS][2];
+    float   ped_layout[CN_MAX_PEDS][2];               /* initial poses (world file) */
+} cn_config;
+
+typedef struct cn_handle cn_handle;
+
+/* Fill *cfg with the reference's training-world constants (3 m room, 14
+ * pedestrians, 360 samples, K = 8).  Replaces the rosparam load of
+ * configs/turtlebot3_world.yaml + the world/xacro constants. */
+int cn_config_default(cn_config* cfg);
+
+/* Observation width (R-1) + 7 + 4K  (start_td3_training.py:88). */
+int cn_obs_dim(const cn_config* cfg);
+
+/* Bytes of the opaque state blob for this config (cn_get_blob / cn_set_blob). */
+size_t cn_blob_bytes(const cn_config* cfg);
+
+/* Allocate one arena of device memory for cfg->n_envs worlds on `device`.
+ * Replaces Env.__init__ (ENV:43-168) + the Gazebo world load. */
+int cn_create(const cn_config* cfg, int device, cn_handle** out);
+int cn_destroy(cn_handle* h);
+
+/* Reset the envs whose mask byte is non-zero (mask_dev == NULL: all) and write
+ * their first observation rows into obs_dev [E, D] (rows of unmasked envs are
+ * untouched).  Replaces Env.reset (ENV:1227-1263) + gazebo/reset_simulation. */
+int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* One control period for every env.  Replaces Env.step (ENV:1164-1225), the
+ * 0.15 s of Gazebo physics + crowd mover behind it, get_state (ENV:245-1044)
+ * and compute_reward (ENV:1046-1162).
+ *   action_dev [E, 2] (v, w); obs_dev [E, D] row-major; reward_dev [E];
+ *   done_dev [E] (1 = episode ended on this step). */
+int cn_step(cn_handle* h, const float* action_dev, float* obs_dev,
+            float* reward_dev, uint8_t* done_dev, void* stream);
+
+/* Per-env counters [E, 4] int32: success, ego violations, social violations,
+ * obstacle-present steps.  Replaces get_episode_status / get_*_violation_status
+ * (ENV:1265-1283). */
+int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream);
+
+/* Clear the sticky done flag (the drivers' `env.done = False`, TD3DRV:116). */
+int cn_clear_done(cn_handle* h, const uint8_t* mask_dev, void* stream);
+
+/* Whole-state snapshot to / from host memory (exact resume, parity fixtures).
+ * Synchronous on `stream`. */
+int cn_get_blob(cn_handle* h, void* host, size_t bytes, void* stream);
+int cn_set_blob(cn_handle* h, const void* host, size_t bytes, void* stream);
+
+/* Debug taps of the last cn_step / cn_reset: pre-rounding ranges [E, R-1] f32
+ * and hit ids [E, R-1] u8 (0xFF none, 0xFE wall, else pedestrian).  Either may
+ * be NULL.  Enabling them adds global stores to the step kernel. */
+int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev);
+
+/* Number of kernels launched by this handle since creation. */
+int64_t cn_launch_count(const cn_handle* h);
+
+const char* cn_last_error(void);
+int cn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWDNAV_H */

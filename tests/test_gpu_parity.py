@@ -1,0 +1,170 @@
+"""GPU-vs-oracle parity, through the C ABI (CrowdNavVecEnv -> libcrowdnav.so).
+
+Bar: BIT-EXACT.  State blobs (integer-grid poses, fp32 fields), observation
+rows, raw LiDAR ranges, hit ids, rewards and done flags must equal the CPU
+oracle's on the same seeded inputs -- stronger than the 1e-4 fp32 tolerance
+BASELINE.json allows for ranges / reward (tolerance used here: 0).
+"""
+import numpy as np
+import pytest
+
+from crowdnav_b200.config import (TABLE_TOWARDS_20, baseline_config, behavior_random, behavior_table, make_config,
+                                  test_world_20)
+from parity_util import bits_equal, describe_blob_diff, describe_obs_diff, random_actions
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cfg):
+    import torch
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    from oracle.oracle import OracleEnv
+    g = CrowdNavVecEnv(cfg, device=0)
+    g.enable_debug_taps()
+    o = OracleEnv(cfg, debug=True)
+    return torch, g, o
+
+
+def _check(cfg, g, o, tag):
+    import torch
+    torch.cuda.synchronize()
+    gb, ob = g.get_state_blob(), o.blob
+    assert bits_equal(gb, ob), "%s: state blob differs\n%s" % (tag, describe_blob_diff(cfg, gb, ob))
+    go = g.obs.cpu().numpy()
+    assert bits_equal(go, o.obs), "%s: observation differs\n%s" % (tag, describe_obs_diff(cfg, go, o.obs))
+
+
+def _rollout(cfg, steps, seed=0, check_every=1, action_fn=None):
+    torch, g, o = _mk(cfg)
+    rng = np.random.default_rng(seed)
+    g.reset()
+    o.reset()
+    assert bits_equal(g.debug_hit_ids.cpu().numpy(), o.hit_ids), "reset: hit ids differ"
+    assert bits_equal(g.debug_ranges.cpu().numpy(), o.ranges), "reset: raw ranges differ"
+    _check(cfg, g, o, "reset")
+    n_done = 0
+    for t in range(steps):
+        a = action_fn(rng, t) if action_fn else random_actions(rng, cfg.n_envs)
+        _, gr, gd = g.step(torch.from_numpy(a).cuda())
+        _, orr, od = o.step(a)
+        if (t + 1) % check_every == 0 or t == steps - 1:
+            tag = "step %d" % (t + 1)
+            assert bits_equal(g.debug_hit_ids.cpu().numpy(), o.hit_ids), tag + ": hit ids differ"
+            assert bits_equal(g.debug_ranges.cpu().numpy(), o.ranges), tag + ": raw ranges differ"
+            _check(cfg, g, o, tag)
+            assert bits_equal(gr.cpu().numpy(), orr), tag + ": reward differs"
+            assert bits_equal(gd.cpu().numpy(), od), tag + ": done differs"
+        n_done += int(od.sum())
+    assert bits_equal(g.counters().cpu().numpy(), o.counters()), "counters differ"
+    g.close()
+    return n_done
+
+
+def test_c1_single_env_200_steps():
+    """BASELINE config 1: 1 env, 5 pedestrians, 36 rays, K=3, random policy, 200 steps."""
+    cfg = baseline_config(0, auto_reset=False)
+    _rollout(cfg, 200)
+
+
+def test_c1_auto_reset_many_envs():
+    cfg = baseline_config(0, n_envs=333, auto_reset=True)
+    n_done = _rollout(cfg, 300, seed=1)
+    assert n_done > 0, "rollout never finished an episode: auto-reset path not exercised"
+
+
+def test_training_world_14_peds():
+    """The reference's training world (3 m room, 14 pedestrians, 360 samples, K=8)."""
+    cfg = make_config(n_envs=200, auto_reset=True, layout_jitter=0.05)
+    n_done = _rollout(cfg, 250, seed=2)
+    assert n_done > 0
+
+
+def test_c2_shape_20_peds_360_rays():
+    """BASELINE config 2 shape at a size the oracle steps in seconds."""
+    cfg = baseline_config(1, n_envs=1024)
+    n_done = _rollout(cfg, 200, seed=3, check_every=10)
+    assert n_done > 0
+
+
+def test_c4_mixed_behaviours_and_sharding_offset():
+    """Config 4 shape: behaviours by env_id % 3, and a non-zero global env id offset."""
+    cfg = baseline_config(3, n_envs=600, env_id_offset=8192)
+    _rollout(cfg, 120, seed=4, check_every=10)
+
+
+def test_c5_50_peds_720_rays_k16():
+    """BASELINE config 5 shape: two pedestrians per lane, 720 rays, K=16."""
+    cfg = baseline_config(4, n_envs=160)
+    _rollout(cfg, 120, seed=5, check_every=10)
+
+
+def test_partial_tile_and_odd_obs_dim():
+    """E not a multiple of the CTA tile, odd observation width (plain-store path)."""
+    cfg = make_config(n_envs=37, n_peds=7, n_samples=38, k_obstacles=2, auto_reset=True, layout_jitter=0.1)
+    _rollout(cfg, 150, seed=6)
+
+
+def test_crowded_contacts():
+    """Dense crowd in a small area: the contact stand-in (repulsion) path is active."""
+    layout = [(-0.3 + 0.11 * (i % 6), -0.3 + 0.11 * (i // 6)) for i in range(30)]
+    cfg = make_config(n_envs=64, n_peds=30, layout=layout, behaviors=[behavior_random(0.2, 0.6)], auto_reset=True,
+                      layout_jitter=0.02, start=(1.0, -1.0, 3.14))
+    _rollout(cfg, 100, seed=7)
+
+
+def test_drive_at_pedestrians_and_walls():
+    """Straight driving so collisions (range < 0.12) and the sensor-minimum clamp occur."""
+    cfg = test_world_20(n_envs=256, behaviors=[behavior_table(TABLE_TOWARDS_20, 0.2)], auto_reset=True,
+                        layout_jitter=0.3, start=(0.9, 0.0, 3.14))
+
+    def act(rng, t):
+        a = np.zeros((256, 2), dtype=np.float32)
+        a[:, 0] = 0.22
+        a[:, 1] = rng.uniform(-0.3, 0.3, 256)
+        return a
+    n_done = _rollout(cfg, 200, seed=8, action_fn=act)
+    assert n_done > 20
+
+
+def test_nonfinite_and_out_of_range_actions():
+    cfg = baseline_config(0, n_envs=32, auto_reset=True)
+
+    def act(rng, t):
+        a = random_actions(rng, 32)
+        a[0, 0] = np.nan
+        a[1, 1] = np.inf
+        a[2, 0] = 50.0
+        a[3, 1] = -50.0
+        return a
+    _rollout(cfg, 40, seed=9, action_fn=act)
+
+
+def test_masked_reset_and_blob_roundtrip():
+    cfg = baseline_config(1, n_envs=100, auto_reset=False)
+    torch, g, o = _mk(cfg)
+    rng = np.random.default_rng(10)
+    g.reset()
+    o.reset()
+    for t in range(30):
+        a = random_actions(rng, 100)
+        g.step(torch.from_numpy(a).cuda())
+        o.step(a)
+    mask = (rng.uniform(size=100) < 0.3).astype(np.uint8)
+    before = g.obs.cpu().numpy().copy()
+    g.reset(torch.from_numpy(mask))
+    o.reset(mask)
+    _check(cfg, g, o, "masked reset")
+    after = g.obs.cpu().numpy()
+    assert bits_equal(after[mask == 0], before[mask == 0]), "masked reset touched unmasked rows"
+    # blob round trip: restore an earlier snapshot and replay
+    snap = g.get_state_blob().copy()
+    acts = [random_actions(rng, 100) for _ in range(10)]
+    outs = []
+    for a in acts:
+        ob, r, d = g.step(torch.from_numpy(a).cuda())
+        outs.append((ob.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+    g.set_state_blob(snap)
+    for a, (ob0, r0, d0) in zip(acts, outs):
+        ob, r, d = g.step(torch.from_numpy(a).cuda())
+        assert bits_equal(ob.cpu().numpy(), ob0) and bits_equal(r.cpu().numpy(), r0) and bits_equal(d.cpu().numpy(), d0)
+    g.close()
