@@ -1,0 +1,77 @@
+"""Multi-GPU layout: one process per GPU, worlds sharded by env id.
+
+Every world is independent (no cross-env read anywhere in the reference's Env),
+so the path has NO data-path exchange: rank r owns the contiguous block of
+global env ids [r * E/G, (r+1) * E/G) and steps it with its own kernel.  RNG
+streams are keyed by GLOBAL env id (cn_config.env_id_offset), so results do not
+depend on G.  The one collective is what BASELINE.json's north_star asks for:
+an all-gather of the observation tensor so every rank (learner replicas) sees
+all E rows.  The step kernel writes straight into this rank's slice of the
+gather buffer and the all-gather runs in place (NCCL over NVLink / NVSwitch).
+"""
+from __future__ import annotations
+
+from typing import Callable, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .config import CnConfig
+
+
+def shard_range(n_envs_global: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous env-id block [lo, hi) of `rank`; sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    base, rem = divmod(n_envs_global, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def local_config(cfg_global: CnConfig, rank: int, world: int) -> CnConfig:
+    """This rank's cn_config: its env count and the global id of its env 0."""
+    lo, hi = shard_range(cfg_global.n_envs, rank, world)
+    cfg = cfg_global.copy()
+    cfg.n_envs = hi - lo
+    cfg.env_id_offset = cfg_global.env_id_offset + lo
+    return cfg
+
+
+class ShardedVecEnv:
+    """E worlds over `world` ranks; step() returns the local (obs, reward, done)
+    views and leaves the gathered [E, D] observation in ``self.obs_all``.
+
+    `make_local(cfg_local, obs_slice)` builds the rank's stepper: on a GPU box it
+    is ``CrowdNavVecEnv(cfg_local, obs_out=obs_slice)``; the CPU gloo tests pass
+    a stand-in with the same reset()/step() surface.
+    """
+
+    def __init__(self, cfg_global: CnConfig, make_local: Callable, device: torch.device,
+                 group: dist.ProcessGroup | None = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if cfg_global.n_envs % self.world != 0:
+            raise ValueError("all_gather_into_tensor needs equal shards: n_envs %% world_size must be 0")
+        self.cfg_global = cfg_global.copy()
+        self.cfg_local = local_config(cfg_global, self.rank, self.world)
+        self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
+        self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
+        self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
+        self.obs_local = self.obs_all[self.lo:self.hi]          # contiguous row block
+        self.env = make_local(self.cfg_local, self.obs_local)
+
+    def gather(self) -> torch.Tensor:
+        """In-place all-gather of the observation rows (sendbuf = recvbuf + rank * count)."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
+        return self.obs_all
+
+    def reset(self) -> torch.Tensor:
+        self.env.reset()
+        return self.gather()
+
+    def step(self, actions_local: torch.Tensor):
+        _, reward, done = self.env.step(actions_local)
+        self.gather()
+        return self.obs_all, reward, done

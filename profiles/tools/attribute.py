@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Attribute executed warp-instructions of an ncu capture to CUDA source lines.
+
+usage: attribute.py <report.ncu-rep> <lib.so> <kernel-substring> [top_n]
+Joins `ncu --page source --print-source=sass --csv` (per-SASS-address executed
+counts, first captured launch) with `nvdisasm -g` line info of the same cubin.
+"""
+import csv, io, os, re, subprocess, sys, tempfile, collections
+
+rep, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
+top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL, check=True)
+addr2line = {}
+for f in os.listdir(tmp):
+    if not f.endswith(".cubin"):
+        continue
+    out = subprocess.run(["nvdisasm", "-g", "-c", f], cwd=tmp, stdout=subprocess.PIPE, text=True).stdout
+    cur_fn, cur = None, None
+    for ln in out.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+        if m:
+            cur_fn = m.group(1); cur = None; continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
+        if m and cur_fn and kname in cur_fn:
+            addr2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source=sass", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+blocks = txt.split('"Kernel Name"')
+per_line = collections.Counter(); per_line_samples = collections.Counter(); total = 0; tot_s = 0
+done = False
+for b in blocks[1:]:
+    rows = list(csv.reader(io.StringIO('"Kernel Name"' + b)))
+    if kname not in rows[0][1].replace("(int)", "").replace(" ", "") and kname not in rows[0][1]:
+        pass
+    hdr = rows[1]
+    ia, ie, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+    base = None
+    for r in rows[2:]:
+        if len(r) <= ie or not r[ia]:
+            continue
+        a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
+        if base is None:
+            base = a
+        key = addr2line.get(a - base, ((None, 0), "?"))[0]
+        n = int(float(r[ie] or 0)); s = int(float(r[isamp] or 0))
+        per_line[key] += n; per_line_samples[key] += s; total += n; tot_s += s
+    break   # first launch only
+src_cache = {}
+def src(fl):
+    f, l = fl
+    if f is None: return ""
+    for d in ("crowdnav_b200/csrc", "include"):
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", d, f)
+        if os.path.exists(p):
+            if p not in src_cache: src_cache[p] = open(p).read().splitlines()
+            return src_cache[p][l - 1].strip()[:90] if l - 1 < len(src_cache[p]) else ""
+    return ""
+print("total warp-instructions executed: %d ; samples %d" % (total, tot_s))
+print("%8s %6s %6s  %-18s %s" % ("inst", "%inst", "%samp", "file:line", "source"))
+for k, n in per_line.most_common(top_n):
+    print("%8d %6.2f %6.2f  %-18s %s" % (n, 100.0 * n / max(total, 1), 100.0 * per_line_samples[k] / max(tot_s, 1),
+                                          "%s:%d" % k if k[0] else "?", src(k)))
