@@ -83,21 +83,39 @@ CN_HD int64_t cn_f2ll(float x) {
 }
 
 /* ---- rounding helpers ---------------------------------------------------
- * cn_round_he : numpy.around's rint (half to even)
- * cn_round_ha : Python-2 round() (half away from zero)
+ * The reference rounds in float64: np.around(x, 3) = rint(x * 1000) / 1000
+ * (half to even) and Python-2 round(x, n) (half away from zero).  In fp32 the
+ * product x * 1000 is itself rounded, which would create ties (and 1e-3 flips
+ * against the reference) that the exact product does not have.  So the nearest
+ * integer is taken of the EXACT product: k = rint(fl(x*c)), then the residual
+ * e = x*c - k from one fma (exact to 2^-24 relative) moves k by one when the
+ * rounded product landed on the wrong side of a half.
  */
-CN_HD float cn_round_he(float x) { return rintf(x); }
-CN_HD float cn_round_ha(float x) {
+CN_HD float cn_round_ha(float x) {          /* half away from zero */
     float t = truncf(x);
     float d = x - t;                       /* exact */
     if (fabsf(d) >= 0.5f) t += (x < 0.0f) ? -1.0f : 1.0f;
     return t;
 }
-/* np.around(x, 3) as numpy does it: rint(x * 1000) / 1000 */
-CN_HD float cn_np_round3(float x) { return cn_round_he(x * 1000.0f) / 1000.0f; }
+CN_HD float cn_fix_scaled(float x, float c, float k) {
+    float e = fmaf(x, c, -k);
+    if (e > 0.5f) k += 1.0f;
+    else if (e < -0.5f) k -= 1.0f;
+    return k;
+}
+CN_HD float cn_rint_scaled(float x, float c)  { return cn_fix_scaled(x, c, rintf(x * c)); }
+CN_HD float cn_round_scaled(float x, float c) { return cn_fix_scaled(x, c, cn_round_ha(x * c)); }
+/* k / 1000 and k / 100 for integer-valued |k| <= 2^24.  q0 = k * RN(1/c) is
+ * within 1 ulp; Markstein's fma correction then yields exactly RN(k / c), i.e.
+ * the same bits as an IEEE division (checked exhaustively in
+ * tests/test_math_primitives.py) at 3 instructions instead of ~12. */
+CN_HD float cn_div1000(float k) { float q = k * 0.001f; return fmaf(fmaf(-q, 1000.0f, k), 0.001f, q); }
+CN_HD float cn_div100(float k)  { float q = k * 0.01f;  return fmaf(fmaf(-q, 100.0f, k), 0.01f, q); }
+/* np.around(x, 3) */
+CN_HD float cn_np_round3(float x) { return cn_div1000(cn_rint_scaled(x, 1000.0f)); }
 /* Python-2 round(x, 3) / round(x, 2) */
-CN_HD float cn_py_round3(float x) { return cn_round_ha(x * 1000.0f) / 1000.0f; }
-CN_HD float cn_py_round2(float x) { return cn_round_ha(x * 100.0f) / 100.0f; }
+CN_HD float cn_py_round3(float x) { return cn_div1000(cn_round_scaled(x, 1000.0f)); }
+CN_HD float cn_py_round2(float x) { return cn_div100(cn_round_scaled(x, 100.0f)); }
 
 /* ---- trigonometry on binary angles --------------------------------------
  * Range reduction is exact integer arithmetic (quadrant = top 2 bits after a
@@ -136,27 +154,25 @@ CN_HD void cn_sincos_rad(float x, float* s_out, float* c_out) {
     cn_sincos_bin(cn_rad2bin(r), s_out, c_out);
 }
 
-/* atan on x >= 0, two-step reduction + degree-9 odd polynomial */
-CN_HD float cn_atan_pos(float x) {
-    float y0, t;
-    if (x > 2.414213562373095f)       { y0 = CN_PIO2; t = -1.0f / x; }
-    else if (x > 0.4142135623730950f) { y0 = CN_PIO4; t = (x - 1.0f) / (x + 1.0f); }
-    else                              { y0 = 0.0f;    t = x; }
-    float z = t * t;
-    float p = fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z,
-                        1.99777106478e-1f), z, -3.33329491539e-1f);
-    return y0 + fmaf(p * z, t, t);
-}
-/* atan2(y, x) in [-pi, pi]; atan2(0, 0) = 0 */
+/* atan2(y, x) in [-pi, pi]; atan2(0, 0) = 0.  One division: t = min/max in
+ * [0, 1], degree-15 odd minimax polynomial (|err| <= 1.3e-7), octant fix-up. */
 CN_HD float cn_atan2(float y, float x) {
-    if (x == 0.0f) {
-        if (y > 0.0f) return CN_PIO2;
-        if (y < 0.0f) return -CN_PIO2;
-        return 0.0f;
-    }
-    float t = cn_atan_pos(fabsf(y / x));
-    if (x < 0.0f) t = CN_PI - t;
-    return (y < 0.0f) ? -t : t;
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    if (mx == 0.0f) return 0.0f;
+    float t = mn / mx;
+    float z = t * t;
+    float p = fmaf(-4.0545530866e-03f, z, 2.1862907262e-02f);
+    p = fmaf(p, z, -5.5912254479e-02f);
+    p = fmaf(p, z, 9.6421920913e-02f);
+    p = fmaf(p, z, -1.3908627529e-01f);
+    p = fmaf(p, z, 1.9946565254e-01f);
+    p = fmaf(p, z, -3.3329860750e-01f);
+    p = fmaf(p, z, 9.9999933557e-01f);
+    float r = p * t;
+    if (ay > ax) r = CN_PIO2 - r;
+    if (x < 0.0f) r = CN_PI - r;
+    return (y < 0.0f) ? -r : r;
 }
 
 /* exp(x) for |x| <= 80: Cody-Waite reduction + degree-6 Taylor on |r| <= ln2/2 */
@@ -174,26 +190,30 @@ CN_HD float cn_exp(float x) {
     return cn_bits2f(cn_f2bits(p) + ((uint32_t)e << 23));
 }
 
-/* ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011) ---------------
- * Stateless: the stream position is (env, episode, step, pedestrian), so a
- * world's random numbers do not depend on how envs are sharded over GPUs.
+/* ---- Philox2x32-10 counter-based RNG (Salmon et al. 2011) ----------------
+ * Stateless: the stream position is (global env id, episode, step, pedestrian),
+ * so a world's random numbers do not depend on how envs are sharded over GPUs.
+ * Two 32-bit outputs per call = one (vx, vy) draw.
  */
-typedef struct { uint32_t v[4]; } cn_u32x4;
+typedef struct { uint32_t v[2]; } cn_u32x2;
 
-CN_HD cn_u32x4 cn_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                             uint32_t k0, uint32_t k1) {
+CN_HD cn_u32x2 cn_philox2x32(uint32_t c0, uint32_t c1, uint32_t k0) {
     for (int i = 0; i < 10; ++i) {
-        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n1 = (uint32_t)p1;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        uint32_t n3 = (uint32_t)p0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        uint64_t p = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p >> 32) ^ k0 ^ c1;
+        c1 = (uint32_t)p;
+        c0 = n0;
+        k0 += 0x9E3779B9u;
     }
-    cn_u32x4 r; r.v[0] = c0; r.v[1] = c1; r.v[2] = c2; r.v[3] = c3;
+    cn_u32x2 r; r.v[0] = c0; r.v[1] = c1;
     return r;
+}
+/* counter/key packing used by the env: one draw per (env, episode, step, pedestrian, purpose) */
+CN_HD cn_u32x2 cn_env_rand(uint32_t seed_lo, uint32_t seed_hi, uint32_t gid, uint32_t episode,
+                           uint32_t step, uint32_t ped, uint32_t purpose) {
+    uint32_t c1 = (step & 0xFFFFu) | ((ped & 0xFFu) << 16) | (purpose << 24);
+    uint32_t key = seed_lo ^ (seed_hi * 0x85EBCA6Bu) ^ (episode * 0xC2B2AE35u);
+    return cn_philox2x32(gid, c1, key);
 }
 /* uniform in [0, 1) from the top 24 bits */
 CN_HD float cn_u01(uint32_t bits) { return (float)(bits >> 8) * 5.9604644775390625e-08f; }

@@ -58,6 +58,7 @@ enum {
 #define CN_ACT_V_LIMIT 1.0f
 #define CN_ACT_W_LIMIT 6.0f
 #define CN_WHEEL_SEP   0.160f   /* XACRO:68 */
+#define CN_INV_WHEEL_SEP 6.25f  /* exactly 1 / 0.16 */
 #define CN_TICKS_PER_STEP 3
 
 typedef struct cn_derived {
@@ -72,6 +73,8 @@ typedef struct cn_derived {
     float    cand_d2;        /* (max_range + ped_radius + 1e-3)^2 : LiDAR candidate cull */
     float    goal_lo_x, goal_hi_x, goal_lo_y, goal_hi_y; /* ENV:1303-1319 */
     float    inv_inc_bin;    /* 1 / inc_bin (span rasterisation only) */
+    float    inv_dt;         /* RN(1 / dt): velocities are displacement * inv_dt */
+    float    inv_cp_span;    /* RN(1 / (max_range - collision_range)), UTL:343 */
     int32_t  obs_dim;
     uint32_t seed_lo, seed_hi;
 } cn_derived;
@@ -103,6 +106,8 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->goal_lo_y = c->goal_y - c->goal_box;
     d->goal_hi_y = c->goal_y + c->goal_box;
     d->inv_inc_bin = (float)(1.0 / (double)d->inc_bin);
+    d->inv_dt = (float)(1.0 / (double)c->dt);
+    d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
     d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
     d->seed_lo = (uint32_t)(c->seed & 0xFFFFFFFFu);
     d->seed_hi = (uint32_t)(c->seed >> 32);

@@ -119,10 +119,10 @@ __device__ __forceinline__ void waypoint(const cn_kparams& P, float xf, float yf
         float delta = ((t - m) - 0.5f) * 0.0981747704246810f;
         float z = delta * delta;
         float cd = fmaf(fmaf(4.1666668e-2f, z, -0.5f), z, 1.0f);
-        float rho = P.d.apothem / cd;
-        if (L >= rho) {
-            wx = xf + rho * (gxr / L);
-            wy = yf + rho * (gyr / L);
+        if (L * cd >= P.d.apothem) {
+            float sc = P.d.apothem / (cd * L);
+            wx = fmaf(sc, gxr, xf);
+            wy = fmaf(sc, gyr, yf);
             return;
         }
     }
@@ -148,7 +148,7 @@ __device__ __forceinline__ float heading_to_wp(const cn_kparams& P, float xf, fl
 }
 __device__ __forceinline__ float cp_dto(const cn_kparams& P, float d) {
     if (d > P.max_range) return 0.0f;
-    return (P.max_range - d) / (P.max_range - P.collision_range);
+    return (P.max_range - d) * P.d.inv_cp_span;
 }
 
 // ------------------------------------------------------------ span walking
@@ -360,7 +360,7 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
     const float pcx = cn_py_round3(xf), pcy = cn_py_round3(yf);
     float agent_vel = 0.0f;
     if (have_prev) {
-        const float vx = (pcx - r.ppx) / P.dt, vy = (pcy - r.ppy) / P.dt;
+        const float vx = (pcx - r.ppx) * P.d.inv_dt, vy = (pcy - r.ppy) * P.d.inv_dt;
         agent_vel = sqrtf(fmaf(vx, vx, vy * vy));
     }
     bool conf[NPL], inblk[NPL];
@@ -380,8 +380,8 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
         if (pfl[s] & CN_PF_TRACKED) {
             chx = hitx[s] - hx; chy = hity[s] - hy;
-            speed = sqrtf(fmaf(chy, chy, chx * chx)) / P.dt;
-            ovx = chx / P.dt; ovy = chy / P.dt;
+            speed = sqrtf(fmaf(chy, chy, chx * chx)) * P.d.inv_dt;
+            ovx = chx * P.d.inv_dt; ovy = chy * P.d.inv_dt;
         }
         hitx[s] = hx; hity[s] = hy; pfl[s] |= CN_PF_TRACKED;
         if (d3 < 0.140f) ego_v = true;
@@ -391,7 +391,8 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         const float L = sqrtf(fmaf(ux, ux, uy * uy));
         bool have_dtc = false; float dtc = 0.0f;
         if (L > 0.0f) {
-            ux = ux / L; uy = uy / L;
+            const float invL = 1.0f / L;
+            ux = ux * invL; uy = uy * invL;
             const float wx_ = hx - r.ppx, wy_ = hy - r.ppy;
             const float b = fmaf(wx_, ux, wy_ * uy);
             const float h = fmaf(wx_, uy, -(wy_ * ux));
@@ -408,8 +409,7 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
             cp = dto;
         } else {
             if (have_dtc) {
-                const float ttc = dtc / resultant;
-                const float q = 0.15f / ttc;
+                const float q = (0.15f * resultant) / dtc;
                 cp_ttc = (q < 1.0f) ? q : 1.0f;
             }
             cp = 0.5f * cp_ttc + 0.5f * dto;
@@ -519,7 +519,7 @@ __device__ __forceinline__ void reset_env(const cn_kparams& P, Robot& r, int lan
     for (int s = 0; s < NPL; ++s) {
         const int n = lane + 32 * s;
         if (n < N) {
-            const cn_u32x4 rnd = cn_philox4x32(gid, episode, 0u, (uint32_t)n | 0x10000u, P.d.seed_lo, P.d.seed_hi);
+            const cn_u32x2 rnd = cn_env_rand(P.d.seed_lo, P.d.seed_hi, gid, episode, 0u, (uint32_t)n, 1u);
             const float px = __ldg(&P.cfg->ped_layout[n][0]) + cn_usym(rnd.v[0], P.layout_jitter);
             const float py = __ldg(&P.cfg->ped_layout[n][1]) + cn_usym(rnd.v[1], P.layout_jitter);
             int32_t xi = cn_f2i(px * CN_INV_GRID), yi = cn_f2i(py * CN_INV_GRID);
@@ -544,9 +544,9 @@ __device__ __forceinline__ void add_rep(const cn_kparams& P, int32_t xi, int32_t
     const float lim = rsum + P.rep_cutoff;
     if (d2 < lim * lim && d2 > 0.0f) {
         const float d = sqrtf(d2);
-        const float f = P.rep_strength * cn_exp((rsum - d) / P.rep_range);
-        vex += f * (dx / d);
-        vey += f * (dy / d);
+        const float f = (P.rep_strength * cn_exp((rsum - d) / P.rep_range)) / d;
+        vex += f * dx;
+        vey += f * dy;
     }
 }
 
@@ -645,8 +645,8 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                     int32_t tm = timer[s] - CN_TICKS_PER_STEP;
                     if (tm <= 0) {
                         if (kind == CN_BEHAVIOR_RANDOM) {
-                            const cn_u32x4 rnd = cn_philox4x32(gid, r.episode, (uint32_t)step_counter, (uint32_t)n,
-                                                               P.d.seed_lo, P.d.seed_hi);
+                            const cn_u32x2 rnd = cn_env_rand(P.d.seed_lo, P.d.seed_hi, gid, r.episode,
+                                                             (uint32_t)step_counter, (uint32_t)n, 0u);
                             vx = cn_usym(rnd.v[0], speed);
                             vy = cn_usym(rnd.v[1], speed);
                         } else {
@@ -677,18 +677,20 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
 
             // ---- R: unicycle, midpoint rule (FAKE:109-118, 156-167)
             {
-                const float half = (aw * CN_WHEEL_SEP) / 2.0f;
+                const float half = (aw * CN_WHEEL_SEP) * 0.5f;
                 const float vl = av - half, vr = av + half;
-                const float ds = ((vr + vl) / 2.0f) * P.dt;
-                const float dth = ((vr - vl) / CN_WHEEL_SEP) * P.dt;
+                const float v_body = (vr + vl) * 0.5f;
+                const float w_body = (vr - vl) * CN_INV_WHEEL_SEP;
+                const float ds = v_body * P.dt;
+                const float dth = w_body * P.dt;
                 const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
                 const uint32_t mid = r.th + (uint32_t)(dth_bin >> 1);
                 float sm, cm; cn_sincos_bin(mid, &sm, &cm);
                 r.xi += cn_f2i((ds * cm) * CN_INV_GRID);
                 r.yi += cn_f2i((ds * sm) * CN_INV_GRID);
                 r.th += (uint32_t)dth_bin;
-                r.v = ds / P.dt;
-                r.w = dth / P.dt;
+                r.v = v_body;
+                r.w = w_body;
             }
 
             // ---- get_state

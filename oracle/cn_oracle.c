@@ -7,10 +7,12 @@
  * PARITY STATUS: "parity unpinned" for the simulator half -- the reference
  * delegates robot kinematics, pedestrian physics and the LiDAR to Gazebo/ODE,
  * which is not in /root/reference and cannot run here.
- * The env half (observation assembly, waypoint, reward, done, CP formulas) is
- * pinned against golden vectors generated by importing the reference's own
- * utils.py / Env methods (tests/golden/, tests/gen_golden.py) through the
- * float64 restatement oracle/ref_f64.py.
+ * The env half (scan cleaning, hit points, waypoint, heading / distance, reward,
+ * done, CP formulas, observation assembly) IS pinned: tests/golden/ holds
+ * vectors and whole-episode traces produced by running the reference's own
+ * utils.py and Env.reset/step/get_state/compute_reward in this container
+ * (tests/ref_harness.py, tests/gen_golden.py) on physics injected from this
+ * simulator; tests/test_oracle_golden.py replays them against this file.
  *
  * One world per call, scalar code, brute-force LiDAR (every ray against every
  * primitive).  Each function cites the reference lines it restates:
@@ -77,10 +79,11 @@ static void waypoint(const orc_ctx* c, float xf, float yf, float* wx, float* wy)
         float delta = ((t - m) - 0.5f) * 0.0981747704246810f; /* pi / 32 */
         float z = delta * delta;
         float cd = fmaf(fmaf(4.1666668e-2f, z, -0.5f), z, 1.0f);
-        float rho = c->d.apothem / cd;
-        if (L >= rho) {
-            *wx = xf + rho * (gxr / L);
-            *wy = yf + rho * (gyr / L);
+        /* crossing at distance rho = apothem / cd; it exists iff L >= rho  <=>  L * cd >= apothem */
+        if (L * cd >= c->d.apothem) {
+            float sc = c->d.apothem / (cd * L);          /* rho / L */
+            *wx = fmaf(sc, gxr, xf);
+            *wy = fmaf(sc, gyr, yf);
             return;
         }
     }
@@ -111,15 +114,34 @@ static float heading_to_wp(const orc_ctx* c, float xf, float yf, float yaw, floa
     return h;
 }
 
-/* ---- L: LiDAR (Gazebo ray sensor configured at XACRO:148-179) -----------
- * sample i (1..R-1) at yaw + i * sweep/(R-1), origin at the scan frame
- * (URDF:134-138); nearest hit over the four inner wall faces, then the
- * pedestrian discs in index order (strict <).  Then UTL:375-392: no hit or
- * > max -> max_range; hits below the sensor minimum read as the minimum.
- * Output in OBS order: obs j = R-1-i (reverse, drop sample 0).
+/* ---- C: utils.get_scan_ranges (UTL:375-392) ------------------------------
+ * inf -> max; NaN -> 0; 0.0 -> max; > max -> max; reverse; drop the last.
+ * raw[R] is in sensor order, out[R-1] in observation order: out[j] = raw[R-1-j].
  */
-static void lidar(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
-                  float* ranges /*[R-1]*/, uint8_t* hid /*[R-1]*/) {
+static void clean_scan(const orc_ctx* c, const float* raw, float* out) {
+    const int R = c->cfg.n_samples;
+    const float maxr = c->cfg.max_range;
+    for (int j = 0; j < R - 1; ++j) {
+        float v = raw[(R - 1) - j];
+        float r;
+        if (isinf(v)) r = maxr;
+        else if (isnan(v)) r = 0.0f;
+        else if (v == 0.0f) r = maxr;
+        else if (v > maxr) r = maxr;
+        else r = v;
+        out[j] = r;
+    }
+}
+
+/* ---- L: LiDAR (Gazebo ray sensor configured at XACRO:148-179) -----------
+ * sample i at yaw + i * sweep/(R-1), origin at the scan frame (URDF:134-138);
+ * nearest hit over the four inner wall faces, then the pedestrian discs in
+ * index order (strict <); no return within max_range -> +inf; returns nearer
+ * than the sensor minimum read as the minimum.  Sample 0 is never observed
+ * (UTL:390 drops it) and is not cast.  hid is filled in OBSERVATION order.
+ */
+static void lidar_raw(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
+                      float* raw /*[R]*/, uint8_t* hid /*[R-1]*/) {
     const cn_config* g = &c->cfg;
     const int R = g->n_samples, N = g->n_peds;
     int32_t xi = (int32_t)rob[CN_R_X], yi = (int32_t)rob[CN_R_Y];
@@ -133,8 +155,10 @@ static void lidar(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
         int32_t pxi = (int32_t)pa[4 * n + 0], pyi = (int32_t)pa[4 * n + 1];
         qx[n] = (float)(pxi - xi) * CN_GRID - offx;
         qy[n] = (float)(pyi - yi) * CN_GRID - offy;
+        /* cheap cull: a disc whose centre is beyond max_range + radius cannot be hit */
         cand[n] = fmaf(qx[n], qx[n], qy[n] * qy[n]) < c->d.cand_d2;
     }
+    raw[0] = INFINITY;
     for (int i = 1; i < R; ++i) {
         float s, co; cn_sincos_bin(th + (uint32_t)i * c->d.inc_bin, &s, &co);
         float best = INFINITY; uint8_t id = CN_HIT_NONE;
@@ -159,18 +183,38 @@ static void lidar(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
             if (t < 0.0f) t = 0.0f;                   /* sensor inside the disc */
             if (t <= g->max_range && t < best) { best = t; id = (uint8_t)n; }
         }
-        float r;
-        if (id == CN_HIT_NONE) r = g->max_range;
-        else r = (best < g->sensor_min_range) ? g->sensor_min_range : best;
-        int j = (R - 1) - i;
-        ranges[j] = r; hid[j] = id;
+        if (id != CN_HIT_NONE && best < g->sensor_min_range) best = g->sensor_min_range;
+        raw[i] = best;
+        hid[(R - 1) - i] = id;
     }
+}
+static void lidar(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
+                  float* ranges /*[R-1]*/, uint8_t* hid /*[R-1]*/) {
+    float raw[4096];
+    lidar_raw(c, rob, pa, raw, hid);
+    clean_scan(c, raw, ranges);
+}
+
+/* C2: utils.convert_laserscan_to_coordinate (UTL:110-126) for observation ray j:
+ * from the ROBOT CENTRE (not the scan frame), angle j * inc_deg - yaw with the
+ * Python-2 integer-degree increment, y negated, both rounded to 3 dp. */
+static void hit_point(const orc_ctx* c, float xf, float yf, uint32_t th, int j, float d, float* hx, float* hy) {
+    float sa, ca; cn_sincos_bin((uint32_t)j * c->d.hit_inc_bin - th, &sa, &ca);
+    *hx = cn_py_round3(xf + d * ca);
+    *hy = cn_py_round3(yf + (d * sa) * -1.0f);
+}
+
+/* UTL:317-323 composed with ENV:835: min(1, 0.15 / (dtc / resultant)); None -> 0 */
+static float cp_ttc_of(int have_dtc, float dtc, float resultant) {
+    if (!have_dtc) return 0.0f;
+    float q = (0.15f * resultant) / dtc;
+    return (q < 1.0f) ? q : 1.0f;
 }
 
 /* UTL:326-345 */
 static float cp_dto(const orc_ctx* c, float d) {
     if (d > c->cfg.max_range) return 0.0f;
-    return (c->cfg.max_range - d) / (c->cfg.max_range - c->cfg.collision_range);
+    return (c->cfg.max_range - d) * c->d.inv_cp_span;
 }
 
 typedef struct { float cp, x, y, vx, vy; int n; } risk_obj;
@@ -218,7 +262,7 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     float p_prev_x = f_of(rob[CN_R_PPX]), p_prev_y = f_of(rob[CN_R_PPY]);
     float agent_vel = 0.0f;
     if (have_prev_pose) {                      /* UTL:227-236 */
-        float vx = (p_cur_x - p_prev_x) / g->dt, vy = (p_cur_y - p_prev_y) / g->dt;
+        float vx = (p_cur_x - p_prev_x) * c->d.inv_dt, vy = (p_cur_y - p_prev_y) * c->d.inv_dt;
         agent_vel = sqrtf(fmaf(vx, vx, vy * vy));
     }
     float sy_, cy_; cn_sincos_bin(th, &sy_, &cy_);
@@ -247,16 +291,14 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
         float d3 = cn_py_round3(d_raw);                    /* ENV:324,384 */
         /* C2: utils.convert_laserscan_to_coordinate (UTL:110-126), from the
          * robot centre with the integer-degree increment */
-        float sa, ca; cn_sincos_bin((uint32_t)jstar * c->d.hit_inc_bin - th, &sa, &ca);
-        float hx = cn_py_round3(xf + d_raw * ca);
-        float hy = cn_py_round3(yf + (d_raw * sa) * -1.0f);
+        float hx, hy; hit_point(c, xf, yf, th, jstar, d_raw, &hx, &hy);
         /* H/I: tracker with ideal association (ENV:656-760) */
         float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
         if (pbn[3] & CN_PF_TRACKED) {
             chx = f_of(pbn[0]) - hx;                      /* last - curr (sic), ENV:806-807 */
             chy = f_of(pbn[1]) - hy;
-            speed = sqrtf(fmaf(chy, chy, chx * chx)) / g->dt;   /* ENV:754-757 */
-            ovx = chx / g->dt; ovy = chy / g->dt;         /* ENV:808-809 */
+            speed = sqrtf(fmaf(chy, chy, chx * chx)) * c->d.inv_dt;   /* ENV:754-757 */
+            ovx = chx * c->d.inv_dt; ovy = chy * c->d.inv_dt;   /* ENV:808-809 */
         }
         pbn[0] = u_of(hx); pbn[1] = u_of(hy); pbn[3] |= CN_PF_TRACKED;
         if (d3 < 0.140f) ego_violation = 1;               /* ENV:1000 */
@@ -267,7 +309,8 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
         float L = sqrtf(fmaf(ux, ux, uy * uy));
         int have_dtc = 0; float dtc = 0.0f;
         if (L > 0.0f) {
-            ux = ux / L; uy = uy / L;
+            float invL = 1.0f / L;
+            ux = ux * invL; uy = uy * invL;
             float wx_ = hx - p_prev_x, wy_ = hy - p_prev_y;
             float b = fmaf(wx_, ux, wy_ * uy);
             float h = fmaf(wx_, uy, -(wy_ * ux));
@@ -283,11 +326,7 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
         if (have_dtc && resultant == 0.0f) {
             cp = dto;                                     /* ENV:828-833 */
         } else {
-            if (have_dtc) {
-                float ttc = dtc / resultant;              /* ENV:835 */
-                float q = 0.15f / ttc;                    /* UTL:319 */
-                cp_ttc = (q < 1.0f) ? q : 1.0f;
-            }
+            cp_ttc = cp_ttc_of(have_dtc, dtc, resultant);
             cp = 0.5f * cp_ttc + 0.5f * dto;              /* ENV:838,851 */
         }
         if (n_obj == 0 || cp_ttc > ego_score) ego_score = cp_ttc;   /* ENV:879 */
@@ -342,6 +381,27 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     return done;
 }
 
+/* W (non-terminal part): step -2, distance +1 iff decreased, heading truth table (ENV:1050-1106) */
+static int shaping_reward(float cur_head, float cur_dist, float prev_head, float prev_dist) {
+    float dd = cur_dist - prev_dist, dh = cur_head - prev_head;
+    int reward = -2;
+    if (dd < 0.0f) reward += 1;                            /* ENV:1076-1078 */
+    int htg = 0;                                           /* ENV:1081-1106 */
+    if (dh > 0.0f) {
+        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head > 0.0f) htg = 0;
+    }
+    if (dh < 0.0f) {
+        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head < 0.0f) htg = 0;
+    }
+    return reward + htg;
+}
+
 /* ---- Z: Env.reset (ENV:1227-1263) + gazebo/reset_simulation -------------- */
 static void reset_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint32_t* pb, float* obs,
                       float* dbg_ranges, uint8_t* dbg_hid) {
@@ -355,7 +415,7 @@ static void reset_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint
     rob[CN_R_X] = (uint32_t)c->d.start_xi; rob[CN_R_Y] = (uint32_t)c->d.start_yi;
     rob[CN_R_TH] = c->d.start_th;
     for (int n = 0; n < N; ++n) {
-        cn_u32x4 r = cn_philox4x32(gid, episode, 0u, (uint32_t)n | 0x10000u, c->d.seed_lo, c->d.seed_hi);
+        cn_u32x2 r = cn_env_rand(c->d.seed_lo, c->d.seed_hi, gid, episode, 0u, (uint32_t)n, 1u);
         float px = g->ped_layout[n][0] + cn_usym(r.v[0], g->layout_jitter);
         float py = g->ped_layout[n][1] + cn_usym(r.v[1], g->layout_jitter);
         int32_t pxi = cn_f2i(px * CN_INV_GRID), pyi = cn_f2i(py * CN_INV_GRID);
@@ -388,9 +448,9 @@ static void add_rep(const orc_ctx* c, int32_t xi, int32_t yi, int32_t xj, int32_
     float lim = rsum + c->cfg.rep_cutoff;
     if (d2 < lim * lim && d2 > 0.0f) {
         float d = sqrtf(d2);
-        float f = c->cfg.rep_strength * cn_exp((rsum - d) / c->cfg.rep_range);
-        *vex += f * (dx / d);
-        *vey += f * (dy / d);
+        float f = (c->cfg.rep_strength * cn_exp((rsum - d) / c->cfg.rep_range)) / d;
+        *vex += f * dx;
+        *vey += f * dy;
     }
 }
 
@@ -427,8 +487,8 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
         int32_t timer = (int32_t)pb[4 * n + 2] - CN_TICKS_PER_STEP;
         if (timer <= 0) {
             if (g->behavior_kind[b] == CN_BEHAVIOR_RANDOM) {
-                cn_u32x4 r = cn_philox4x32(gid, episode, (uint32_t)step_counter, (uint32_t)n,
-                                           c->d.seed_lo, c->d.seed_hi);
+                cn_u32x2 r = cn_env_rand(c->d.seed_lo, c->d.seed_hi, gid, episode, (uint32_t)step_counter,
+                                         (uint32_t)n, 0u);
                 vx = cn_usym(r.v[0], g->behavior_speed[b]);
                 vy = cn_usym(r.v[1], g->behavior_speed[b]);
             } else {
@@ -454,10 +514,12 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     }
 
     /* R: unicycle, midpoint rule (FAKE:109-118, 156-167) */
-    float half = (aw * CN_WHEEL_SEP) / 2.0f;
-    float vl = av - half, vr = av + half;
-    float ds = ((vr + vl) / 2.0f) * g->dt;
-    float dth = ((vr - vl) / CN_WHEEL_SEP) * g->dt;
+    float half = (aw * CN_WHEEL_SEP) * 0.5f;
+    float vl = av - half, vr = av + half;                 /* FAKE:116-117 */
+    float v_body = (vr + vl) * 0.5f;                      /* FAKE:156,165: delta_s / dt     */
+    float w_body = (vr - vl) * CN_INV_WHEEL_SEP;          /* FAKE:157,167: delta_theta / dt */
+    float ds = v_body * g->dt;
+    float dth = w_body * g->dt;
     int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
     uint32_t th = rob[CN_R_TH];
     uint32_t mid = th + (uint32_t)(dth_bin >> 1);
@@ -465,8 +527,8 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     rob[CN_R_X] = (uint32_t)(rxi + cn_f2i((ds * cm) * CN_INV_GRID));
     rob[CN_R_Y] = (uint32_t)(ryi + cn_f2i((ds * sm) * CN_INV_GRID));
     rob[CN_R_TH] = th + (uint32_t)dth_bin;
-    rob[CN_R_V] = u_of(ds / g->dt);
-    rob[CN_R_W] = u_of(dth / g->dt);
+    rob[CN_R_V] = u_of(v_body);
+    rob[CN_R_W] = u_of(w_body);
 
     /* get_state */
     int done_now = observe(c, rob, pa, pb, step_counter, 1, obs, dbg_ranges, dbg_hid);
@@ -476,23 +538,7 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     const int NR = g->n_samples - 1;
     float cur_head = obs[NR + 0], cur_dist = obs[NR + 1];
     float prev_head = f_of(rob[CN_R_PHEAD]), prev_dist = f_of(rob[CN_R_PDIST]);
-    float dd = cur_dist - prev_dist, dh = cur_head - prev_head;
-    int reward = -2;
-    if (dd < 0.0f) reward += 1;                            /* ENV:1076-1078 */
-    int htg = 0;                                           /* ENV:1081-1106 */
-    if (dh > 0.0f) {
-        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
-        if (cur_head < 0.0f && prev_head < 0.0f) htg = 1;
-        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
-        if (cur_head > 0.0f && prev_head > 0.0f) htg = 0;
-    }
-    if (dh < 0.0f) {
-        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
-        if (cur_head > 0.0f && prev_head > 0.0f) htg = 1;
-        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
-        if (cur_head < 0.0f && prev_head < 0.0f) htg = 0;
-    }
-    reward += htg;
+    int reward = shaping_reward(cur_head, cur_dist, prev_head, prev_dist);
     float xf = (float)(int32_t)rob[CN_R_X] * CN_GRID, yf = (float)(int32_t)rob[CN_R_Y] * CN_GRID;
     float wx = f_of(rob[CN_R_WPX]), wy = f_of(rob[CN_R_WPY]);
     if (in_box(xf, yf, wx - g->goal_box, wx + g->goal_box, wy - g->goal_box, wy + g->goal_box)) {
@@ -574,9 +620,28 @@ void orc_exp(const float* x, float* o, int n) { for (int i = 0; i < n; ++i) o[i]
 void orc_round(const float* x, float* np3, float* py3, float* py2, int n) {
     for (int i = 0; i < n; ++i) { np3[i] = cn_np_round3(x[i]); py3[i] = cn_py_round3(x[i]); py2[i] = cn_py_round2(x[i]); }
 }
-void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
-    cn_u32x4 r = cn_philox4x32(c0, c1, c2, c3, k0, k1);
-    memcpy(out, r.v, 16);
+void orc_philox2x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t* out) {
+    cn_u32x2 r = cn_philox2x32(c0, c1, k0);
+    memcpy(out, r.v, 8);
 }
+/* exhaustive check helper: count k in [lo, hi] where the Markstein forms differ from IEEE division */
+long orc_div_const_mismatches(int lo, int hi) {
+    long bad = 0;
+    for (int k = lo; k <= hi; ++k) {
+        float f = (float)k;
+        if (cn_div1000(f) != f / 1000.0f) ++bad;
+        if (cn_div100(f) != f / 100.0f) ++bad;
+    }
+    return bad;
+}
+void orc_clean_scan(const orc_ctx* c, const float* raw, float* out) { clean_scan(c, raw, out); }
+void orc_hit_points(const orc_ctx* c, float x, float y, uint32_t th, const float* scans, float* out_xy) {
+    for (int j = 0; j < c->cfg.n_samples - 1; ++j) hit_point(c, x, y, th, j, scans[j], out_xy + 2 * j, out_xy + 2 * j + 1);
+}
+float orc_cp_ttc(int have_dtc, float dtc, float resultant) { return cp_ttc_of(have_dtc, dtc, resultant); }
+float orc_cp_dto(const orc_ctx* c, float d) { return cp_dto(c, d); }
+int orc_shaping_reward(float ch, float cd, float ph, float pd) { return shaping_reward(ch, cd, ph, pd); }
+int orc_in_goal_box(const orc_ctx* c, float x, float y) { return in_goal_box(c, x, y); }
+float orc_distance(float x, float y, float wx, float wy) { return dist_to_wp(x, y, wx, wy); }
 void orc_waypoint(const orc_ctx* c, float x, float y, float* wx, float* wy) { waypoint(c, x, y, wx, wy); }
 float orc_heading(const orc_ctx* c, float x, float y, float yaw, float wx, float wy) { return heading_to_wp(c, x, y, yaw, wx, wy); }

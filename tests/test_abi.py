@@ -1,0 +1,73 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/crowdnav.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from crowdnav_b200 import _lib
+from crowdnav_b200.config import CnConfig, make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    _lib.build_library()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "crowdnav.h")).read()
+    declared = set(re.findall(r"\b(cn_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.ABI_SYMBOLS), "include/crowdnav.h and _lib.ABI_SYMBOLS disagree"
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "libcrowdnav.so does not export %s" % sym
+
+
+def test_struct_layout_and_pure_entry_points(L):
+    cfg = CnConfig()
+    assert L.cn_config_default(C.byref(cfg)) == 0
+    assert cfg.struct_size == C.sizeof(CnConfig), "ctypes mirror of cn_config is out of sync with the header"
+    assert (cfg.n_peds, cfg.n_samples, cfg.k_obstacles) == (14, 360, 8)
+    assert L.cn_obs_dim(C.byref(cfg)) == 398 == cfg.obs_dim
+    py = make_config()
+    for f in ("dt", "room_xmin", "room_xmax", "room_ymin", "room_ymax", "start_x", "start_y", "start_yaw", "goal_x",
+              "goal_y", "heading_off_x", "heading_off_y", "max_range", "collision_range", "sensor_min_range",
+              "sensor_sweep", "mount_x", "hit_angle_inc_deg", "ped_radius", "robot_radius", "cp_radius",
+              "waypoint_radius", "goal_box"):
+        assert getattr(cfg, f) == getattr(py, f), f
+    assert L.cn_blob_bytes(C.byref(cfg)) == 4 * (16 + 16 + 2 * 14 * 4)
+    assert L.cn_abi_version() == 1
+
+
+def test_errors_are_codes_not_crashes(L):
+    h = C.c_void_p()
+    bad = make_config()
+    bad.struct_size = 12
+    assert L.cn_create(C.byref(bad), 0, C.byref(h)) == -1 and b"struct_size" in L.cn_last_error()
+    bad = make_config(n_peds=14)
+    bad.n_peds = 100
+    assert L.cn_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert L.cn_step(None, None, None, None, None, None) == -1
+    assert L.cn_reset(None, None, None, None) == -1
+    assert L.cn_destroy(None) == 0
+    import torch
+    if not torch.cuda.is_available():
+        # no device here: creation must fail loudly with a CUDA error code, never fall back to a CPU path
+        rc = L.cn_create(C.byref(make_config()), 0, C.byref(h))
+        assert rc in (-2, -1) and L.cn_last_error()
+        from crowdnav_b200.vec_env import CrowdNavVecEnv
+        with pytest.raises(_lib.CrowdNavError):
+            CrowdNavVecEnv(make_config())
+
+
+def test_product_never_imports_the_oracle():
+    """Nothing under crowdnav_b200/ may reference oracle/ (the product must not route through the checker)."""
+    pkg = os.path.join(ROOT, "crowdnav_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "cn_oracle" not in txt.replace(
+                    "oracle/cn_oracle.c", ""), f

@@ -168,3 +168,35 @@ def test_masked_reset_and_blob_roundtrip():
         ob, r, d = g.step(torch.from_numpy(a).cuda())
         assert bits_equal(ob.cpu().numpy(), ob0) and bits_equal(r.cpu().numpy(), r0) and bits_equal(d.cpu().numpy(), d0)
     g.close()
+
+
+def test_full_size_c2_4096_envs():
+    """BASELINE configs[1] at its full size: 4096 envs x 60 steps, bit-exact at every 20th step."""
+    _rollout(baseline_config(1), 60, seed=21, check_every=20)
+
+
+def test_full_size_c3_16384_envs():
+    """BASELINE configs[2] at its full size: 16384 envs x 20 steps."""
+    _rollout(baseline_config(2), 20, seed=22, check_every=20)
+
+
+def test_sharding_invariance_on_device():
+    """Envs [lo, hi) of a 4096-env launch == a (hi-lo)-env launch with env_id_offset = lo (what each rank of the
+    8-GPU config computes): concatenated results are independent of the number of GPUs."""
+    import torch
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    E, lo, hi = 4096, 1024, 1536
+    full = CrowdNavVecEnv(baseline_config(3, n_envs=E), device=0)
+    part = CrowdNavVecEnv(baseline_config(3, n_envs=hi - lo, env_id_offset=lo), device=0)
+    rng = np.random.default_rng(23)
+    full.reset()
+    part.reset()
+    for t in range(50):
+        a = torch.from_numpy(random_actions(rng, E)).cuda()
+        fo, fr, fd = full.step(a)
+        po, pr, pd = part.step(a[lo:hi].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(fo[lo:hi], po) and torch.equal(fr[lo:hi], pr) and torch.equal(fd[lo:hi], pd)
+    assert bits_equal(full.get_state_blob()[16 + lo * 16:16 + hi * 16], part.get_state_blob()[16:16 + (hi - lo) * 16])
+    full.close()
+    part.close()

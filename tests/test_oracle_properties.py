@@ -1,0 +1,114 @@
+"""Size-independent properties of the env-step (run on the oracle; the GPU suite repeats the
+sharding / determinism ones on the device at full BASELINE sizes)."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from crowdnav_b200.config import baseline_config, make_config
+from oracle.oracle import OracleEnv
+from parity_util import bits_equal, random_actions
+
+
+def _run(cfg, steps, seed):
+    env = OracleEnv(cfg, debug=True)
+    env.reset()
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(steps):
+        o, r, d = env.step(random_actions(rng, cfg.n_envs))
+        out.append((o.copy(), r.copy(), d.copy(), env.ranges.copy()))
+    return env, out
+
+
+def test_ranges_bounded_and_rounded_to_millimetres():
+    cfg = baseline_config(1, n_envs=64)
+    env, out = _run(cfg, 60, 0)
+    NR = cfg.n_samples - 1
+    for o, r, d, raw in out:
+        assert raw.min() >= cfg.sensor_min_range - 1e-7 and raw.max() <= cfg.max_range + 1e-7
+        rays = o[:, :NR].astype(np.float64)
+        assert np.abs(rays * 1000 - np.rint(rays * 1000)).max() < 1e-3       # multiples of 0.001
+        assert set(np.unique(r)).issubset({-2.0, -1.0, 0.0, 198.0, 199.0, 200.0, -202.0, -201.0, -200.0,
+                                           398.0, 399.0, 400.0})              # reward is integer-valued
+
+
+def test_sharding_invariance_env_id_offset():
+    """Worlds [lo, hi) of an E-world batch == an (hi-lo)-world batch with env_id_offset = lo: bit-identical."""
+    E, lo, hi = 24, 8, 20
+    cfg = baseline_config(3, n_envs=E)
+    rng = np.random.default_rng(5)
+    acts = [random_actions(rng, E) for _ in range(40)]
+    full = OracleEnv(cfg)
+    part = OracleEnv(baseline_config(3, n_envs=hi - lo, env_id_offset=lo))
+    full.reset()
+    part.reset()
+    assert bits_equal(full.obs[lo:hi], part.obs)
+    for a in acts:
+        fo, fr, fd = full.step(a)
+        po, pr, pd = part.step(a[lo:hi])
+        assert bits_equal(fo[lo:hi], po) and bits_equal(fr[lo:hi], pr) and bits_equal(fd[lo:hi], pd)
+
+
+def test_determinism_and_seed_sensitivity():
+    cfg = baseline_config(1, n_envs=16)
+    a, _ = _run(cfg, 30, 1)
+    b, _ = _run(cfg, 30, 1)
+    assert bits_equal(a.blob, b.blob) and bits_equal(a.obs, b.obs)
+    c, _ = _run(baseline_config(1, n_envs=16, seed=99), 30, 1)
+    assert not bits_equal(a.blob, c.blob)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 19), st.floats(0.66, 2.0), st.floats(0, 6.28))
+def test_pedestrian_beyond_sensor_reach_never_changes_the_scan(ped, dist, ang):
+    """Moving a pedestrian anywhere farther than max_range + radius from the sensor leaves the scan unchanged."""
+    cfg = baseline_config(1, n_envs=1, auto_reset=False)
+    env = OracleEnv(cfg, debug=True)
+    env.reset()
+    # park every pedestrian far away, cast; then move one of them around outside the reach
+    pa = env.ped_a()
+    pa[0, :, 0] = np.int32(int(-2.3 * 2 ** 24)).view(np.uint32)
+    pa[0, :, 1] = np.int32(int(-2.3 * 2 ** 24)).view(np.uint32)
+    env.ped_a()[0, :, 2:] = 0
+    env.ped_b()[0, :, 2] = 10 ** 6            # never resample
+    env.step(np.zeros((1, 2), np.float32))
+    base = env.ranges.copy()
+    rx, ry, _ = env.robot_pose()[0]
+    x, y = rx + (dist + 0.04) * np.cos(ang), ry + (dist + 0.04) * np.sin(ang)
+    x, y = np.clip(x, -2.3, 2.3), np.clip(y, -2.3, 2.3)
+    if np.hypot(x - rx, y - ry) < 0.66 + 0.04:
+        return
+    pa = env.ped_a()
+    pa[0, ped, 0] = np.int32(int(x * 2 ** 24)).view(np.uint32)
+    pa[0, ped, 1] = np.int32(int(y * 2 ** 24)).view(np.uint32)
+    env.step(np.zeros((1, 2), np.float32))
+    assert bits_equal(env.ranges, base)
+
+
+def test_contact_free_pedestrians_move_at_constant_velocity():
+    """With nothing in contact the stand-in for ODE is exactly zero: x += v * dt on the integer grid."""
+    cfg = make_config(n_envs=1, n_peds=2, layout=[(-1.0, -1.0), (1.0, 1.0)], auto_reset=False)
+    env = OracleEnv(cfg)
+    env.reset()
+    env.ped_b()[0, :, 2] = 10 ** 6
+    env.ped_a()[0, 0, 2:] = np.array([0.1, -0.05], np.float32).view(np.uint32)
+    env.ped_a()[0, 1, 2:] = np.array([-0.2, 0.0], np.float32).view(np.uint32)
+    p0 = env.ped_a()[0, :, :2].view(np.int32).copy()
+    for _ in range(5):
+        env.step(np.zeros((1, 2), np.float32))
+    p1 = env.ped_a()[0, :, :2].view(np.int32)
+    step0 = np.rint(np.float32(np.float32(0.1) * np.float32(0.15)) * np.float32(2 ** 24))
+    assert p1[0, 0] - p0[0, 0] == 5 * int(step0)
+    assert abs((p1[1, 0] - p0[1, 0]) / 2 ** 24 - (-0.2 * 0.15 * 5)) < 1e-6 and p1[1, 1] == p0[1, 1]
+
+
+def test_blob_is_the_whole_state():
+    cfg = baseline_config(1, n_envs=8)
+    env, _ = _run(cfg, 20, 3)
+    snap = env.blob.copy()
+    rng = np.random.default_rng(9)
+    acts = [random_actions(rng, 8) for _ in range(10)]
+    first = [tuple(x.copy() for x in env.step(a)) for a in acts]
+    env.blob[:] = snap
+    again = [tuple(x.copy() for x in env.step(a)) for a in acts]
+    for f, g in zip(first, again):
+        assert all(bits_equal(x, y) for x, y in zip(f, g))

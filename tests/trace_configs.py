@@ -1,0 +1,19 @@
+"""Configs of the reference-in-the-loop traces (shared by gen_golden.py and the replay test)."""
+from crowdnav_b200.config import baseline_config, make_config
+
+
+def trace_config(name):
+    if name == "c1":       # BASELINE configs[0]: 37 samples, K=3, 5 pedestrians, 3 m room
+        cfg = baseline_config(0, auto_reset=False)
+        cfg.max_steps = 120
+        return cfg, {"/turtlebot3/scan_ranges": 37}, dict(n_steps=600, seed=11, seek_goal=False)
+    if name == "train":    # the reference's training world: 360 samples, K=8, 14 pedestrians
+        cfg = make_config(n_envs=1, auto_reset=False, layout_jitter=0.05, max_steps=150)
+        return cfg, {"/turtlebot3/scan_ranges": 360}, dict(n_steps=500, seed=12, seek_goal=False)
+    if name == "goal":     # goal seeking: waypoint (+200) / goal (+200) rewards, success episodes
+        cfg = make_config(n_envs=1, auto_reset=False, layout_jitter=0.05, max_steps=400, seed=77)
+        return cfg, {"/turtlebot3/scan_ranges": 360}, dict(n_steps=700, seed=13, seek_goal=True)
+    raise KeyError(name)
+
+
+TRACES = ("c1", "train", "goal")
