@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",                                  # no FMA contraction: cn_math.h is the numeric spec
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
 ]
 
 

@@ -75,6 +75,7 @@ typedef struct cn_derived {
     float    inv_inc_bin;    /* 1 / inc_bin (span rasterisation only) */
     float    inv_dt;         /* RN(1 / dt): velocities are displacement * inv_dt */
     float    inv_cp_span;    /* RN(1 / (max_range - collision_range)), UTL:343 */
+    float    max_range_r3;   /* np.around(max_range, 3): the value of a ray with no return */
     int32_t  obs_dim;
     uint32_t seed_lo, seed_hi;
 } cn_derived;
@@ -108,6 +109,7 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->inv_inc_bin = (float)(1.0 / (double)d->inc_bin);
     d->inv_dt = (float)(1.0 / (double)c->dt);
     d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
+    d->max_range_r3 = cn_np_round3(c->max_range);
     d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
     d->seed_lo = (uint32_t)(c->seed & 0xFFFFFFFFu);
     d->seed_hi = (uint32_t)(c->seed >> 32);

@@ -11,21 +11,30 @@
  *   -> waypoint / heading / distance (ENV:246-265), done (ENV:1011-1023),
  *      reward (ENV:1046-1162), optional in-kernel auto-reset (ENV:1227-1263).
  *
- * Mapping.  A CTA owns a tile of TILE consecutive worlds.  The three state
+ * Mapping.  A CTA owns a tile of CN_TILE consecutive worlds.  The three state
  * planes of the tile (cn_state.h) are contiguous in HBM, so thread 0 pulls them
- * into shared memory with three 1-D bulk TMA copies (cp.async.bulk ->
- * UBLKCP) completing on one mbarrier, and pushes them -- plus the tile's
- * [TILE, D] block of observation rows, which is contiguous too -- back with
- * bulk stores.  In between, ONE WARP OWNS ONE WORLD: lanes are pedestrians for
- * the integration / risk phases and rays for the LiDAR / observation phases,
- * and all reductions (min range, centre-ray argmin, top-K rank) are warp
- * shuffles / redux / ballots; there is no inter-warp communication.
+ * into shared memory with three 1-D bulk TMA copies (cp.async.bulk -> UBLKCP)
+ * completing on one mbarrier, and pushes them -- plus the tile's [TILE, D] block
+ * of observation rows, which is contiguous too -- back with bulk stores.
  *
- * LiDAR is span rasterisation, not brute force: the scan row starts at +inf and
- * each primitive (wall face within range, pedestrian within range + radius)
- * min-updates only the rays inside a conservative angular interval around it.
- * The interval is a superset by construction and the per-ray intersection
- * arithmetic is the oracle's, so results equal the brute-force cast bit for bit.
+ * Work inside the CTA is laid out so that no instruction is spent 32 times on
+ * a value that exists once per world:
+ *   phase A  (lane = WORLD, warps 0..2)  everything get_state / compute_reward
+ *            derive from the pose alone: robot kinematics, waypoint, heading,
+ *            distance, agent velocity, rounded pose, reward shaping, goal boxes.
+ *            Results go to a per-world scalar record in shared memory and
+ *            straight into the observation row.
+ *   phase P  (lane = PEDESTRIAN, one warp per world, concurrent with A)
+ *            resample / contact / integrate.
+ *   phase L  (lane = RAY, one warp per world) LiDAR by SPAN RASTERISATION: the
+ *            row starts at its no-return value and each primitive (wall face in
+ *            range, pedestrian within range + radius) min-updates only the rays
+ *            inside a conservative angular interval; 32-ray chunks that no span
+ *            touched are never visited again.  The interval is a superset by
+ *            construction and the per-ray arithmetic is the oracle's, so the
+ *            result equals the brute-force cast bit for bit.
+ *   phase R  (lane = PEDESTRIAN) ray ownership count + centre ray (REDUX),
+ *            collision cone, CP, top-K by ballot-ranked selection.
  *
  * Numerics: every value that reaches an output goes through cn_math.h
  * primitives; compile with -fmad=false (no contraction).  The only approximate
@@ -80,31 +89,25 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ------------------------------------------------------------- env registers
-struct Robot {          // warp-uniform copy of one robot / episode record
-    int32_t xi, yi;
-    uint32_t th;
-    float v, w, wpx, wpy, pdist, phead, ppx, ppy;
-    int32_t step;
-    uint32_t episode, flags, cnt0, cnt1;
+// ------------------------------------------------------ per-world scalar record
+// Written by phase A (or, on the auto-reset path, by the world's own warp),
+// read by the world's warp.  One float4-aligned 128-byte record per world.
+enum {
+    S_XI = 0, S_YI, S_TH, S_V, S_W,        // new pose / body twist (bit patterns)
+    S_WPX, S_WPY,                          // waypoint after get_state + compute_reward
+    S_HEAD, S_DIST,                        // rounded heading / distance (= new previous_*)
+    S_PCX, S_PCY,                          // round(pose, 3) (= new agent_pose_deque[0])
+    S_PPX, S_PPY,                          // previous rounded pose (collision cone)
+    S_XF, S_YF, S_OFFX, S_OFFY,            // float pose, sensor offset
+    S_AVEL,                                // agent speed from the rounded poses
+    S_REWARD,                              // int: shaping + waypoint bonus (terminal part added later)
+    S_PRE,                                 // bit0 in goal box, bit1 timeout
+    S_BAD,                                 // int: 1 if the action was sanitised
+    S_WORDS = 32
 };
 
-__device__ __forceinline__ void robot_load(Robot& r, const uint32_t* s) {
-    r.xi = (int32_t)s[CN_R_X]; r.yi = (int32_t)s[CN_R_Y]; r.th = s[CN_R_TH];
-    r.v = __uint_as_float(s[CN_R_V]); r.w = __uint_as_float(s[CN_R_W]);
-    r.wpx = __uint_as_float(s[CN_R_WPX]); r.wpy = __uint_as_float(s[CN_R_WPY]);
-    r.pdist = __uint_as_float(s[CN_R_PDIST]); r.phead = __uint_as_float(s[CN_R_PHEAD]);
-    r.ppx = __uint_as_float(s[CN_R_PPX]); r.ppy = __uint_as_float(s[CN_R_PPY]);
-    r.step = (int32_t)s[CN_R_STEP]; r.episode = s[CN_R_EPISODE]; r.flags = s[CN_R_FLAGS];
-    r.cnt0 = s[CN_R_CNT0]; r.cnt1 = s[CN_R_CNT1];
-}
-__device__ __forceinline__ void robot_store(const Robot& r, uint32_t* s) {
-    uint4* q = reinterpret_cast<uint4*>(s);
-    q[0] = make_uint4((uint32_t)r.xi, (uint32_t)r.yi, r.th, __float_as_uint(r.v));
-    q[1] = make_uint4(__float_as_uint(r.w), __float_as_uint(r.wpx), __float_as_uint(r.wpy), __float_as_uint(r.pdist));
-    q[2] = make_uint4(__float_as_uint(r.phead), __float_as_uint(r.ppx), __float_as_uint(r.ppy), (uint32_t)r.step);
-    q[3] = make_uint4(r.episode, r.flags, r.cnt0, r.cnt1);
-}
+__device__ __forceinline__ float f_of(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t u_of(float f) { return __float_as_uint(f); }
 
 // ------------------------------------------------------------ scalar formulas
 // (same operation sequences as oracle/cn_oracle.c; see the citations there)
@@ -150,85 +153,201 @@ __device__ __forceinline__ float cp_dto(const cn_kparams& P, float d) {
     if (d > P.max_range) return 0.0f;
     return (P.max_range - d) * P.d.inv_cp_span;
 }
+__device__ __forceinline__ int shaping_reward(float cur_head, float cur_dist, float prev_head, float prev_dist) {
+    const float dd = cur_dist - prev_dist, dh = cur_head - prev_head;
+    int reward = -2;
+    if (dd < 0.0f) reward += 1;
+    int htg = 0;
+    if (dh > 0.0f) {
+        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head > 0.0f) htg = 0;
+    }
+    if (dh < 0.0f) {
+        if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head > 0.0f) htg = 1;
+        if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
+        if (cur_head < 0.0f && prev_head < 0.0f) htg = 0;
+    }
+    return reward + htg;
+}
+
+// ------------------------------------------------------------------ phase A
+// The part of Env.step / get_state / compute_reward that depends on the pose
+// alone, for ONE world held by the calling thread.  `part` selects a slice of
+// the work so three warps can share it (0: waypoint chain, 1: velocities and
+// rounded pose, 2: reward boxes + K-block padding); part < 0 = everything
+// (auto-reset path, executed warp-uniformly by the world's own warp).
+//   rob   : the world's robot record (state BEFORE this step; not modified)
+//   sc    : the world's scalar record      row : the world's observation row
+struct PoseIn { int32_t xi, yi; uint32_t th; float v, w; };
+
+__device__ __forceinline__ PoseIn advance_robot(const cn_kparams& P, const uint32_t* rob, const float* action, int& bad) {
+    // T2 (ENV:1190-1192), sanitised; R: unicycle, midpoint rule (FAKE:109-118, 156-167)
+    float av = action[0], aw = action[1];
+    bad = 0;
+    if (!(fabsf(av) <= 3.0e38f) || !(fabsf(aw) <= 3.0e38f)) { av = 0.0f; aw = 0.0f; bad = 1; }
+    av = fminf(fmaxf(av, -CN_ACT_V_LIMIT), CN_ACT_V_LIMIT);
+    aw = fminf(fmaxf(aw, -CN_ACT_W_LIMIT), CN_ACT_W_LIMIT);
+    const float half = (aw * CN_WHEEL_SEP) * 0.5f;
+    const float vl = av - half, vr = av + half;
+    const float v_body = (vr + vl) * 0.5f;
+    const float w_body = (vr - vl) * CN_INV_WHEEL_SEP;
+    const float ds = v_body * P.dt;
+    const float dth = w_body * P.dt;
+    const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
+    const uint32_t th = rob[CN_R_TH];
+    const uint32_t mid = th + (uint32_t)(dth_bin >> 1);
+    float sm, cm; cn_sincos_bin(mid, &sm, &cm);
+    PoseIn p;
+    p.xi = (int32_t)rob[CN_R_X] + cn_f2i((ds * cm) * CN_INV_GRID);
+    p.yi = (int32_t)rob[CN_R_Y] + cn_f2i((ds * sm) * CN_INV_GRID);
+    p.th = th + (uint32_t)dth_bin;
+    p.v = v_body; p.w = w_body;
+    return p;
+}
+
+__device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& p, int part,
+                                             float wpx, float wpy, float prev_dist, float prev_head,
+                                             float ppx, float ppy, int step_counter, bool have_prev, bool is_step,
+                                             int bad, uint32_t* sc, float* row) {
+    const int NR = P.n_samples - 1, K = P.k_obstacles;
+    const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
+    const float yaw = cn_bin2rad(p.th);
+    if (part <= 0) {
+        // A: waypoint / distance / heading (ENV:246-265); the refresh target depends only on (pose, goal)
+        float nwx, nwy;
+        waypoint(P, xf, yf, nwx, nwy);
+        float wx = wpx, wy = wpy;
+        if (step_counter == 1) { wx = nwx; wy = nwy; }
+        const float dist = cn_py_round2(dist_to_wp(xf, yf, wx, wy));
+        const float head = cn_py_round2(heading_to_wp(P, xf, yf, yaw, wx, wy));
+        if (step_counter % 5 == 0 || dist < prev_dist) { wx = nwx; wy = nwy; }
+        int reward = 0;
+        if (is_step) {
+            // W: compute_reward (ENV:1046-1125); np.around(., 3) of a 2-dp value is the identity
+            reward = shaping_reward(head, dist, prev_head, prev_dist);
+            if (in_box(xf, yf, wx - P.goal_box, wx + P.goal_box, wy - P.goal_box, wy + P.goal_box)) {
+                wx = nwx; wy = nwy;                               // ENV:1109-1116
+                reward += 200;
+                if (in_goal_box(P, wx, wy)) { wx = P.goal_x; wy = P.goal_y; }   // ENV:1121-1123
+            }
+        }
+        sc[S_WPX] = u_of(wx); sc[S_WPY] = u_of(wy);
+        sc[S_HEAD] = u_of(head); sc[S_DIST] = u_of(dist);
+        sc[S_REWARD] = (uint32_t)reward;
+        row[NR + 0] = head; row[NR + 1] = dist;
+    }
+    if (part < 0 || part == 1) {
+        // B (ENV:267-268, yaw RATE used as an angle), rounded pose (ENV:1025-1027), agent speed (UTL:227-236)
+        float sw, cw; cn_sincos_rad(p.w, &sw, &cw);
+        const float avx = -1.0f * (p.v * cw), avy = p.v * sw;
+        const float pcx = cn_py_round3(xf), pcy = cn_py_round3(yf);
+        float agent_vel = 0.0f;
+        if (have_prev) {
+            const float vx = (pcx - ppx) * P.d.inv_dt, vy = (pcy - ppy) * P.d.inv_dt;
+            agent_vel = sqrtf(fmaf(vx, vx, vy * vy));
+        }
+        float sy, cy; cn_sincos_bin(p.th, &sy, &cy);
+        sc[S_XI] = (uint32_t)p.xi; sc[S_YI] = (uint32_t)p.yi; sc[S_TH] = p.th;
+        sc[S_V] = u_of(p.v); sc[S_W] = u_of(p.w);
+        sc[S_PCX] = u_of(pcx); sc[S_PCY] = u_of(pcy);
+        sc[S_PPX] = u_of(ppx); sc[S_PPY] = u_of(ppy);
+        sc[S_XF] = u_of(xf); sc[S_YF] = u_of(yf);
+        sc[S_OFFX] = u_of(P.mount_x * cy); sc[S_OFFY] = u_of(P.mount_x * sy);
+        sc[S_AVEL] = u_of(agent_vel);
+        sc[S_BAD] = (uint32_t)bad;
+        row[NR + 2] = pcx; row[NR + 3] = pcy;
+        row[NR + 4] = cn_py_round3(yaw);
+        row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
+    }
+    if (part < 0 || part == 2) {
+        uint32_t pre = 0;
+        if (in_goal_box(P, xf, yf)) pre |= 1u;                    // ENV:1017
+        if (step_counter >= P.max_steps) pre |= 2u;               // ENV:1021
+        sc[S_PRE] = pre;
+        // K-block padding (ENV:866-876, 895-898): [x, y, 0, 0] with the UNROUNDED pose, then np.around
+        const float padx = cn_np_round3(xf), pady = cn_np_round3(yf);
+        float* b = row + NR + 7;                                  // 16-B alignment is not guaranteed: scalar stores
+        for (int s = 0; s < K; ++s) { b[4 * s] = padx; b[4 * s + 1] = pady; b[4 * s + 2] = 0.0f; b[4 * s + 3] = 0.0f; }
+    }
+}
 
 // ------------------------------------------------------------ span walking
-// Visit every scan index i in [1, NR] whose ray angle i*inc lies within
-// +-alpha of the relative bearing `brel` (binary angle, robot frame), padded.
-// `f(i, valid)` is called by ALL lanes (valid = lane has an index) so it may
-// contain warp-synchronous code; loop bounds are warp-uniform.
-template <class F>
-__device__ __forceinline__ void seg_walk(int s0, int s1, int lane, F& f) {
-    for (int base = s0; base <= s1; base += 32) {
-        int i = base + lane;
-        f(i, i <= s1);
-    }
-}
-template <class F>
-__device__ __forceinline__ void span_walk(const cn_kparams& P, uint32_t brel, float alpha_rad, int lane, F& f) {
+// A span is up to two ranges of scan indices [a0, a1] U [b0, b1] within
+// [1, NR]; walking it calls f(i, valid) for ALL lanes with warp-uniform loop
+// bounds, so f may contain warp-synchronous code.
+struct Span { int a0, a1, b0, b1; };
+
+// rays whose angle i*inc lies within +-alpha of the relative bearing brel (padded, conservative)
+__device__ __forceinline__ Span make_span(const cn_kparams& P, uint32_t brel, float alpha_rad) {
     const int NR = P.n_samples - 1;
-    if (!(alpha_rad < 3.0f)) { seg_walk(1, NR, lane, f); return; }
+    Span s; s.b0 = 1; s.b1 = 0;
+    if (!(alpha_rad < 3.0f)) { s.a0 = 1; s.a1 = NR; return s; }
     const float two32 = 4294967296.0f;
-    float a = alpha_rad * CN_RAD2BIN;
-    float c = (float)brel;
-    float lo = c - a, hi = c + a;
-    float inv = P.d.inv_inc_bin;
-    int i0 = (int)floorf(fmaxf(lo, 0.0f) * inv) - 1;
-    int i1 = (int)(fminf(hi, two32) * inv) + 2;
-    seg_walk(max(i0, 1), min(i1, NR), lane, f);
-    if (lo < 0.0f) {
-        int w0 = (int)floorf((lo + two32) * inv) - 1;
-        seg_walk(max(max(w0, 1), min(i1, NR) + 1), NR, lane, f);
-    }
-    if (hi >= two32) {
-        int w1 = (int)((hi - two32) * inv) + 2;
-        seg_walk(1, min(min(w1, NR), max(i0, 1) - 1), lane, f);
-    }
+    const float a = alpha_rad * CN_RAD2BIN;
+    const float c = (float)brel;
+    const float lo = c - a, hi = c + a;
+    const float inv = P.d.inv_inc_bin;
+    const int i0 = max((int)floorf(fmaxf(lo, 0.0f) * inv) - 1, 1);
+    const int i1 = min((int)(fminf(hi, two32) * inv) + 2, NR);
+    s.a0 = i0; s.a1 = i1;
+    if (lo < 0.0f) { s.b0 = max(max((int)floorf((lo + two32) * inv) - 1, 1), i1 + 1); s.b1 = NR; }
+    else if (hi >= two32) { s.b0 = 1; s.b1 = min(min((int)((hi - two32) * inv) + 2, NR), i0 - 1); }
+    return s;
+}
+template <class F>
+__device__ __forceinline__ void walk(const Span& s, int lane, F& f) {
+    for (int base = s.a0; base <= s.a1; base += 32) { const int i = base + lane; f(i, i <= s.a1); }
+    for (int base = s.b0; base <= s.b1; base += 32) { const int i = base + lane; f(i, i <= s.b1); }
+}
+// 32-ray chunks of the observation row (index j = NR - i) a span can touch
+__device__ __forceinline__ uint32_t chunk_bits(int j_lo, int j_hi) {
+    const int lo = j_lo >> 5, hi = min(j_hi >> 5, 31);
+    if (hi < lo) return 0u;
+    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+__device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
+    uint32_t m = 0;
+    if (s.a1 >= s.a0) m |= chunk_bits(NR - s.a1, NR - s.a0);
+    if (s.b1 >= s.b0) m |= chunk_bits(NR - s.b1, NR - s.b0);
+    return m;
 }
 
-// ------------------------------------------------------------------ observe
-// Env.get_state for the warp's world.  Per-lane pedestrian state in registers
-// (slot s of lane l is pedestrian l + 32 s).  Returns this step's done flag.
+// ------------------------------------------------------------- ray phases
+// LiDAR + perceived-risk block for the warp's world (Env.get_state from
+// ENV:277 on).  Pedestrian state is per lane (slot s of lane l = pedestrian
+// l + 32 s).  Returns min(scan) < collision_range.
 template <int NPL>
-__device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane, int step_counter, bool have_prev,
-                                        const int32_t (&pxi)[NPL], const int32_t (&pyi)[NPL],
-                                        float (&hitx)[NPL], float (&hity)[NPL], uint32_t (&pfl)[NPL],
-                                        float* row, uint8_t* hid, size_t dbg_row) {
+__device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_t* sc, int lane, bool have_prev,
+                                              const int32_t (&pxi)[NPL], const int32_t (&pyi)[NPL],
+                                              float (&hitx)[NPL], float (&hity)[NPL], uint32_t (&pfl)[NPL],
+                                              float* row, uint8_t* hid, size_t dbg_row,
+                                              uint32_t& cnt0, uint32_t& cnt1) {
     const int N = P.n_peds, R = P.n_samples, K = P.k_obstacles, NR = R - 1;
-    const float xf = (float)r.xi * CN_GRID, yf = (float)r.yi * CN_GRID;
-    const uint32_t th = r.th;
-    const float yaw = cn_bin2rad(th);
-
-    // ---- A: waypoint / distance / heading (ENV:246-265).  The refresh target
-    // depends only on (pose, goal), so it is evaluated once and reused.
-    float nwx, nwy;
-    waypoint(P, xf, yf, nwx, nwy);
-    float wx = r.wpx, wy = r.wpy;
-    if (step_counter == 1) { wx = nwx; wy = nwy; }
-    const float dist = cn_py_round2(dist_to_wp(xf, yf, wx, wy));
-    const float head = cn_py_round2(heading_to_wp(P, xf, yf, yaw, wx, wy));
-    if (step_counter % 5 == 0 || dist < r.pdist) { wx = nwx; wy = nwy; }
-    r.wpx = wx; r.wpy = wy;
-
-    // ---- B: ENV:267-268
-    float sw, cw; cn_sincos_rad(r.w, &sw, &cw);
-    const float avx = -1.0f * (r.v * cw), avy = r.v * sw;
-
-    // ---- L: LiDAR by span rasterisation
-    for (int j = lane; j < NR; j += 32) row[j] = INFINITY;
-    {
-        uint32_t* h32 = reinterpret_cast<uint32_t*>(hid);
-        for (int j = lane; j < (NR + 3) / 4; j += 32) h32[j] = 0xFFFFFFFFu;
-    }
-    __syncwarp();
-    float sy, cy; cn_sincos_bin(th, &sy, &cy);
-    const float offx = P.mount_x * cy, offy = P.mount_x * sy;
+    const int32_t rxi = (int32_t)sc[S_XI], ryi = (int32_t)sc[S_YI];
+    const uint32_t th = sc[S_TH];
+    const float xf = f_of(sc[S_XF]), yf = f_of(sc[S_YF]);
+    const float offx = f_of(sc[S_OFFX]), offy = f_of(sc[S_OFFY]);
     const float ox = xf + offx, oy = yf + offy;
     const float maxr = P.max_range;
+    const int n_chunks = (NR + 31) >> 5;
+    const bool track_chunks = n_chunks <= 32;
 
-    // walls: x faces, then y faces (oracle order)
+    // ---- row <- "no return" (already in its final rounded form), hit ids <- none
+    {
+        const float fill = P.d.max_range_r3;
+        for (int j = lane; j < NR; j += 32) row[j] = fill;
+        uint4* h4 = reinterpret_cast<uint4*>(hid);
+        for (int j = lane; j < (NR + 15) / 16; j += 32) h4[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncwarp();
+    uint32_t dirty = 0;
+
+    // ---- walls: x faces, then y faces (oracle order).  acos(u) <= (pi/2) sqrt(1-u)
 #pragma unroll 1
-    for (int face = 0; face < 4; ++face) {
-        // face 0: +x, 1: -x, 2: +y, 3: -y
+    for (int face = 0; face < 4; ++face) {      // 0: +x, 1: -x, 2: +y, 3: -y
         const bool xface = face < 2;
         const bool pos = (face & 1) == 0;
         const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
@@ -236,9 +355,10 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         const float D = pos ? (wall - o) : (o - wall);
         if (!(D > 0.0f) || D > maxr * 1.0001f) continue;
         const uint32_t normal = xface ? (pos ? 0u : 0x80000000u) : (pos ? 0x40000000u : 0xC0000000u);
-        // rays with cos(angle to normal) >= D / maxr ; acos(u) <= (pi/2) sqrt(1-u)
         const float alpha = CN_PIO2 * sqrtf(fmaxf(1.0f - D / maxr, 0.0f)) + 0.02f;
         const float num = wall - o;
+        const Span sp = make_span(P, normal - th, alpha);
+        dirty |= span_chunks(sp, NR);
         auto f = [&](int i, bool valid) {
             if (!valid) return;
             float s, co; cn_sincos_bin(th + (uint32_t)i * P.d.inc_bin, &s, &co);
@@ -246,33 +366,36 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
             if (pos ? !(den > 0.0f) : !(den < 0.0f)) return;
             const float t = num / den;
             const int j = NR - i;
-            if (t > 0.0f && t <= maxr && t < row[j]) { row[j] = t; hid[j] = CN_HIT_WALL; }
+            if (t > 0.0f && t < maxr && t < row[j]) { row[j] = t; hid[j] = CN_HIT_WALL; }
         };
-        span_walk(P, normal - th, alpha, lane, f);
+        walk(sp, lane, f);
         __syncwarp();
     }
 
-    // pedestrians: per-lane candidate test, then a warp-uniform loop over candidates
-    float qx[NPL], qy[NPL], alpha[NPL];
+    // ---- pedestrians: per-lane candidate test + span, then a warp-uniform loop over candidates
+    float qx[NPL], qy[NPL];
     uint32_t bearing[NPL];
+    Span span[NPL];
     bool cand[NPL];
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
         const int n = lane + 32 * s;
-        cand[s] = false; qx[s] = 0.0f; qy[s] = 0.0f; alpha[s] = 0.0f; bearing[s] = 0u;
+        cand[s] = false; qx[s] = 0.0f; qy[s] = 0.0f; bearing[s] = 0u;
+        span[s].a0 = 1; span[s].a1 = 0; span[s].b0 = 1; span[s].b1 = 0;
         if (n < N) {
-            qx[s] = (float)(pxi[s] - r.xi) * CN_GRID - offx;
-            qy[s] = (float)(pyi[s] - r.yi) * CN_GRID - offy;
+            qx[s] = (float)(pxi[s] - rxi) * CN_GRID - offx;
+            qy[s] = (float)(pyi[s] - ryi) * CN_GRID - offy;
             const float d2 = fmaf(qx[s], qx[s], qy[s] * qy[s]);
             cand[s] = d2 < P.d.cand_d2;
             if (cand[s]) {
                 bearing[s] = cn_rad2bin(cn_atan2(qy[s], qx[s]));
-                const float d = sqrtf(d2);
-                if (d <= P.ped_radius * 1.001f) alpha[s] = 4.0f;       // sensor inside / touching: all rays
-                else {
-                    const float u = P.ped_radius / d;                   // asin(u) <= u + (pi/2 - 1) u^3
-                    alpha[s] = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
+                float alpha = 4.0f;                                    // sensor inside / touching the disc: all rays
+                const float rlim = P.ped_radius * 1.001f;
+                if (d2 > rlim * rlim) {
+                    const float u = P.ped_radius * rsqrtf(d2) * 1.0001f;   // asin(u) <= u + (pi/2 - 1) u^3
+                    alpha = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
                 }
+                span[s] = make_span(P, bearing[s] - th, alpha);
             }
         }
     }
@@ -286,8 +409,10 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         while (m) {
             const int src = __ffs(m) - 1; m &= m - 1;
             const float cqx = __shfl_sync(FULL, qx[s], src), cqy = __shfl_sync(FULL, qy[s], src);
-            const float cal = __shfl_sync(FULL, alpha[s], src);
-            const uint32_t cb = __shfl_sync(FULL, bearing[s], src);
+            Span sp;
+            sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
+            sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
+            dirty |= span_chunks(sp, NR);
             const uint8_t id = (uint8_t)(src + 32 * s);
             auto f = [&](int i, bool valid) {
                 if (!valid) return;
@@ -301,9 +426,9 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
                 float t = b - sq;
                 if (t < 0.0f) t = 0.0f;
                 const int j = NR - i;
-                if (t <= maxr && t < row[j]) { row[j] = t; hid[j] = id; }
+                if (t < maxr && t < row[j]) { row[j] = t; hid[j] = id; }
             };
-            span_walk(P, cb - th, cal, lane, f);
+            walk(sp, lane, f);
             __syncwarp();
         }
     }
@@ -317,8 +442,10 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         uint32_t m = cmask[s];
         while (m) {
             const int src = __ffs(m) - 1; m &= m - 1;
-            const float cal = __shfl_sync(FULL, alpha[s], src);
             const uint32_t cb = __shfl_sync(FULL, bearing[s], src);
+            Span sp;
+            sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
+            sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
             const uint8_t id = (uint8_t)(src + 32 * s);
             int c = 0; uint32_t bkey = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
             auto f = [&](int i, bool valid) {
@@ -335,41 +462,52 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
                 }
                 c += __popc(__ballot_sync(FULL, hit));
             };
-            span_walk(P, cb - th, cal, lane, f);
-            const uint32_t kmin = __reduce_min_sync(FULL, bkey);
-            const int jm = (int)__reduce_min_sync(FULL, (uint32_t)(bkey == kmin ? bj : 0x7FFFFFFF));
-            if (lane == src) { cnt[s] = c; jstar[s] = jm; }
+            walk(sp, lane, f);
+            if (c >= 4) {
+                const uint32_t kmin = __reduce_min_sync(FULL, bkey);
+                const int jm = (int)__reduce_min_sync(FULL, (uint32_t)(bkey == kmin ? bj : 0x7FFFFFFF));
+                if (lane == src) { cnt[s] = c; jstar[s] = jm; }
+            }
         }
     }
 
-    // ---- clean + min (UTL:375-392, ENV:1012)
-    float mn = INFINITY;
-    for (int j = lane; j < NR; j += 32) {
-        float t = row[j];
-        float rr = (hid[j] == CN_HIT_NONE) ? maxr : ((t < P.sensor_min_range) ? P.sensor_min_range : t);
-        row[j] = rr;
-        mn = fminf(mn, rr);
-        if (P.dbg_ranges) P.dbg_ranges[dbg_row * NR + j] = rr;
-        if (P.dbg_hid) P.dbg_hid[dbg_row * NR + j] = hid[j];
+    // ---- debug taps (tests only): raw cleaned ranges + hit ids for every ray
+    if (P.dbg_ranges || P.dbg_hid) {
+        for (int j = lane; j < NR; j += 32) {
+            const uint8_t h = hid[j];
+            const float t = row[j];
+            const float rr = (h == CN_HIT_NONE) ? maxr : ((t < P.sensor_min_range) ? P.sensor_min_range : t);
+            if (P.dbg_ranges) P.dbg_ranges[dbg_row * NR + j] = rr;
+            if (P.dbg_hid) P.dbg_hid[dbg_row * NR + j] = h;
+        }
+    }
+
+    // ---- clean + min (UTL:375-392, ENV:1012) + np.around, only where a span went
+    float mn = maxr;
+    for (int c = 0; c < n_chunks; ++c) {
+        if (track_chunks && !((dirty >> c) & 1u)) continue;
+        const int j = (c << 5) + lane;
+        if (j < NR && hid[j] != CN_HIT_NONE) {
+            const float t = row[j];
+            const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
+            mn = fminf(mn, rr);
+            row[j] = rr;            // raw for the centre-ray lookups below; rounded afterwards
+        }
     }
     __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
 
     // ---- H-J: per confirmed pedestrian (lane-parallel)
-    const float pcx = cn_py_round3(xf), pcy = cn_py_round3(yf);
-    float agent_vel = 0.0f;
-    if (have_prev) {
-        const float vx = (pcx - r.ppx) * P.d.inv_dt, vy = (pcy - r.ppy) * P.d.inv_dt;
-        agent_vel = sqrtf(fmaf(vx, vx, vy * vy));
-    }
+    const float pcx = f_of(sc[S_PCX]), pcy = f_of(sc[S_PCY]);
+    const float ppx = f_of(sc[S_PPX]), ppy = f_of(sc[S_PPY]);
+    const float agent_vel = f_of(sc[S_AVEL]);
     bool conf[NPL], inblk[NPL];
     float o_cp[NPL], o_x[NPL], o_y[NPL], o_vx[NPL], o_vy[NPL], o_ttc[NPL];
     bool ego_v = false;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
-        const int n = lane + 32 * s;
-        conf[s] = (n < N) && cand[s] && cnt[s] >= 4;
+        conf[s] = cnt[s] >= 4;
         inblk[s] = false; o_cp[s] = 0.0f; o_x[s] = 0.0f; o_y[s] = 0.0f; o_vx[s] = 0.0f; o_vy[s] = 0.0f; o_ttc[s] = 0.0f;
         if (!conf[s]) { pfl[s] &= ~CN_PF_TRACKED; continue; }
         const float d_raw = row[jstar[s]];
@@ -387,13 +525,13 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         if (d3 < 0.140f) ego_v = true;
         if (!have_prev) continue;
         const float tx = pcx + chx, ty = pcy + chy;
-        float ux = tx - r.ppx, uy = ty - r.ppy;
+        float ux = tx - ppx, uy = ty - ppy;
         const float L = sqrtf(fmaf(ux, ux, uy * uy));
         bool have_dtc = false; float dtc = 0.0f;
         if (L > 0.0f) {
             const float invL = 1.0f / L;
             ux = ux * invL; uy = uy * invL;
-            const float wx_ = hx - r.ppx, wy_ = hy - r.ppy;
+            const float wx_ = hx - ppx, wy_ = hy - ppy;
             const float b = fmaf(wx_, ux, wy_ * uy);
             const float h = fmaf(wx_, uy, -(wy_ * ux));
             const float disc = fmaf(-h, h, P.d.cp_r2);
@@ -423,97 +561,87 @@ __device__ __forceinline__ bool observe(const cn_kparams& P, Robot& r, int lane,
         confm[s] = __ballot_sync(FULL, conf[s]); blkm[s] = __ballot_sync(FULL, inblk[s]);
         n_seen += __popc(confm[s]); n_obj += __popc(blkm[s]);
     }
-    const bool ego_violation = __any_sync(FULL, ego_v);
-    float ego_score = 0.0f;
-    if (n_obj > 0) {
-        float e = -INFINITY;
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) if (inblk[s]) e = fmaxf(e, o_ttc[s]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e = fmaxf(e, __shfl_xor_sync(FULL, e, o));
-        ego_score = e;
+    __syncwarp();
+
+    // ---- np.around of the rays a span touched (everything else already holds the rounded no-return value)
+    for (int c = 0; c < n_chunks; ++c) {
+        if (track_chunks && !((dirty >> c) & 1u)) continue;
+        const int j = (c << 5) + lane;
+        if (j < NR && hid[j] != CN_HIT_NONE) row[j] = cn_np_round3(row[j]);
     }
 
-    // ---- K: top-K block (ENV:862-907): pad, then rank-select
-    float* blk = row + NR + 7;
-    for (int k = lane; k < 4 * K; k += 32) {
-        const int c4 = k & 3;
-        blk[k] = (c4 == 0) ? xf : ((c4 == 1) ? yf : 0.0f);
-    }
-    __syncwarp();
-    if (n_obj > 0) {
-        int rank[NPL];
+    if (n_seen > 0) {
+        const bool ego_violation = __any_sync(FULL, ego_v);
+        float ego_score = 0.0f;
+        if (n_obj > 0) {
+            float e = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) rank[s] = 0;
+            for (int s = 0; s < NPL; ++s) if (inblk[s]) e = fmaxf(e, o_ttc[s]);
 #pragma unroll
-        for (int sb = 0; sb < NPL; ++sb) {
-            uint32_t m = blkm[sb];
-            while (m) {
-                const int src = __ffs(m) - 1; m &= m - 1;
-                const float cpb = __shfl_sync(FULL, o_cp[sb], src);
-                const int nb = src + 32 * sb;
+            for (int o = 16; o > 0; o >>= 1) e = fmaxf(e, __shfl_xor_sync(FULL, e, o));
+            ego_score = e;
+
+            // ---- K: top-K block (ENV:862-907): stable rank by CP, keep [-K:]; padding is already in the row
+            float* blk = row + NR + 7;
+            int rank[NPL];
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) {
-                    const int n = lane + 32 * s;
-                    if (nb != n && (cpb > o_cp[s] || (cpb == o_cp[s] && nb < n))) ++rank[s];
+            for (int s = 0; s < NPL; ++s) rank[s] = 0;
+#pragma unroll
+            for (int sb = 0; sb < NPL; ++sb) {
+                uint32_t m = blkm[sb];
+                while (m) {
+                    const int src = __ffs(m) - 1; m &= m - 1;
+                    const float cpb = __shfl_sync(FULL, o_cp[sb], src);
+                    const int nb = src + 32 * sb;
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        const int n = lane + 32 * s;
+                        if (nb != n && (cpb > o_cp[s] || (cpb == o_cp[s] && nb < n))) ++rank[s];
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            if (!inblk[s]) continue;
-            int slot = (P.flags & CN_FLAG_TOPK_HIGHEST) ? rank[s] : rank[s] - (n_obj > K ? n_obj - K : 0);
-            if (slot < 0 || slot >= K) continue;
-            blk[4 * slot + 0] = o_x[s]; blk[4 * slot + 1] = o_y[s];
-            blk[4 * slot + 2] = o_vx[s]; blk[4 * slot + 3] = o_vy[s];
+            for (int s = 0; s < NPL; ++s) {
+                if (!inblk[s]) continue;
+                const int slot = (P.flags & CN_FLAG_TOPK_HIGHEST) ? rank[s] : rank[s] - (n_obj > K ? n_obj - K : 0);
+                if (slot < 0 || slot >= K) continue;
+                blk[4 * slot + 0] = o_x[s]; blk[4 * slot + 1] = o_y[s];          // already multiples of 0.001
+                blk[4 * slot + 2] = cn_np_round3(o_vx[s]); blk[4 * slot + 3] = cn_np_round3(o_vy[s]);
+            }
         }
-    }
-
-    // ---- M: counters (ENV:653-654, 998-1005)
-    {
-        uint32_t ego = r.cnt0 & 0xFFFFu, soc = r.cnt0 >> 16;
-        uint32_t pres = r.cnt1 & 0xFFFFu, bad = r.cnt1 >> 16;
-        if (n_seen > 0 && pres < 0xFFFFu) ++pres;
+        // ---- M: counters (ENV:653-654, 998-1005)
+        uint32_t ego = cnt0 & 0xFFFFu, soc = cnt0 >> 16;
+        uint32_t pres = cnt1 & 0xFFFFu;
+        if (pres < 0xFFFFu) ++pres;
         if (ego_violation && ego < 0xFFFFu) ++ego;
         if (ego_score > 0.4f && soc < 0xFFFFu) ++soc;
-        r.cnt0 = ego | (soc << 16);
-        r.cnt1 = pres | (bad << 16);
-    }
-
-    // ---- N: done (ENV:1011-1023)
-    bool done = false;
-    if (mn < P.collision_range) done = true;
-    if (in_goal_box(P, xf, yf)) done = true;
-    if (step_counter >= P.max_steps) done = true;
-
-    // ---- O: assemble + round (ENV:1025-1042)
-    if (lane == 0) {
-        row[NR + 0] = head; row[NR + 1] = dist;
-        row[NR + 2] = pcx; row[NR + 3] = pcy;
-        row[NR + 4] = cn_py_round3(yaw);
-        row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
+        cnt0 = ego | (soc << 16);
+        cnt1 = pres | (cnt1 & 0xFFFF0000u);
     }
     __syncwarp();
-    for (int k = lane; k < P.d.obs_dim; k += 32) row[k] = cn_np_round3(row[k]);
-    __syncwarp();
-
-    r.ppx = pcx; r.ppy = pcy;
-    return done;
+    return mn < P.collision_range;
 }
 
-// ----------------------------------------------------------------- reset_env
-// Env.reset (ENV:1227-1263) + gazebo/reset_simulation for the warp's world.
+__device__ __forceinline__ void add_rep(const cn_kparams& P, int32_t xi, int32_t yi, int32_t xj, int32_t yj,
+                                        float rsum, float& vex, float& vey) {
+    const float dx = (float)(xi - xj) * CN_GRID, dy = (float)(yi - yj) * CN_GRID;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float lim = rsum + P.rep_cutoff;
+    if (d2 < lim * lim && d2 > 0.0f) {
+        const float d = sqrtf(d2);
+        const float f = (P.rep_strength * cn_exp((rsum - d) / P.rep_range)) / d;
+        vex += f * dx;
+        vey += f * dy;
+    }
+}
+
+// reset a world's pedestrians (lane = pedestrian): gazebo/reset_simulation
 template <int NPL>
-__device__ __forceinline__ void reset_env(const cn_kparams& P, Robot& r, int lane, uint32_t gid,
-                                          int32_t (&pxi)[NPL], int32_t (&pyi)[NPL], float (&pvx)[NPL], float (&pvy)[NPL],
-                                          float (&hitx)[NPL], float (&hity)[NPL], int32_t (&timer)[NPL], uint32_t (&pfl)[NPL],
-                                          float* row, uint8_t* hid, size_t dbg_row) {
+__device__ __forceinline__ void reset_peds(const cn_kparams& P, int lane, uint32_t gid, uint32_t episode,
+                                           int32_t (&pxi)[NPL], int32_t (&pyi)[NPL], float (&pvx)[NPL], float (&pvy)[NPL],
+                                           float (&hitx)[NPL], float (&hity)[NPL], int32_t (&timer)[NPL], uint32_t (&pfl)[NPL]) {
     const int N = P.n_peds;
-    const uint32_t episode = r.episode + 1u;
     const int b = (int)(gid % (uint32_t)P.n_behaviors);
-    r.xi = P.d.start_xi; r.yi = P.d.start_yi; r.th = P.d.start_th;
-    r.v = 0.0f; r.w = 0.0f; r.step = 0; r.episode = episode; r.flags = 0; r.cnt0 = 0; r.cnt1 = 0;
-    r.ppx = 0.0f; r.ppy = 0.0f;
     const int stagger = __ldg(&P.cfg->behavior_stagger_ticks[b]);
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
@@ -528,25 +656,6 @@ __device__ __forceinline__ void reset_env(const cn_kparams& P, Robot& r, int lan
             pxi[s] = xi; pyi[s] = yi; pvx[s] = 0.0f; pvy[s] = 0.0f;
             hitx[s] = 0.0f; hity[s] = 0.0f; timer[s] = (n + 1) * stagger; pfl[s] = 0u;
         }
-    }
-    const float xf = (float)r.xi * CN_GRID, yf = (float)r.yi * CN_GRID;
-    r.wpx = P.goal_x; r.wpy = P.goal_y;
-    r.pdist = dist_to_wp(xf, yf, r.wpx, r.wpy);
-    r.phead = heading_to_wp(P, xf, yf, cn_bin2rad(r.th), r.wpx, r.wpy);
-    (void)observe<NPL>(P, r, lane, 0, false, pxi, pyi, hitx, hity, pfl, row, hid, dbg_row);
-    r.cnt0 = 0; r.cnt1 = 0;
-}
-
-__device__ __forceinline__ void add_rep(const cn_kparams& P, int32_t xi, int32_t yi, int32_t xj, int32_t yj,
-                                        float rsum, float& vex, float& vey) {
-    const float dx = (float)(xi - xj) * CN_GRID, dy = (float)(yi - yj) * CN_GRID;
-    const float d2 = fmaf(dx, dx, dy * dy);
-    const float lim = rsum + P.rep_cutoff;
-    if (d2 < lim * lim && d2 > 0.0f) {
-        const float d = sqrtf(d2);
-        const float f = (P.rep_strength * cn_exp((rsum - d) / P.rep_range)) / d;
-        vex += f * dx;
-        vey += f * dy;
     }
 }
 
@@ -568,7 +677,8 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     float* s_obs = reinterpret_cast<float*>(s_pb + CN_TILE * N * 4);            // [TILE][D]
     const int hid_stride = (NR + 15) & ~15;
     uint8_t* s_hid = reinterpret_cast<uint8_t*>(s_obs + (((size_t)CN_TILE * D + 3) & ~(size_t)3));  // [TILE][hid_stride]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hid + (size_t)CN_TILE * hid_stride);
+    uint32_t* s_sc = reinterpret_cast<uint32_t*>(s_hid + (size_t)CN_TILE * hid_stride);              // [TILE][S_WORDS]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sc + CN_TILE * S_WORDS);
 
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
     const uint32_t ped_bytes = (uint32_t)nE * (uint32_t)N * 16u;
@@ -589,63 +699,52 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     bool active = warp < nE;
     if (MODE == 1 && active && P.mask) active = P.mask[e] != 0;
     float* row = s_obs + (size_t)warp * D;
-    if (active) {
-        uint8_t* hid = s_hid + (size_t)warp * hid_stride;
-        uint32_t* srob = s_robot + warp * CN_ROBOT_WORDS;
-        uint4* spa = reinterpret_cast<uint4*>(s_pa) + (size_t)warp * N;
-        uint4* spb = reinterpret_cast<uint4*>(s_pb) + (size_t)warp * N;
-        const uint32_t gid = (uint32_t)(P.env_id_offset + e);
-        const int b = (int)(gid % (uint32_t)P.n_behaviors);
+    uint8_t* hid = s_hid + (size_t)warp * hid_stride;
+    uint32_t* srob = s_robot + warp * CN_ROBOT_WORDS;
+    uint32_t* sc = s_sc + warp * S_WORDS;
+    uint4* spa = reinterpret_cast<uint4*>(s_pa) + (size_t)warp * N;
+    uint4* spb = reinterpret_cast<uint4*>(s_pb) + (size_t)warp * N;
+    const uint32_t gid = (uint32_t)(P.env_id_offset + e);
 
-        Robot r; robot_load(r, srob);
-        int32_t pxi[NPL], pyi[NPL], timer[NPL];
-        float pvx[NPL], pvy[NPL], hitx[NPL], hity[NPL];
-        uint32_t pfl[NPL];
-#pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            const int n = lane + 32 * s;
-            pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u;
-            if (n < N) {
-                const uint4 a = spa[n], bb = spb[n];
-                pxi[s] = (int32_t)a.x; pyi[s] = (int32_t)a.y; pvx[s] = __uint_as_float(a.z); pvy[s] = __uint_as_float(a.w);
-                hitx[s] = __uint_as_float(bb.x); hity[s] = __uint_as_float(bb.y); timer[s] = (int32_t)bb.z; pfl[s] = bb.w;
-            }
+    int32_t pxi[NPL], pyi[NPL], timer[NPL];
+    float pvx[NPL], pvy[NPL], hitx[NPL], hity[NPL];
+    uint32_t pfl[NPL];
+
+    if (MODE == 0) {
+        // ---- phase A: lane = world, three warps share the pose-only work of the whole tile
+        if (warp < 3 && lane < nE) {
+            const uint32_t* rob = s_robot + lane * CN_ROBOT_WORDS;
+            int bad;
+            const PoseIn p = advance_robot(P, rob, P.action + 2 * (size_t)(e0 + lane), bad);
+            pose_scalars(P, p, warp, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]), f_of(rob[CN_R_PHEAD]),
+                         f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1, true, true, bad,
+                         s_sc + lane * S_WORDS, s_obs + (size_t)lane * D);
         }
-
-        if (MODE == 1) {
-            reset_env<NPL>(P, r, lane, gid, pxi, pyi, pvx, pvy, hitx, hity, timer, pfl, row, hid, (size_t)e);
-            r.flags = 0;
-        } else {
-            const int step_counter = r.step + 1;
-            // ---- T2: action (ENV:1190-1192), sanitised
-            float av = P.action[2 * (size_t)e], aw = P.action[2 * (size_t)e + 1];
-            if (!(fabsf(av) <= 3.0e38f) || !(fabsf(aw) <= 3.0e38f)) {
-                av = 0.0f; aw = 0.0f;
-                uint32_t bad = r.cnt1 >> 16;
-                if (bad < 0xFFFFu) ++bad;
-                r.cnt1 = (r.cnt1 & 0xFFFFu) | (bad << 16);
-            }
-            av = fminf(fmaxf(av, -CN_ACT_V_LIMIT), CN_ACT_V_LIMIT);
-            aw = fminf(fmaxf(aw, -CN_ACT_W_LIMIT), CN_ACT_W_LIMIT);
-
-            // ---- P: pedestrians, Jacobi on the old positions still in s_pa
+        // ---- phase P: lane = pedestrian, Jacobi on the old positions in s_pa / old robot pose in s_robot
+        if (active) {
+            const int b = (int)(gid % (uint32_t)P.n_behaviors);
             const int kind = __ldg(&P.cfg->behavior_kind[b]);
             const float speed = __ldg(&P.cfg->behavior_speed[b]);
             const int period = __ldg(&P.cfg->behavior_period_ticks[b]);
             const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
-            // conservative integer prefilter for the contact test
-            const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;
-            int32_t nxi[NPL], nyi[NPL];
+            const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative prefilter
+            const uint32_t lim2 = 2u * (uint32_t)lim_i;
+            const int32_t rxi = (int32_t)srob[CN_R_X], ryi = (int32_t)srob[CN_R_Y];
+            const uint32_t episode = srob[CN_R_EPISODE];
+            const int step_counter = (int)srob[CN_R_STEP] + 1;
 #pragma unroll
             for (int s = 0; s < NPL; ++s) {
                 const int n = lane + 32 * s;
-                nxi[s] = pxi[s]; nyi[s] = pyi[s];
+                pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u;
                 if (n < N) {
-                    float vx = pvx[s], vy = pvy[s];
-                    int32_t tm = timer[s] - CN_TICKS_PER_STEP;
+                    const uint4 a = spa[n], bb = spb[n];
+                    const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
+                    float vx = f_of(a.z), vy = f_of(a.w);
+                    hitx[s] = f_of(bb.x); hity[s] = f_of(bb.y); pfl[s] = bb.w;
+                    int32_t tm = (int32_t)bb.z - CN_TICKS_PER_STEP;
                     if (tm <= 0) {
                         if (kind == CN_BEHAVIOR_RANDOM) {
-                            const cn_u32x2 rnd = cn_env_rand(P.d.seed_lo, P.d.seed_hi, gid, r.episode,
+                            const cn_u32x2 rnd = cn_env_rand(P.d.seed_lo, P.d.seed_hi, gid, episode,
                                                              (uint32_t)step_counter, (uint32_t)n, 0u);
                             vx = cn_usym(rnd.v[0], speed);
                             vy = cn_usym(rnd.v[1], speed);
@@ -656,91 +755,72 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                         tm += period;
                     }
                     float vex = vx, vey = vy;
+                    const uint32_t bx = (uint32_t)(x0 + lim_i), by = (uint32_t)(y0 + lim_i);
+#pragma unroll 4
                     for (int m = 0; m < N; ++m) {
                         const uint2 o = *reinterpret_cast<const uint2*>(&spa[m]);
-                        const int32_t dxi = pxi[s] - (int32_t)o.x, dyi = pyi[s] - (int32_t)o.y;
-                        if (m != n && abs(dxi) < lim_i && abs(dyi) < lim_i)
-                            add_rep(P, pxi[s], pyi[s], (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                        if ((bx - o.x) < lim2 && (by - o.y) < lim2 && m != n)
+                            add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
                     }
-                    add_rep(P, pxi[s], pyi[s], r.xi, r.yi, rrob, vex, vey);
-                    int32_t nx = pxi[s] + cn_f2i((vex * P.dt) * CN_INV_GRID);
-                    int32_t ny = pyi[s] + cn_f2i((vey * P.dt) * CN_INV_GRID);
+                    add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
+                    int32_t nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
+                    int32_t ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
                     if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
                     if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
                     if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
                     if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
-                    nxi[s] = nx; nyi[s] = ny; pvx[s] = vx; pvy[s] = vy; timer[s] = tm;
+                    pxi[s] = nx; pyi[s] = ny; pvx[s] = vx; pvy[s] = vy; timer[s] = tm;
                 }
             }
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) { pxi[s] = nxi[s]; pyi[s] = nyi[s]; }
+        }
+        __syncthreads();        // scalar records + observation-row scalars of the whole tile are in place
+    }
 
-            // ---- R: unicycle, midpoint rule (FAKE:109-118, 156-167)
-            {
-                const float half = (aw * CN_WHEEL_SEP) * 0.5f;
-                const float vl = av - half, vr = av + half;
-                const float v_body = (vr + vl) * 0.5f;
-                const float w_body = (vr - vl) * CN_INV_WHEEL_SEP;
-                const float ds = v_body * P.dt;
-                const float dth = w_body * P.dt;
-                const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
-                const uint32_t mid = r.th + (uint32_t)(dth_bin >> 1);
-                float sm, cm; cn_sincos_bin(mid, &sm, &cm);
-                r.xi += cn_f2i((ds * cm) * CN_INV_GRID);
-                r.yi += cn_f2i((ds * sm) * CN_INV_GRID);
-                r.th += (uint32_t)dth_bin;
-                r.v = v_body;
-                r.w = w_body;
-            }
-
-            // ---- get_state
-            const bool done_now = observe<NPL>(P, r, lane, step_counter, true, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e);
-            const bool done = ((r.flags & CN_RF_DONE) != 0) || done_now;
-
-            // ---- W: compute_reward (ENV:1046-1162) on the rounded heading / distance
-            const float cur_head = row[NR + 0], cur_dist = row[NR + 1];
-            const float prev_head = r.phead, prev_dist = r.pdist;
-            const float dd = cur_dist - prev_dist, dh = cur_head - prev_head;
-            int reward = -2;
-            if (dd < 0.0f) reward += 1;
-            int htg = 0;
-            if (dh > 0.0f) {
-                if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
-                if (cur_head < 0.0f && prev_head < 0.0f) htg = 1;
-                if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
-                if (cur_head > 0.0f && prev_head > 0.0f) htg = 0;
-            }
-            if (dh < 0.0f) {
-                if (cur_head < 0.0f && prev_head > 0.0f) htg = 1;
-                if (cur_head > 0.0f && prev_head > 0.0f) htg = 1;
-                if (cur_head > 0.0f && prev_head < 0.0f) htg = 1;
-                if (cur_head < 0.0f && prev_head < 0.0f) htg = 0;
-            }
-            reward += htg;
-            const float xf = (float)r.xi * CN_GRID, yf = (float)r.yi * CN_GRID;
-            if (in_box(xf, yf, r.wpx - P.goal_box, r.wpx + P.goal_box, r.wpy - P.goal_box, r.wpy + P.goal_box)) {
-                float wx, wy; waypoint(P, xf, yf, wx, wy);
-                reward += 200;
-                if (in_goal_box(P, wx, wy)) { wx = P.goal_x; wy = P.goal_y; }
-                r.wpx = wx; r.wpy = wy;
-            }
-            r.pdist = cur_dist; r.phead = cur_head;
+    if (active) {
+        uint32_t flags = srob[CN_R_FLAGS], cnt0 = srob[CN_R_CNT0], cnt1 = srob[CN_R_CNT1];
+        uint32_t episode = srob[CN_R_EPISODE];
+        int step = (int)srob[CN_R_STEP];
+        bool do_reset = (MODE == 1);
+        if (MODE == 0) {
+            // ---- phases L + R, then done / reward (ENV:1011-1023, 1136-1159)
+            if (sc[S_BAD]) { uint32_t bad = cnt1 >> 16; if (bad < 0xFFFFu) ++bad; cnt1 = (cnt1 & 0xFFFFu) | (bad << 16); }
+            const bool collided = scan_and_risk<NPL>(P, sc, lane, true, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e, cnt0, cnt1);
+            const uint32_t pre = sc[S_PRE];
+            const bool done = ((flags & CN_RF_DONE) != 0) || collided || pre != 0u;
+            int reward = (int)sc[S_REWARD];
             if (done) {
-                r.flags |= CN_RF_DONE;
-                if (in_goal_box(P, xf, yf)) { r.flags |= CN_RF_SUCCESS; r.flags &= ~CN_RF_FAILURE; reward += 200; }
-                else { r.flags |= CN_RF_FAILURE; r.flags &= ~CN_RF_SUCCESS; reward -= 200; }
+                flags |= CN_RF_DONE;
+                if (pre & 1u) { flags |= CN_RF_SUCCESS; flags &= ~CN_RF_FAILURE; reward += 200; }
+                else { flags |= CN_RF_FAILURE; flags &= ~CN_RF_SUCCESS; reward -= 200; }
             }
-            r.step = step_counter;
+            step += 1;
             if (lane == 0) {
                 P.reward[e] = (float)reward;
                 P.done[e] = done ? 1 : 0;
             }
-            if (done && (P.flags & CN_FLAG_AUTO_RESET)) {
-                const uint32_t keep = r.flags & (CN_RF_SUCCESS | CN_RF_FAILURE);
-                __syncwarp();
-                reset_env<NPL>(P, r, lane, gid, pxi, pyi, pvx, pvy, hitx, hity, timer, pfl, row, hid, (size_t)e);
-                r.flags |= keep;
-            }
+            do_reset = done && (P.flags & CN_FLAG_AUTO_RESET);
+        } else {
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) { pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u; }
+        }
+        if (do_reset) {
+            // ---- Z: Env.reset (ENV:1227-1263) by the world's own warp (pose scalars computed warp-uniformly)
+            const uint32_t keep = (MODE == 0) ? (flags & (CN_RF_SUCCESS | CN_RF_FAILURE)) : 0u;
+            __syncwarp();
+            episode += 1u;
+            reset_peds<NPL>(P, lane, gid, episode, pxi, pyi, pvx, pvy, hitx, hity, timer, pfl);
+            PoseIn p; p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; p.v = 0.0f; p.w = 0.0f;
+            const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
+            const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);                           // ENV:1243-1244, unrounded
+            const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
+            if (lane == 0) pose_scalars(P, p, -1, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, sc, row);
+            __syncwarp();
+            cnt0 = 0; cnt1 = 0;
+            (void)scan_and_risk<NPL>(P, sc, lane, false, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e, cnt0, cnt1);
+            cnt0 = 0; cnt1 = 0;                                                                // ENV:1260-1262
+            flags = keep; step = 0;
+            if (lane == 0) { sc[S_HEAD] = u_of(ph); sc[S_DIST] = u_of(pd); }                    // previous_* stay unrounded
+            __syncwarp();
         }
 
         // ---- write the world back into the shared tile
@@ -748,11 +828,17 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
         for (int s = 0; s < NPL; ++s) {
             const int n = lane + 32 * s;
             if (n < N) {
-                spa[n] = make_uint4((uint32_t)pxi[s], (uint32_t)pyi[s], __float_as_uint(pvx[s]), __float_as_uint(pvy[s]));
-                spb[n] = make_uint4(__float_as_uint(hitx[s]), __float_as_uint(hity[s]), (uint32_t)timer[s], pfl[s]);
+                spa[n] = make_uint4((uint32_t)pxi[s], (uint32_t)pyi[s], u_of(pvx[s]), u_of(pvy[s]));
+                spb[n] = make_uint4(u_of(hitx[s]), u_of(hity[s]), (uint32_t)timer[s], pfl[s]);
             }
         }
-        if (lane == 0) robot_store(r, srob);
+        if (lane == 0) {
+            uint4* q = reinterpret_cast<uint4*>(srob);
+            q[0] = make_uint4(sc[S_XI], sc[S_YI], sc[S_TH], sc[S_V]);
+            q[1] = make_uint4(sc[S_W], sc[S_WPX], sc[S_WPY], sc[S_DIST]);
+            q[2] = make_uint4(sc[S_HEAD], sc[S_PCX], sc[S_PCY], (uint32_t)step);
+            q[3] = make_uint4(episode, flags, cnt0, cnt1);
+        }
         // observation row: plain coalesced stores when the tile cannot go out as one bulk copy
         const bool bulk_obs = (MODE == 0) && (((size_t)nE * D) % 4 == 0) && P.obs_bulk_ok;
         if (!bulk_obs) {
@@ -803,6 +889,7 @@ size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim) {
     b += 2 * (size_t)CN_TILE * n_peds * 16;
     b += (((size_t)CN_TILE * obs_dim + 3) & ~(size_t)3) * 4;
     b += (size_t)CN_TILE * ((NR + 15) & ~15);
+    b += (size_t)CN_TILE * S_WORDS * 4;
     b += 16;
     return b;
 }

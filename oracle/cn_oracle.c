@@ -136,7 +136,7 @@ static void clean_scan(const orc_ctx* c, const float* raw, float* out) {
 /* ---- L: LiDAR (Gazebo ray sensor configured at XACRO:148-179) -----------
  * sample i at yaw + i * sweep/(R-1), origin at the scan frame (URDF:134-138);
  * nearest hit over the four inner wall faces, then the pedestrian discs in
- * index order (strict <); no return within max_range -> +inf; returns nearer
+ * index order (strict <); no return strictly inside max_range -> +inf; returns nearer
  * than the sensor minimum read as the minimum.  Sample 0 is never observed
  * (UTL:390 drops it) and is not cast.  hid is filled in OBSERVATION order.
  */
@@ -165,11 +165,11 @@ static void lidar_raw(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
         /* walls: x faces then y faces */
         if (co != 0.0f) {
             float t = ((co > 0.0f ? g->room_xmax : g->room_xmin) - ox) / co;
-            if (t > 0.0f && t <= g->max_range && t < best) { best = t; id = CN_HIT_WALL; }
+            if (t > 0.0f && t < g->max_range && t < best) { best = t; id = CN_HIT_WALL; }
         }
         if (s != 0.0f) {
             float t = ((s > 0.0f ? g->room_ymax : g->room_ymin) - oy) / s;
-            if (t > 0.0f && t <= g->max_range && t < best) { best = t; id = CN_HIT_WALL; }
+            if (t > 0.0f && t < g->max_range && t < best) { best = t; id = CN_HIT_WALL; }
         }
         for (int n = 0; n < N; ++n) {
             if (!cand[n]) continue;
@@ -181,7 +181,7 @@ static void lidar_raw(const orc_ctx* c, const uint32_t* rob, const uint32_t* pa,
             if (!(b + sq > 0.0f)) continue;           /* disc entirely behind */
             float t = b - sq;
             if (t < 0.0f) t = 0.0f;                   /* sensor inside the disc */
-            if (t <= g->max_range && t < best) { best = t; id = (uint8_t)n; }
+            if (t < g->max_range && t < best) { best = t; id = (uint8_t)n; }
         }
         if (id != CN_HIT_NONE && best < g->sensor_min_range) best = g->sensor_min_range;
         raw[i] = best;
