@@ -77,12 +77,13 @@ typedef struct cn_derived {
     float    inv_cp_span;    /* RN(1 / (max_range - collision_range)), UTL:343 */
     float    max_range_r3;   /* np.around(max_range, 3): the value of a ray with no return */
     int32_t  obs_dim;
+    int32_t  pair_cell_shift; /* log2 (grid units) of the contact-prefilter cell: cell / 2 >= contact range */
     uint32_t seed_lo, seed_hi;
 } cn_derived;
 
 static inline int cn_derive(const cn_config* c, cn_derived* d) {
     if (c->n_envs < 1 || c->n_peds < 0 || c->n_peds > CN_MAX_PEDS) return -1;
-    if (c->n_samples < 3 || c->n_samples > 4096) return -1;
+    if (c->n_samples < 3 || c->n_samples > 1025) return -1;   /* 32 chunks of 32 rays */
     if (c->k_obstacles < 0 || c->k_obstacles > CN_MAX_PEDS) return -1;
     if (c->n_behaviors < 1 || c->n_behaviors > CN_MAX_BEHAVIORS) return -1;
     if (!(c->dt > 0.0f) || !(c->max_range > 0.0f)) return -1;
@@ -111,6 +112,13 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
     d->max_range_r3 = cn_np_round3(c->max_range);
     d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
+    {
+        double lim = (double)(c->ped_radius + (c->ped_radius > c->robot_radius ? c->ped_radius : c->robot_radius))
+                     + c->rep_cutoff + 1e-4;
+        int sh = 1;
+        while (sh < 29 && ldexp(1.0, sh - 1 - 24) < lim) ++sh;
+        d->pair_cell_shift = sh;
+    }
     d->seed_lo = (uint32_t)(c->seed & 0xFFFFFFFFu);
     d->seed_hi = (uint32_t)(c->seed >> 32);
     return 0;

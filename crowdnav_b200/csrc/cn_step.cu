@@ -62,6 +62,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -103,7 +106,9 @@ enum {
     S_REWARD,                              // int: shaping + waypoint bonus (terminal part added later)
     S_PRE,                                 // bit0 in goal box, bit1 timeout
     S_BAD,                                 // int: 1 if the action was sanitised
-    S_WORDS = 32
+    S_WDIRTY,                              // chunks of the row the wall spans touch
+    S_WSPAN = 24,                          // 4 wall faces x (a0, a1, b0, b1): rays that can see the face
+    S_WORDS = 40
 };
 
 __device__ __forceinline__ float f_of(uint32_t u) { return __uint_as_float(u); }
@@ -171,6 +176,47 @@ __device__ __forceinline__ int shaping_reward(float cur_head, float cur_dist, fl
         if (cur_head < 0.0f && prev_head < 0.0f) htg = 0;
     }
     return reward + htg;
+}
+
+// ------------------------------------------------------------ span walking
+// A span is up to two ranges of scan indices [a0, a1] U [b0, b1] within
+// [1, NR]; walking it calls f(i, valid) for ALL lanes with warp-uniform loop
+// bounds, so f may contain warp-synchronous code.
+struct Span { int a0, a1, b0, b1; };
+
+// rays whose angle i*inc lies within +-alpha of the relative bearing brel (padded, conservative)
+__device__ __forceinline__ Span make_span(const cn_kparams& P, uint32_t brel, float alpha_rad) {
+    const int NR = P.n_samples - 1;
+    Span s; s.b0 = 1; s.b1 = 0;
+    if (!(alpha_rad < 3.0f)) { s.a0 = 1; s.a1 = NR; return s; }
+    const float two32 = 4294967296.0f;
+    const float a = alpha_rad * CN_RAD2BIN;
+    const float c = (float)brel;
+    const float lo = c - a, hi = c + a;
+    const float inv = P.d.inv_inc_bin;
+    const int i0 = max((int)floorf(fmaxf(lo, 0.0f) * inv) - 1, 1);
+    const int i1 = min((int)(fminf(hi, two32) * inv) + 2, NR);
+    s.a0 = i0; s.a1 = i1;
+    if (lo < 0.0f) { s.b0 = max(max((int)floorf((lo + two32) * inv) - 1, 1), i1 + 1); s.b1 = NR; }
+    else if (hi >= two32) { s.b0 = 1; s.b1 = min(min((int)((hi - two32) * inv) + 2, NR), i0 - 1); }
+    return s;
+}
+template <class F>
+__device__ __forceinline__ void walk(const Span& s, int lane, F& f) {
+    for (int base = s.a0; base <= s.a1; base += 32) { const int i = base + lane; f(i, i <= s.a1); }
+    for (int base = s.b0; base <= s.b1; base += 32) { const int i = base + lane; f(i, i <= s.b1); }
+}
+// 32-ray chunks of the observation row (index j = NR - i) a span can touch
+__device__ __forceinline__ uint32_t chunk_bits(int j_lo, int j_hi) {
+    const int lo = j_lo >> 5, hi = min(j_hi >> 5, 31);
+    if (hi < lo) return 0u;
+    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+__device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
+    uint32_t m = 0;
+    if (s.a1 >= s.a0) m |= chunk_bits(NR - s.a1, NR - s.a0);
+    if (s.b1 >= s.b0) m |= chunk_bits(NR - s.b1, NR - s.b0);
+    return m;
 }
 
 // ------------------------------------------------------------------ phase A
@@ -267,52 +313,36 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         if (in_goal_box(P, xf, yf)) pre |= 1u;                    // ENV:1017
         if (step_counter >= P.max_steps) pre |= 2u;               // ENV:1021
         sc[S_PRE] = pre;
+        // walls in range of the sensor: the rays that can see each face.  acos(u) <= (pi/2) sqrt(1-u)
+        {
+            float sy, cy; cn_sincos_bin(p.th, &sy, &cy);
+            const float ox = xf + P.mount_x * cy, oy = yf + P.mount_x * sy;
+            const float maxr = P.max_range;
+            uint32_t wdirty = 0;
+#pragma unroll
+            for (int face = 0; face < 4; ++face) {      // 0: +x, 1: -x, 2: +y, 3: -y
+                const bool xface = face < 2;
+                const bool pos = (face & 1) == 0;
+                const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
+                const float o = xface ? ox : oy;
+                const float Dw = pos ? (wall - o) : (o - wall);
+                Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
+                if (Dw > 0.0f && Dw <= maxr * 1.0001f) {
+                    const uint32_t normal = xface ? (pos ? 0u : 0x80000000u) : (pos ? 0x40000000u : 0xC0000000u);
+                    const float alpha = CN_PIO2 * sqrtf(fmaxf(1.0f - Dw / maxr, 0.0f)) + 0.02f;
+                    sp = make_span(P, normal - p.th, alpha);
+                    wdirty |= span_chunks(sp, NR);
+                }
+                sc[S_WSPAN + 4 * face + 0] = (uint32_t)sp.a0; sc[S_WSPAN + 4 * face + 1] = (uint32_t)sp.a1;
+                sc[S_WSPAN + 4 * face + 2] = (uint32_t)sp.b0; sc[S_WSPAN + 4 * face + 3] = (uint32_t)sp.b1;
+            }
+            sc[S_WDIRTY] = wdirty;
+        }
         // K-block padding (ENV:866-876, 895-898): [x, y, 0, 0] with the UNROUNDED pose, then np.around
         const float padx = cn_np_round3(xf), pady = cn_np_round3(yf);
         float* b = row + NR + 7;                                  // 16-B alignment is not guaranteed: scalar stores
         for (int s = 0; s < K; ++s) { b[4 * s] = padx; b[4 * s + 1] = pady; b[4 * s + 2] = 0.0f; b[4 * s + 3] = 0.0f; }
     }
-}
-
-// ------------------------------------------------------------ span walking
-// A span is up to two ranges of scan indices [a0, a1] U [b0, b1] within
-// [1, NR]; walking it calls f(i, valid) for ALL lanes with warp-uniform loop
-// bounds, so f may contain warp-synchronous code.
-struct Span { int a0, a1, b0, b1; };
-
-// rays whose angle i*inc lies within +-alpha of the relative bearing brel (padded, conservative)
-__device__ __forceinline__ Span make_span(const cn_kparams& P, uint32_t brel, float alpha_rad) {
-    const int NR = P.n_samples - 1;
-    Span s; s.b0 = 1; s.b1 = 0;
-    if (!(alpha_rad < 3.0f)) { s.a0 = 1; s.a1 = NR; return s; }
-    const float two32 = 4294967296.0f;
-    const float a = alpha_rad * CN_RAD2BIN;
-    const float c = (float)brel;
-    const float lo = c - a, hi = c + a;
-    const float inv = P.d.inv_inc_bin;
-    const int i0 = max((int)floorf(fmaxf(lo, 0.0f) * inv) - 1, 1);
-    const int i1 = min((int)(fminf(hi, two32) * inv) + 2, NR);
-    s.a0 = i0; s.a1 = i1;
-    if (lo < 0.0f) { s.b0 = max(max((int)floorf((lo + two32) * inv) - 1, 1), i1 + 1); s.b1 = NR; }
-    else if (hi >= two32) { s.b0 = 1; s.b1 = min(min((int)((hi - two32) * inv) + 2, NR), i0 - 1); }
-    return s;
-}
-template <class F>
-__device__ __forceinline__ void walk(const Span& s, int lane, F& f) {
-    for (int base = s.a0; base <= s.a1; base += 32) { const int i = base + lane; f(i, i <= s.a1); }
-    for (int base = s.b0; base <= s.b1; base += 32) { const int i = base + lane; f(i, i <= s.b1); }
-}
-// 32-ray chunks of the observation row (index j = NR - i) a span can touch
-__device__ __forceinline__ uint32_t chunk_bits(int j_lo, int j_hi) {
-    const int lo = j_lo >> 5, hi = min(j_hi >> 5, 31);
-    if (hi < lo) return 0u;
-    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
-}
-__device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
-    uint32_t m = 0;
-    if (s.a1 >= s.a0) m |= chunk_bits(NR - s.a1, NR - s.a0);
-    if (s.b1 >= s.b0) m |= chunk_bits(NR - s.b1, NR - s.b0);
-    return m;
 }
 
 // ------------------------------------------------------------- ray phases
@@ -332,45 +362,9 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
     const float offx = f_of(sc[S_OFFX]), offy = f_of(sc[S_OFFY]);
     const float ox = xf + offx, oy = yf + offy;
     const float maxr = P.max_range;
-    const int n_chunks = (NR + 31) >> 5;
-    const bool track_chunks = n_chunks <= 32;
+    const int D = P.d.obs_dim;
 
-    // ---- row <- "no return" (already in its final rounded form), hit ids <- none
-    {
-        const float fill = P.d.max_range_r3;
-        for (int j = lane; j < NR; j += 32) row[j] = fill;
-        uint4* h4 = reinterpret_cast<uint4*>(hid);
-        for (int j = lane; j < (NR + 15) / 16; j += 32) h4[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-    __syncwarp();
-    uint32_t dirty = 0;
-
-    // ---- walls: x faces, then y faces (oracle order).  acos(u) <= (pi/2) sqrt(1-u)
-#pragma unroll 1
-    for (int face = 0; face < 4; ++face) {      // 0: +x, 1: -x, 2: +y, 3: -y
-        const bool xface = face < 2;
-        const bool pos = (face & 1) == 0;
-        const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
-        const float o = xface ? ox : oy;
-        const float D = pos ? (wall - o) : (o - wall);
-        if (!(D > 0.0f) || D > maxr * 1.0001f) continue;
-        const uint32_t normal = xface ? (pos ? 0u : 0x80000000u) : (pos ? 0x40000000u : 0xC0000000u);
-        const float alpha = CN_PIO2 * sqrtf(fmaxf(1.0f - D / maxr, 0.0f)) + 0.02f;
-        const float num = wall - o;
-        const Span sp = make_span(P, normal - th, alpha);
-        dirty |= span_chunks(sp, NR);
-        auto f = [&](int i, bool valid) {
-            if (!valid) return;
-            float s, co; cn_sincos_bin(th + (uint32_t)i * P.d.inc_bin, &s, &co);
-            const float den = xface ? co : s;
-            if (pos ? !(den > 0.0f) : !(den < 0.0f)) return;
-            const float t = num / den;
-            const int j = NR - i;
-            if (t > 0.0f && t < maxr && t < row[j]) { row[j] = t; hid[j] = CN_HIT_WALL; }
-        };
-        walk(sp, lane, f);
-        __syncwarp();
-    }
+    uint32_t dirty = sc[S_WDIRTY];
 
     // ---- pedestrians: per-lane candidate test + span, then a warp-uniform loop over candidates
     float qx[NPL], qy[NPL];
@@ -400,8 +394,56 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
         }
     }
     uint32_t cmask[NPL];
+    {
+        uint32_t mine = 0;
 #pragma unroll
-    for (int s = 0; s < NPL; ++s) cmask[s] = __ballot_sync(FULL, cand[s]);
+        for (int s = 0; s < NPL; ++s) {
+            cmask[s] = __ballot_sync(FULL, cand[s]);
+            if (cand[s]) mine |= span_chunks(span[s], NR);
+        }
+        dirty |= __reduce_or_sync(FULL, mine);
+    }
+
+    // ---- row <- "no return" (already in its final rounded form) where nothing can hit; the chunks a span
+    // touches get the same value and are the only ones visited again.  hit ids <- none.
+    {
+        const float fill = P.d.max_range_r3;
+        float2* r2 = reinterpret_cast<float2*>(row);          // rows are 8-byte aligned (D even) or handled below
+        if ((D & 1) == 0) {
+            for (int j = lane; j < (NR >> 1); j += 32) r2[j] = make_float2(fill, fill);
+            if ((NR & 1) && lane == 0) row[NR - 1] = fill;
+        } else {
+            for (int j = lane; j < NR; j += 32) row[j] = fill;
+        }
+        uint4* h4 = reinterpret_cast<uint4*>(hid);
+        for (int j = lane; j < (NR + 15) / 16; j += 32) h4[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncwarp();
+
+    // ---- walls: x faces, then y faces (oracle order)
+    if (dirty)
+#pragma unroll 1
+    for (int face = 0; face < 4; ++face) {
+        Span sp;
+        sp.a0 = (int)sc[S_WSPAN + 4 * face + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * face + 1];
+        sp.b0 = (int)sc[S_WSPAN + 4 * face + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * face + 3];
+        if (sp.a1 < sp.a0) continue;
+        const bool xface = face < 2;
+        const bool pos = (face & 1) == 0;
+        const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
+        const float num = wall - (xface ? ox : oy);
+        auto f = [&](int i, bool valid) {
+            if (!valid) return;
+            float s, co; cn_sincos_bin(th + (uint32_t)i * P.d.inc_bin, &s, &co);
+            const float den = xface ? co : s;
+            if (pos ? !(den > 0.0f) : !(den < 0.0f)) return;
+            const float t = num / den;
+            const int j = NR - i;
+            if (t > 0.0f && t < maxr && t < row[j]) { row[j] = t; hid[j] = CN_HIT_WALL; }
+        };
+        walk(sp, lane, f);
+        __syncwarp();
+    }
 
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
@@ -412,7 +454,6 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
             Span sp;
             sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
             sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
-            dirty |= span_chunks(sp, NR);
             const uint8_t id = (uint8_t)(src + 32 * s);
             auto f = [&](int i, bool valid) {
                 if (!valid) return;
@@ -484,9 +525,8 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
 
     // ---- clean + min (UTL:375-392, ENV:1012) + np.around, only where a span went
     float mn = maxr;
-    for (int c = 0; c < n_chunks; ++c) {
-        if (track_chunks && !((dirty >> c) & 1u)) continue;
-        const int j = (c << 5) + lane;
+    for (uint32_t dm = dirty; dm; dm &= dm - 1) {
+        const int j = ((__ffs(dm) - 1) << 5) + lane;
         if (j < NR && hid[j] != CN_HIT_NONE) {
             const float t = row[j];
             const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
@@ -564,9 +604,8 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
     __syncwarp();
 
     // ---- np.around of the rays a span touched (everything else already holds the rounded no-return value)
-    for (int c = 0; c < n_chunks; ++c) {
-        if (track_chunks && !((dirty >> c) & 1u)) continue;
-        const int j = (c << 5) + lane;
+    for (uint32_t dm = dirty; dm; dm &= dm - 1) {
+        const int j = ((__ffs(dm) - 1) << 5) + lane;
         if (j < NR && hid[j] != CN_HIT_NONE) row[j] = cn_np_round3(row[j]);
     }
 
@@ -679,11 +718,13 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     uint8_t* s_hid = reinterpret_cast<uint8_t*>(s_obs + (((size_t)CN_TILE * D + 3) & ~(size_t)3));  // [TILE][hid_stride]
     uint32_t* s_sc = reinterpret_cast<uint32_t*>(s_hid + (size_t)CN_TILE * hid_stride);              // [TILE][S_WORDS]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sc + CN_TILE * S_WORDS);
+    uint64_t* s_barA = s_bar + 1;       // phase A done: one arrival per phase-A warp
 
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
     const uint32_t ped_bytes = (uint32_t)nE * (uint32_t)N * 16u;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
+        mbar_init(s_barA, 3);
         fence_mbar_init();
         mbar_expect_tx(s_bar, rob_bytes + 2u * ped_bytes);
         tma_load(s_robot, P.robot + (size_t)e0 * CN_ROBOT_WORDS, rob_bytes, s_bar);
@@ -720,6 +761,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                          f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1, true, true, bad,
                          s_sc + lane * S_WORDS, s_obs + (size_t)lane * D);
         }
+        if (warp < 3) { __syncwarp(); if (lane == 0) mbar_arrive(s_barA); }
         // ---- phase P: lane = pedestrian, Jacobi on the old positions in s_pa / old robot pose in s_robot
         if (active) {
             const int b = (int)(gid % (uint32_t)P.n_behaviors);
@@ -732,6 +774,21 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             const int32_t rxi = (int32_t)srob[CN_R_X], ryi = (int32_t)srob[CN_R_Y];
             const uint32_t episode = srob[CN_R_EPISODE];
             const int step_counter = (int)srob[CN_R_STEP] + 1;
+            uint32_t peers = 0;
+            if (NPL == 1) {
+                const int sh = P.d.pair_cell_shift;
+                uint32_t cx0 = 0xFFFF0000u | (uint32_t)lane, cx1 = cx0, cy0 = 0u, cy1 = 0u;   // unmatched dummy for lanes >= N
+                if (lane < N) {
+                    const uint2 a = *reinterpret_cast<const uint2*>(&spa[lane]);
+                    const uint32_t bx = a.x + 0x40000000u, by = a.y + 0x40000000u;
+                    const uint32_t half = 1u << (sh - 1);
+                    cx0 = bx >> sh; cx1 = (bx + half) >> sh;
+                    cy0 = (by >> sh) << 12; cy1 = ((by + half) >> sh) << 12;
+                }
+                peers = __match_any_sync(FULL, cx0 | cy0) | __match_any_sync(FULL, cx1 | cy0) |
+                        __match_any_sync(FULL, cx0 | cy1) | __match_any_sync(FULL, cx1 | cy1);
+                peers &= ~(1u << lane);
+            }
 #pragma unroll
             for (int s = 0; s < NPL; ++s) {
                 const int n = lane + 32 * s;
@@ -755,14 +812,25 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                         tm += period;
                     }
                     float vex = vx, vey = vy;
-                    const uint32_t bx = (uint32_t)(x0 + lim_i), by = (uint32_t)(y0 + lim_i);
-#pragma unroll 4
-                    for (int m = 0; m < N; ++m) {
-                        const uint2 o = *reinterpret_cast<const uint2*>(&spa[m]);
-                        if ((bx - o.x) < lim2 && (by - o.y) < lim2 && m != n)
+                    if (NPL == 1) {
+                        // contacts are rare: only pedestrians sharing a cell of one of four half-shifted grids
+                        // (cell >= 2 * contact range) can touch; visit those, in index order like the oracle
+                        for (uint32_t pm = peers; pm; pm &= pm - 1) {
+                            const int m = __ffs(pm) - 1;
+                            const uint2 o = *reinterpret_cast<const uint2*>(&spa[m]);
                             add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                        }
+                    } else {
+                        const uint32_t bx = (uint32_t)(x0 + lim_i), by = (uint32_t)(y0 + lim_i);
+#pragma unroll 4
+                        for (int m = 0; m < N; ++m) {
+                            const uint2 o = *reinterpret_cast<const uint2*>(&spa[m]);
+                            if ((bx - o.x) < lim2 && (by - o.y) < lim2 && m != n)
+                                add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                        }
                     }
-                    add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
+                    if ((uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2)
+                        add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
                     int32_t nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
                     int32_t ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
                     if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
@@ -773,7 +841,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                 }
             }
         }
-        __syncthreads();        // scalar records + observation-row scalars of the whole tile are in place
+        mbar_wait(s_barA, 0);   // scalar records + observation-row scalars of the whole tile are in place
     }
 
     if (active) {

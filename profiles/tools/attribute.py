@@ -15,21 +15,29 @@ addr2line = {}
 for f in os.listdir(tmp):
     if not f.endswith(".cubin"):
         continue
-    out = subprocess.run(["nvdisasm", "-g", "-c", f], cwd=tmp, stdout=subprocess.PIPE, text=True).stdout
-    cur_fn, cur = None, None
+    out = subprocess.run(["nvdisasm", "-gi", "-c", f], cwd=tmp, stdout=subprocess.PIPE, text=True).stdout
+    cur_fn, cur, chain, fresh = None, None, [], True
     for ln in out.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
         if m:
-            cur_fn = m.group(1); cur = None; continue
+            cur_fn = m.group(1); cur = None; chain = []; continue
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
+            if fresh:
+                chain = []; fresh = False
+            chain.append((os.path.basename(m.group(1)), int(m.group(2)))); continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
-        if m and cur_fn and kname in cur_fn:
-            addr2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
+        if m:
+            fresh = True
+            if cur_fn and kname in cur_fn and chain:
+                leaf = chain[0]
+                # innermost frame that lies in the kernel source (for phase attribution)
+                outer = next((c for c in chain if c[0].endswith(".cu")), leaf)
+                addr2line[int(m.group(1), 16)] = (leaf, m.group(2).strip(), outer)
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source=sass", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 blocks = txt.split('"Kernel Name"')
 per_line = collections.Counter(); per_line_samples = collections.Counter(); total = 0; tot_s = 0
+per_outer = collections.Counter(); per_outer_s = collections.Counter()
 done = False
 for b in blocks[1:]:
     rows = list(csv.reader(io.StringIO('"Kernel Name"' + b)))
@@ -44,9 +52,11 @@ for b in blocks[1:]:
         a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
         if base is None:
             base = a
-        key = addr2line.get(a - base, ((None, 0), "?"))[0]
+        ent = addr2line.get(a - base, ((None, 0), "?", (None, 0)))
+        key = ent[0]
         n = int(float(r[ie] or 0)); s = int(float(r[isamp] or 0))
         per_line[key] += n; per_line_samples[key] += s; total += n; tot_s += s
+        per_outer[ent[2]] += n; per_outer_s[ent[2]] += s
     break   # first launch only
 src_cache = {}
 def src(fl):
@@ -63,3 +73,22 @@ print("%8s %6s %6s  %-18s %s" % ("inst", "%inst", "%samp", "file:line", "source"
 for k, n in per_line.most_common(top_n):
     print("%8d %6.2f %6.2f  %-18s %s" % (n, 100.0 * n / max(total, 1), 100.0 * per_line_samples[k] / max(tot_s, 1),
                                           "%s:%d" % k if k[0] else "?", src(k)))
+
+# ---- by phase: kernel-source lines grouped under the nearest preceding "// ----" marker
+cu = [p for p in src_cache if p.endswith(".cu")]
+import glob
+cu_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "crowdnav_b200", "csrc", "cn_step.cu")
+lines = open(cu_path).read().splitlines()
+label, labels = "(prologue)", []
+for l in lines:
+    m = re.match(r"\s*// -{3,}\s*(.*?)\s*-*$", l)
+    if m and m.group(1):
+        label = m.group(1)[:70]
+    labels.append(label)
+phase = collections.Counter(); phase_s = collections.Counter()
+for (f, l), n in per_outer.items():
+    lab = labels[l - 1] if f and f.endswith(".cu") and 0 < l <= len(labels) else "(other)"
+    phase[lab] += n; phase_s[lab] += per_outer_s[(f, l)]
+print("\nby phase (innermost kernel-source frame):")
+for lab, n in phase.most_common():
+    print("%9d %6.2f%% inst %6.2f%% samples  %s" % (n, 100.0 * n / max(total, 1), 100.0 * phase_s[lab] / max(tot_s, 1), lab))
