@@ -144,6 +144,10 @@ static void pack(const cn_handle* h, cn_kparams* P) {
     P->mount_x = c->mount_x; P->ped_radius = c->ped_radius; P->robot_radius = c->robot_radius; P->goal_box = c->goal_box;
     P->rep_strength = c->rep_strength; P->rep_range = c->rep_range; P->rep_cutoff = c->rep_cutoff;
     P->layout_jitter = c->layout_jitter;
+    for (int b = 0; b < CN_MAX_BEHAVIORS; ++b) {
+        P->beh_kind[b] = c->behavior_kind[b]; P->beh_speed[b] = c->behavior_speed[b];
+        P->beh_period[b] = c->behavior_period_ticks[b]; P->beh_stagger[b] = c->behavior_stagger_ticks[b];
+    }
 }
 
 int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
@@ -161,6 +165,7 @@ int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward
     cn_kparams P; pack(h, &P);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
     P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0 && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;
+    P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;

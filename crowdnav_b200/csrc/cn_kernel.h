@@ -25,6 +25,11 @@ struct cn_kparams {
     int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors;
     uint32_t flags;
     int obs_bulk_ok;            /* obs base is 16-B aligned: tile rows may leave by bulk store */
+    int act_bulk_ok;            /* action base is 16-B aligned: the tile's actions arrive by bulk load */
+    int beh_kind[CN_MAX_BEHAVIORS];
+    float beh_speed[CN_MAX_BEHAVIORS];
+    int beh_period[CN_MAX_BEHAVIORS];
+    int beh_stagger[CN_MAX_BEHAVIORS];
     float dt;
     float room_xmin, room_xmax, room_ymin, room_ymax;
     float goal_x, goal_y, heading_off_x, heading_off_y;

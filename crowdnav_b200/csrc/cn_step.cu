@@ -47,6 +47,14 @@
 
 #define FULL 0xFFFFFFFFu
 
+#ifdef CN_TIMELINE
+__device__ unsigned long long* g_timeline;      // [n_warps][8] globaltimer stamps (debug builds only)
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAMP(k) do { if (lane == 0 && g_timeline) g_timeline[((size_t)blockIdx.x * CN_TILE + warp) * 16 + (k)] = gtime(); } while (0)
+#else
+#define STAMP(k) do { } while (0)
+#endif
+
 namespace {
 
 // ---------------------------------------------------------------- PTX helpers
@@ -107,6 +115,7 @@ enum {
     S_PRE,                                 // bit0 in goal box, bit1 timeout
     S_BAD,                                 // int: 1 if the action was sanitised
     S_WDIRTY,                              // chunks of the row the wall spans touch
+    S_NPDIST, S_NPHEAD,                    // next previous_distance / previous_heading (unrounded after a reset)
     S_WSPAN = 24,                          // 4 wall faces x (a0, a1, b0, b1): rays that can see the face
     S_WORDS = 40
 };
@@ -203,8 +212,15 @@ __device__ __forceinline__ Span make_span(const cn_kparams& P, uint32_t brel, fl
 }
 template <class F>
 __device__ __forceinline__ void walk(const Span& s, int lane, F& f) {
-    for (int base = s.a0; base <= s.a1; base += 32) { const int i = base + lane; f(i, i <= s.a1); }
-    for (int base = s.b0; base <= s.b1; base += 32) { const int i = base + lane; f(i, i <= s.b1); }
+    // one loop over both ranges (range a padded to whole 32-ray rounds) so the body is instantiated once
+    const int la = (s.a1 >= s.a0) ? ((s.a1 - s.a0 + 32) & ~31) : 0;
+    const int lb = (s.b1 >= s.b0) ? (s.b1 - s.b0 + 1) : 0;
+    for (int base = 0; base < la + lb; base += 32) {      // warp-uniform trip count: f may vote
+        const int k = base + lane;
+        const bool in_a = k < la;
+        const int i = in_a ? s.a0 + k : s.b0 + (k - la);
+        f(i, in_a ? (i <= s.a1) : (i <= s.b1));
+    }
 }
 // 32-ray chunks of the observation row (index j = NR - i) a span can touch
 __device__ __forceinline__ uint32_t chunk_bits(int j_lo, int j_hi) {
@@ -261,7 +277,7 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
     const int NR = P.n_samples - 1, K = P.k_obstacles;
     const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
     const float yaw = cn_bin2rad(p.th);
-    if (part <= 0) {
+    if (part == 0) {
         // A: waypoint / distance / heading (ENV:246-265); the refresh target depends only on (pose, goal)
         float nwx, nwy;
         waypoint(P, xf, yf, nwx, nwy);
@@ -282,10 +298,12 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         }
         sc[S_WPX] = u_of(wx); sc[S_WPY] = u_of(wy);
         sc[S_HEAD] = u_of(head); sc[S_DIST] = u_of(dist);
+        // ENV:1133-1134 after a step; ENV:1243-1244 (unrounded, w.r.t. the goal) after a reset
+        sc[S_NPDIST] = u_of(is_step ? dist : prev_dist); sc[S_NPHEAD] = u_of(is_step ? head : prev_head);
         sc[S_REWARD] = (uint32_t)reward;
         row[NR + 0] = head; row[NR + 1] = dist;
     }
-    if (part < 0 || part == 1) {
+    if (part == 1) {
         // B (ENV:267-268, yaw RATE used as an angle), rounded pose (ENV:1025-1027), agent speed (UTL:227-236)
         float sw, cw; cn_sincos_rad(p.w, &sw, &cw);
         const float avx = -1.0f * (p.v * cw), avy = p.v * sw;
@@ -308,7 +326,7 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         row[NR + 4] = cn_py_round3(yaw);
         row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
     }
-    if (part < 0 || part == 2) {
+    if (part == 2) {
         uint32_t pre = 0;
         if (in_goal_box(P, xf, yf)) pre |= 1u;                    // ENV:1017
         if (step_counter >= P.max_steps) pre |= 2u;               // ENV:1021
@@ -681,7 +699,7 @@ __device__ __forceinline__ void reset_peds(const cn_kparams& P, int lane, uint32
                                            float (&hitx)[NPL], float (&hity)[NPL], int32_t (&timer)[NPL], uint32_t (&pfl)[NPL]) {
     const int N = P.n_peds;
     const int b = (int)(gid % (uint32_t)P.n_behaviors);
-    const int stagger = __ldg(&P.cfg->behavior_stagger_ticks[b]);
+    const int stagger = P.beh_stagger[b];
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
         const int n = lane + 32 * s;
@@ -699,7 +717,7 @@ __device__ __forceinline__ void reset_peds(const cn_kparams& P, int lane, uint32
 }
 
 // ------------------------------------------------------------------- kernel
-// MODE 0: step, MODE 1: reset (masked)
+// MODE 0: step (with next-step auto-reset), MODE 1: reset of the masked worlds.
 template <int NPL, int MODE>
 __global__ void __launch_bounds__(32 * CN_TILE, (NPL == 1) ? 2 : 1)
 cn_env_kernel(const __grid_constant__ cn_kparams P) {
@@ -708,6 +726,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     const int e0 = blockIdx.x * CN_TILE;
     const int nE = min(CN_TILE, P.n_envs - e0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    STAMP(0);
 
     // shared-memory carve-up (tile planes first: they are TMA targets)
     uint32_t* s_robot = reinterpret_cast<uint32_t*>(smem);                     // [TILE][16]
@@ -719,14 +738,18 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     uint32_t* s_sc = reinterpret_cast<uint32_t*>(s_hid + (size_t)CN_TILE * hid_stride);              // [TILE][S_WORDS]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sc + CN_TILE * S_WORDS);
     uint64_t* s_barA = s_bar + 1;       // phase A done: one arrival per phase-A warp
+    float* s_act = reinterpret_cast<float*>(s_bar + 2);                                              // [TILE][2]
 
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
     const uint32_t ped_bytes = (uint32_t)nE * (uint32_t)N * 16u;
+    const bool act_smem = (MODE == 0) && P.act_bulk_ok && (nE % 2) == 0;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
         mbar_init(s_barA, 3);
         fence_mbar_init();
-        mbar_expect_tx(s_bar, rob_bytes + 2u * ped_bytes);
+        const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
+        mbar_expect_tx(s_bar, rob_bytes + 2u * ped_bytes + act_bytes);
+        if (act_bytes) tma_load(s_act, P.action + 2 * (size_t)e0, act_bytes, s_bar);
         tma_load(s_robot, P.robot + (size_t)e0 * CN_ROBOT_WORDS, rob_bytes, s_bar);
         if (ped_bytes) {
             tma_load(s_pa, P.ped_a + (size_t)e0 * N * 4, ped_bytes, s_bar);
@@ -735,6 +758,38 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     }
     __syncthreads();            // barrier init visible to every waiter
     mbar_wait(s_bar, 0);
+    STAMP(1);
+
+    // ---- phase A: lane = world, three warps share the pose-only work of the whole tile
+    if (warp < 3) {
+        if (lane < nE) {
+            const uint32_t* rob = s_robot + lane * CN_ROBOT_WORDS;
+            bool run = true, reset_now = (MODE == 1);
+            if (MODE == 1) run = !P.mask || P.mask[e0 + lane] != 0;
+            else reset_now = (rob[CN_R_FLAGS] & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET);
+            if (run) {
+                uint32_t* scl = s_sc + lane * S_WORDS;
+                float* rowl = s_obs + (size_t)lane * D;
+                if (reset_now) {
+                    // Z: Env.reset (ENV:1227-1263): spawn pose, waypoint = goal, unrounded previous_* (ENV:1243-1244)
+                    PoseIn p; p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; p.v = 0.0f; p.w = 0.0f;
+                    const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
+                    const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);
+                    const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
+                    pose_scalars(P, p, warp, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
+                } else {
+                    int bad;
+                    const PoseIn p = advance_robot(P, rob, act_smem ? s_act + 2 * lane : P.action + 2 * (size_t)(e0 + lane), bad);
+                    pose_scalars(P, p, warp, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
+                                 f_of(rob[CN_R_PHEAD]), f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1,
+                                 true, true, bad, scl, rowl);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_barA);
+    }
+    STAMP(2);
 
     const int e = e0 + warp;
     bool active = warp < nE;
@@ -747,52 +802,58 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     uint4* spb = reinterpret_cast<uint4*>(s_pb) + (size_t)warp * N;
     const uint32_t gid = (uint32_t)(P.env_id_offset + e);
 
-    int32_t pxi[NPL], pyi[NPL], timer[NPL];
-    float pvx[NPL], pvy[NPL], hitx[NPL], hity[NPL];
-    uint32_t pfl[NPL];
+    if (active) {
+        uint32_t flags = srob[CN_R_FLAGS], cnt0 = srob[CN_R_CNT0], cnt1 = srob[CN_R_CNT1];
+        uint32_t episode = srob[CN_R_EPISODE];
+        int step = (int)srob[CN_R_STEP];
+        const bool reset_now = (MODE == 1) || ((flags & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET));
 
-    if (MODE == 0) {
-        // ---- phase A: lane = world, three warps share the pose-only work of the whole tile
-        if (warp < 3 && lane < nE) {
-            const uint32_t* rob = s_robot + lane * CN_ROBOT_WORDS;
-            int bad;
-            const PoseIn p = advance_robot(P, rob, P.action + 2 * (size_t)(e0 + lane), bad);
-            pose_scalars(P, p, warp, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]), f_of(rob[CN_R_PHEAD]),
-                         f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1, true, true, bad,
-                         s_sc + lane * S_WORDS, s_obs + (size_t)lane * D);
-        }
-        if (warp < 3) { __syncwarp(); if (lane == 0) mbar_arrive(s_barA); }
-        // ---- phase P: lane = pedestrian, Jacobi on the old positions in s_pa / old robot pose in s_robot
-        if (active) {
-            const int b = (int)(gid % (uint32_t)P.n_behaviors);
-            const int kind = __ldg(&P.cfg->behavior_kind[b]);
-            const float speed = __ldg(&P.cfg->behavior_speed[b]);
-            const int period = __ldg(&P.cfg->behavior_period_ticks[b]);
+        int32_t pxi[NPL], pyi[NPL], timer[NPL];
+        float pvx[NPL], pvy[NPL], hitx[NPL], hity[NPL];
+        uint32_t pfl[NPL];
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) { pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u; }
+
+        // ---- phase P: lane = pedestrian
+        if (reset_now) {
+            episode += 1u;
+            reset_peds<NPL>(P, lane, gid, episode, pxi, pyi, pvx, pvy, hitx, hity, timer, pfl);
+        } else {
+            // P: CROWD:98-144 + contact stand-in, Jacobi on the old positions in s_pa / old robot pose in s_robot
+            const int b = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
+            const int kind = P.beh_kind[b];
+            const float speed = P.beh_speed[b];
+            const int period = P.beh_period[b];
             const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
             const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative prefilter
             const uint32_t lim2 = 2u * (uint32_t)lim_i;
             const int32_t rxi = (int32_t)srob[CN_R_X], ryi = (int32_t)srob[CN_R_Y];
-            const uint32_t episode = srob[CN_R_EPISODE];
-            const int step_counter = (int)srob[CN_R_STEP] + 1;
+            const int step_counter = step + 1;
             uint32_t peers = 0;
             if (NPL == 1) {
-                const int sh = P.d.pair_cell_shift;
-                uint32_t cx0 = 0xFFFF0000u | (uint32_t)lane, cx1 = cx0, cy0 = 0u, cy1 = 0u;   // unmatched dummy for lanes >= N
-                if (lane < N) {
-                    const uint2 a = *reinterpret_cast<const uint2*>(&spa[lane]);
-                    const uint32_t bx = a.x + 0x40000000u, by = a.y + 0x40000000u;
-                    const uint32_t half = 1u << (sh - 1);
-                    cx0 = bx >> sh; cx1 = (bx + half) >> sh;
-                    cy0 = (by >> sh) << 12; cy1 = ((by + half) >> sh) << 12;
+                // contacts are rare: find the pairs within the (conservative, integer) contact box by rotating the
+                // pedestrian list against itself -- N/2 shuffle rounds instead of an N-iteration loop per lane
+                int32_t mx = 0x20000000 + (lane << 20), my = mx;          // far-apart dummies for lanes >= N
+                if (lane < N) { const uint2 a = *reinterpret_cast<const uint2*>(&spa[lane]); mx = (int32_t)a.x; my = (int32_t)a.y; }
+                const int half = N >> 1;
+                int partner = lane;
+                for (int r = 1; r <= half; ++r) {
+                    partner = (partner + 1 >= N) ? partner + 1 - N : partner + 1;       // (lane + r) mod N
+                    const int src = (lane < N) ? partner : lane;
+                    const int32_t ox_ = __shfl_sync(FULL, mx, src), oy_ = __shfl_sync(FULL, my, src);
+                    const bool hit = lane < N && (uint32_t)(mx - ox_ + lim_i) < lim2 && (uint32_t)(my - oy_ + lim_i) < lim2;
+                    const uint32_t hm = __ballot_sync(FULL, hit);
+                    if (hm) {                                                           // rare
+                        if (hit) peers |= 1u << partner;
+                        const int back = (lane - r < 0) ? lane - r + N : lane - r;      // the lane whose partner I am
+                        if (lane < N && ((hm >> back) & 1u)) peers |= 1u << back;
+                    }
                 }
-                peers = __match_any_sync(FULL, cx0 | cy0) | __match_any_sync(FULL, cx1 | cy0) |
-                        __match_any_sync(FULL, cx0 | cy1) | __match_any_sync(FULL, cx1 | cy1);
                 peers &= ~(1u << lane);
             }
 #pragma unroll
             for (int s = 0; s < NPL; ++s) {
                 const int n = lane + 32 * s;
-                pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u;
                 if (n < N) {
                     const uint4 a = spa[n], bb = spb[n];
                     const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
@@ -813,9 +874,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                     }
                     float vex = vx, vey = vy;
                     if (NPL == 1) {
-                        // contacts are rare: only pedestrians sharing a cell of one of four half-shifted grids
-                        // (cell >= 2 * contact range) can touch; visit those, in index order like the oracle
-                        for (uint32_t pm = peers; pm; pm &= pm - 1) {
+                        for (uint32_t pm = peers; pm; pm &= pm - 1) {          // index order, like the oracle
                             const int m = __ffs(pm) - 1;
                             const uint2 o = *reinterpret_cast<const uint2*>(&spa[m]);
                             add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
@@ -841,18 +900,20 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                 }
             }
         }
-        mbar_wait(s_barA, 0);   // scalar records + observation-row scalars of the whole tile are in place
-    }
+        STAMP(3);
+        mbar_wait(s_barA, 0);   // this world's scalar record + observation-row scalars are in place
+        STAMP(4);
 
-    if (active) {
-        uint32_t flags = srob[CN_R_FLAGS], cnt0 = srob[CN_R_CNT0], cnt1 = srob[CN_R_CNT1];
-        uint32_t episode = srob[CN_R_EPISODE];
-        int step = (int)srob[CN_R_STEP];
-        bool do_reset = (MODE == 1);
-        if (MODE == 0) {
-            // ---- phases L + R, then done / reward (ENV:1011-1023, 1136-1159)
-            if (sc[S_BAD]) { uint32_t bad = cnt1 >> 16; if (bad < 0xFFFFu) ++bad; cnt1 = (cnt1 & 0xFFFFu) | (bad << 16); }
-            const bool collided = scan_and_risk<NPL>(P, sc, lane, true, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e, cnt0, cnt1);
+        // ---- phases L + R (Env.get_state from ENV:277 on)
+        if (!reset_now && sc[S_BAD]) { uint32_t bad = cnt1 >> 16; if (bad < 0xFFFFu) ++bad; cnt1 = (cnt1 & 0xFFFFu) | (bad << 16); }
+        const bool collided = scan_and_risk<NPL>(P, sc, lane, !reset_now, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e, cnt0, cnt1);
+        if (reset_now) {
+            cnt0 = 0; cnt1 = 0;                                                 // ENV:1260-1262
+            flags = (MODE == 0) ? (flags & (CN_RF_SUCCESS | CN_RF_FAILURE)) : 0u;   // last episode's status stays readable
+            step = 0;
+            if (MODE == 0 && lane == 0) { P.reward[e] = 0.0f; P.done[e] = 2; }
+        } else {
+            // ---- N + W: done (ENV:1011-1023), terminal reward (ENV:1136-1159; a time-out is -200 too)
             const uint32_t pre = sc[S_PRE];
             const bool done = ((flags & CN_RF_DONE) != 0) || collided || pre != 0u;
             int reward = (int)sc[S_REWARD];
@@ -862,33 +923,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                 else { flags |= CN_RF_FAILURE; flags &= ~CN_RF_SUCCESS; reward -= 200; }
             }
             step += 1;
-            if (lane == 0) {
-                P.reward[e] = (float)reward;
-                P.done[e] = done ? 1 : 0;
-            }
-            do_reset = done && (P.flags & CN_FLAG_AUTO_RESET);
-        } else {
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) { pxi[s] = 0; pyi[s] = 0; timer[s] = 0; pvx[s] = 0.0f; pvy[s] = 0.0f; hitx[s] = 0.0f; hity[s] = 0.0f; pfl[s] = 0u; }
-        }
-        if (do_reset) {
-            // ---- Z: Env.reset (ENV:1227-1263) by the world's own warp (pose scalars computed warp-uniformly)
-            const uint32_t keep = (MODE == 0) ? (flags & (CN_RF_SUCCESS | CN_RF_FAILURE)) : 0u;
-            __syncwarp();
-            episode += 1u;
-            reset_peds<NPL>(P, lane, gid, episode, pxi, pyi, pvx, pvy, hitx, hity, timer, pfl);
-            PoseIn p; p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; p.v = 0.0f; p.w = 0.0f;
-            const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
-            const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);                           // ENV:1243-1244, unrounded
-            const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
-            if (lane == 0) pose_scalars(P, p, -1, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, sc, row);
-            __syncwarp();
-            cnt0 = 0; cnt1 = 0;
-            (void)scan_and_risk<NPL>(P, sc, lane, false, pxi, pyi, hitx, hity, pfl, row, hid, (size_t)e, cnt0, cnt1);
-            cnt0 = 0; cnt1 = 0;                                                                // ENV:1260-1262
-            flags = keep; step = 0;
-            if (lane == 0) { sc[S_HEAD] = u_of(ph); sc[S_DIST] = u_of(pd); }                    // previous_* stay unrounded
-            __syncwarp();
+            if (lane == 0) { P.reward[e] = (float)reward; P.done[e] = done ? 1 : 0; }
         }
 
         // ---- write the world back into the shared tile
@@ -903,8 +938,8 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
         if (lane == 0) {
             uint4* q = reinterpret_cast<uint4*>(srob);
             q[0] = make_uint4(sc[S_XI], sc[S_YI], sc[S_TH], sc[S_V]);
-            q[1] = make_uint4(sc[S_W], sc[S_WPX], sc[S_WPY], sc[S_DIST]);
-            q[2] = make_uint4(sc[S_HEAD], sc[S_PCX], sc[S_PCY], (uint32_t)step);
+            q[1] = make_uint4(sc[S_W], sc[S_WPX], sc[S_WPY], sc[S_NPDIST]);
+            q[2] = make_uint4(sc[S_NPHEAD], sc[S_PCX], sc[S_PCY], (uint32_t)step);
             q[3] = make_uint4(episode, flags, cnt0, cnt1);
         }
         // observation row: plain coalesced stores when the tile cannot go out as one bulk copy
@@ -914,11 +949,15 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             float* g = P.obs + (size_t)e * D;
             for (int k = lane; k < D; k += 32) g[k] = row[k];
         }
+    } else {
+        mbar_wait(s_barA, 0);
     }
 
     // ---- tile write-back: bulk TMA stores from shared memory
+    STAMP(5);
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
     __syncthreads();
+    STAMP(6);
     if (threadIdx.x == 0) {
         tma_store(P.robot + (size_t)e0 * CN_ROBOT_WORDS, s_robot, rob_bytes);
         if (ped_bytes) {
@@ -929,6 +968,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
         if (bulk_obs) tma_store(P.obs + (size_t)e0 * D, s_obs, (uint32_t)((size_t)nE * D * 4));
         tma_store_commit_and_wait();
     }
+    STAMP(7);
 }
 
 // sticky-done clear / counters: trivial elementwise kernels
@@ -958,7 +998,7 @@ size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim) {
     b += (((size_t)CN_TILE * obs_dim + 3) & ~(size_t)3) * 4;
     b += (size_t)CN_TILE * ((NR + 15) & ~15);
     b += (size_t)CN_TILE * S_WORDS * 4;
-    b += 16;
+    b += 16 + (size_t)CN_TILE * 8;
     return b;
 }
 
@@ -982,6 +1022,12 @@ cudaError_t cn_launch_env_kernel(const cn_kparams& P, int mode, cudaStream_t str
     if (P.n_peds <= 32) return mode == 0 ? launch_t<1, 0>(P, smem, stream) : launch_t<1, 1>(P, smem, stream);
     return mode == 0 ? launch_t<2, 0>(P, smem, stream) : launch_t<2, 1>(P, smem, stream);
 }
+
+#ifdef CN_TIMELINE
+extern "C" int cn_debug_set_timeline(unsigned long long* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr));
+}
+#endif
 
 cudaError_t cn_launch_clear_done(uint32_t* robot, const uint8_t* mask, int E, cudaStream_t stream) {
     cn_clear_done_kernel<<<(E + 255) / 256, 256, 0, stream>>>(robot, mask, E);

@@ -45,7 +45,9 @@ typedef enum cn_status {
 } cn_status;
 
 /* cn_config.flags */
-#define CN_FLAG_AUTO_RESET      1u  /* done envs re-seed themselves inside cn_step */
+#define CN_FLAG_AUTO_RESET      1u  /* a world that ended on step t restarts DURING step t+1: that step ignores
+                                       its action and returns the new episode's first observation, reward 0,
+                                       done = 2 ("next-step" auto-reset: every world does one get_state per launch) */
 #define CN_FLAG_TOPK_HIGHEST    2u  /* keep the K highest-CP objects instead of the
                                        reference's `[-K:]` (= K lowest), ENV:883 */
 
@@ -129,7 +131,8 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
  * 0.15 s of Gazebo physics + crowd mover behind it, get_state (ENV:245-1044)
  * and compute_reward (ENV:1046-1162).
  *   action_dev [E, 2] (v, w); obs_dev [E, D] row-major; reward_dev [E];
- *   done_dev [E] (1 = episode ended on this step). */
+ *   done_dev [E]: 0 running, 1 = episode ended on this step (obs row is the terminal observation),
+ *   2 = this step was an auto-reset (CN_FLAG_AUTO_RESET only; transition to be skipped). */
 int cn_step(cn_handle* h, const float* action_dev, float* obs_dev,
             float* reward_dev, uint8_t* done_dev, void* stream);
 

@@ -465,6 +465,18 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     int step_counter = (int)rob[CN_R_STEP] + 1;
     uint32_t episode = rob[CN_R_EPISODE];
 
+    /* Auto-reset ("next-step" mode): a world whose episode ended on the previous step spends this step
+     * restarting -- the action is ignored, the row is the first observation of the new episode, reward 0,
+     * done = 2 (a transition the trainer must not store).  Every world does exactly one get_state per step. */
+    if ((rob[CN_R_FLAGS] & CN_RF_DONE) && (g->flags & CN_FLAG_AUTO_RESET)) {
+        uint32_t keep = rob[CN_R_FLAGS] & (CN_RF_SUCCESS | CN_RF_FAILURE);
+        reset_env(c, e, rob, pa, pb, obs, dbg_ranges, dbg_hid);
+        rob[CN_R_FLAGS] |= keep;   /* last episode's status stays readable (ENV:1265-1267) */
+        *reward_out = 0.0f;
+        *done_out = 2;
+        return;
+    }
+
     /* T2: action, applied verbatim (ENV:1190-1192) after sanitising */
     float av = action[0], aw = action[1];
     if (!(fabsf(av) <= 3.0e38f) || !(fabsf(aw) <= 3.0e38f)) {
@@ -558,13 +570,6 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     rob[CN_R_STEP] = (uint32_t)step_counter;
     *reward_out = (float)reward;
     *done_out = (uint8_t)(done ? 1 : 0);
-
-    if (done && (g->flags & CN_FLAG_AUTO_RESET)) {
-        /* the row handed to the policy is the first observation of the next episode */
-        uint32_t keep = rob[CN_R_FLAGS] & (CN_RF_SUCCESS | CN_RF_FAILURE);
-        reset_env(c, e, rob, pa, pb, obs, dbg_ranges, dbg_hid);
-        rob[CN_R_FLAGS] |= keep;   /* last episode's status stays readable (ENV:1265-1267) */
-    }
 }
 
 /* ---- batch entry points -------------------------------------------------- */
