@@ -164,7 +164,7 @@ int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward
         return fail(CN_ERR_INVALID, "cn_step: null argument%s", NULL);
     cn_kparams P; pack(h, &P);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
-    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0 && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;
+    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0 && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;   /* every tile starts 16-B aligned */
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
     h->launches += 1;

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include "cn_state.h"
 
-#define CN_TILE 16   /* worlds (= warps) per CTA */
+#define CN_TILE 14       /* worlds per CTA: one warp each */
+#define CN_POSE_WARPS 2   /* extra warps that do the pose-only work of the whole tile (lane = world) */
+#define CN_CTA_THREADS (32 * (CN_TILE + CN_POSE_WARPS))
 
 /* Everything the step kernel needs, passed by value (constant bank); the
  * per-behaviour tables and the layout stay in the device copy of cn_config. */

@@ -50,7 +50,7 @@
 #ifdef CN_TIMELINE
 __device__ unsigned long long* g_timeline;      // [n_warps][8] globaltimer stamps (debug builds only)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define STAMP(k) do { if (lane == 0 && g_timeline) g_timeline[((size_t)blockIdx.x * CN_TILE + warp) * 16 + (k)] = gtime(); } while (0)
+#define STAMP(k) do { if ((threadIdx.x & 31) == 0 && g_timeline) g_timeline[((size_t)blockIdx.x * (CN_TILE + CN_POSE_WARPS) + (threadIdx.x >> 5)) * 16 + (k)] = gtime(); } while (0)
 #else
 #define STAMP(k) do { } while (0)
 #endif
@@ -238,8 +238,8 @@ __device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
 // ------------------------------------------------------------------ phase A
 // The part of Env.step / get_state / compute_reward that depends on the pose
 // alone, for ONE world held by the calling thread.  `part` selects a slice of
-// the work so three warps can share it (0: waypoint chain, 1: velocities and
-// rounded pose, 2: reward boxes + K-block padding); part < 0 = everything
+// the work so the CTA's two pose warps can share it (0: waypoint chain + reward
+// shaping, 1: velocities, rounded pose, goal boxes, wall spans, K-block padding)
 // (auto-reset path, executed warp-uniformly by the world's own warp).
 //   rob   : the world's robot record (state BEFORE this step; not modified)
 //   sc    : the world's scalar record      row : the world's observation row
@@ -326,7 +326,7 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         row[NR + 4] = cn_py_round3(yaw);
         row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
     }
-    if (part == 2) {
+    if (part == 1) {
         uint32_t pre = 0;
         if (in_goal_box(P, xf, yf)) pre |= 1u;                    // ENV:1017
         if (step_counter >= P.max_steps) pre |= 2u;               // ENV:1021
@@ -437,6 +437,7 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
         for (int j = lane; j < (NR + 15) / 16; j += 32) h4[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     __syncwarp();
+    STAMP(9);
 
     // ---- walls: x faces, then y faces (oracle order)
     if (dirty)
@@ -492,6 +493,7 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
         }
     }
 
+    STAMP(10);
     // ---- E-I: per candidate, count the rays it owns and find its centre ray
     int cnt[NPL], jstar[NPL];
 #pragma unroll
@@ -530,6 +532,7 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
         }
     }
 
+    STAMP(11);
     // ---- debug taps (tests only): raw cleaned ranges + hit ids for every ray
     if (P.dbg_ranges || P.dbg_hid) {
         for (int j = lane; j < NR; j += 32) {
@@ -556,6 +559,7 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
 
+    STAMP(12);
     // ---- H-J: per confirmed pedestrian (lane-parallel)
     const float pcx = f_of(sc[S_PCX]), pcy = f_of(sc[S_PCY]);
     const float ppx = f_of(sc[S_PPX]), ppy = f_of(sc[S_PPY]);
@@ -621,6 +625,7 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
     }
     __syncwarp();
 
+    STAMP(13);
     // ---- np.around of the rays a span touched (everything else already holds the rounded no-return value)
     for (uint32_t dm = dirty; dm; dm &= dm - 1) {
         const int j = ((__ffs(dm) - 1) << 5) + lane;
@@ -719,7 +724,7 @@ __device__ __forceinline__ void reset_peds(const cn_kparams& P, int lane, uint32
 // ------------------------------------------------------------------- kernel
 // MODE 0: step (with next-step auto-reset), MODE 1: reset of the masked worlds.
 template <int NPL, int MODE>
-__global__ void __launch_bounds__(32 * CN_TILE, (NPL == 1) ? 2 : 1)
+__global__ void __launch_bounds__(CN_CTA_THREADS, (NPL == 1) ? 2 : 1)
 cn_env_kernel(const __grid_constant__ cn_kparams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int N = P.n_peds, NR = P.n_samples - 1, D = P.d.obs_dim;
@@ -745,7 +750,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     const bool act_smem = (MODE == 0) && P.act_bulk_ok && (nE % 2) == 0;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
-        mbar_init(s_barA, 3);
+        mbar_init(s_barA, CN_POSE_WARPS);
         fence_mbar_init();
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
         mbar_expect_tx(s_bar, rob_bytes + 2u * ped_bytes + act_bytes);
@@ -760,8 +765,10 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     mbar_wait(s_bar, 0);
     STAMP(1);
 
-    // ---- phase A: lane = world, three warps share the pose-only work of the whole tile
-    if (warp < 3) {
+    // ---- phase A: lane = world, the CTA's two extra warps share the pose-only work of the whole tile
+    // (they own no world, so nobody waits for them longer than for the pedestrian phase)
+    if (warp >= CN_TILE) {
+        const int part = warp - CN_TILE;
         if (lane < nE) {
             const uint32_t* rob = s_robot + lane * CN_ROBOT_WORDS;
             bool run = true, reset_now = (MODE == 1);
@@ -776,11 +783,11 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                     const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
                     const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);
                     const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
-                    pose_scalars(P, p, warp, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
+                    pose_scalars(P, p, part, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
                 } else {
                     int bad;
                     const PoseIn p = advance_robot(P, rob, act_smem ? s_act + 2 * lane : P.action + 2 * (size_t)(e0 + lane), bad);
-                    pose_scalars(P, p, warp, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
+                    pose_scalars(P, p, part, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
                                  f_of(rob[CN_R_PHEAD]), f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1,
                                  true, true, bad, scl, rowl);
                 }
@@ -792,7 +799,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     STAMP(2);
 
     const int e = e0 + warp;
-    bool active = warp < nE;
+    bool active = warp < nE;        // pose warps (warp >= CN_TILE >= nE) own no world
     if (MODE == 1 && active && P.mask) active = P.mask[e] != 0;
     float* row = s_obs + (size_t)warp * D;
     uint8_t* hid = s_hid + (size_t)warp * hid_stride;
@@ -851,6 +858,8 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                 }
                 peers &= ~(1u << lane);
             }
+            if (peers == 0x12345678u) STAMP(15);
+            STAMP(8);
 #pragma unroll
             for (int s = 0; s < NPL; ++s) {
                 const int n = lane + 32 * s;
@@ -1013,7 +1022,7 @@ static cudaError_t launch_t(const cn_kparams& P, size_t smem, cudaStream_t strea
         attr_set = true; attr_smem = smem;
     }
     const int grid = (P.n_envs + CN_TILE - 1) / CN_TILE;
-    k<<<grid, 32 * CN_TILE, smem, stream>>>(P);
+    k<<<grid, CN_CTA_THREADS, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
