@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = the step kernel stores its rows into every peer's gather buffer (symmetric "
+                         "memory, NVLink) + a barrier; 'nccl' = separate in-place ncclAllGather after the kernel")
     ap.add_argument("--with-policy", action="store_true",
                     help="run the TD3 actor forward (torch) inside each step instead of replaying action batches")
     args = ap.parse_args()
@@ -196,7 +199,20 @@ def main():
     wl = args.workload
     per_gpu = args.envs_per_gpu or PER_GPU_ENVS[wl]
     cfg_global = baseline_config(WORKLOADS[wl], n_envs=per_gpu * world, auto_reset=True)
-    senv = ShardedVecEnv(cfg_global, lambda c, o: CrowdNavVecEnv(c, device=local_rank, obs_out=o), dev)
+    gather_mode = "none"
+    if world > 1:
+        gather_mode = "fused" if args.gather == "fused" else "collective"
+    try:
+        senv = ShardedVecEnv(cfg_global, lambda c, o: CrowdNavVecEnv(c, device=local_rank, obs_out=o), dev,
+                             gather=gather_mode if world > 1 else "collective")
+    except Exception as exc:                       # symmetric memory unavailable: say so, use the collective
+        if gather_mode != "fused":
+            raise
+        if rank == 0:
+            print("fused gather unavailable (%s); using ncclAllGather" % exc, file=sys.stderr)
+        gather_mode = "collective"
+        senv = ShardedVecEnv(cfg_global, lambda c, o: CrowdNavVecEnv(c, device=local_rank, obs_out=o), dev,
+                             gather="collective")
     env = senv.env
     E_local, E_total, D = env.E, cfg_global.n_envs, env.D
     bytes_per_env = algorithmic_bytes_per_env_step(cfg_global.n_peds, cfg_global.n_samples, cfg_global.k_obstacles)
@@ -242,10 +258,12 @@ def main():
             s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             s0.record()
             a = policy(senv.obs_local) if args.with_policy else ring[i % 16]
-            env.step(a)
+            if world > 1:
+                senv.begin_step()
+            env.step(a)                 # the kernel (in fused mode it also stores the rows into the peers)
             s1.record()
-            if not kernel_only:
-                senv.gather()
+            if world > 1:
+                senv.gather()           # ncclAllGather, or just the cross-rank barrier in fused mode
             s2.record()
             if timed:
                 evs.append((s0, s1, s2))
@@ -276,7 +294,7 @@ def main():
     for i in range(K):
         env.step_host(h_actions[i % 16])        # pinned H2D + kernel + D2H + stream sync, every step
         if world > 1:
-            senv.gather()
+            senv.gather()                       # (in fused mode the rows already went to the peers)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -306,8 +324,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[wl], "envs_per_gpu": E_local, "envs_total": E_total,
                        "n_peds": cfg_global.n_peds, "n_samples": cfg_global.n_samples, "k_obstacles": cfg_global.k_obstacles,
-                       "obs_dim": D, "parallelism": "env-id sharding x%d, one in-place NCCL all-gather of obs per step" % world
-                       if world > 1 else "single GPU",
+                       "obs_dim": D, "parallelism": ("single GPU" if world == 1 else
+                                                     "env-id sharding x%d, obs all-gather %s" % (world, {
+                                                         "fused": "fused into the step kernel (bulk TMA stores into every peer's "
+                                                                  "symmetric-memory buffer over NVLink) + stream barrier",
+                                                         "collective": "by one in-place ncclAllGather per step"}[gather_mode])),
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "actions": ("TD3 actor forward inside each step" if args.with_policy else
                                    "ring of 16 batches from a random-init TD3 actor + N(0,1) exploration noise, clipped")},

@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     L.cn_destroy.argtypes = [vp]
     L.cn_reset.argtypes = [vp, vp, vp, vp]
     L.cn_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cn_step_gather.argtypes = [vp, vp, vp, C.POINTER(vp), i32, vp, vp, vp]
     L.cn_get_counters.argtypes = [vp, vp, vp]
     L.cn_clear_done.argtypes = [vp, vp, vp]
     L.cn_get_blob.argtypes = [vp, vp, sz, vp]
@@ -90,7 +91,7 @@ def check(rc: int, what: str) -> None:
 
 
 ABI_SYMBOLS = [
-    "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step",
+    "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_gather",
     "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count",
     "cn_last_error", "cn_abi_version",
 ]

@@ -171,6 +171,28 @@ int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward
     return CN_OK;
 }
 
+int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peer_obs_dev, int n_peers,
+                   float* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_step_gather: null argument%s", NULL);
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_obs_dev))
+        return fail(CN_ERR_INVALID, "cn_step_gather: 0..8 peer buffers%s", NULL);
+    cn_kparams P; pack(h, &P);
+    P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
+    bool aligned = (((uintptr_t)obs_dev) & 15u) == 0;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_obs_dev[p]) return fail(CN_ERR_INVALID, "cn_step_gather: null peer buffer%s", NULL);
+        P.obs_peers[p] = peer_obs_dev[p];
+        aligned = aligned && (((uintptr_t)peer_obs_dev[p]) & 15u) == 0;
+    }
+    P.n_obs_peers = n_peers;
+    P.obs_bulk_ok = aligned && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;
+    P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
+    CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
 int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream) {
     if (!h || !out_dev) return fail(CN_ERR_INVALID, "cn_get_counters: null argument%s", NULL);
     if (((uintptr_t)out_dev) & 15u) return fail(CN_ERR_INVALID, "cn_get_counters: out_dev must be 16-byte aligned%s", NULL);

@@ -22,6 +22,8 @@ struct cn_kparams {
     const uint8_t* mask;
     float* dbg_ranges;
     uint8_t* dbg_hid;
+    float* obs_peers[8];        /* fused all-gather: this rank's row block inside each PEER's [E_total, D] buffer */
+    int n_obs_peers;
     const cn_config* cfg;       /* device copy */
     cn_derived d;
     int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors;

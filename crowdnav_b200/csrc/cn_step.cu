@@ -957,6 +957,10 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             __syncwarp();
             float* g = P.obs + (size_t)e * D;
             for (int k = lane; k < D; k += 32) g[k] = row[k];
+            for (int p = 0; p < P.n_obs_peers; ++p) {          // fused all-gather, ragged-tile path
+                float* gp = P.obs_peers[p] + (size_t)e * D;
+                for (int k = lane; k < D; k += 32) gp[k] = row[k];
+            }
         }
     } else {
         mbar_wait(s_barA, 0);
@@ -974,7 +978,12 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             tma_store(P.ped_b + (size_t)e0 * N * 4, s_pb, ped_bytes);
         }
         const bool bulk_obs = (MODE == 0) && (((size_t)nE * D) % 4 == 0) && P.obs_bulk_ok;
-        if (bulk_obs) tma_store(P.obs + (size_t)e0 * D, s_obs, (uint32_t)((size_t)nE * D * 4));
+        if (bulk_obs) {
+            tma_store(P.obs + (size_t)e0 * D, s_obs, (uint32_t)((size_t)nE * D * 4));
+            // fused all-gather: the same tile goes straight into every peer's gather buffer over NVLink
+            for (int p = 0; p < P.n_obs_peers; ++p)
+                tma_store(P.obs_peers[p] + (size_t)e0 * D, s_obs, (uint32_t)((size_t)nE * D * 4));
+        }
         tma_store_commit_and_wait();
     }
     STAMP(7);

@@ -47,7 +47,7 @@ class ShardedVecEnv:
     """
 
     def __init__(self, cfg_global: CnConfig, make_local: Callable, device: torch.device,
-                 group: dist.ProcessGroup | None = None):
+                 group: dist.ProcessGroup | None = None, gather: str = "collective"):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -57,21 +57,65 @@ class ShardedVecEnv:
         self.cfg_local = local_config(cfg_global, self.rank, self.world)
         self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
         self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
-        self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
+        self.gather_mode = gather if self.world > 1 else "none"
+        self._symm = None
+        if self.gather_mode == "fused":
+            # Gather buffers in symmetric memory: every rank can address every peer's copy, so the step kernel
+            # stores its rows into all of them itself (bulk TMA stores over NVLink) -- no collective launch.
+            # TWO buffers, alternating per step: a peer's step t+1 kernel may start while this rank still reads
+            # step t, so it must not land in the buffer being read; the barrier that ends step t+1 is only passed
+            # once every rank has enqueued (hence, in stream order, finished reading) step t.
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self._bufs, self._symm, self._peers = [], [], []
+            for _ in range(2):
+                buf = symm_mem.empty((self.E, self.D), dtype=torch.float32, device=device)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, grp)
+                off = self.lo * self.D * 4
+                self._bufs.append(buf)
+                self._symm.append(hdl)
+                self._peers.append([int(p) + off for r, p in enumerate(hdl.buffer_ptrs) if r != self.rank])
+            self._cur = 0
+            self.obs_all = self._bufs[0]
+        else:
+            self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
         self.obs_local = self.obs_all[self.lo:self.hi]          # contiguous row block
         self.env = make_local(self.cfg_local, self.obs_local)
+        if self.gather_mode == "fused":
+            self.env.set_obs_peers(self._peers[0])
 
     def gather(self) -> torch.Tensor:
-        """In-place all-gather of the observation rows (sendbuf = recvbuf + rank * count)."""
-        if self.world > 1:
+        """Make obs_all complete on every rank: in 'collective' mode an in-place all-gather of the rows
+        (sendbuf = recvbuf + rank * count); in 'fused' mode the kernels already wrote every peer's copy and only
+        a cross-rank barrier on the stream is needed."""
+        if self.gather_mode == "collective":
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
+        elif self.gather_mode == "fused":
+            self._symm[self._cur].barrier(channel=0)
         return self.obs_all
 
     def reset(self) -> torch.Tensor:
         self.env.reset()
+        if self.gather_mode == "fused":
+            # cn_reset writes the local rows only: publish them once with the collective
+            self._symm[self._cur].barrier(channel=0)
+            dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
+            self._symm[self._cur].barrier(channel=0)
+            return self.obs_all
         return self.gather()
 
+    def begin_step(self) -> None:
+        """Fused mode: point the kernel at the other gather buffer (see __init__)."""
+        if self.gather_mode == "fused":
+            self._cur ^= 1
+            self.obs_all = self._bufs[self._cur]
+            self.obs_local = self.obs_all[self.lo:self.hi]
+            self.env.obs = self.obs_local
+            self.env.set_obs_peers(self._peers[self._cur])
+
     def step(self, actions_local: torch.Tensor):
+        self.begin_step()
         _, reward, done = self.env.step(actions_local)
         self.gather()
         return self.obs_all, reward, done

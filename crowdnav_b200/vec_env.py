@@ -47,6 +47,7 @@ class CrowdNavVecEnv:
             self._counters = torch.zeros((self.E, 4), dtype=torch.int32, device=self.device)
         self._dbg_ranges = None
         self._dbg_hid = None
+        self._peer_ptrs = None          # fused all-gather targets (set_obs_peers)
         # pinned staging for the host-buffer path
         self._h_act = self._h_obs = self._h_rew = self._h_done = None
 
@@ -80,10 +81,23 @@ class CrowdNavVecEnv:
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
                 or actions.numel() != 2 * self.E:
             raise ValueError("actions must be a contiguous float32 [E, 2] tensor on %s" % self.device)
-        _lib.check(self._L.cn_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
-                                   C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
-                                   self._stream()), "cn_step")
+        if self._peer_ptrs is not None:
+            _lib.check(self._L.cn_step_gather(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                              self._peer_ptrs, len(self._peer_ptrs), C.c_void_p(self.reward.data_ptr()),
+                                              C.c_void_p(self.done.data_ptr()), self._stream()), "cn_step_gather")
+        else:
+            _lib.check(self._L.cn_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                       C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                       self._stream()), "cn_step")
         return self.obs, self.reward, self.done
+
+    def set_obs_peers(self, ptrs) -> None:
+        """Fuse the observation all-gather into the step kernel: `ptrs` are peer-mapped device addresses of this
+        rank's row block inside each PEER's [E_total, D] gather buffer (see ShardedVecEnv, gather='fused')."""
+        ptrs = [int(p) for p in ptrs]
+        if len(ptrs) > 8:
+            raise ValueError("at most 8 peers")
+        self._peer_ptrs = (C.c_void_p * len(ptrs))(*ptrs) if ptrs else None
 
     def step_host(self, actions: np.ndarray):
         """Same step through HOST buffers: pinned H2D of the actions, the kernel,

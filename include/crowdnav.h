@@ -136,6 +136,15 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
 int cn_step(cn_handle* h, const float* action_dev, float* obs_dev,
             float* reward_dev, uint8_t* done_dev, void* stream);
 
+/* cn_step with the observation all-gather FUSED into the kernel (multi-GPU, one process per GPU):
+ * besides obs_dev (this rank's [E, D] row block inside its own [E_total, D] gather buffer) the kernel
+ * stores every tile of rows into the same row block of each peer's gather buffer -- peer-mapped device
+ * pointers (CUDA IPC / symmetric memory), already offset to this rank's first row -- with bulk TMA stores
+ * over NVLink.  The caller orders consumers behind the launch with a cross-rank barrier.  Replaces the
+ * ncclAllGather SURVEY.md 8(e) puts after the step.  n_peers <= 8 (0 = plain cn_step). */
+int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peer_obs_dev, int n_peers,
+                   float* reward_dev, uint8_t* done_dev, void* stream);
+
 /* Per-env counters [E, 4] int32: success, ego violations, social violations,
  * obstacle-present steps.  Replaces get_episode_status / get_*_violation_status
  * (ENV:1265-1283). */
