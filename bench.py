@@ -152,10 +152,29 @@ def run_reference(args):
         "note": "reference's own Gazebo+ROS loop is not runnable here; its logged rate is 5.5-8.0 env-steps/s "
                 "(BASELINE.md section 2) and it is capped at 6.67/s by time.sleep(0.15)",
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -192,6 +211,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     K = args.steps
@@ -267,8 +287,14 @@ def main():
             s2.record()
             if timed:
                 evs.append((s0, s1, s2))
+        # pipelined gather (fused mode): the last barriers finish after the last step's events
+        tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tail0.record()
+        if world > 1:
+            senv.wait_gathered()
+        tail1.record()
         torch.cuda.synchronize()
-        step_ms = sum(a.elapsed_time(c) for a, b, c in evs)
+        step_ms = sum(a.elapsed_time(c) for a, b, c in evs) + (tail0.elapsed_time(tail1) if timed else 0.0)
         kern_ms = sum(a.elapsed_time(b) for a, b, c in evs)
         return step_ms, kern_ms
 
@@ -299,8 +325,13 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    # keep the GPU busy long enough for the clock sampler to see it under load
-    while time.perf_counter() - t_wall0 < 2.5:
+    # keep the GPU busy long enough for the clock sampler to see it under load; every rank must run the SAME
+    # number of extra steps (each step holds a cross-rank barrier / collective), so rank 0 decides
+    remaining = max(0.0, 2.5 - (time.perf_counter() - t_wall0))
+    rounds = torch.tensor([int(remaining / max(50 * (step_ms / K) * 1e-3, 1e-4)) + 1], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(rounds, src=0)
+    for _ in range(min(int(rounds.item()), 2000)):
         run_steps(50, False, False)
     clocks = sampler.stop() if sampler else None
 
@@ -327,7 +358,8 @@ def main():
                        "obs_dim": D, "parallelism": ("single GPU" if world == 1 else
                                                      "env-id sharding x%d, obs all-gather %s" % (world, {
                                                          "fused": "fused into the step kernel (bulk TMA stores into every peer's "
-                                                                  "symmetric-memory buffer over NVLink) + stream barrier",
+                                                                  "symmetric-memory buffer over NVLink); cross-rank barrier on a "
+                                                                  "side stream, 3 rotating buffers",
                                                          "collective": "by one in-place ncclAllGather per step"}[gather_mode])),
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "actions": ("TD3 actor forward inside each step" if args.with_policy else
@@ -348,7 +380,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

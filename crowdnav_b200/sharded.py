@@ -62,13 +62,15 @@ class ShardedVecEnv:
         if self.gather_mode == "fused":
             # Gather buffers in symmetric memory: every rank can address every peer's copy, so the step kernel
             # stores its rows into all of them itself (bulk TMA stores over NVLink) -- no collective launch.
-            # TWO buffers, alternating per step: a peer's step t+1 kernel may start while this rank still reads
-            # step t, so it must not land in the buffer being read; the barrier that ends step t+1 is only passed
-            # once every rank has enqueued (hence, in stream order, finished reading) step t.
+            # What is left of the collective is a cross-rank barrier ("every shard of step t has landed"); it runs
+            # on a side stream, off the stepping stream's critical path.  THREE buffers rotate: the kernel of
+            # step t writes buffer t % 3 on every rank, which a slow peer may still be reading from step t-3; that
+            # peer finished reading before it launched step t-2, which is what barrier t-2 certifies -- so the
+            # stepping stream only ever waits for a barrier issued two steps earlier.
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else dist.group.WORLD
             self._bufs, self._symm, self._peers = [], [], []
-            for _ in range(2):
+            for _ in range(3):
                 buf = symm_mem.empty((self.E, self.D), dtype=torch.float32, device=device)
                 buf.zero_()
                 hdl = symm_mem.rendezvous(buf, grp)
@@ -77,6 +79,8 @@ class ShardedVecEnv:
                 self._symm.append(hdl)
                 self._peers.append([int(p) + off for r, p in enumerate(hdl.buffer_ptrs) if r != self.rank])
             self._cur = 0
+            self._comm = torch.cuda.Stream(device=device, priority=-1)   # barrier kernels jump the queue
+            self._ready = [None, None, None]                # event: barrier of the step that wrote buffer i is done
             self.obs_all = self._bufs[0]
         else:
             self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
@@ -86,13 +90,27 @@ class ShardedVecEnv:
             self.env.set_obs_peers(self._peers[0])
 
     def gather(self) -> torch.Tensor:
-        """Make obs_all complete on every rank: in 'collective' mode an in-place all-gather of the rows
-        (sendbuf = recvbuf + rank * count); in 'fused' mode the kernels already wrote every peer's copy and only
-        a cross-rank barrier on the stream is needed."""
+        """Make obs_all complete on every rank.  'collective': an in-place all-gather of the rows (sendbuf =
+        recvbuf + rank * count) on the stepping stream.  'fused': the kernels already wrote every peer's copy; the
+        cross-rank barrier is enqueued on the side stream -- call wait_gathered() before reading other ranks' rows."""
         if self.gather_mode == "collective":
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
         elif self.gather_mode == "fused":
-            self._symm[self._cur].barrier(channel=0)
+            main = torch.cuda.current_stream(self.obs_all.device)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._comm.wait_event(done)
+            with torch.cuda.stream(self._comm):
+                self._symm[self._cur].barrier(channel=0)
+                ev = torch.cuda.Event()
+                ev.record(self._comm)
+            self._ready[self._cur] = ev
+        return self.obs_all
+
+    def wait_gathered(self) -> torch.Tensor:
+        """Order the current stream behind the arrival of every rank's rows of the latest step."""
+        if self.gather_mode == "fused" and self._ready[self._cur] is not None:
+            torch.cuda.current_stream(self.obs_all.device).wait_event(self._ready[self._cur])
         return self.obs_all
 
     def reset(self) -> torch.Tensor:
@@ -106,9 +124,12 @@ class ShardedVecEnv:
         return self.gather()
 
     def begin_step(self) -> None:
-        """Fused mode: point the kernel at the other gather buffer (see __init__)."""
+        """Fused mode: rotate to the next gather buffer (see __init__) once its previous readers are done."""
         if self.gather_mode == "fused":
-            self._cur ^= 1
+            self._cur = (self._cur + 1) % 3
+            guard = self._ready[(self._cur + 1) % 3]         # barrier of two steps ago
+            if guard is not None:
+                torch.cuda.current_stream(self.obs_all.device).wait_event(guard)
             self.obs_all = self._bufs[self._cur]
             self.obs_local = self.obs_all[self.lo:self.hi]
             self.env.obs = self.obs_local
