@@ -87,6 +87,9 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     if (c->k_obstacles < 0 || c->k_obstacles > CN_MAX_PEDS) return -1;
     if (c->n_behaviors < 1 || c->n_behaviors > CN_MAX_BEHAVIORS) return -1;
     if (!(c->dt > 0.0f) || !(c->max_range > 0.0f)) return -1;
+    /* the packed contact prefilter keeps 14-bit coordinates at 2^-8 m: worlds within +-30 m, contact range < 0.24 m */
+    if (c->room_xmin < -30.0f || c->room_xmax > 30.0f || c->room_ymin < -30.0f || c->room_ymax > 30.0f) return -1;
+    if (c->ped_radius + (c->ped_radius > c->robot_radius ? c->ped_radius : c->robot_radius) + c->rep_cutoff > 0.24f) return -1;
     const double two_pi = 6.283185307179586476925286766559;
     double inc = (double)c->sensor_sweep / (double)(c->n_samples - 1);
     d->inc_bin = (uint32_t)llrint(inc / two_pi * 4294967296.0);
@@ -111,6 +114,7 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->inv_dt = (float)(1.0 / (double)c->dt);
     d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
     d->max_range_r3 = cn_np_round3(c->max_range);
+    if (d->max_range_r3 != c->max_range) return -1;   /* the no-return value must be a whole number of millimetres */
     d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
     {
         double lim = (double)(c->ped_radius + (c->ped_radius > c->robot_radius ? c->ped_radius : c->robot_radius))

@@ -411,16 +411,27 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
             }
         }
     }
-    uint32_t cmask[NPL];
-    {
-        uint32_t mine = 0;
+    // chunks each candidate can touch; `dup` = chunks claimed by more than one primitive (walls included).  A
+    // candidate whose chunks are all its own is final as soon as it is rasterised: its ray count and centre ray are
+    // taken in the same pass.  Only overlapping candidates need the separate ownership pass below.
+    uint32_t cmask[NPL], cchunks[NPL];
+    uint32_t dup = 0;
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            cmask[s] = __ballot_sync(FULL, cand[s]);
-            if (cand[s]) mine |= span_chunks(span[s], NR);
-        }
-        dirty |= __reduce_or_sync(FULL, mine);
+    for (int s = 0; s < NPL; ++s) {
+        cmask[s] = __ballot_sync(FULL, cand[s]);
+        cchunks[s] = cand[s] ? span_chunks(span[s], NR) : 0u;
     }
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        for (uint32_t m = cmask[s]; m; m &= m - 1) {
+            const uint32_t cm = __shfl_sync(FULL, cchunks[s], __ffs(m) - 1);
+            dup |= dirty & cm;
+            dirty |= cm;
+        }
+    }
+    int cnt[NPL], jstar[NPL];
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) { cnt[s] = 0; jstar[s] = 0; }
 
     // ---- row <- "no return" (already in its final rounded form) where nothing can hit; the chunks a span
     // touches get the same value and are the only ones visited again.  hit ids <- none.
@@ -470,40 +481,8 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
         while (m) {
             const int src = __ffs(m) - 1; m &= m - 1;
             const float cqx = __shfl_sync(FULL, qx[s], src), cqy = __shfl_sync(FULL, qy[s], src);
-            Span sp;
-            sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
-            sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
-            const uint8_t id = (uint8_t)(src + 32 * s);
-            auto f = [&](int i, bool valid) {
-                if (!valid) return;
-                float sn, co; cn_sincos_bin(th + (uint32_t)i * P.d.inc_bin, &sn, &co);
-                const float b = fmaf(cqx, co, cqy * sn);
-                const float h = fmaf(cqx, sn, -(cqy * co));
-                const float disc = fmaf(-h, h, P.d.ped_r2);
-                if (disc < 0.0f) return;
-                const float sq = sqrtf(disc);
-                if (!(b + sq > 0.0f)) return;
-                float t = b - sq;
-                if (t < 0.0f) t = 0.0f;
-                const int j = NR - i;
-                if (t < maxr && t < row[j]) { row[j] = t; hid[j] = id; }
-            };
-            walk(sp, lane, f);
-            __syncwarp();
-        }
-    }
-
-    STAMP(10);
-    // ---- E-I: per candidate, count the rays it owns and find its centre ray
-    int cnt[NPL], jstar[NPL];
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) { cnt[s] = 0; jstar[s] = 0; }
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        uint32_t m = cmask[s];
-        while (m) {
-            const int src = __ffs(m) - 1; m &= m - 1;
             const uint32_t cb = __shfl_sync(FULL, bearing[s], src);
+            const bool iso = (__shfl_sync(FULL, cchunks[s], src) & dup) == 0u;
             Span sp;
             sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
             sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
@@ -512,22 +491,75 @@ __device__ __forceinline__ bool scan_and_risk(const cn_kparams& P, const uint32_
             auto f = [&](int i, bool valid) {
                 bool hit = false;
                 if (valid) {
-                    const int j = NR - i;
-                    hit = hid[j] == id;
-                    if (hit) {
-                        const int32_t delta = (int32_t)(th + (uint32_t)i * P.d.inc_bin - cb);
-                        const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
-                        const uint32_t key = (ad & ~1u) | (delta < 0 ? 1u : 0u);
-                        if (key < bkey || (key == bkey && j < bj)) { bkey = key; bj = j; }
+                    float sn, co; cn_sincos_bin(th + (uint32_t)i * P.d.inc_bin, &sn, &co);
+                    const float b = fmaf(cqx, co, cqy * sn);
+                    const float h = fmaf(cqx, sn, -(cqy * co));
+                    const float disc = fmaf(-h, h, P.d.ped_r2);
+                    if (disc >= 0.0f) {
+                        const float sq = sqrtf(disc);
+                        if (b + sq > 0.0f) {
+                            float t = b - sq;
+                            if (t < 0.0f) t = 0.0f;
+                            const int j = NR - i;
+                            if (t < maxr && t < row[j]) {
+                                row[j] = t; hid[j] = id; hit = true;
+                                if (iso) {          // E-I in the same pass: nothing else can touch these rays
+                                    const int32_t delta = (int32_t)(th + (uint32_t)i * P.d.inc_bin - cb);
+                                    const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
+                                    const uint32_t key = (ad & ~1u) | (delta < 0 ? 1u : 0u);
+                                    if (key < bkey || (key == bkey && j < bj)) { bkey = key; bj = j; }
+                                }
+                            }
+                        }
                     }
                 }
-                c += __popc(__ballot_sync(FULL, hit));
+                if (iso) c += __popc(__ballot_sync(FULL, hit));
             };
             walk(sp, lane, f);
-            if (c >= 4) {
+            __syncwarp();
+            if (iso && c >= 4) {
                 const uint32_t kmin = __reduce_min_sync(FULL, bkey);
                 const int jm = (int)__reduce_min_sync(FULL, (uint32_t)(bkey == kmin ? bj : 0x7FFFFFFF));
                 if (lane == src) { cnt[s] = c; jstar[s] = jm; }
+            }
+        }
+    }
+
+    STAMP(10);
+    // ---- E-I for candidates that share chunks with another primitive: count the rays each still owns and
+    // find its centre ray once everything is rasterised
+    if (dup) {
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            uint32_t m = __ballot_sync(FULL, cand[s] && (cchunks[s] & dup) != 0u);
+            while (m) {
+                const int src = __ffs(m) - 1; m &= m - 1;
+                const uint32_t cb = __shfl_sync(FULL, bearing[s], src);
+                Span sp;
+                sp.a0 = __shfl_sync(FULL, span[s].a0, src); sp.a1 = __shfl_sync(FULL, span[s].a1, src);
+                sp.b0 = __shfl_sync(FULL, span[s].b0, src); sp.b1 = __shfl_sync(FULL, span[s].b1, src);
+                const uint8_t id = (uint8_t)(src + 32 * s);
+                int c = 0; uint32_t bkey = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
+                auto f = [&](int i, bool valid) {
+                    bool hit = false;
+                    if (valid) {
+                        const int j = NR - i;
+                        hit = hid[j] == id;
+                        if (hit) {
+                            const int32_t delta = (int32_t)(th + (uint32_t)i * P.d.inc_bin - cb);
+                            const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
+                            const uint32_t key = (ad & ~1u) | (delta < 0 ? 1u : 0u);
+                            if (key < bkey || (key == bkey && j < bj)) { bkey = key; bj = j; }
+                        }
+                    }
+                    c += __popc(__ballot_sync(FULL, hit));
+                };
+                walk(sp, lane, f);
+                if (c >= 4) {
+                    const uint32_t kmin = __reduce_min_sync(FULL, bkey);
+                    const int jm = (int)__reduce_min_sync(FULL, (uint32_t)(bkey == kmin ? bj : 0x7FFFFFFF));
+                    if (lane == src) { cnt[s] = c; jstar[s] = jm; }
+                }
             }
         }
     }
@@ -838,17 +870,21 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             const int step_counter = step + 1;
             uint32_t peers = 0;
             if (NPL == 1) {
-                // contacts are rare: find the pairs within the (conservative, integer) contact box by rotating the
-                // pedestrian list against itself -- N/2 shuffle rounds instead of an N-iteration loop per lane
-                int32_t mx = 0x20000000 + (lane << 20), my = mx;          // far-apart dummies for lanes >= N
-                if (lane < N) { const uint2 a = *reinterpret_cast<const uint2*>(&spa[lane]); mx = (int32_t)a.x; my = (int32_t)a.y; }
+                // contacts are rare: find the pairs inside a conservative contact box by rotating the pedestrian list
+                // against itself (N/2 shuffle rounds).  Both coordinates travel in ONE word: 14-bit fields at
+                // 2^-8 m with a guard bit each, so "|dx| < 64 q and |dy| < 64 q" is one subtract and one mask test.
+                uint32_t pk = 0u;
+                if (lane < N) {
+                    const uint2 a = *reinterpret_cast<const uint2*>(&spa[lane]);
+                    pk = (((a.x + 0x20000000u) >> 16) & 0x3FFFu) | ((((a.y + 0x20000000u) >> 16) & 0x3FFFu) << 16);
+                }
+                const uint32_t pk_biased = (pk | 0x80008000u) + 0x00400040u;
                 const int half = N >> 1;
                 int partner = lane;
                 for (int r = 1; r <= half; ++r) {
                     partner = (partner + 1 >= N) ? partner + 1 - N : partner + 1;       // (lane + r) mod N
-                    const int src = (lane < N) ? partner : lane;
-                    const int32_t ox_ = __shfl_sync(FULL, mx, src), oy_ = __shfl_sync(FULL, my, src);
-                    const bool hit = lane < N && (uint32_t)(mx - ox_ + lim_i) < lim2 && (uint32_t)(my - oy_ + lim_i) < lim2;
+                    const uint32_t other = __shfl_sync(FULL, pk, (lane < N) ? partner : lane);
+                    const bool hit = lane < N && ((pk_biased - other) & 0xFF80FF80u) == 0x80008000u;
                     const uint32_t hm = __ballot_sync(FULL, hit);
                     if (hm) {                                                           // rare
                         if (hit) peers |= 1u << partner;
