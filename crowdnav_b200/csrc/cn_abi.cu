@@ -60,6 +60,7 @@ int cn_config_default(cn_config* c) {
     c->ped_radius = 0.0505f; c->robot_radius = 0.105f; c->cp_radius = 0.178f;
     c->waypoint_radius = 0.3f; c->goal_box = 0.20f;
     c->rep_strength = 0.5f; c->rep_range = 0.05f; c->rep_cutoff = 0.05f; c->layout_jitter = 0.0f;
+    c->wheel_accel = 0.0f; c->n_substeps = 1;
     c->n_behaviors = 1;
     c->behavior_kind[0] = CN_BEHAVIOR_RANDOM; c->behavior_speed[0] = 0.2f;
     c->behavior_period_ticks[0] = 30; c->behavior_stagger_ticks[0] = 2;
@@ -137,6 +138,7 @@ static void pack(const cn_handle* h, cn_kparams* P) {
     P->cfg = h->cfg_dev; P->d = h->d;
     P->n_envs = c->n_envs; P->n_peds = c->n_peds; P->n_samples = c->n_samples; P->k_obstacles = c->k_obstacles;
     P->max_steps = c->max_steps; P->env_id_offset = c->env_id_offset; P->n_behaviors = c->n_behaviors;
+    P->n_substeps = c->n_substeps;
     P->flags = c->flags; P->dt = c->dt;
     P->room_xmin = c->room_xmin; P->room_xmax = c->room_xmax; P->room_ymin = c->room_ymin; P->room_ymax = c->room_ymax;
     P->goal_x = c->goal_x; P->goal_y = c->goal_y; P->heading_off_x = c->heading_off_x; P->heading_off_y = c->heading_off_y;

@@ -26,7 +26,7 @@ struct cn_kparams {
     int n_obs_peers;
     const cn_config* cfg;       /* device copy */
     cn_derived d;
-    int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors;
+    int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors, n_substeps;
     uint32_t flags;
     int obs_bulk_ok;            /* obs base is 16-B aligned: tile rows may leave by bulk store */
     int act_bulk_ok;            /* action base is 16-B aligned: the tile's actions arrive by bulk load */

@@ -76,6 +76,8 @@ typedef struct cn_derived {
     float    inv_dt;         /* RN(1 / dt): velocities are displacement * inv_dt */
     float    inv_cp_span;    /* RN(1 / (max_range - collision_range)), UTL:343 */
     float    max_range_r3;   /* np.around(max_range, 3): the value of a ray with no return */
+    float    dt_sub;         /* dt / n_substeps */
+    float    wheel_step;     /* wheel_accel * dt_sub: largest wheel-speed change per sub-step (0 = unlimited) */
     int32_t  obs_dim;
     int32_t  pair_cell_shift; /* log2 (grid units) of the contact-prefilter cell: cell / 2 >= contact range */
     uint32_t seed_lo, seed_hi;
@@ -111,6 +113,9 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->goal_lo_y = c->goal_y - c->goal_box;
     d->goal_hi_y = c->goal_y + c->goal_box;
     d->inv_inc_bin = (float)(1.0 / (double)d->inc_bin);
+    if (c->n_substeps < 1 || c->n_substeps > 64 || !(c->wheel_accel >= 0.0f)) return -1;
+    d->dt_sub = (c->n_substeps == 1) ? c->dt : (float)((double)c->dt / (double)c->n_substeps);
+    d->wheel_step = c->wheel_accel * d->dt_sub;
     d->inv_dt = (float)(1.0 / (double)c->dt);
     d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
     d->max_range_r3 = cn_np_round3(c->max_range);

@@ -253,19 +253,34 @@ __device__ __forceinline__ PoseIn advance_robot(const cn_kparams& P, const uint3
     av = fminf(fmaxf(av, -CN_ACT_V_LIMIT), CN_ACT_V_LIMIT);
     aw = fminf(fmaxf(aw, -CN_ACT_W_LIMIT), CN_ACT_W_LIMIT);
     const float half = (aw * CN_WHEEL_SEP) * 0.5f;
-    const float vl = av - half, vr = av + half;
-    const float v_body = (vr + vl) * 0.5f;
-    const float w_body = (vr - vl) * CN_INV_WHEEL_SEP;
-    const float ds = v_body * P.dt;
-    const float dth = w_body * P.dt;
-    const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
-    const uint32_t th = rob[CN_R_TH];
-    const uint32_t mid = th + (uint32_t)(dth_bin >> 1);
-    float sm, cm; cn_sincos_bin(mid, &sm, &cm);
+    const float tl = av - half, tr = av + half;           // wheel speed targets
+    float cl = tl, cr = tr;
+    const float st = P.d.wheel_step;
+    if (st > 0.0f) {                                       // libgazebo_ros_diff_drive ramp (XACRO:65,70)
+        const float cv = f_of(rob[CN_R_V]), cw = f_of(rob[CN_R_W]);
+        const float ch = (cw * CN_WHEEL_SEP) * 0.5f;
+        cl = cv - ch; cr = cv + ch;
+    }
     PoseIn p;
-    p.xi = (int32_t)rob[CN_R_X] + cn_f2i((ds * cm) * CN_INV_GRID);
-    p.yi = (int32_t)rob[CN_R_Y] + cn_f2i((ds * sm) * CN_INV_GRID);
-    p.th = th + (uint32_t)dth_bin;
+    p.xi = (int32_t)rob[CN_R_X]; p.yi = (int32_t)rob[CN_R_Y]; p.th = rob[CN_R_TH];
+    float v_body = 0.0f, w_body = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < P.n_substeps; ++k) {
+        if (st > 0.0f) {
+            cl += fminf(fmaxf(tl - cl, -st), st);
+            cr += fminf(fmaxf(tr - cr, -st), st);
+        }
+        v_body = (cr + cl) * 0.5f;
+        w_body = (cr - cl) * CN_INV_WHEEL_SEP;
+        const float ds = v_body * P.d.dt_sub;
+        const float dth = w_body * P.d.dt_sub;
+        const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
+        const uint32_t mid = p.th + (uint32_t)(dth_bin >> 1);
+        float sm, cm; cn_sincos_bin(mid, &sm, &cm);
+        p.xi += cn_f2i((ds * cm) * CN_INV_GRID);
+        p.yi += cn_f2i((ds * sm) * CN_INV_GRID);
+        p.th += (uint32_t)dth_bin;
+    }
     p.v = v_body; p.w = w_body;
     return p;
 }

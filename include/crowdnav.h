@@ -94,6 +94,8 @@ typedef struct cn_config {
     float rep_range;             /*                   B  [m]     */
     float rep_cutoff;            /* extra gap beyond r_i + r_j where the term is 0 */
     float layout_jitter;         /* U(-j, j) added to each pedestrian start pose */
+    float wheel_accel;           /* wheel-speed ramp of libgazebo_ros_diff_drive [m/s^2] (XACRO:70); 0 = instantaneous */
+    int32_t n_substeps;          /* kinematic sub-steps per control period (XACRO:65: 100 Hz -> 15); >= 1 */
 
     int32_t n_behaviors;         /* env behaviour = global_env_id % n_behaviors */
     int32_t behavior_kind[CN_MAX_BEHAVIORS];

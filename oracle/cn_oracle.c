@@ -525,22 +525,41 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
         pb[4 * n + 2] = (uint32_t)timer;
     }
 
-    /* R: unicycle, midpoint rule (FAKE:109-118, 156-167) */
-    float half = (aw * CN_WHEEL_SEP) * 0.5f;
-    float vl = av - half, vr = av + half;                 /* FAKE:116-117 */
-    float v_body = (vr + vl) * 0.5f;                      /* FAKE:156,165: delta_s / dt     */
-    float w_body = (vr - vl) * CN_INV_WHEEL_SEP;          /* FAKE:157,167: delta_theta / dt */
-    float ds = v_body * g->dt;
-    float dth = w_body * g->dt;
-    int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
-    uint32_t th = rob[CN_R_TH];
-    uint32_t mid = th + (uint32_t)(dth_bin >> 1);
-    float sm, cm; cn_sincos_bin(mid, &sm, &cm);
-    rob[CN_R_X] = (uint32_t)(rxi + cn_f2i((ds * cm) * CN_INV_GRID));
-    rob[CN_R_Y] = (uint32_t)(ryi + cn_f2i((ds * sm) * CN_INV_GRID));
-    rob[CN_R_TH] = th + (uint32_t)dth_bin;
-    rob[CN_R_V] = u_of(v_body);
-    rob[CN_R_W] = u_of(w_body);
+    /* R: unicycle, midpoint rule (FAKE:109-118, 156-167), in n_substeps sub-steps; with wheel_accel > 0 the wheel
+     * speeds ramp toward their targets like libgazebo_ros_diff_drive (XACRO:65,70) instead of jumping */
+    {
+        float half = (aw * CN_WHEEL_SEP) * 0.5f;
+        float tl = av - half, tr = av + half;                 /* FAKE:116-117: wheel speed targets */
+        float cl = tl, cr = tr;
+        if (c->d.wheel_step > 0.0f) {                         /* current wheel speeds from the achieved body twist */
+            float cv = f_of(rob[CN_R_V]), cw = f_of(rob[CN_R_W]);
+            float ch = (cw * CN_WHEEL_SEP) * 0.5f;
+            cl = cv - ch; cr = cv + ch;
+        }
+        int32_t xi = rxi, yi = ryi;
+        uint32_t th = rob[CN_R_TH];
+        float v_body = 0.0f, w_body = 0.0f;
+        for (int k = 0; k < g->n_substeps; ++k) {
+            if (c->d.wheel_step > 0.0f) {
+                float st = c->d.wheel_step;
+                cl += fminf(fmaxf(tl - cl, -st), st);
+                cr += fminf(fmaxf(tr - cr, -st), st);
+            }
+            v_body = (cr + cl) * 0.5f;                        /* FAKE:156,165: delta_s / dt     */
+            w_body = (cr - cl) * CN_INV_WHEEL_SEP;            /* FAKE:157,167: delta_theta / dt */
+            float ds = v_body * c->d.dt_sub;
+            float dth = w_body * c->d.dt_sub;
+            int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
+            uint32_t mid = th + (uint32_t)(dth_bin >> 1);
+            float sm, cm; cn_sincos_bin(mid, &sm, &cm);
+            xi += cn_f2i((ds * cm) * CN_INV_GRID);
+            yi += cn_f2i((ds * sm) * CN_INV_GRID);
+            th += (uint32_t)dth_bin;
+        }
+        rob[CN_R_X] = (uint32_t)xi; rob[CN_R_Y] = (uint32_t)yi; rob[CN_R_TH] = th;
+        rob[CN_R_V] = u_of(v_body);
+        rob[CN_R_W] = u_of(w_body);
+    }
 
     /* get_state */
     int done_now = observe(c, rob, pa, pb, step_counter, 1, obs, dbg_ranges, dbg_hid);

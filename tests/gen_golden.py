@@ -10,6 +10,8 @@ Fixtures (all small, committed):
   env_methods.npz     Env.get_heading_to_goal / get_distance_to_goal / goal boxes /
                       compute_reward on a grid of states (reward truth table)
   waypoints.npz       utils.get_local_goal_waypoints (through the shapely stand-in)
+  td3_actor_k8_ep2500.npz
+                      the shipped K=8 TD3 actor's state_dict (checkpoint drop-in fixture)
   trace_c1.npz, trace_train.npz, trace_goal.npz
                       reference-in-the-loop traces: the reference's Env.reset/step
                       (get_state + compute_reward, unmodified) observing physics
@@ -214,8 +216,19 @@ def gen_trace(ref, name, cfg, n_steps, seed, params, seek_goal=False):
         name, len(arrays["action"]), n_ep, succ, arrays["ref_reward"].min(), arrays["ref_reward"].max()))
 
 
+def gen_actor_fixture():
+    """The shipped K=8 TD3 actor (398 -> 256 -> 256 -> 2) as an npz of its state_dict tensors: the checkpoint
+    drop-in fixture of SURVEY.md section 4 (weights are data the reference ships, not code)."""
+    import torch
+    src = "/root/reference/turtlebot3_rl_sim/src/models/td3/turtlebot3_top_8_obstacle/td3_actor_model_ep2500.pt"
+    sd = torch.load(src, map_location="cpu")
+    np.savez_compressed(os.path.join(OUT, "td3_actor_k8_ep2500.npz"), **{k: v.numpy() for k, v in sd.items()})
+    print("td3_actor_k8_ep2500: ", {k: tuple(v.shape) for k, v in sd.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gen_actor_fixture()
     ref = Reference()
     gen_utils(ref)
     gen_env_methods(ref)

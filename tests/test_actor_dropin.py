@@ -1,0 +1,66 @@
+"""Checkpoint drop-in (fixture row 1): the reference's shipped K=8 TD3 actor
+(models/td3/turtlebot3_top_8_obstacle/td3_actor_model_ep2500.pt, committed as an npz of its tensors) consumes this
+environment's observations unchanged and reaches the goal at a rate in the ballpark of its Gazebo logs (0.58)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from crowdnav_b200.config import make_config, shipped_actor_world
+from crowdnav_b200.rollout import ReplayRing, TD3Learner, collect, load_reference_actor
+
+ACTOR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "td3_actor_k8_ep2500.npz")
+
+
+def test_actor_input_width_is_the_observation_width():
+    actor = load_reference_actor(ACTOR)
+    assert actor.linear1.in_features == make_config(k_obstacles=8).obs_dim == 398
+    a = actor(torch.zeros(3, 398))
+    assert a.shape == (3, 2) and (a[:, 0] >= 0).all() and (a[:, 0] <= 0.22).all() and (a[:, 1].abs() <= 2.0).all()
+
+
+def test_shipped_actor_reaches_goal_on_the_oracle():
+    """CPU: 192 worlds on the oracle.  Success in the ballpark of the logged 0.58; failures are collisions."""
+    from oracle.oracle import OracleEnv
+    actor = load_reference_actor(ACTOR)
+    E = 192
+    env = OracleEnv(shipped_actor_world(n_envs=E, max_steps=600))
+    obs = env.reset().copy()
+    alive = np.ones(E, bool)
+    succ = 0
+    for t in range(600):
+        with torch.no_grad():
+            a = actor(torch.from_numpy(obs)).numpy().astype(np.float32)
+        o, r, d = env.step(a)
+        ended = alive & (d > 0)
+        succ += int(env.counters()[ended, 0].sum())
+        alive &= ~ended
+        obs = o.copy()
+        if not alive.any():
+            break
+    rate = succ / E
+    assert 0.35 <= rate <= 0.85, "success rate %.2f is not in the ballpark of the logged 0.58" % rate
+
+
+@pytest.mark.gpu
+def test_shipped_actor_rollout_on_gpu_and_td3_update():
+    """GPU: batched rollout of the shipped actor (4096 worlds), device replay ring, a few TD3 updates."""
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    dev = torch.device("cuda", 0)
+    actor = load_reference_actor(ACTOR, dev)
+    env = CrowdNavVecEnv(shipped_actor_world(n_envs=4096, max_steps=600, auto_reset=True), device=0)
+    env.reset()
+    replay = ReplayRing(200_000, env.D, dev)
+    stats = collect(env, actor, 400, sigma=0.0, replay=replay)
+    assert stats["episodes"] > 3000
+    assert 0.35 <= stats["success_rate"] <= 0.85, stats
+    assert len(replay) == 200_000
+    s, a, r, s2, d = replay.sample(128)
+    assert s.shape == (128, 398) and set(torch.unique(d).tolist()) <= {0.0, 1.0}
+    learner = TD3Learner(env.D, dev)
+    losses = [learner.learn(replay.sample(128)) for _ in range(6)]
+    assert all(np.isfinite(v) for l in losses for v in l.values()) and any("actor" in l for l in losses)
+    # exploration (TD3:67-78) keeps actions inside the box
+    noisy = collect(env, actor, 20, sigma=1.0)
+    assert noisy["episodes"] >= 0

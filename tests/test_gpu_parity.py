@@ -200,3 +200,11 @@ def test_sharding_invariance_on_device():
     assert bits_equal(full.get_state_blob()[16 + lo * 16:16 + hi * 16], part.get_state_blob()[16:16 + (hi - lo) * 16])
     full.close()
     part.close()
+
+
+def test_wheel_ramp_and_substeps():
+    """libgazebo_ros_diff_drive-like dynamics: 15 kinematic sub-steps, 1 m/s^2 wheel ramp, 0.19 s period."""
+    from crowdnav_b200.config import shipped_actor_world
+    cfg = shipped_actor_world(n_envs=300, auto_reset=True, max_steps=200)
+    n_done = _rollout(cfg, 150, seed=31)
+    assert n_done > 0
