@@ -208,3 +208,33 @@ def test_wheel_ramp_and_substeps():
     cfg = shipped_actor_world(n_envs=300, auto_reset=True, max_steps=200)
     n_done = _rollout(cfg, 150, seed=31)
     assert n_done > 0
+
+
+def test_cuda_graph_capture_of_cn_step():
+    """cn_step enqueues on the caller's stream with no hidden synchronisation: it can be captured into a CUDA graph
+    and replayed (what a launch-bound rollout loop does); results equal the oracle's."""
+    import torch
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    from oracle.oracle import OracleEnv
+    cfg = baseline_config(1, n_envs=512)
+    g, o = CrowdNavVecEnv(cfg, device=0), OracleEnv(cfg)
+    g.reset()
+    o.reset()
+    rng = np.random.default_rng(41)
+    act = torch.zeros((512, 2), device="cuda")
+    a0 = random_actions(rng, 512)
+    act.copy_(torch.from_numpy(a0))
+    g.step(act)                      # warm-up launch outside capture (sets the kernel attributes)
+    o.step(a0)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g.step(act)
+    for _ in range(25):
+        a = random_actions(rng, 512)
+        act.copy_(torch.from_numpy(a))
+        graph.replay()
+        o.step(a)
+    torch.cuda.synchronize()
+    assert bits_equal(g.obs.cpu().numpy(), o.obs) and bits_equal(g.get_state_blob(), o.blob)
+    g.close()
