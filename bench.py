@@ -366,7 +366,7 @@ def main():
                                    "ring of 16 batches from a random-init TD3 actor + N(0,1) exploration noise, clipped")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(wl), "peak_source": peak_src,
-                         "kernel": "cn_env_kernel<step>", "kernel_us": kern_s * 1e6,
+                         "kernel": "%s<step>, %d worlds per CTA" % (env.kernel_name, env.kernel_tile), "kernel_us": kern_s * 1e6,
                          "algorithmic_bytes_per_env_step": bytes_per_env, "envs_per_launch": E_local,
                          "l2_warm": {"kernel_us": warm_kern_s * 1e6,
                                      "achieved": E_local * bytes_per_env / warm_kern_s / 1e9,

@@ -13,8 +13,8 @@ from .config import CnConfig
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.path.join(_PKG, "libcrowdnav.so")
-SOURCES = ["cn_abi.cu", "cn_step.cu"]
-HEADERS = ["cn_math.h", "cn_state.h", "cn_kernel.h", os.path.join("..", "..", "include", "crowdnav.h")]
+SOURCES = ["cn_abi.cu", "cn_step.cu", "cn_flat.cu"]
+HEADERS = ["cn_math.h", "cn_state.h", "cn_kernel.h", "cn_dev.h", os.path.join("..", "..", "include", "crowdnav.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only
@@ -80,6 +80,9 @@ def load() -> C.CDLL:
     L.cn_set_debug_taps.argtypes = [vp, vp, vp]
     L.cn_launch_count.restype = C.c_int64
     L.cn_launch_count.argtypes = [vp]
+    L.cn_kernel_name.restype = C.c_char_p
+    L.cn_kernel_name.argtypes = [vp]
+    L.cn_kernel_tile.argtypes = [vp]
     _lib = L
     return L
 
@@ -92,6 +95,6 @@ def check(rc: int, what: str) -> None:
 
 ABI_SYMBOLS = [
     "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_gather",
-    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count",
+    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile",
     "cn_last_error", "cn_abi_version",
 ]

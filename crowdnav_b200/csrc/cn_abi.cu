@@ -23,7 +23,15 @@ struct cn_handle {
     float* dbg_ranges;
     uint8_t* dbg_hid;
     int64_t launches;
+    int use_flat;           /* 1: cn_flat.cu (compacted work lists, default), 0: cn_step.cu (warp per world; CN_KERNEL=warp) */
+    cn_flat_layout flat;
 };
+
+static cudaError_t launch_env(const cn_handle* h, cn_kparams& P, int mode, cudaStream_t s) {
+    if (h->use_flat) return cn_launch_flat_kernel(P, h->flat, mode, s);
+    P.obs_bulk_ok = P.obs_bulk_ok && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;   /* every tile starts 16-B aligned */
+    return cn_launch_env_kernel(P, mode, s);
+}
 
 static thread_local char g_err[512] = "";
 
@@ -96,13 +104,35 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     CN_CUDA(cudaSetDevice(device));
     int max_smem = 0;
     CN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    const size_t smem = cn_kernel_smem_bytes(cfg->n_peds, cfg->n_samples, d.obs_dim);
-    if (smem > (size_t)max_smem)
-        return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
+    const char* kern = getenv("CN_KERNEL");
+    const int use_flat = !(kern && strcmp(kern, "warp") == 0);
+    cn_flat_layout flat; memset(&flat, 0, sizeof(flat));
+    if (use_flat) {
+        /* CN_FLAT_TILE=W[,threads] overrides the automatic choice (experiments) */
+        const char* tile = getenv("CN_FLAT_TILE");
+        int max_sm = 0;
+        CN_CUDA(cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+        int rc;
+        if (tile) {
+            int tw = atoi(tile), tt = 256;
+            const char* comma = strchr(tile, ',');
+            if (comma) tt = atoi(comma + 1);
+            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, &flat);
+        } else {
+            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, (size_t)max_sm, &flat);
+        }
+        if (rc != 0 || flat.total > (size_t)max_smem)
+            return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
+    } else {
+        const size_t smem = cn_kernel_smem_bytes(cfg->n_peds, cfg->n_samples, d.obs_dim);
+        if (smem > (size_t)max_smem)
+            return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
+    }
 
     cn_handle* h = new (std::nothrow) cn_handle();
     if (!h) return fail(CN_ERR_NOMEM, "cn_create: host allocation failed%s", NULL);
     h->cfg = *cfg; h->d = d; h->device = device; h->launches = 0;
+    h->use_flat = use_flat; h->flat = flat;
     h->dbg_ranges = NULL; h->dbg_hid = NULL;
     const size_t cfg_b = align_up(sizeof(cn_config), 256);
     const size_t rob_b = align_up(cn_robot_words(cfg) * 4, 256);
@@ -156,7 +186,7 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
     if (!h || !obs_dev) return fail(CN_ERR_INVALID, "cn_reset: null argument%s", NULL);
     cn_kparams P; pack(h, &P);
     P.mask = mask_dev; P.obs = obs_dev; P.obs_bulk_ok = 0;
-    CN_CUDA(cn_launch_env_kernel(P, 1, (cudaStream_t)stream));
+    CN_CUDA(launch_env(h, P, 1, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -166,9 +196,9 @@ int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward
         return fail(CN_ERR_INVALID, "cn_step: null argument%s", NULL);
     cn_kparams P; pack(h, &P);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
-    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0 && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;   /* every tile starts 16-B aligned */
+    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
-    CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
+    CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -188,9 +218,9 @@ int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float*
         aligned = aligned && (((uintptr_t)peer_obs_dev[p]) & 15u) == 0;
     }
     P.n_obs_peers = n_peers;
-    P.obs_bulk_ok = aligned && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;
+    P.obs_bulk_ok = aligned;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
-    CN_CUDA(cn_launch_env_kernel(P, 0, (cudaStream_t)stream));
+    CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -255,5 +285,7 @@ int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev) {
 }
 
 int64_t cn_launch_count(const cn_handle* h) { return h ? h->launches : 0; }
+const char* cn_kernel_name(const cn_handle* h) { return (h && !h->use_flat) ? "cn_env_kernel" : "cn_flat_kernel"; }
+int cn_kernel_tile(const cn_handle* h) { return !h ? 0 : (h->use_flat ? h->flat.W : CN_TILE); }
 
 }  /* extern "C" */

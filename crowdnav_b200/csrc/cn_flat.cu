@@ -1,0 +1,882 @@
+/*
+ * cn_flat.cu -- the fused env-step kernel for sm_100a, "compacted work list" design.
+ *
+ * One launch advances E independent 2-D worlds by one control period (the same
+ * path as cn_step.cu: CROWD:98-144 pedestrians -> FAKE:109-167 unicycle ->
+ * XACRO:148-179 LiDAR -> UTL:375-392 scan cleaning -> ENV:568-907 perceived-risk
+ * block -> ENV:246-265 waypoint, ENV:1011-1023 done, ENV:1046-1162 reward,
+ * ENV:1227-1263 reset).  Results are bit-identical to cn_step.cu and to the
+ * CPU oracle; only the mapping of work to threads differs.
+ *
+ * Why another mapping.  With one warp per world (cn_step.cu) most instructions
+ * are issued for one or two useful lanes: two of twenty pedestrians resample
+ * per step, one pedestrian in twenty is inside LiDAR range, one confirmed
+ * object per world goes through the collision cone.  The ncu capture of that
+ * kernel shows 1 620 warp-instructions per world at 20 of 32 lanes active, and
+ * the kernel is issue-bound at 14 % of the HBM roofline.  Here a CTA owns a tile
+ * of W consecutive worlds and every phase runs over a FLAT list of work items
+ * gathered across the whole tile, so rare work is compacted into full warps:
+ *
+ *   phase 0   thread 0 issues the bulk TMA loads of the tile's three state
+ *             planes + actions; meanwhile all threads pre-fill the observation
+ *             rows with the no-return value and the per-ray hit keys with
+ *             "nothing" (16-byte stores).
+ *   phase 1   warps 0-1: lane = WORLD, the pose-only part of get_state /
+ *             compute_reward (unicycle, waypoint, heading, distance, reward
+ *             shaping, wall spans).  Warps 2-15: thread = PEDESTRIAN of the
+ *             tile: timers; contact prefilter over packed coordinates; Philox
+ *             only for the compacted list of pedestrians that resample (or are
+ *             re-spawned) this step; integrate + wall clamp.
+ *   phase 2   thread = pedestrian: LiDAR candidate test -> compact candidate
+ *             list; thread = candidate: bearing, angular span; every span (wall
+ *             faces too) is cut into groups of 8 rays appended to a group list.
+ *   phase 3   8 lanes per ray group: ray-disc / ray-face intersection with the
+ *             oracle's per-ray arithmetic, 64-bit atomicMin of (range bits,
+ *             primitive order) on the ray's key in shared memory -- the minimum
+ *             reproduces the oracle's "walls first, then pedestrians in index
+ *             order, strict <" rule exactly.
+ *   phase 4   same groups: rays a primitive still owns get their final cleaned,
+ *             rounded value in the observation row; min(scan); rays owned per
+ *             pedestrian.
+ *   phase 5   thread = candidate: centre ray, hit point, tracker, collision
+ *             cone, CP (ENV:656-860).
+ *   phase 6   thread = candidate: top-K rank + slot write; thread = pedestrian:
+ *             tracker flags; lane = world: counters, done, reward, robot record.
+ *   phase 7   bulk TMA stores of the state planes and the [W, D] block of rows
+ *             (and, for cn_step_gather, of the same block into every peer GPU).
+ *
+ * Numerics: everything that reaches an output goes through cn_math.h
+ * primitives in the oracle's operation order; -fmad=false.  Approximate
+ * arithmetic appears only in choosing (padded, conservative) span bounds.
+ */
+#include "cn_dev.h"
+
+#define CF_POSE_WARPS 2
+
+namespace {
+
+// scalar-record words beyond the pose-phase record of cn_dev.h (S_* < S_WORDS = 40)
+enum {
+    F_MINBITS = 40,     // min over the cleaned scan, float bits (ranges are > 0)
+    F_CONF0, F_CONF1,   // pedestrians confirmed as objects this step (bit n)
+    F_XFLAGS,           // XF_*
+    F_OVF_FACES,        // wall faces whose ray groups did not fit the group list
+    F_NOBJ,             // objects of this world in the K block (entries of its object list)
+    F_WORDS = 48
+};
+#define XF_ACTIVE 1u    // the world is processed by this launch
+#define XF_RESET  2u    // ... as a reset (MODE 1, or next-step auto-reset)
+#define XF_EGO    4u    // an object's centre range < 0.140 (ENV:1000)
+
+enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_WORDS = 8 };
+
+// candidate record (8 words per pedestrian slot).  Phases 2-4: q (sensor-relative centre), bearing, span,
+// owned-ray count, robot yaw.  Phase 5 overwrites it with the object's CP row for phase 6.
+enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_TH, Q_WN };     // Q_WN: world | pedestrian << 8 | overflow << 31
+enum { O_CP = 0, O_X, O_Y, O_VX, O_VY, O_TTC };
+#define WN_OVF 0x80000000u
+
+// ray-group entry: up to 8 consecutive scan indices of one primitive
+//   bits 0-2 count - 1, bits 3-13 first index, bits 14-31 primitive (pedestrian slot, or world * 4 + face)
+#define GRP_NONE 0xFFFFFFFFu
+
+struct Ptrs {
+    uint32_t* robot; uint32_t* pa; uint32_t* pb; float* act; float* obs; unsigned long long* keys;
+    uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint16_t* rlist; uint16_t* olist;
+    uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ int world_of(int idx, int N, uint32_t magic) {
+    return (N == 1) ? idx : (int)__umulhi((uint32_t)idx, magic);
+}
+__device__ __forceinline__ void unpack_span(uint32_t a, uint32_t b, Span& s) {
+    s.a0 = (int)(a & 0xFFFFu); s.a1 = (int)(a >> 16); s.b0 = (int)(b & 0xFFFFu); s.b1 = (int)(b >> 16);
+}
+__device__ __forceinline__ int span_len_a(const Span& s) { return (s.a1 >= s.a0) ? (s.a1 - s.a0 + 1) : 0; }
+__device__ __forceinline__ int span_len_b(const Span& s) { return (s.b1 >= s.b0) ? (s.b1 - s.b0 + 1) : 0; }
+// ray `pos` of the concatenation [a0, a1] ++ [b0, b1]; -1 when past the end
+__device__ __forceinline__ int span_ray(const Span& s, int pos) {
+    const int la = span_len_a(s), lb = span_len_b(s);
+    if (pos >= la + lb) return -1;
+    return (pos < la) ? s.a0 + pos : s.b0 + (pos - la);
+}
+
+// append the ray groups of one primitive to a group list; returns false when they did not fit
+__device__ __forceinline__ bool push_groups(uint32_t* list, uint32_t* counter, int cap, uint32_t tag, const Span& sp) {
+    const int la = span_len_a(sp), lb = span_len_b(sp);
+    const int ga = (la + 7) >> 3, gb = (lb + 7) >> 3;
+    if (ga + gb == 0) return true;
+    const int base = (int)atomicAdd(counter, (uint32_t)(ga + gb));
+    if (base + ga + gb <= cap) {
+        uint32_t* out = list + base;
+        for (int k = 0; k < ga; ++k) {
+            const int first = sp.a0 + 8 * k, cntm1 = min(8, sp.a1 - first + 1) - 1;
+            out[k] = (tag << 14) | ((uint32_t)first << 3) | (uint32_t)cntm1;
+        }
+        out += ga;
+        for (int k = 0; k < gb; ++k) {
+            const int first = sp.b0 + 8 * k, cntm1 = min(8, sp.b1 - first + 1) - 1;
+            out[k] = (tag << 14) | ((uint32_t)first << 3) | (uint32_t)cntm1;
+        }
+        return true;
+    }
+    for (int k = base; k < cap; ++k) list[k] = GRP_NONE;        // neutral entries; the primitive takes the slow path
+    return false;
+}
+// scan index handled by this lane of a group, or -1
+__device__ __forceinline__ int group_ray(uint32_t ent, int lane8) {
+    if (ent == GRP_NONE || lane8 > (int)(ent & 7u)) return -1;
+    return (int)((ent >> 3) & 0x7FFu) + lane8;
+}
+
+// ---- phase 3: one ray of one primitive -> atomicMin on the ray's key
+__device__ __forceinline__ void raster_wall(const cn_kparams& P, const Ptrs& S, int key_stride, int q, int i) {
+    const int NR = P.n_samples - 1;
+    const int w = q >> 2, face = q & 3;
+    const uint32_t* sc = S.sc + w * F_WORDS;
+    const bool xface = face < 2;
+    const bool posf = (face & 1) == 0;
+    const float wall = xface ? (posf ? P.room_xmax : P.room_xmin) : (posf ? P.room_ymax : P.room_ymin);
+    const float o = xface ? (f_of(sc[S_XF]) + f_of(sc[S_OFFX])) : (f_of(sc[S_YF]) + f_of(sc[S_OFFY]));
+    const float num = wall - o;
+    float s, co; cn_sincos_bin(sc[S_TH] + (uint32_t)i * P.d.inc_bin, &s, &co);
+    const float den = xface ? co : s;
+    if (posf ? !(den > 0.0f) : !(den < 0.0f)) return;
+    const float t = num / den;
+    if (t > 0.0f && t < P.max_range) {
+        const unsigned long long key = ((unsigned long long)u_of(t) << 32) | (xface ? 0ull : 1ull);
+        atomicMin(S.keys + (size_t)w * key_stride + (NR - i), key);
+    }
+}
+__device__ __forceinline__ void raster_ped(const cn_kparams& P, const Ptrs& S, int key_stride, int slot, int i) {
+    const int NR = P.n_samples - 1;
+    const uint32_t* rec = S.rec + slot * 8;
+    const uint32_t wn = rec[Q_WN];
+    const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
+    const float cqx = f_of(rec[Q_QX]), cqy = f_of(rec[Q_QY]);
+    float sn, co; cn_sincos_bin(rec[Q_TH] + (uint32_t)i * P.d.inc_bin, &sn, &co);
+    const float b = fmaf(cqx, co, cqy * sn);
+    const float h = fmaf(cqx, sn, -(cqy * co));
+    const float disc = fmaf(-h, h, P.d.ped_r2);
+    if (disc >= 0.0f) {
+        const float sq = sqrtf(disc);
+        if (b + sq > 0.0f) {
+            float t = b - sq;
+            if (t < 0.0f) t = 0.0f;
+            if (t < P.max_range) {
+                const unsigned long long key = ((unsigned long long)u_of(t) << 32) | (unsigned long long)(n + 2);
+                atomicMin(S.keys + (size_t)w * key_stride + (NR - i), key);
+            }
+        }
+    }
+}
+
+// ---- phase 4: a ray the primitive still owns gets its final value (UTL:375-392 + np.around, ENV:1042)
+__device__ __forceinline__ void finish_ray(const cn_kparams& P, const Ptrs& S, int w, int j, unsigned long long key) {
+    const float t = f_of((uint32_t)(key >> 32));
+    const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
+    S.obs[(size_t)w * P.d.obs_dim + j] = cn_np_round3(rr);
+    atomicMin(S.sc + w * F_WORDS + F_MINBITS, u_of(rr));
+}
+__device__ __forceinline__ void own_wall(const cn_kparams& P, const Ptrs& S, int key_stride, int q, int i) {
+    const int w = q >> 2, face = q & 3;
+    const int j = (P.n_samples - 1) - i;
+    const unsigned long long key = S.keys[(size_t)w * key_stride + j];
+    if ((uint32_t)key == ((face < 2) ? 0u : 1u)) finish_ray(P, S, w, j, key);
+}
+__device__ __forceinline__ bool own_ped(const cn_kparams& P, const Ptrs& S, int key_stride, int slot, int i) {
+    const uint32_t wn = S.rec[slot * 8 + Q_WN];
+    const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
+    const int j = (P.n_samples - 1) - i;
+    const unsigned long long key = S.keys[(size_t)w * key_stride + j];
+    if ((uint32_t)key != (uint32_t)(n + 2)) return false;
+    finish_ray(P, S, w, j, key);
+    return true;
+}
+
+// centre-ray ordering of the oracle: smaller |ray angle - bearing| first, then smaller j
+__device__ __forceinline__ void centre_try(uint32_t rel, uint32_t inc, int NR, int i, uint32_t& bkey, int& bj) {
+    const int32_t delta = (int32_t)((uint32_t)i * inc - rel);
+    const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
+    const uint32_t key = (ad & ~1u) | (delta < 0 ? 1u : 0u);
+    const int j = NR - i;
+    if (key < bkey || (key == bkey && j < bj)) { bkey = key; bj = j; }
+}
+
+template <int T, class V>
+__device__ __forceinline__ void fill16(V* base, int n, V v, int tid) {      // n 16-byte elements, strided over the CTA
+    V* p = base + tid;
+    V* const end = base + n;
+#pragma unroll 4
+    for (; p < end; p += T) *p = v;
+}
+
+// ------------------------------------------------------------------- kernel
+template <int MODE, int T>
+__global__ void __launch_bounds__(T, 1024 / T)
+cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
+    constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int W = L.W, N = P.n_peds, NR = P.n_samples - 1, D = P.d.obs_dim, K = P.k_obstacles;
+    const int e0 = blockIdx.x * W;
+    const int nE = min(W, P.n_envs - e0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int KS = (int)L.key_stride;
+
+    Ptrs S;
+    S.robot = reinterpret_cast<uint32_t*>(smem);
+    S.pa = reinterpret_cast<uint32_t*>(smem + L.off_pa);
+    S.pb = reinterpret_cast<uint32_t*>(smem + L.off_pb);
+    S.act = reinterpret_cast<float*>(smem + L.off_act);
+    S.obs = reinterpret_cast<float*>(smem + L.off_obs);
+    S.keys = reinterpret_cast<unsigned long long*>(smem + L.off_keys);
+    S.sc = reinterpret_cast<uint32_t*>(smem + L.off_sc);
+    S.rec = reinterpret_cast<uint32_t*>(smem + L.off_rec);
+    S.pk = reinterpret_cast<uint32_t*>(smem + L.off_pk);
+    S.peers = reinterpret_cast<uint32_t*>(smem + L.off_peers);
+    S.clist = reinterpret_cast<uint16_t*>(smem + L.off_clist);
+    S.rlist = reinterpret_cast<uint16_t*>(smem + L.off_rlist);
+    S.olist = reinterpret_cast<uint16_t*>(smem + L.off_olist);
+    S.wg = reinterpret_cast<uint32_t*>(smem + L.off_wg);
+    S.pg = reinterpret_cast<uint32_t*>(smem + L.off_pg);
+    S.cnt = reinterpret_cast<uint32_t*>(smem + L.off_cnt);
+    S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+
+    const int n_items = nE * N;                       // pedestrians of the tile (<= PED_THREADS by construction)
+    const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
+    const uint32_t ped_bytes = (uint32_t)n_items * 16u;
+    const bool act_smem = (MODE == 0) && P.act_bulk_ok && (W % 2) == 0 && (nE % 2) == 0;
+
+    // ---------------------------------------------------------------- phase 0
+    if (tid == 0) {
+        mbar_init(S.bar, 1);
+        fence_mbar_init();
+        const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
+        mbar_expect_tx(S.bar, rob_bytes + 2u * ped_bytes + act_bytes);
+        if (act_bytes) tma_load(S.act, P.action + 2 * (size_t)e0, act_bytes, S.bar);
+        tma_load(S.robot, P.robot + (size_t)e0 * CN_ROBOT_WORDS, rob_bytes, S.bar);
+        if (ped_bytes) {
+            tma_load(S.pa, P.ped_a + (size_t)e0 * N * 4, ped_bytes, S.bar);
+            tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
+        }
+    }
+    {
+        fill16<T>(reinterpret_cast<uint4*>(S.keys), (nE * KS) >> 1, make_uint4(~0u, ~0u, ~0u, ~0u), tid);   // KS is even
+        const float fill = P.d.max_range_r3;                                // a ray with no return, already rounded
+        const int tot = nE * D, n4 = tot >> 2;
+        fill16<T>(reinterpret_cast<float4*>(S.obs), n4, make_float4(fill, fill, fill, fill), tid);
+        if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+        if (tid < C_WORDS) S.cnt[tid] = 0u;
+        if (tid < nE) {
+            uint32_t* sc = S.sc + tid * F_WORDS;
+            sc[F_MINBITS] = u_of(P.max_range); sc[F_CONF0] = 0u; sc[F_CONF1] = 0u; sc[F_XFLAGS] = 0u; sc[F_OVF_FACES] = 0u;
+            sc[F_NOBJ] = 0u;
+        }
+    }
+    __syncthreads();            // fills done, barrier init visible
+    mbar_wait(S.bar, 0);        // state tile + actions have landed
+
+    // ---------------------------------------------------------------- phase 1
+    if (warp < CF_POSE_WARPS) {
+        // lane = world: everything get_state / compute_reward derive from the pose alone (cn_dev.h)
+        const int part = warp;
+        for (int w = lane; w < nE; w += 32) {
+            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            bool run = true, reset_now = (MODE == 1);
+            if (MODE == 1) run = !P.mask || P.mask[e0 + w] != 0;
+            else reset_now = (rob[CN_R_FLAGS] & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET);
+            uint32_t* scl = S.sc + w * F_WORDS;
+            float* rowl = S.obs + (size_t)w * D;
+            if (part == 0) scl[F_XFLAGS] = (run ? XF_ACTIVE : 0u) | ((run && reset_now) ? XF_RESET : 0u);
+            if (!run) continue;
+            if (reset_now) {
+                // Z: Env.reset (ENV:1227-1263): spawn pose, waypoint = goal, unrounded previous_* (ENV:1243-1244)
+                PoseIn p; p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; p.v = 0.0f; p.w = 0.0f;
+                const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
+                const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);
+                const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
+                pose_scalars(P, p, part, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
+            } else {
+                int bad;
+                const PoseIn p = advance_robot(P, rob, act_smem ? S.act + 2 * w : P.action + 2 * (size_t)(e0 + w), bad);
+                pose_scalars(P, p, part, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
+                             f_of(rob[CN_R_PHEAD]), f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1,
+                             true, true, bad, scl, rowl);
+            }
+        }
+    } else {
+        // thread = pedestrian of the tile (P: CROWD:98-144 + contact stand-in, Jacobi on the old positions)
+        const int ptid = tid - 32 * CF_POSE_WARPS;
+        const bool has = ptid < n_items;
+        int w = 0, n = 0, b = 0;
+        bool p_active = false, p_reset = false;
+        if (has) {
+            w = world_of(ptid, N, L.magic_n); n = ptid - w * N;
+            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            p_active = true; p_reset = (MODE == 1);
+            if (MODE == 1) p_active = !P.mask || P.mask[e0 + w] != 0;
+            else p_reset = (rob[CN_R_FLAGS] & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET);
+            const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + w);
+            b = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
+        }
+        const bool moves = has && p_active && !p_reset;
+        uint4* spa4 = reinterpret_cast<uint4*>(S.pa);
+        int32_t x0 = 0, y0 = 0;
+        uint32_t pk = 0u;
+
+        // -- alpha: timers, packed coordinates, who needs random numbers
+        if (has && p_active && p_reset) {
+            const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
+            S.rlist[pos] = (uint16_t)(ptid | 0x8000);
+        }
+        if (moves) {
+            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * ptid);
+            x0 = (int32_t)a.x; y0 = (int32_t)a.y;
+            // both coordinates in one word: 14-bit fields at 2^-8 m with a guard bit each (cn_derive bounds the room);
+            // the world's list is stored twice back to back so that "partner (n + r) mod N" is a plain offset
+            pk = (((a.x + 0x20000000u) >> 16) & 0x3FFFu) | ((((a.y + 0x20000000u) >> 16) & 0x3FFFu) << 16);
+            S.pk[2 * w * N + n] = pk; S.pk[2 * w * N + N + n] = pk;
+            S.peers[2 * ptid] = 0u; S.peers[2 * ptid + 1] = 0u;
+            int32_t tm = (int32_t)S.pb[4 * ptid + 2] - CN_TICKS_PER_STEP;
+            if (tm <= 0) {
+                tm += P.beh_period[b];
+                if (P.beh_kind[b] == CN_BEHAVIOR_RANDOM) {
+                    const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
+                    S.rlist[pos] = (uint16_t)ptid;
+                } else {
+                    const float speed = P.beh_speed[b];
+                    S.pa[4 * ptid + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
+                    S.pa[4 * ptid + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
+                }
+            }
+            S.pb[4 * ptid + 2] = (uint32_t)tm;
+        }
+        named_bar_sync(1, PED_THREADS);
+
+        // -- beta: contact prefilter (each unordered pair once: partner = n + r mod N, r <= N/2) ...
+        if (moves) {
+            const uint32_t pk_biased = (pk | 0x80008000u) + 0x00400040u;
+            const uint32_t* pp = S.pk + 2 * w * N + n;
+            const int half = N >> 1;
+            uint32_t hits = 0u;
+#pragma unroll 5
+            for (int r = 1; r <= half; ++r)
+                if (((pk_biased - pp[r]) & 0xFF80FF80u) == 0x80008000u) hits |= 1u << (r - 1);     // |dx|, |dy| < 0.25 m
+            while (hits) {                                                                         // rare
+                const int r = __ffs(hits); hits &= hits - 1;
+                const int partner = (n + r >= N) ? n + r - N : n + r;
+                atomicOr(&S.peers[2 * ptid + (partner >> 5)], 1u << (partner & 31));
+                atomicOr(&S.peers[2 * (w * N + partner) + (n >> 5)], 1u << (n & 31));
+            }
+        }
+        // ... and Philox for the compacted list of pedestrians that draw this step
+        {
+            const int n_res = (int)S.cnt[C_NRES];
+            for (int q = ptid; q < n_res; q += PED_THREADS) {
+                const uint32_t ent = S.rlist[q];
+                const int idx = (int)(ent & 0x7FFFu);
+                const bool respawn = (ent & 0x8000u) != 0u;
+                const int ww = world_of(idx, N, L.magic_n), nn = idx - ww * N;
+                const uint32_t* rob = S.robot + ww * CN_ROBOT_WORDS;
+                const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + ww);
+                const int bb = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
+                const uint32_t episode = rob[CN_R_EPISODE] + (respawn ? 1u : 0u);
+                const uint32_t stepc = respawn ? 0u : rob[CN_R_STEP] + 1u;
+                const cn_u32x2 rnd = cn_env_rand(P.d.seed_lo, P.d.seed_hi, gid, episode, stepc, (uint32_t)nn, respawn ? 1u : 0u);
+                if (respawn) {
+                    // gazebo/reset_simulation: world-file layout (+ seeded jitter), first command after (n+1) staggers
+                    const float px = __ldg(&P.cfg->ped_layout[nn][0]) + cn_usym(rnd.v[0], P.layout_jitter);
+                    const float py = __ldg(&P.cfg->ped_layout[nn][1]) + cn_usym(rnd.v[1], P.layout_jitter);
+                    int32_t xi = cn_f2i(px * CN_INV_GRID), yi = cn_f2i(py * CN_INV_GRID);
+                    xi = max(xi, P.d.ped_xmin); xi = min(xi, P.d.ped_xmax);
+                    yi = max(yi, P.d.ped_ymin); yi = min(yi, P.d.ped_ymax);
+                    spa4[idx] = make_uint4((uint32_t)xi, (uint32_t)yi, u_of(0.0f), u_of(0.0f));
+                    reinterpret_cast<uint4*>(S.pb)[idx] = make_uint4(0u, 0u, (uint32_t)((nn + 1) * P.beh_stagger[bb]), 0u);
+                } else {
+                    const float speed = P.beh_speed[bb];
+                    S.pa[4 * idx + 2] = u_of(cn_usym(rnd.v[0], speed));
+                    S.pa[4 * idx + 3] = u_of(cn_usym(rnd.v[1], speed));
+                }
+            }
+        }
+        named_bar_sync(1, PED_THREADS);
+
+        // -- gamma: repulsion for the rare pairs found, integrate, frictionless wall clamp
+        int32_t nx = 0, ny = 0;
+        float vx = 0.0f, vy = 0.0f;
+        if (moves) {
+            vx = f_of(S.pa[4 * ptid + 2]); vy = f_of(S.pa[4 * ptid + 3]);
+            float vex = vx, vey = vy;
+            const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
+            const uint32_t p0 = S.peers[2 * ptid], p1 = S.peers[2 * ptid + 1];
+            if (p0 | p1) {                                                  // index order, like the oracle
+                for (uint32_t pm = p0; pm; pm &= pm - 1) {
+                    const int m = __ffs(pm) - 1;
+                    const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                    add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                }
+                for (uint32_t pm = p1; pm; pm &= pm - 1) {
+                    const int m = __ffs(pm) + 31;
+                    const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                    add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                }
+            }
+            const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative prefilter
+            const uint32_t lim2 = 2u * (uint32_t)lim_i;
+            const int32_t rxi = (int32_t)S.robot[w * CN_ROBOT_WORDS + CN_R_X], ryi = (int32_t)S.robot[w * CN_ROBOT_WORDS + CN_R_Y];
+            if ((uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2)
+                add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
+            nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
+            ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
+            if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
+            if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
+            if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
+            if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
+        }
+        named_bar_sync(1, PED_THREADS);             // every old position has been read
+        if (moves) spa4[ptid] = make_uint4((uint32_t)nx, (uint32_t)ny, u_of(vx), u_of(vy));
+    }
+    __syncthreads();            // #A: new poses, scalar records, new pedestrian positions
+
+    // ---------------------------------------------------------------- phase 2a
+    if (tid < n_items) {
+        const int w = world_of(tid, N, L.magic_n);
+        const uint32_t* sc = S.sc + w * F_WORDS;
+        if (sc[F_XFLAGS] & XF_ACTIVE) {
+            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * tid);
+            const float qx = (float)((int32_t)a.x - (int32_t)sc[S_XI]) * CN_GRID - f_of(sc[S_OFFX]);
+            const float qy = (float)((int32_t)a.y - (int32_t)sc[S_YI]) * CN_GRID - f_of(sc[S_OFFY]);
+            if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
+                const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
+                S.clist[pos] = (uint16_t)tid;
+                uint32_t* rec = S.rec + tid * 8;
+                rec[Q_QX] = u_of(qx); rec[Q_QY] = u_of(qy);
+                rec[Q_TH] = sc[S_TH];
+                rec[Q_WN] = (uint32_t)w | ((uint32_t)(tid - w * N) << 8);
+            }
+        }
+    }
+    for (int q = T - 1 - tid; q < nE * 4; q += T) {                         // wall faces, from the far end of the CTA
+        uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
+        if (!(sc[F_XFLAGS] & XF_ACTIVE)) continue;
+        const int face = q & 3;
+        Span sp;
+        sp.a0 = (int)sc[S_WSPAN + 4 * face + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * face + 1];
+        sp.b0 = (int)sc[S_WSPAN + 4 * face + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * face + 3];
+        if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)q, sp)) {
+            atomicOr(&sc[F_OVF_FACES], 1u << face);
+            S.cnt[C_OVF] = 1u;
+        }
+    }
+    __syncthreads();            // #B
+    const int n_cand = (int)S.cnt[C_NCAND];
+
+    // ---------------------------------------------------------------- phase 2b
+    for (int q = tid; q < n_cand; q += T) {
+        const int slot = (int)S.clist[q];
+        uint32_t* rec = S.rec + slot * 8;
+        const float qx = f_of(rec[Q_QX]), qy = f_of(rec[Q_QY]);
+        const float d2 = fmaf(qx, qx, qy * qy);
+        const uint32_t bearing = cn_rad2bin(cn_atan2(qy, qx));
+        float alpha = 4.0f;                                    // sensor inside / touching the disc: all rays
+        const float rlim = P.ped_radius * 1.001f;
+        if (d2 > rlim * rlim) {
+            const float u = P.ped_radius * rsqrtf(d2) * 1.0001f;   // asin(u) <= u + (pi/2 - 1) u^3
+            alpha = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
+        }
+        const Span sp = make_span(P, bearing - rec[Q_TH], alpha);
+        rec[Q_BEAR] = bearing;
+        rec[Q_SPA] = (uint32_t)sp.a0 | ((uint32_t)sp.a1 << 16);
+        rec[Q_SPB] = (uint32_t)sp.b0 | ((uint32_t)sp.b1 << 16);
+        rec[Q_CNT] = 0u;
+        if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
+            rec[Q_WN] |= WN_OVF;
+            S.cnt[C_OVF] = 1u;
+        }
+    }
+    __syncthreads();            // #C
+    const int n_wg = min((int)S.cnt[C_NWG], (int)L.cap_wg);
+    const int n_pg = min((int)S.cnt[C_NPG], (int)L.cap_pg);
+    const bool overflow = S.cnt[C_OVF] != 0u;
+    const int lane8 = tid & 7;
+
+    // ---------------------------------------------------------------- phase 3: rasterise (L: XACRO:148-179)
+    for (int gi = tid >> 3; gi < n_wg; gi += T / 8) {
+        const uint32_t ent = S.wg[gi];
+        const int i = group_ray(ent, lane8);
+        if (i >= 0) raster_wall(P, S, KS, (int)(ent >> 14), i);
+    }
+    for (int gi = tid >> 3; gi < n_pg; gi += T / 8) {
+        const uint32_t ent = S.pg[gi];
+        const int i = group_ray(ent, lane8);
+        if (i >= 0) raster_ped(P, S, KS, (int)(ent >> 14), i);
+    }
+    if (overflow) {             // primitives whose groups did not fit: the whole CTA walks each of them
+        for (int q = 0; q < nE * 4; ++q) {
+            const uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
+            if (!((sc[F_OVF_FACES] >> (q & 3)) & 1u)) continue;
+            Span sp;
+            sp.a0 = (int)sc[S_WSPAN + 4 * (q & 3) + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * (q & 3) + 1];
+            sp.b0 = (int)sc[S_WSPAN + 4 * (q & 3) + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * (q & 3) + 3];
+            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) raster_wall(P, S, KS, q, i); }
+        }
+        for (int q = 0; q < n_cand; ++q) {
+            const int slot = (int)S.clist[q];
+            const uint32_t* rec = S.rec + slot * 8;
+            if (!(rec[Q_WN] & WN_OVF)) continue;
+            Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
+            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) raster_ped(P, S, KS, slot, i); }
+        }
+    }
+    __syncthreads();            // #D: keys final
+
+    // ---------------------------------------------------------------- phase 4: ownership, final ray values
+    for (int gi = tid >> 3; gi < n_wg; gi += T / 8) {
+        const uint32_t ent = S.wg[gi];
+        const int i = group_ray(ent, lane8);
+        if (i >= 0) own_wall(P, S, KS, (int)(ent >> 14), i);
+    }
+    for (int g0 = warp * 4; g0 < n_pg; g0 += (T / 32) * 4) {                // warp-uniform trip count: ballots inside
+        const int gi = g0 + (lane >> 3);
+        bool owned = false;
+        int slot = 0;
+        if (gi < n_pg) {
+            const uint32_t ent = S.pg[gi];
+            const int i = group_ray(ent, lane8);
+            slot = (int)(ent >> 14);
+            if (i >= 0) owned = own_ped(P, S, KS, slot, i);
+        }
+        const uint32_t bm = __ballot_sync(FULL, owned);
+        const int c = __popc((bm >> (lane & 24)) & 0xFFu);
+        if (lane8 == 0 && c) atomicAdd(&S.rec[slot * 8 + Q_CNT], (uint32_t)c);
+    }
+    if (overflow) {
+        for (int q = 0; q < nE * 4; ++q) {
+            const uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
+            if (!((sc[F_OVF_FACES] >> (q & 3)) & 1u)) continue;
+            Span sp;
+            sp.a0 = (int)sc[S_WSPAN + 4 * (q & 3) + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * (q & 3) + 1];
+            sp.b0 = (int)sc[S_WSPAN + 4 * (q & 3) + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * (q & 3) + 3];
+            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) own_wall(P, S, KS, q, i); }
+        }
+        for (int q = 0; q < n_cand; ++q) {
+            const int slot = (int)S.clist[q];
+            const uint32_t* rec = S.rec + slot * 8;
+            if (!(rec[Q_WN] & WN_OVF)) continue;
+            Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
+            for (int pos = tid; pos < NR; pos += T) {
+                const int i = span_ray(sp, pos);
+                if (i >= 0 && own_ped(P, S, KS, slot, i)) atomicAdd(&S.rec[slot * 8 + Q_CNT], 1u);
+            }
+        }
+    }
+    __syncthreads();            // #E: rows' ray part final, owned-ray counts final
+
+    // ---------------------------------------------------------------- phase 5: E-J per candidate (ENV:568-860)
+    for (int q = tid; q < n_cand; q += T) {
+        const int slot = (int)S.clist[q];
+        uint32_t* rec = S.rec + slot * 8;
+        if (rec[Q_CNT] < 4u) continue;                                      // ENV:573: fewer than 4 rays is no object
+        const uint32_t wn = rec[Q_WN];
+        const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
+        uint32_t* sc = S.sc + w * F_WORDS;
+        // centre ray: the owned ray nearest the pedestrian's centre line.  The nearest ray overall is one of the two
+        // neighbours of the bearing on the circle; if the pedestrian owns it, it is the answer.
+        const uint32_t th = rec[Q_TH];
+        const uint32_t inc = P.d.inc_bin;
+        const uint32_t rel = rec[Q_BEAR] - th;
+        const unsigned long long* krow = S.keys + (size_t)w * KS;
+        const uint32_t me = (uint32_t)(n + 2);
+        int jstar;
+        {
+            const int i0 = (int)(rel / inc);
+            uint32_t bkey = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
+            centre_try(rel, inc, NR, min(max(i0, 1), NR), bkey, bj);
+            centre_try(rel, inc, NR, min(max(i0 + 1, 1), NR), bkey, bj);
+            centre_try(rel, inc, NR, 1, bkey, bj);
+            centre_try(rel, inc, NR, NR, bkey, bj);
+            jstar = bj;
+            if ((uint32_t)krow[jstar] != me) {                              // centre ray occluded: search the span
+                Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
+                const int tot = span_len_a(sp) + span_len_b(sp);
+                bkey = 0xFFFFFFFFu; bj = 0x7FFFFFFF;
+                for (int pos = 0; pos < tot; ++pos) {
+                    const int i = span_ray(sp, pos);
+                    if ((uint32_t)krow[NR - i] == me) centre_try(rel, inc, NR, i, bkey, bj);
+                }
+                jstar = bj;
+            }
+        }
+        const float xf = f_of(sc[S_XF]), yf = f_of(sc[S_YF]);
+        const float t_raw = f_of((uint32_t)(krow[jstar] >> 32));
+        const float d_raw = (t_raw < P.sensor_min_range) ? P.sensor_min_range : t_raw;
+        const float d3 = cn_py_round3(d_raw);                               // ENV:324,384
+        float sa, ca; cn_sincos_bin((uint32_t)jstar * P.d.hit_inc_bin - th, &sa, &ca);     // C2: UTL:110-126
+        const float hx = cn_py_round3(xf + d_raw * ca);
+        const float hy = cn_py_round3(yf + (d_raw * sa) * -1.0f);
+        // H/I: tracker with ideal association (ENV:656-760)
+        float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
+        if (S.pb[4 * slot + 3] & CN_PF_TRACKED) {
+            chx = f_of(S.pb[4 * slot + 0]) - hx; chy = f_of(S.pb[4 * slot + 1]) - hy;      // last - curr (sic), ENV:806-807
+            speed = sqrtf(fmaf(chy, chy, chx * chx)) * P.d.inv_dt;
+            ovx = chx * P.d.inv_dt; ovy = chy * P.d.inv_dt;
+        }
+        S.pb[4 * slot + 0] = u_of(hx); S.pb[4 * slot + 1] = u_of(hy);
+        atomicOr(&sc[F_CONF0 + (n >> 5)], 1u << (n & 31));
+        if (d3 < 0.140f) atomicOr(&sc[F_XFLAGS], XF_EGO);                   // ENV:1000
+        if (sc[F_XFLAGS] & XF_RESET) continue;                              // ENV:769: no previous pose at step 0
+        // J: collision cone (ENV:765-860, UTL:251-293 as a true ray-circle test)
+        const float pcx = f_of(sc[S_PCX]), pcy = f_of(sc[S_PCY]);
+        const float ppx = f_of(sc[S_PPX]), ppy = f_of(sc[S_PPY]);
+        const float agent_vel = f_of(sc[S_AVEL]);
+        const float tx = pcx + chx, ty = pcy + chy;
+        float ux = tx - ppx, uy = ty - ppy;
+        const float Ln = sqrtf(fmaf(ux, ux, uy * uy));
+        bool have_dtc = false; float dtc = 0.0f;
+        if (Ln > 0.0f) {
+            const float invL = 1.0f / Ln;
+            ux = ux * invL; uy = uy * invL;
+            const float wx_ = hx - ppx, wy_ = hy - ppy;
+            const float b = fmaf(wx_, ux, wy_ * uy);
+            const float h = fmaf(wx_, uy, -(wy_ * ux));
+            const float disc = fmaf(-h, h, P.d.cp_r2);
+            if (disc > 0.0f) {
+                const float t = b - sqrtf(disc);
+                if (t > 0.0f) { have_dtc = true; dtc = t; }
+            }
+        }
+        const float resultant = agent_vel - speed;
+        float cp_ttc = 0.0f, cp;
+        const float dto = cp_dto(P, d3);
+        if (have_dtc && resultant == 0.0f) {
+            cp = dto;
+        } else {
+            if (have_dtc) {
+                const float qq = (0.15f * resultant) / dtc;
+                cp_ttc = (qq < 1.0f) ? qq : 1.0f;
+            }
+            cp = 0.5f * cp_ttc + 0.5f * dto;
+        }
+        rec[O_CP] = u_of(cp); rec[O_X] = u_of(hx); rec[O_Y] = u_of(hy);
+        rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);
+        const uint32_t k = atomicAdd(&sc[F_NOBJ], 1u);                      // the world's object list (any order)
+        S.olist[w * N + k] = (uint16_t)slot;
+    }
+    __syncthreads();            // #F
+
+    // ---------------------------------------------------------------- phase 6
+    // 6a  K: top-K block (ENV:862-907): stable rank by CP among the world's objects, keep [-K:]; padding is in the row
+    //     (thread = object: entry k of world w's list, flattened over the tile)
+    for (int q = tid; q < n_items; q += T) {
+        const int w = world_of(q, N, L.magic_n), k = q - w * N;
+        const int n_obj = (int)S.sc[w * F_WORDS + F_NOBJ];
+        if (k >= n_obj) continue;
+        const uint16_t* ol = S.olist + w * N;
+        const uint32_t* rec = S.rec + (int)ol[k] * 8;
+        const int n = (int)((rec[Q_WN] >> 8) & 0xFFu);
+        const float my_cp = f_of(rec[O_CP]);
+        int rank = 0;
+        for (int k2 = 0; k2 < n_obj; ++k2) {
+            const uint32_t* r2 = S.rec + (int)ol[k2] * 8;
+            const int n2 = (int)((r2[Q_WN] >> 8) & 0xFFu);
+            const float cpb = f_of(r2[O_CP]);
+            if (n2 != n && (cpb > my_cp || (cpb == my_cp && n2 < n))) ++rank;
+        }
+        const int slot_k = (P.flags & CN_FLAG_TOPK_HIGHEST) ? rank : rank - (n_obj > K ? n_obj - K : 0);
+        if (slot_k < 0 || slot_k >= K) continue;
+        float* blk = S.obs + (size_t)w * D + NR + 7 + 4 * slot_k;
+        blk[0] = f_of(rec[O_X]); blk[1] = f_of(rec[O_Y]);                  // already multiples of 0.001
+        blk[2] = cn_np_round3(f_of(rec[O_VX])); blk[3] = cn_np_round3(f_of(rec[O_VY]));
+    }
+    // 6b  tracker flags: a pedestrian is tracked next step iff it was confirmed now (ENV:656-743, ideal association)
+    if (tid < n_items) {
+        const int w = world_of(tid, N, L.magic_n), n = tid - w * N;
+        const uint32_t* sc = S.sc + w * F_WORDS;
+        if (sc[F_XFLAGS] & XF_ACTIVE) {
+            const uint32_t bit = (sc[F_CONF0 + (n >> 5)] >> (n & 31)) & 1u;
+            S.pb[4 * tid + 3] = (S.pb[4 * tid + 3] & ~CN_PF_TRACKED) | (bit ? CN_PF_TRACKED : 0u);
+        }
+    }
+    // 6c  lane = world (last warp): M counters, N done, W terminal reward, robot record
+    if (warp == T / 32 - 1) {
+        for (int w = lane; w < nE; w += 32) {
+            uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            const uint32_t* sc = S.sc + w * F_WORDS;
+            const uint32_t xfl = sc[F_XFLAGS];
+            if (!(xfl & XF_ACTIVE)) continue;
+            const int e = e0 + w;
+            uint32_t flags = rob[CN_R_FLAGS], cnt0 = rob[CN_R_CNT0], cnt1 = rob[CN_R_CNT1];
+            uint32_t episode = rob[CN_R_EPISODE];
+            int step = (int)rob[CN_R_STEP];
+            const bool reset_now = (xfl & XF_RESET) != 0u;
+            if (reset_now) episode += 1u;
+            if (!reset_now && sc[S_BAD]) { uint32_t bad = cnt1 >> 16; if (bad < 0xFFFFu) ++bad; cnt1 = (cnt1 & 0xFFFFu) | (bad << 16); }
+            const int n_seen = __popc(sc[F_CONF0]) + __popc(sc[F_CONF1]);
+            if (n_seen > 0) {                                               // M: ENV:653-654, 998-1005
+                float ego_score = 0.0f, emax = -INFINITY;
+                const int n_obj = (int)sc[F_NOBJ];
+                for (int k2 = 0; k2 < n_obj; ++k2) emax = fmaxf(emax, f_of(S.rec[(int)S.olist[w * N + k2] * 8 + O_TTC]));
+                if (n_obj > 0) ego_score = emax;                            // ENV:879
+                uint32_t ego = cnt0 & 0xFFFFu, soc = cnt0 >> 16;
+                uint32_t pres = cnt1 & 0xFFFFu;
+                if (pres < 0xFFFFu) ++pres;
+                if ((xfl & XF_EGO) && ego < 0xFFFFu) ++ego;
+                if (ego_score > 0.4f && soc < 0xFFFFu) ++soc;
+                cnt0 = ego | (soc << 16);
+                cnt1 = pres | (cnt1 & 0xFFFF0000u);
+            }
+            const bool collided = f_of(sc[F_MINBITS]) < P.collision_range;  // ENV:1012
+            if (reset_now) {
+                cnt0 = 0; cnt1 = 0;                                                 // ENV:1260-1262
+                flags = (MODE == 0) ? (flags & (CN_RF_SUCCESS | CN_RF_FAILURE)) : 0u;   // last episode's status stays readable
+                step = 0;
+                if (MODE == 0) { P.reward[e] = 0.0f; P.done[e] = 2; }
+            } else {
+                // N + W: done (ENV:1011-1023), terminal reward (ENV:1136-1159; a time-out is -200 too)
+                const uint32_t pre = sc[S_PRE];
+                const bool done = ((flags & CN_RF_DONE) != 0) || collided || pre != 0u;
+                int reward = (int)sc[S_REWARD];
+                if (done) {
+                    flags |= CN_RF_DONE;
+                    if (pre & 1u) { flags |= CN_RF_SUCCESS; flags &= ~CN_RF_FAILURE; reward += 200; }
+                    else { flags |= CN_RF_FAILURE; flags &= ~CN_RF_SUCCESS; reward -= 200; }
+                }
+                step += 1;
+                P.reward[e] = (float)reward; P.done[e] = done ? 1 : 0;
+            }
+            uint4* qd = reinterpret_cast<uint4*>(rob);
+            qd[0] = make_uint4(sc[S_XI], sc[S_YI], sc[S_TH], sc[S_V]);
+            qd[1] = make_uint4(sc[S_W], sc[S_WPX], sc[S_WPY], sc[S_NPDIST]);
+            qd[2] = make_uint4(sc[S_NPHEAD], sc[S_PCX], sc[S_PCY], (uint32_t)step);
+            qd[3] = make_uint4(episode, flags, cnt0, cnt1);
+        }
+    }
+
+    // ---------------------------------------------------------------- phase 7: write-back
+    fence_async_smem();          // generic-proxy writes -> visible to the async proxy
+    __syncthreads();             // #G
+    const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
+    if (tid == 0) {
+        tma_store(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, rob_bytes);
+        if (ped_bytes) {
+            tma_store(P.ped_a + (size_t)e0 * N * 4, S.pa, ped_bytes);
+            tma_store(P.ped_b + (size_t)e0 * N * 4, S.pb, ped_bytes);
+        }
+        if (bulk_obs) {
+            tma_store(P.obs + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
+            // fused all-gather: the same tile goes straight into every peer's gather buffer over NVLink
+            for (int p = 0; p < P.n_obs_peers; ++p)
+                tma_store(P.obs_peers[p] + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
+        }
+        tma_store_commit_and_wait();
+    }
+    if (!bulk_obs) {             // plain coalesced stores (reset launches, unaligned or ragged tiles)
+        for (int w = warp; w < nE; w += T / 32) {
+            if (!(S.sc[w * F_WORDS + F_XFLAGS] & XF_ACTIVE)) continue;
+            const float* row = S.obs + (size_t)w * D;
+            float* g = P.obs + (size_t)(e0 + w) * D;
+            for (int k = lane; k < D; k += 32) g[k] = row[k];
+            for (int p = 0; p < P.n_obs_peers; ++p) {
+                float* gp = P.obs_peers[p] + (size_t)(e0 + w) * D;
+                for (int k = lane; k < D; k += 32) gp[k] = row[k];
+            }
+        }
+    }
+    // debug taps (tests only): raw cleaned ranges + hit ids for every ray
+    if (P.dbg_ranges || P.dbg_hid) {
+        for (int w = warp; w < nE; w += T / 32) {
+            if (!(S.sc[w * F_WORDS + F_XFLAGS] & XF_ACTIVE)) continue;
+            const size_t base = (size_t)(e0 + w) * NR;
+            for (int j = lane; j < NR; j += 32) {
+                const unsigned long long key = S.keys[(size_t)w * KS + j];
+                const uint32_t lo = (uint32_t)key;
+                const float t = f_of((uint32_t)(key >> 32));
+                const uint8_t h = (lo == 0xFFFFFFFFu) ? CN_HIT_NONE : (lo < 2u ? CN_HIT_WALL : (uint8_t)(lo - 2u));
+                const float rr = (h == CN_HIT_NONE) ? P.max_range : ((t < P.sensor_min_range) ? P.sensor_min_range : t);
+                if (P.dbg_ranges) P.dbg_ranges[base + j] = rr;
+                if (P.dbg_hid) P.dbg_hid[base + j] = h;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------- host side
+static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L) {
+    const int N = n_peds, NR = n_samples - 1, D = obs_dim, W = tile;
+    if (threads != 256 && threads != 512) return -1;
+    if (W < 1 || W > 32 || (size_t)W * N > (size_t)(threads - 32 * CF_POSE_WARPS)) return -1;
+    if ((size_t)W * N > 0x3FFF || (size_t)W * 4 > 0x3FFF) return -1;        // group-entry / list-entry fields
+    L->W = W;
+    L->threads = threads;
+    L->magic_n = (N > 1) ? (uint32_t)(((1ull << 32) + (uint64_t)N - 1) / (uint64_t)N) : 0u;
+    L->key_stride = (uint32_t)((NR + 1) & ~1);
+    L->cap_wg = (uint32_t)W * 32u;
+    L->cap_pg = (uint32_t)W * 24u;
+    size_t o = 0;
+    o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
+    o += (size_t)W * N * 16;                        L->off_pb = (uint32_t)o;
+    o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
+    o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
+    o = up16(o + (size_t)W * D * 4);                L->off_keys = (uint32_t)o;
+    o += (size_t)W * L->key_stride * 8;             L->off_sc = (uint32_t)o;
+    o += (size_t)W * F_WORDS * 4;                   L->off_rec = (uint32_t)o;
+    o += (size_t)W * N * 32;                        L->off_pk = (uint32_t)o;
+    o += (size_t)W * N * 8;                         L->off_peers = (uint32_t)o;
+    o += (size_t)W * N * 8;                         L->off_clist = (uint32_t)o;
+    o = up16(o + (size_t)W * N * 2);                L->off_rlist = (uint32_t)o;
+    o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
+    o = up16(o + (size_t)W * N * 2);                L->off_wg = (uint32_t)o;
+    o += (size_t)L->cap_wg * 4;                     L->off_pg = (uint32_t)o;
+    o = up16(o + (size_t)L->cap_pg * 4);            L->off_cnt = (uint32_t)o;
+    o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
+    o += 16;
+    L->total = (uint32_t)o;
+    return 0;
+}
+
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, size_t smem_per_sm, cn_flat_layout* L) {
+    // 256-thread CTAs, four per SM: the largest tile whose shared memory allows that, preferring tiles whose row
+    // block can leave by bulk store.  Falls back to 512-thread CTAs, two per SM, for wide worlds.
+    for (int pass = 0; pass < 2; ++pass) {
+        const int threads = pass == 0 ? 256 : 512;
+        const int ctas = 1024 / threads;
+        const size_t budget = smem_per_sm / ctas - 1024;
+        int best = 0;
+        for (int W = 16; W >= 1; --W) {
+            cn_flat_layout t;
+            if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, &t) != 0 || t.total > budget) continue;
+            const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
+            if (!best) best = W;
+            if (bulk) { best = W; break; }
+            if (W < best - 3) break;
+        }
+        if (best >= 4 || (pass == 1 && best >= 1)) return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, L);
+    }
+    return -1;
+}
+
+template <int MODE, int T>
+static cudaError_t launch_flat_t(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream) {
+    auto k = cn_flat_kernel<MODE, T>;
+    static size_t attr_smem = 0;
+    if (L.total > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (e != cudaSuccess) return e;
+        attr_smem = L.total;
+    }
+    const int grid = (P.n_envs + L.W - 1) / L.W;
+    k<<<grid, T, L.total, stream>>>(P, L);
+    return cudaGetLastError();
+}
+
+cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream) {
+    if (L.threads == 256) return mode == 0 ? launch_flat_t<0, 256>(P, L, stream) : launch_flat_t<1, 256>(P, L, stream);
+    return mode == 0 ? launch_flat_t<0, 512>(P, L, stream) : launch_flat_t<1, 512>(P, L, stream);
+}

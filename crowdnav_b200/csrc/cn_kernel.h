@@ -28,7 +28,7 @@ struct cn_kparams {
     cn_derived d;
     int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors, n_substeps;
     uint32_t flags;
-    int obs_bulk_ok;            /* obs base is 16-B aligned: tile rows may leave by bulk store */
+    int obs_bulk_ok;            /* obs base (and every peer's) is 16-B aligned: tile rows may leave by bulk store if the tile size allows */
     int act_bulk_ok;            /* action base is 16-B aligned: the tile's actions arrive by bulk load */
     int beh_kind[CN_MAX_BEHAVIORS];
     float beh_speed[CN_MAX_BEHAVIORS];
@@ -41,6 +41,21 @@ struct cn_kparams {
     float ped_radius, robot_radius, goal_box;
     float rep_strength, rep_range, rep_cutoff, layout_jitter;
 };
+
+/* cn_flat.cu: shared-memory layout of one tile of W worlds (byte offsets), computed once per handle on the host */
+struct cn_flat_layout {
+    int W;                      /* worlds per CTA */
+    int threads;                /* threads per CTA: 256 (four CTAs per SM) or 512 (two) */
+    uint32_t magic_n;           /* ceil(2^32 / N): world index of a flat pedestrian index by __umulhi */
+    uint32_t key_stride;        /* 64-bit hit keys per world row (rays rounded up to even) */
+    uint32_t cap_wg, cap_pg;    /* capacity of the wall / pedestrian ray-group lists */
+    uint32_t off_pa, off_pb, off_act, off_obs, off_keys, off_sc, off_rec, off_pk, off_peers,
+             off_clist, off_rlist, off_olist, off_wg, off_pg, off_cnt, off_bar;
+    uint32_t total;             /* dynamic shared memory per CTA */
+};
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L);
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, size_t smem_per_sm, cn_flat_layout* L);
+cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream);
 
 size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim);
 cudaError_t cn_launch_env_kernel(const cn_kparams& P, int mode /*0 step, 1 reset*/, cudaStream_t stream);

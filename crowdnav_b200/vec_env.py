@@ -170,3 +170,12 @@ class CrowdNavVecEnv:
     @property
     def launch_count(self) -> int:
         return int(self._L.cn_launch_count(self._h))
+
+    @property
+    def kernel_name(self) -> str:
+        """Step-kernel variant behind this handle (see cn_kernel_name in include/crowdnav.h)."""
+        return self._L.cn_kernel_name(self._h).decode()
+
+    @property
+    def kernel_tile(self) -> int:
+        return int(self._L.cn_kernel_tile(self._h))

@@ -167,6 +167,11 @@ int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev);
 
 /* Number of kernels launched by this handle since creation. */
 int64_t cn_launch_count(const cn_handle* h);
+/* Name of the step-kernel variant this handle launches ("cn_flat_kernel": compacted work lists, the default;
+ * "cn_env_kernel": one warp per world, selected with the environment variable CN_KERNEL=warp at cn_create) and
+ * the number of worlds per CTA it uses.  For benchmarks and profiles; results are bit-identical. */
+const char* cn_kernel_name(const cn_handle* h);
+int cn_kernel_tile(const cn_handle* h);
 
 const char* cn_last_error(void);
 int cn_abi_version(void);

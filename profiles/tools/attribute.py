@@ -75,20 +75,34 @@ for k, n in per_line.most_common(top_n):
                                           "%s:%d" % k if k[0] else "?", src(k)))
 
 # ---- by phase: kernel-source lines grouped under the nearest preceding "// ----" marker
-cu = [p for p in src_cache if p.endswith(".cu")]
-import glob
-cu_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "crowdnav_b200", "csrc", "cn_step.cu")
-lines = open(cu_path).read().splitlines()
-label, labels = "(prologue)", []
-for l in lines:
-    m = re.match(r"\s*// -{3,}\s*(.*?)\s*-*$", l)
-    if m and m.group(1):
-        label = m.group(1)[:70]
-    labels.append(label)
+csrc_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "crowdnav_b200", "csrc")
+labels_by_file = {}
+def labels_of(fname):
+    if fname not in labels_by_file:
+        label, labels = "(prologue)", []
+        try:
+            lines = open(os.path.join(csrc_dir, fname)).read().splitlines()
+        except OSError:
+            lines = []
+        for l in lines:
+            m = re.match(r"\s*// -{3,}\s*(.*?)\s*-*$", l)
+            if m and m.group(1):
+                label = m.group(1)[:70]
+            labels.append(label)
+        labels_by_file[fname] = labels
+    return labels_by_file[fname]
 phase = collections.Counter(); phase_s = collections.Counter()
 for (f, l), n in per_outer.items():
-    lab = labels[l - 1] if f and f.endswith(".cu") and 0 < l <= len(labels) else "(other)"
+    labels = labels_of(f) if f and f.endswith(".cu") else []
+    lab = labels[l - 1] if 0 < l <= len(labels) else "(other)"
     phase[lab] += n; phase_s[lab] += per_outer_s[(f, l)]
 print("\nby phase (innermost kernel-source frame):")
 for lab, n in phase.most_common():
     print("%9d %6.2f%% inst %6.2f%% samples  %s" % (n, 100.0 * n / max(total, 1), 100.0 * phase_s[lab] / max(tot_s, 1), lab))
+
+# optional: per kernel-source line (outer frame) dump, in line order: CN_ATTR_DUMP=<path>
+if os.environ.get("CN_ATTR_DUMP"):
+    with open(os.environ["CN_ATTR_DUMP"], "w") as fh:
+        for (f, l), n in sorted(per_outer.items(), key=lambda kv: (str(kv[0][0]), kv[0][1])):
+            fh.write("%-14s %5d %9d %6.2f%% inst %6.2f%% samp  %s\n" % (f, l, n, 100.0 * n / max(total, 1),
+                     100.0 * per_outer_s[(f, l)] / max(tot_s, 1), src((f, l))))
