@@ -121,6 +121,7 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
         } else {
             rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, (size_t)max_sm, &flat);
         }
+        { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
         if (rc != 0 || flat.total > (size_t)max_smem)
             return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
     } else {

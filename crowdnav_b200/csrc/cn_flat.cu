@@ -19,28 +19,29 @@
  *
  *   phase 0   thread 0 issues the bulk TMA loads of the tile's three state
  *             planes + actions; meanwhile all threads pre-fill the observation
- *             rows with the no-return value and the per-ray hit keys with
- *             "nothing" (16-byte stores).
+ *             rows with the no-return value (16-byte stores).
  *   phase 1   warps 0-1: lane = WORLD, the pose-only part of get_state /
  *             compute_reward (unicycle, waypoint, heading, distance, reward
- *             shaping, wall spans).  Warps 2-15: thread = PEDESTRIAN of the
+ *             shaping, wall spans).  Other warps: item = PEDESTRIAN of the
  *             tile: timers; contact prefilter over packed coordinates; Philox
  *             only for the compacted list of pedestrians that resample (or are
- *             re-spawned) this step; integrate + wall clamp.
- *   phase 2   thread = pedestrian: LiDAR candidate test -> compact candidate
- *             list; thread = candidate: bearing, angular span; every span (wall
- *             faces too) is cut into groups of 8 rays appended to a group list.
+ *             re-spawned) this step; integrate + wall clamp into a second copy
+ *             of the position plane (Jacobi on the old one).
+ *   phase 2   item = pedestrian: LiDAR candidate test -> compact candidate
+ *             lists (per tile and per world); item = candidate: bearing,
+ *             angular span, centre ray; every span (wall faces too) is cut into
+ *             groups of <= 8 consecutive rays appended to a group list.
  *   phase 3   8 lanes per ray group: ray-disc / ray-face intersection with the
- *             oracle's per-ray arithmetic, 64-bit atomicMin of (range bits,
- *             primitive order) on the ray's key in shared memory -- the minimum
- *             reproduces the oracle's "walls first, then pedestrians in index
- *             order, strict <" rule exactly.
- *   phase 4   same groups: rays a primitive still owns get their final cleaned,
- *             rounded value in the observation row; min(scan); rays owned per
- *             pedestrian.
- *   phase 5   thread = candidate: centre ray, hit point, tracker, collision
+ *             oracle's per-ray arithmetic.  Whether the primitive OWNS the ray
+ *             (oracle: walls first, then pedestrians in index order, strict <)
+ *             is decided on the spot by intersecting the same ray with the few
+ *             other primitives of that world whose span contains it -- no
+ *             per-ray key array, no atomics on rays.  An owned ray gets its
+ *             final cleaned, rounded value in the observation row; min(scan)
+ *             and rays owned per pedestrian are accumulated.
+ *   phase 5   item = candidate: centre ray, hit point, tracker, collision
  *             cone, CP (ENV:656-860).
- *   phase 6   thread = candidate: top-K rank + slot write; thread = pedestrian:
+ *   phase 6   item = object: top-K rank + slot write; item = pedestrian:
  *             tracker flags; lane = world: counters, done, reward, robot record.
  *   phase 7   bulk TMA stores of the state planes and the [W, D] block of rows
  *             (and, for cn_step_gather, of the same block into every peer GPU).
@@ -53,6 +54,13 @@
 
 #define CF_POSE_WARPS 2
 
+#ifdef CN_TIMELINE
+// debug builds only: %globaltimer stamps per (CTA, warp), 16 slots each (profiles/tools/timeline_flat.py)
+#define FSTAMP(k) do { if ((threadIdx.x & 31) == 0 && g_timeline) g_timeline[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16 + (k)] = gtime(); } while (0)
+#else
+#define FSTAMP(k) do { } while (0)
+#endif
+
 namespace {
 
 // scalar-record words beyond the pose-phase record of cn_dev.h (S_* < S_WORDS = 40)
@@ -62,6 +70,7 @@ enum {
     F_XFLAGS,           // XF_*
     F_OVF_FACES,        // wall faces whose ray groups did not fit the group list
     F_NOBJ,             // objects of this world in the K block (entries of its object list)
+    F_NCAND,            // LiDAR candidates of this world (entries of its candidate list)
     F_WORDS = 48
 };
 #define XF_ACTIVE 1u    // the world is processed by this launch
@@ -70,20 +79,21 @@ enum {
 
 enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_WORDS = 8 };
 
-// candidate record (8 words per pedestrian slot).  Phases 2-4: q (sensor-relative centre), bearing, span,
-// owned-ray count, robot yaw.  Phase 5 overwrites it with the object's CP row for phase 6.
-enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_TH, Q_WN };     // Q_WN: world | pedestrian << 8 | overflow << 31
-enum { O_CP = 0, O_X, O_Y, O_VX, O_VY, O_TTC };
-#define WN_OVF 0x80000000u
+// candidate record (8 words per pedestrian slot).  Phases 2-3: q (sensor-relative centre), bearing, span,
+// owned-ray count, centre ray.  Phase 5 puts the object's CP row for phase 6 into the words nobody else reads
+// (q and the span stay: another candidate's occluded-centre search may still need them).
+enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_MISC, Q_CKEY };  // Q_MISC: overflow << 31
+enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY: min centre-ray key over the owned rays
+#define MISC_OVF 0x80000000u
 
 // ray-group entry: up to 8 consecutive scan indices of one primitive
 //   bits 0-2 count - 1, bits 3-13 first index, bits 14-31 primitive (pedestrian slot, or world * 4 + face)
 #define GRP_NONE 0xFFFFFFFFu
 
 struct Ptrs {
-    uint32_t* robot; uint32_t* pa; uint32_t* pb; float* act; float* obs; unsigned long long* keys;
-    uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint16_t* rlist; uint16_t* olist;
-    uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
+    uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
+    uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
+    uint16_t* olist; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -95,8 +105,15 @@ __device__ __forceinline__ int world_of(int idx, int N, uint32_t magic) {
 __device__ __forceinline__ void unpack_span(uint32_t a, uint32_t b, Span& s) {
     s.a0 = (int)(a & 0xFFFFu); s.a1 = (int)(a >> 16); s.b0 = (int)(b & 0xFFFFu); s.b1 = (int)(b >> 16);
 }
+__device__ __forceinline__ void wall_span(const uint32_t* sc, int face, Span& s) {
+    s.a0 = (int)sc[S_WSPAN + 4 * face + 0]; s.a1 = (int)sc[S_WSPAN + 4 * face + 1];
+    s.b0 = (int)sc[S_WSPAN + 4 * face + 2]; s.b1 = (int)sc[S_WSPAN + 4 * face + 3];
+}
 __device__ __forceinline__ int span_len_a(const Span& s) { return (s.a1 >= s.a0) ? (s.a1 - s.a0 + 1) : 0; }
 __device__ __forceinline__ int span_len_b(const Span& s) { return (s.b1 >= s.b0) ? (s.b1 - s.b0 + 1) : 0; }
+__device__ __forceinline__ bool in_span(const Span& s, int i) {
+    return (i >= s.a0 && i <= s.a1) || (i >= s.b0 && i <= s.b1);
+}
 // ray `pos` of the concatenation [a0, a1] ++ [b0, b1]; -1 when past the end
 __device__ __forceinline__ int span_ray(const Span& s, int pos) {
     const int la = span_len_a(s), lb = span_len_b(s);
@@ -132,91 +149,149 @@ __device__ __forceinline__ int group_ray(uint32_t ent, int lane8) {
     return (int)((ent >> 3) & 0x7FFu) + lane8;
 }
 
-// ---- phase 3: one ray of one primitive -> atomicMin on the ray's key
-__device__ __forceinline__ void raster_wall(const cn_kparams& P, const Ptrs& S, int key_stride, int q, int i) {
-    const int NR = P.n_samples - 1;
-    const int w = q >> 2, face = q & 3;
-    const uint32_t* sc = S.sc + w * F_WORDS;
-    const bool xface = face < 2;
-    const bool posf = (face & 1) == 0;
-    const float wall = xface ? (posf ? P.room_xmax : P.room_xmin) : (posf ? P.room_ymax : P.room_ymin);
-    const float o = xface ? (f_of(sc[S_XF]) + f_of(sc[S_OFFX])) : (f_of(sc[S_YF]) + f_of(sc[S_OFFY]));
-    const float num = wall - o;
-    float s, co; cn_sincos_bin(sc[S_TH] + (uint32_t)i * P.d.inc_bin, &s, &co);
-    const float den = xface ? co : s;
-    if (posf ? !(den > 0.0f) : !(den < 0.0f)) return;
-    const float t = num / den;
-    if (t > 0.0f && t < P.max_range) {
-        const unsigned long long key = ((unsigned long long)u_of(t) << 32) | (xface ? 0ull : 1ull);
-        atomicMin(S.keys + (size_t)w * key_stride + (NR - i), key);
-    }
-}
-__device__ __forceinline__ void raster_ped(const cn_kparams& P, const Ptrs& S, int key_stride, int slot, int i) {
-    const int NR = P.n_samples - 1;
-    const uint32_t* rec = S.rec + slot * 8;
-    const uint32_t wn = rec[Q_WN];
-    const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
-    const float cqx = f_of(rec[Q_QX]), cqy = f_of(rec[Q_QY]);
-    float sn, co; cn_sincos_bin(rec[Q_TH] + (uint32_t)i * P.d.inc_bin, &sn, &co);
+// ---- L: one ray against one primitive (XACRO:148-179; the oracle's lidar_raw arithmetic).  < 0: no return.
+__device__ __forceinline__ float ped_t(const cn_kparams& P, float cqx, float cqy, float sn, float co) {
     const float b = fmaf(cqx, co, cqy * sn);
     const float h = fmaf(cqx, sn, -(cqy * co));
     const float disc = fmaf(-h, h, P.d.ped_r2);
-    if (disc >= 0.0f) {
-        const float sq = sqrtf(disc);
-        if (b + sq > 0.0f) {
-            float t = b - sq;
-            if (t < 0.0f) t = 0.0f;
-            if (t < P.max_range) {
-                const unsigned long long key = ((unsigned long long)u_of(t) << 32) | (unsigned long long)(n + 2);
-                atomicMin(S.keys + (size_t)w * key_stride + (NR - i), key);
-            }
-        }
-    }
+    if (disc < 0.0f) return -1.0f;
+    const float sq = sqrtf(disc);
+    if (!(b + sq > 0.0f)) return -1.0f;                       // disc entirely behind
+    float t = b - sq;
+    if (t < 0.0f) t = 0.0f;                                   // sensor inside the disc
+    return (t < P.max_range) ? t : -1.0f;
+}
+__device__ __forceinline__ float wall_t(const cn_kparams& P, const uint32_t* sc, int face, float sn, float co) {
+    const bool xface = face < 2;
+    const bool posf = (face & 1) == 0;                        // 0: +x, 1: -x, 2: +y, 3: -y
+    const float den = xface ? co : sn;
+    if (posf ? !(den > 0.0f) : !(den < 0.0f)) return -1.0f;
+    const float wall = xface ? (posf ? P.room_xmax : P.room_xmin) : (posf ? P.room_ymax : P.room_ymin);
+    const float o = xface ? (f_of(sc[S_XF]) + f_of(sc[S_OFFX])) : (f_of(sc[S_YF]) + f_of(sc[S_OFFY]));
+    const float t = (wall - o) / den;
+    return (t > 0.0f && t < P.max_range) ? t : -1.0f;
 }
 
-// ---- phase 4: a ray the primitive still owns gets its final value (UTL:375-392 + np.around, ENV:1042)
-__device__ __forceinline__ void finish_ray(const cn_kparams& P, const Ptrs& S, int w, int j, unsigned long long key) {
-    const float t = f_of((uint32_t)(key >> 32));
+// A ray the primitive owns gets its final value: UTL:375-392 (sensor minimum) + np.around (ENV:1042); ENV:1012 min
+__device__ __forceinline__ void finish_ray(const cn_kparams& P, const Ptrs& S, int w, int e, int j, float t, uint8_t hid) {
     const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
     S.obs[(size_t)w * P.d.obs_dim + j] = cn_np_round3(rr);
     atomicMin(S.sc + w * F_WORDS + F_MINBITS, u_of(rr));
+    if (P.dbg_ranges) P.dbg_ranges[(size_t)e * (P.n_samples - 1) + j] = rr;
+    if (P.dbg_hid) P.dbg_hid[(size_t)e * (P.n_samples - 1) + j] = hid;
 }
-__device__ __forceinline__ void own_wall(const cn_kparams& P, const Ptrs& S, int key_stride, int q, int i) {
-    const int w = q >> 2, face = q & 3;
-    const int j = (P.n_samples - 1) - i;
-    const unsigned long long key = S.keys[(size_t)w * key_stride + j];
-    if ((uint32_t)key == ((face < 2) ? 0u : 1u)) finish_ray(P, S, w, j, key);
+
+// Does pedestrian n of world w return ray i, and is it the primitive the oracle would report (walls first, then
+// pedestrians in index order, strict <)?  The other primitives are tried only where their span contains the ray.
+__device__ __forceinline__ bool ped_ray_eval(const cn_kparams& P, const Ptrs& S, int w, int n, int slot, int i, float& t_out,
+                                             uint32_t& ang_out) {
+    const int N = P.n_peds, NR = P.n_samples - 1;
+    const uint32_t* rec = S.rec + slot * 8;
+    const uint32_t* sc = S.sc + w * F_WORDS;
+    const uint32_t ang = sc[S_TH] + (uint32_t)i * P.d.inc_bin;
+    ang_out = ang;
+    float sn, co; cn_sincos_bin(ang, &sn, &co);
+    const float t = ped_t(P, f_of(rec[Q_QX]), f_of(rec[Q_QY]), sn, co);
+    t_out = t;
+    if (t < 0.0f) return false;
+    bool own = true;
+    const int j = NR - i;
+    if ((sc[S_WDIRTY] >> min(j >> 5, 31)) & 1u) {
+#pragma unroll
+        for (int face = 0; face < 4; ++face) {
+            Span ws; wall_span(sc, face, ws);
+            if (!in_span(ws, i)) continue;
+            const float tw = wall_t(P, sc, face, sn, co);
+            if (tw >= 0.0f && tw <= t) own = false;             // the wall came first and the pedestrian is not nearer
+        }
+    }
+    const int nc = (int)sc[F_NCAND];
+    if (nc > 1) {
+        const uint8_t* cl = S.clw + w * N;
+        for (int k = 0; k < nc; ++k) {
+            const int n2 = (int)cl[k];
+            if (n2 == n) continue;
+            const uint32_t* r2 = S.rec + (w * N + n2) * 8;
+            Span s2; unpack_span(r2[Q_SPA], r2[Q_SPB], s2);
+            if (!in_span(s2, i)) continue;
+            const float t2 = ped_t(P, f_of(r2[Q_QX]), f_of(r2[Q_QY]), sn, co);
+            if (t2 >= 0.0f && (t2 < t || (t2 == t && n2 < n))) own = false;
+        }
+    }
+    return own;
 }
-__device__ __forceinline__ bool own_ped(const cn_kparams& P, const Ptrs& S, int key_stride, int slot, int i) {
-    const uint32_t wn = S.rec[slot * 8 + Q_WN];
-    const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
-    const int j = (P.n_samples - 1) - i;
-    const unsigned long long key = S.keys[(size_t)w * key_stride + j];
-    if ((uint32_t)key != (uint32_t)(n + 2)) return false;
-    finish_ray(P, S, w, j, key);
+// phase 3, one ray of a pedestrian's span; returns true when the pedestrian owns it
+__device__ __forceinline__ bool cast_ped(const cn_kparams& P, const Ptrs& S, uint32_t magic, int e0, int slot, int i) {
+    const int N = P.n_peds;
+    const int w = world_of(slot, N, magic), n = slot - w * N;
+    float t; uint32_t ang;
+    if (!ped_ray_eval(P, S, w, n, slot, i, t, ang)) return false;
+    finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, t, (uint8_t)n);
+    // centre ray (ENV:577 collapsed by ideal association): the owned ray nearest the pedestrian's centre line, in the
+    // oracle's order -- smaller |ray angle - bearing| first (sign in the low bit).  Distinct rays have distinct keys
+    // (adjacent rays are inc_bin >> 2 apart), so the minimum key identifies the ray; phase 5 decodes it.
+    uint32_t* rec = S.rec + slot * 8;
+    const int32_t delta = (int32_t)(ang - rec[Q_BEAR]);
+    const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
+    atomicMin(&rec[Q_CKEY], (ad & ~1u) | (delta < 0 ? 1u : 0u));
     return true;
 }
-
-// centre-ray ordering of the oracle: smaller |ray angle - bearing| first, then smaller j
-__device__ __forceinline__ void centre_try(uint32_t rel, uint32_t inc, int NR, int i, uint32_t& bkey, int& bj) {
-    const int32_t delta = (int32_t)((uint32_t)i * inc - rel);
-    const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
-    const uint32_t key = (ad & ~1u) | (delta < 0 ? 1u : 0u);
-    const int j = NR - i;
-    if (key < bkey || (key == bkey && j < bj)) { bkey = key; bj = j; }
+// phase 3, one ray of a wall face's span
+__device__ __forceinline__ void cast_wall(const cn_kparams& P, const Ptrs& S, int e0, int q, int i) {
+    const int N = P.n_peds;
+    const int w = q >> 2, face = q & 3;
+    const uint32_t* sc = S.sc + w * F_WORDS;
+    float sn, co; cn_sincos_bin(sc[S_TH] + (uint32_t)i * P.d.inc_bin, &sn, &co);
+    const float tw = wall_t(P, sc, face, sn, co);
+    if (tw < 0.0f) return;
+    const bool xface = face < 2;
+    bool own = true;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                               // the faces of the other axis (x faces come first)
+        const int f2 = (xface ? 2 : 0) + k;
+        Span ws; wall_span(sc, f2, ws);
+        if (!in_span(ws, i)) continue;
+        const float t2 = wall_t(P, sc, f2, sn, co);
+        if (t2 >= 0.0f && (xface ? (t2 < tw) : (t2 <= tw))) own = false;
+    }
+    const int nc = (int)sc[F_NCAND];
+    const uint8_t* cl = S.clw + w * N;
+    for (int k = 0; k < nc; ++k) {
+        const uint32_t* r2 = S.rec + (w * N + (int)cl[k]) * 8;
+        Span s2; unpack_span(r2[Q_SPA], r2[Q_SPB], s2);
+        if (!in_span(s2, i)) continue;
+        const float t2 = ped_t(P, f_of(r2[Q_QX]), f_of(r2[Q_QY]), sn, co);
+        if (t2 >= 0.0f && t2 < tw) own = false;
+    }
+    if (own) finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, tw, CN_HIT_WALL);
 }
 
-template <int T, class V>
-__device__ __forceinline__ void fill16(V* base, int n, V v, int tid) {      // n 16-byte elements, strided over the CTA
-    V* p = base + tid;
-    V* const end = base + n;
+// n 16-byte elements of shared memory, strided over the CTA
+template <int T>
+__device__ __forceinline__ void fill16(void* base, int n, uint32_t word, int tid) {
+    uint32_t a = smem_u32(base) + (uint32_t)tid * 16u;
+    int i = tid;
+    for (; i + 3 * T < n; i += 4 * T, a += 64u * T) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(word) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 16u * T), "r"(word) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 32u * T), "r"(word) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 48u * T), "r"(word) : "memory");
+    }
+    for (; i < n; i += T, a += 16u * T)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(word) : "memory");
+}
+
+// n 16-byte elements from shared to global memory, strided over `nthreads` threads (fire-and-forget stores)
+__device__ __forceinline__ void copy16_out(void* gdst, const void* ssrc, int n, int t, int nthreads) {
+    uint4* g = reinterpret_cast<uint4*>(gdst);
+    const uint4* s = reinterpret_cast<const uint4*>(ssrc);
 #pragma unroll 4
-    for (; p < end; p += T) *p = v;
+    for (int i = t; i < n; i += nthreads) g[i] = s[i];
 }
 
 // ------------------------------------------------------------------- kernel
 template <int MODE, int T>
-__global__ void __launch_bounds__(T, 1024 / T)
+__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 256 ? 4 : 8))
 cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
     constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -224,20 +299,20 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     const int e0 = blockIdx.x * W;
     const int nE = min(W, P.n_envs - e0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int KS = (int)L.key_stride;
 
     Ptrs S;
     S.robot = reinterpret_cast<uint32_t*>(smem);
     S.pa = reinterpret_cast<uint32_t*>(smem + L.off_pa);
     S.pb = reinterpret_cast<uint32_t*>(smem + L.off_pb);
+    S.pa2 = reinterpret_cast<uint32_t*>(smem + L.off_pa2);
     S.act = reinterpret_cast<float*>(smem + L.off_act);
     S.obs = reinterpret_cast<float*>(smem + L.off_obs);
-    S.keys = reinterpret_cast<unsigned long long*>(smem + L.off_keys);
     S.sc = reinterpret_cast<uint32_t*>(smem + L.off_sc);
     S.rec = reinterpret_cast<uint32_t*>(smem + L.off_rec);
     S.pk = reinterpret_cast<uint32_t*>(smem + L.off_pk);
     S.peers = reinterpret_cast<uint32_t*>(smem + L.off_peers);
     S.clist = reinterpret_cast<uint16_t*>(smem + L.off_clist);
+    S.clw = reinterpret_cast<uint8_t*>(smem + L.off_clw);
     S.rlist = reinterpret_cast<uint16_t*>(smem + L.off_rlist);
     S.olist = reinterpret_cast<uint16_t*>(smem + L.off_olist);
     S.wg = reinterpret_cast<uint32_t*>(smem + L.off_wg);
@@ -245,7 +320,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.cnt = reinterpret_cast<uint32_t*>(smem + L.off_cnt);
     S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
 
-    const int n_items = nE * N;                       // pedestrians of the tile (<= PED_THREADS by construction)
+    FSTAMP(0);
+    const int n_items = nE * N;                       // pedestrians of the tile
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
     const uint32_t ped_bytes = (uint32_t)n_items * 16u;
     const bool act_smem = (MODE == 0) && P.act_bulk_ok && (W % 2) == 0 && (nE % 2) == 0;
@@ -264,20 +340,31 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         }
     }
     {
-        fill16<T>(reinterpret_cast<uint4*>(S.keys), (nE * KS) >> 1, make_uint4(~0u, ~0u, ~0u, ~0u), tid);   // KS is even
         const float fill = P.d.max_range_r3;                                // a ray with no return, already rounded
         const int tot = nE * D, n4 = tot >> 2;
-        fill16<T>(reinterpret_cast<float4*>(S.obs), n4, make_float4(fill, fill, fill, fill), tid);
+        fill16<T>(S.obs, n4, u_of(fill), tid);
         if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
         if (tid < C_WORDS) S.cnt[tid] = 0u;
         if (tid < nE) {
             uint32_t* sc = S.sc + tid * F_WORDS;
             sc[F_MINBITS] = u_of(P.max_range); sc[F_CONF0] = 0u; sc[F_CONF1] = 0u; sc[F_XFLAGS] = 0u; sc[F_OVF_FACES] = 0u;
-            sc[F_NOBJ] = 0u;
+            sc[F_NOBJ] = 0u; sc[F_NCAND] = 0u;
+        }
+        if (P.dbg_ranges || P.dbg_hid) {                                    // debug taps (tests only): "no return" everywhere
+            for (int w = warp; w < nE; w += T / 32) {
+                if (MODE == 1 && P.mask && P.mask[e0 + w] == 0) continue;
+                const size_t base = (size_t)(e0 + w) * NR;
+                for (int j = lane; j < NR; j += 32) {
+                    if (P.dbg_ranges) P.dbg_ranges[base + j] = P.max_range;
+                    if (P.dbg_hid) P.dbg_hid[base + j] = CN_HIT_NONE;
+                }
+            }
         }
     }
     __syncthreads();            // fills done, barrier init visible
+    FSTAMP(11);
     mbar_wait(S.bar, 0);        // state tile + actions have landed
+    FSTAMP(1);
 
     // ---------------------------------------------------------------- phase 1
     if (warp < CF_POSE_WARPS) {
@@ -308,67 +395,69 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
     } else {
-        // thread = pedestrian of the tile (P: CROWD:98-144 + contact stand-in, Jacobi on the old positions)
+        // item = pedestrian of the tile (P: CROWD:98-144 + contact stand-in, Jacobi: old positions in pa, new in pa2)
         const int ptid = tid - 32 * CF_POSE_WARPS;
-        const bool has = ptid < n_items;
-        int w = 0, n = 0, b = 0;
-        bool p_active = false, p_reset = false;
-        if (has) {
-            w = world_of(ptid, N, L.magic_n); n = ptid - w * N;
-            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-            p_active = true; p_reset = (MODE == 1);
-            if (MODE == 1) p_active = !P.mask || P.mask[e0 + w] != 0;
-            else p_reset = (rob[CN_R_FLAGS] & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET);
-            const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + w);
-            b = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
-        }
-        const bool moves = has && p_active && !p_reset;
         uint4* spa4 = reinterpret_cast<uint4*>(S.pa);
-        int32_t x0 = 0, y0 = 0;
-        uint32_t pk = 0u;
+        uint4* spa2_4 = reinterpret_cast<uint4*>(S.pa2);
+        uint4* spb4 = reinterpret_cast<uint4*>(S.pb);
+        const bool auto_reset = (P.flags & CN_FLAG_AUTO_RESET) != 0u;
 
         // -- alpha: timers, packed coordinates, who needs random numbers
-        if (has && p_active && p_reset) {
-            const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
-            S.rlist[pos] = (uint16_t)(ptid | 0x8000);
-        }
-        if (moves) {
-            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * ptid);
-            x0 = (int32_t)a.x; y0 = (int32_t)a.y;
+        for (int it = ptid; it < n_items; it += PED_THREADS) {
+            const int w = world_of(it, N, L.magic_n), n = it - w * N;
+            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            bool active = true, respawn = (MODE == 1);
+            if (MODE == 1) active = !P.mask || P.mask[e0 + w] != 0;
+            else respawn = (rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset;
+            if (!active) { spa2_4[it] = spa4[it]; continue; }           // untouched world: state goes back as it came
+            if (respawn) {
+                const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
+                S.rlist[pos] = (uint16_t)(it | 0x8000);
+                continue;
+            }
+            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
             // both coordinates in one word: 14-bit fields at 2^-8 m with a guard bit each (cn_derive bounds the room);
             // the world's list is stored twice back to back so that "partner (n + r) mod N" is a plain offset
-            pk = (((a.x + 0x20000000u) >> 16) & 0x3FFFu) | ((((a.y + 0x20000000u) >> 16) & 0x3FFFu) << 16);
+            const uint32_t pk = (((a.x + 0x20000000u) >> 16) & 0x3FFFu) | ((((a.y + 0x20000000u) >> 16) & 0x3FFFu) << 16);
             S.pk[2 * w * N + n] = pk; S.pk[2 * w * N + N + n] = pk;
-            S.peers[2 * ptid] = 0u; S.peers[2 * ptid + 1] = 0u;
-            int32_t tm = (int32_t)S.pb[4 * ptid + 2] - CN_TICKS_PER_STEP;
+            S.peers[2 * it] = 0u; S.peers[2 * it + 1] = 0u;
+            int32_t tm = (int32_t)S.pb[4 * it + 2] - CN_TICKS_PER_STEP;
             if (tm <= 0) {
+                const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + w);
+                const int b = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
                 tm += P.beh_period[b];
                 if (P.beh_kind[b] == CN_BEHAVIOR_RANDOM) {
                     const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
-                    S.rlist[pos] = (uint16_t)ptid;
+                    S.rlist[pos] = (uint16_t)it;
                 } else {
                     const float speed = P.beh_speed[b];
-                    S.pa[4 * ptid + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
-                    S.pa[4 * ptid + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
+                    S.pa[4 * it + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
+                    S.pa[4 * it + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
                 }
             }
-            S.pb[4 * ptid + 2] = (uint32_t)tm;
+            S.pb[4 * it + 2] = (uint32_t)tm;
         }
         named_bar_sync(1, PED_THREADS);
 
         // -- beta: contact prefilter (each unordered pair once: partner = n + r mod N, r <= N/2) ...
-        if (moves) {
-            const uint32_t pk_biased = (pk | 0x80008000u) + 0x00400040u;
+        for (int it = ptid; it < n_items; it += PED_THREADS) {
+            const int w = world_of(it, N, L.magic_n), n = it - w * N;
+            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            if (MODE == 1) continue;                                        // a reset launch moves nobody
+            if ((rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset) continue;
             const uint32_t* pp = S.pk + 2 * w * N + n;
+            const uint32_t pk_biased = (pp[0] | 0x80008000u) + 0x00400040u;
             const int half = N >> 1;
             uint32_t hits = 0u;
 #pragma unroll 5
-            for (int r = 1; r <= half; ++r)
-                if (((pk_biased - pp[r]) & 0xFF80FF80u) == 0x80008000u) hits |= 1u << (r - 1);     // |dx|, |dy| < 0.25 m
-            while (hits) {                                                                         // rare
+            for (int r = 1; r <= half; ++r) {
+                const uint32_t d = (pk_biased - pp[r]) & 0xFF80FF80u;       // |dx|, |dy| < 0.25 m
+                hits |= (d == 0x80008000u) ? (1u << (r - 1)) : 0u;
+            }
+            while (hits) {                                                  // rare
                 const int r = __ffs(hits); hits &= hits - 1;
                 const int partner = (n + r >= N) ? n + r - N : n + r;
-                atomicOr(&S.peers[2 * ptid + (partner >> 5)], 1u << (partner & 31));
+                atomicOr(&S.peers[2 * it + (partner >> 5)], 1u << (partner & 31));
                 atomicOr(&S.peers[2 * (w * N + partner) + (n >> 5)], 1u << (n & 31));
             }
         }
@@ -393,8 +482,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     int32_t xi = cn_f2i(px * CN_INV_GRID), yi = cn_f2i(py * CN_INV_GRID);
                     xi = max(xi, P.d.ped_xmin); xi = min(xi, P.d.ped_xmax);
                     yi = max(yi, P.d.ped_ymin); yi = min(yi, P.d.ped_ymax);
-                    spa4[idx] = make_uint4((uint32_t)xi, (uint32_t)yi, u_of(0.0f), u_of(0.0f));
-                    reinterpret_cast<uint4*>(S.pb)[idx] = make_uint4(0u, 0u, (uint32_t)((nn + 1) * P.beh_stagger[bb]), 0u);
+                    spa2_4[idx] = make_uint4((uint32_t)xi, (uint32_t)yi, u_of(0.0f), u_of(0.0f));
+                    spb4[idx] = make_uint4(0u, 0u, (uint32_t)((nn + 1) * P.beh_stagger[bb]), 0u);
                 } else {
                     const float speed = P.beh_speed[bb];
                     S.pa[4 * idx + 2] = u_of(cn_usym(rnd.v[0], speed));
@@ -405,78 +494,83 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         named_bar_sync(1, PED_THREADS);
 
         // -- gamma: repulsion for the rare pairs found, integrate, frictionless wall clamp
-        int32_t nx = 0, ny = 0;
-        float vx = 0.0f, vy = 0.0f;
-        if (moves) {
-            vx = f_of(S.pa[4 * ptid + 2]); vy = f_of(S.pa[4 * ptid + 3]);
-            float vex = vx, vey = vy;
+        if (MODE == 0) {
             const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
-            const uint32_t p0 = S.peers[2 * ptid], p1 = S.peers[2 * ptid + 1];
-            if (p0 | p1) {                                                  // index order, like the oracle
-                for (uint32_t pm = p0; pm; pm &= pm - 1) {
-                    const int m = __ffs(pm) - 1;
-                    const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
-                    add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
-                }
-                for (uint32_t pm = p1; pm; pm &= pm - 1) {
-                    const int m = __ffs(pm) + 31;
-                    const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
-                    add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
-                }
-            }
             const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative prefilter
             const uint32_t lim2 = 2u * (uint32_t)lim_i;
-            const int32_t rxi = (int32_t)S.robot[w * CN_ROBOT_WORDS + CN_R_X], ryi = (int32_t)S.robot[w * CN_ROBOT_WORDS + CN_R_Y];
-            if ((uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2)
-                add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
-            nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
-            ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
-            if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
-            if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
-            if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
-            if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
+            for (int it = ptid; it < n_items; it += PED_THREADS) {
+                const int w = world_of(it, N, L.magic_n);
+                const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+                if ((rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset) continue;
+                const uint4 a = spa4[it];
+                const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
+                float vx = f_of(a.z), vy = f_of(a.w);
+                float vex = vx, vey = vy;
+                const uint32_t p0 = S.peers[2 * it], p1 = S.peers[2 * it + 1];
+                if (p0 | p1) {                                              // index order, like the oracle
+                    for (uint32_t pm = p0; pm; pm &= pm - 1) {
+                        const int m = __ffs(pm) - 1;
+                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                        add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                    }
+                    for (uint32_t pm = p1; pm; pm &= pm - 1) {
+                        const int m = __ffs(pm) + 31;
+                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                        add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
+                    }
+                }
+                const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
+                if ((uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2)
+                    add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
+                int32_t nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
+                int32_t ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
+                if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
+                if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
+                if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
+                if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
+                spa2_4[it] = make_uint4((uint32_t)nx, (uint32_t)ny, u_of(vx), u_of(vy));
+            }
         }
-        named_bar_sync(1, PED_THREADS);             // every old position has been read
-        if (moves) spa4[ptid] = make_uint4((uint32_t)nx, (uint32_t)ny, u_of(vx), u_of(vy));
     }
+    FSTAMP(9);
     __syncthreads();            // #A: new poses, scalar records, new pedestrian positions
+    FSTAMP(2);
 
     // ---------------------------------------------------------------- phase 2a
-    if (tid < n_items) {
-        const int w = world_of(tid, N, L.magic_n);
-        const uint32_t* sc = S.sc + w * F_WORDS;
-        if (sc[F_XFLAGS] & XF_ACTIVE) {
-            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * tid);
-            const float qx = (float)((int32_t)a.x - (int32_t)sc[S_XI]) * CN_GRID - f_of(sc[S_OFFX]);
-            const float qy = (float)((int32_t)a.y - (int32_t)sc[S_YI]) * CN_GRID - f_of(sc[S_OFFY]);
-            if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
-                const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
-                S.clist[pos] = (uint16_t)tid;
-                uint32_t* rec = S.rec + tid * 8;
-                rec[Q_QX] = u_of(qx); rec[Q_QY] = u_of(qy);
-                rec[Q_TH] = sc[S_TH];
-                rec[Q_WN] = (uint32_t)w | ((uint32_t)(tid - w * N) << 8);
-            }
+    for (int it = tid; it < n_items; it += T) {
+        const int w = world_of(it, N, L.magic_n);
+        uint32_t* sc = S.sc + w * F_WORDS;
+        if (!(sc[F_XFLAGS] & XF_ACTIVE)) continue;
+        const uint2 a = *reinterpret_cast<const uint2*>(S.pa2 + 4 * it);
+        const float qx = (float)((int32_t)a.x - (int32_t)sc[S_XI]) * CN_GRID - f_of(sc[S_OFFX]);
+        const float qy = (float)((int32_t)a.y - (int32_t)sc[S_YI]) * CN_GRID - f_of(sc[S_OFFY]);
+        if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
+            const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
+            S.clist[pos] = (uint16_t)it;
+            const uint32_t k = atomicAdd(&sc[F_NCAND], 1u);
+            S.clw[w * N + k] = (uint8_t)(it - w * N);
+            uint32_t* rec = S.rec + it * 8;
+            rec[Q_QX] = u_of(qx); rec[Q_QY] = u_of(qy);
+            rec[Q_SPA] = 1u; rec[Q_SPB] = 1u;                               // empty span until phase 2b
         }
     }
     for (int q = T - 1 - tid; q < nE * 4; q += T) {                         // wall faces, from the far end of the CTA
         uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
         if (!(sc[F_XFLAGS] & XF_ACTIVE)) continue;
-        const int face = q & 3;
-        Span sp;
-        sp.a0 = (int)sc[S_WSPAN + 4 * face + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * face + 1];
-        sp.b0 = (int)sc[S_WSPAN + 4 * face + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * face + 3];
+        Span sp; wall_span(sc, q & 3, sp);
         if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)q, sp)) {
-            atomicOr(&sc[F_OVF_FACES], 1u << face);
+            atomicOr(&sc[F_OVF_FACES], 1u << (q & 3));
             S.cnt[C_OVF] = 1u;
         }
     }
     __syncthreads();            // #B
+    FSTAMP(3);
     const int n_cand = (int)S.cnt[C_NCAND];
 
     // ---------------------------------------------------------------- phase 2b
     for (int q = tid; q < n_cand; q += T) {
         const int slot = (int)S.clist[q];
+        const int w = world_of(slot, N, L.magic_n);
         uint32_t* rec = S.rec + slot * 8;
         const float qx = f_of(rec[Q_QX]), qy = f_of(rec[Q_QY]);
         const float d2 = fmaf(qx, qx, qy * qy);
@@ -487,57 +581,32 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             const float u = P.ped_radius * rsqrtf(d2) * 1.0001f;   // asin(u) <= u + (pi/2 - 1) u^3
             alpha = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
         }
-        const Span sp = make_span(P, bearing - rec[Q_TH], alpha);
+        const uint32_t rel = bearing - S.sc[w * F_WORDS + S_TH];
+        const Span sp = make_span(P, rel, alpha);
         rec[Q_BEAR] = bearing;
         rec[Q_SPA] = (uint32_t)sp.a0 | ((uint32_t)sp.a1 << 16);
         rec[Q_SPB] = (uint32_t)sp.b0 | ((uint32_t)sp.b1 << 16);
         rec[Q_CNT] = 0u;
+        rec[Q_CKEY] = 0xFFFFFFFFu;
+        uint32_t misc = 0u;
         if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
-            rec[Q_WN] |= WN_OVF;
+            misc |= MISC_OVF;
             S.cnt[C_OVF] = 1u;
         }
+        rec[Q_MISC] = misc;
     }
     __syncthreads();            // #C
+    FSTAMP(4);
     const int n_wg = min((int)S.cnt[C_NWG], (int)L.cap_wg);
     const int n_pg = min((int)S.cnt[C_NPG], (int)L.cap_pg);
     const bool overflow = S.cnt[C_OVF] != 0u;
     const int lane8 = tid & 7;
 
-    // ---------------------------------------------------------------- phase 3: rasterise (L: XACRO:148-179)
+    // ---------------------------------------------------------------- phase 3: cast + ownership (L, C: XACRO:148-179, UTL:375-392)
     for (int gi = tid >> 3; gi < n_wg; gi += T / 8) {
         const uint32_t ent = S.wg[gi];
         const int i = group_ray(ent, lane8);
-        if (i >= 0) raster_wall(P, S, KS, (int)(ent >> 14), i);
-    }
-    for (int gi = tid >> 3; gi < n_pg; gi += T / 8) {
-        const uint32_t ent = S.pg[gi];
-        const int i = group_ray(ent, lane8);
-        if (i >= 0) raster_ped(P, S, KS, (int)(ent >> 14), i);
-    }
-    if (overflow) {             // primitives whose groups did not fit: the whole CTA walks each of them
-        for (int q = 0; q < nE * 4; ++q) {
-            const uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
-            if (!((sc[F_OVF_FACES] >> (q & 3)) & 1u)) continue;
-            Span sp;
-            sp.a0 = (int)sc[S_WSPAN + 4 * (q & 3) + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * (q & 3) + 1];
-            sp.b0 = (int)sc[S_WSPAN + 4 * (q & 3) + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * (q & 3) + 3];
-            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) raster_wall(P, S, KS, q, i); }
-        }
-        for (int q = 0; q < n_cand; ++q) {
-            const int slot = (int)S.clist[q];
-            const uint32_t* rec = S.rec + slot * 8;
-            if (!(rec[Q_WN] & WN_OVF)) continue;
-            Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
-            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) raster_ped(P, S, KS, slot, i); }
-        }
-    }
-    __syncthreads();            // #D: keys final
-
-    // ---------------------------------------------------------------- phase 4: ownership, final ray values
-    for (int gi = tid >> 3; gi < n_wg; gi += T / 8) {
-        const uint32_t ent = S.wg[gi];
-        const int i = group_ray(ent, lane8);
-        if (i >= 0) own_wall(P, S, KS, (int)(ent >> 14), i);
+        if (i >= 0) cast_wall(P, S, e0, (int)(ent >> 14), i);
     }
     for (int g0 = warp * 4; g0 < n_pg; g0 += (T / 32) * 4) {                // warp-uniform trip count: ballots inside
         const int gi = g0 + (lane >> 3);
@@ -547,71 +616,54 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             const uint32_t ent = S.pg[gi];
             const int i = group_ray(ent, lane8);
             slot = (int)(ent >> 14);
-            if (i >= 0) owned = own_ped(P, S, KS, slot, i);
+            if (i >= 0) owned = cast_ped(P, S, L.magic_n, e0, slot, i);
         }
         const uint32_t bm = __ballot_sync(FULL, owned);
         const int c = __popc((bm >> (lane & 24)) & 0xFFu);
         if (lane8 == 0 && c) atomicAdd(&S.rec[slot * 8 + Q_CNT], (uint32_t)c);
     }
-    if (overflow) {
+    if (overflow) {             // primitives whose groups did not fit: the whole CTA walks each of them
         for (int q = 0; q < nE * 4; ++q) {
             const uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
             if (!((sc[F_OVF_FACES] >> (q & 3)) & 1u)) continue;
-            Span sp;
-            sp.a0 = (int)sc[S_WSPAN + 4 * (q & 3) + 0]; sp.a1 = (int)sc[S_WSPAN + 4 * (q & 3) + 1];
-            sp.b0 = (int)sc[S_WSPAN + 4 * (q & 3) + 2]; sp.b1 = (int)sc[S_WSPAN + 4 * (q & 3) + 3];
-            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) own_wall(P, S, KS, q, i); }
+            Span sp; wall_span(sc, q & 3, sp);
+            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) cast_wall(P, S, e0, q, i); }
         }
         for (int q = 0; q < n_cand; ++q) {
             const int slot = (int)S.clist[q];
             const uint32_t* rec = S.rec + slot * 8;
-            if (!(rec[Q_WN] & WN_OVF)) continue;
+            if (!(rec[Q_MISC] & MISC_OVF)) continue;
             Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
             for (int pos = tid; pos < NR; pos += T) {
                 const int i = span_ray(sp, pos);
-                if (i >= 0 && own_ped(P, S, KS, slot, i)) atomicAdd(&S.rec[slot * 8 + Q_CNT], 1u);
+                if (i >= 0 && cast_ped(P, S, L.magic_n, e0, slot, i)) atomicAdd(&S.rec[slot * 8 + Q_CNT], 1u);
             }
         }
     }
+    FSTAMP(10);
     __syncthreads();            // #E: rows' ray part final, owned-ray counts final
+    FSTAMP(5);
 
     // ---------------------------------------------------------------- phase 5: E-J per candidate (ENV:568-860)
     for (int q = tid; q < n_cand; q += T) {
         const int slot = (int)S.clist[q];
         uint32_t* rec = S.rec + slot * 8;
         if (rec[Q_CNT] < 4u) continue;                                      // ENV:573: fewer than 4 rays is no object
-        const uint32_t wn = rec[Q_WN];
-        const int w = (int)(wn & 0xFFu), n = (int)((wn >> 8) & 0xFFu);
+        const int w = world_of(slot, N, L.magic_n), n = slot - w * N;
         uint32_t* sc = S.sc + w * F_WORDS;
-        // centre ray: the owned ray nearest the pedestrian's centre line.  The nearest ray overall is one of the two
-        // neighbours of the bearing on the circle; if the pedestrian owns it, it is the answer.
-        const uint32_t th = rec[Q_TH];
-        const uint32_t inc = P.d.inc_bin;
-        const uint32_t rel = rec[Q_BEAR] - th;
-        const unsigned long long* krow = S.keys + (size_t)w * KS;
-        const uint32_t me = (uint32_t)(n + 2);
-        int jstar;
+        const uint32_t th = sc[S_TH];
+        // decode the centre ray from its key: ray angle = bearing +- |delta|, scan index = angle / inc (exact to rounding)
+        const uint32_t ckey = rec[Q_CKEY];
+        const uint32_t adk = ckey & ~1u;
+        const uint32_t rel2 = (rec[Q_BEAR] - th) + ((ckey & 1u) ? (0u - adk) : adk);
+        const int istar = (int)fmaf((float)rel2, P.d.inv_inc_bin, 0.5f);
+        const int jstar = NR - istar;
+        float t_raw;
         {
-            const int i0 = (int)(rel / inc);
-            uint32_t bkey = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
-            centre_try(rel, inc, NR, min(max(i0, 1), NR), bkey, bj);
-            centre_try(rel, inc, NR, min(max(i0 + 1, 1), NR), bkey, bj);
-            centre_try(rel, inc, NR, 1, bkey, bj);
-            centre_try(rel, inc, NR, NR, bkey, bj);
-            jstar = bj;
-            if ((uint32_t)krow[jstar] != me) {                              // centre ray occluded: search the span
-                Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
-                const int tot = span_len_a(sp) + span_len_b(sp);
-                bkey = 0xFFFFFFFFu; bj = 0x7FFFFFFF;
-                for (int pos = 0; pos < tot; ++pos) {
-                    const int i = span_ray(sp, pos);
-                    if ((uint32_t)krow[NR - i] == me) centre_try(rel, inc, NR, i, bkey, bj);
-                }
-                jstar = bj;
-            }
+            float sn, co; cn_sincos_bin(th + (uint32_t)istar * P.d.inc_bin, &sn, &co);
+            t_raw = ped_t(P, f_of(rec[Q_QX]), f_of(rec[Q_QY]), sn, co);     // the same arithmetic as in phase 3
         }
         const float xf = f_of(sc[S_XF]), yf = f_of(sc[S_YF]);
-        const float t_raw = f_of((uint32_t)(krow[jstar] >> 32));
         const float d_raw = (t_raw < P.sensor_min_range) ? P.sensor_min_range : t_raw;
         const float d3 = cn_py_round3(d_raw);                               // ENV:324,384
         float sa, ca; cn_sincos_bin((uint32_t)jstar * P.d.hit_inc_bin - th, &sa, &ca);     // C2: UTL:110-126
@@ -660,44 +712,46 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
             cp = 0.5f * cp_ttc + 0.5f * dto;
         }
-        rec[O_CP] = u_of(cp); rec[O_X] = u_of(hx); rec[O_Y] = u_of(hy);
-        rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);
+        rec[O_CP] = u_of(cp); rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);   // x, y: ped_b
         const uint32_t k = atomicAdd(&sc[F_NOBJ], 1u);                      // the world's object list (any order)
         S.olist[w * N + k] = (uint16_t)slot;
     }
     __syncthreads();            // #F
+    FSTAMP(6);
 
     // ---------------------------------------------------------------- phase 6
     // 6a  K: top-K block (ENV:862-907): stable rank by CP among the world's objects, keep [-K:]; padding is in the row
-    //     (thread = object: entry k of world w's list, flattened over the tile)
-    for (int q = tid; q < n_items; q += T) {
+    //     (item = object: entry k of world w's list, flattened over the tile)
+    constexpr int T6 = T - 32;                                              // the last warp does 6c meanwhile
+    for (int q = tid; q < n_items && tid < T6; q += T6) {
         const int w = world_of(q, N, L.magic_n), k = q - w * N;
         const int n_obj = (int)S.sc[w * F_WORDS + F_NOBJ];
         if (k >= n_obj) continue;
         const uint16_t* ol = S.olist + w * N;
-        const uint32_t* rec = S.rec + (int)ol[k] * 8;
-        const int n = (int)((rec[Q_WN] >> 8) & 0xFFu);
+        const int slot = (int)ol[k];
+        const uint32_t* rec = S.rec + slot * 8;
+        const int n = slot - w * N;
         const float my_cp = f_of(rec[O_CP]);
         int rank = 0;
         for (int k2 = 0; k2 < n_obj; ++k2) {
-            const uint32_t* r2 = S.rec + (int)ol[k2] * 8;
-            const int n2 = (int)((r2[Q_WN] >> 8) & 0xFFu);
-            const float cpb = f_of(r2[O_CP]);
+            const int s2 = (int)ol[k2];
+            const int n2 = s2 - w * N;
+            const float cpb = f_of(S.rec[s2 * 8 + O_CP]);
             if (n2 != n && (cpb > my_cp || (cpb == my_cp && n2 < n))) ++rank;
         }
         const int slot_k = (P.flags & CN_FLAG_TOPK_HIGHEST) ? rank : rank - (n_obj > K ? n_obj - K : 0);
         if (slot_k < 0 || slot_k >= K) continue;
         float* blk = S.obs + (size_t)w * D + NR + 7 + 4 * slot_k;
-        blk[0] = f_of(rec[O_X]); blk[1] = f_of(rec[O_Y]);                  // already multiples of 0.001
+        blk[0] = f_of(S.pb[4 * slot + 0]); blk[1] = f_of(S.pb[4 * slot + 1]);      // hit point: already multiples of 0.001
         blk[2] = cn_np_round3(f_of(rec[O_VX])); blk[3] = cn_np_round3(f_of(rec[O_VY]));
     }
     // 6b  tracker flags: a pedestrian is tracked next step iff it was confirmed now (ENV:656-743, ideal association)
-    if (tid < n_items) {
-        const int w = world_of(tid, N, L.magic_n), n = tid - w * N;
+    for (int it = tid; it < n_items && tid < T6; it += T6) {
+        const int w = world_of(it, N, L.magic_n), n = it - w * N;
         const uint32_t* sc = S.sc + w * F_WORDS;
         if (sc[F_XFLAGS] & XF_ACTIVE) {
             const uint32_t bit = (sc[F_CONF0 + (n >> 5)] >> (n & 31)) & 1u;
-            S.pb[4 * tid + 3] = (S.pb[4 * tid + 3] & ~CN_PF_TRACKED) | (bit ? CN_PF_TRACKED : 0u);
+            S.pb[4 * it + 3] = (S.pb[4 * it + 3] & ~CN_PF_TRACKED) | (bit ? CN_PF_TRACKED : 0u);
         }
     }
     // 6c  lane = world (last warp): M counters, N done, W terminal reward, robot record
@@ -757,12 +811,26 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 
     // ---------------------------------------------------------------- phase 7: write-back
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
+    FSTAMP(12);
     __syncthreads();             // #G
+    FSTAMP(7);
     const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
-    if (tid == 0) {
+    if (L.plain_store) {
+        // cooperative 16-byte stores: nothing to wait for, the CTA's slot is free as soon as they are issued
+        copy16_out(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, (int)(rob_bytes >> 4), tid, T);
+        if (ped_bytes) {
+            copy16_out(P.ped_a + (size_t)e0 * N * 4, S.pa2, n_items, tid, T);
+            copy16_out(P.ped_b + (size_t)e0 * N * 4, S.pb, n_items, tid, T);
+        }
+        if (bulk_obs) {
+            copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
+            for (int p = 0; p < P.n_obs_peers; ++p)                         // fused all-gather over NVLink
+                copy16_out(P.obs_peers[p] + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
+        }
+    } else if (tid == 0) {
         tma_store(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, rob_bytes);
         if (ped_bytes) {
-            tma_store(P.ped_a + (size_t)e0 * N * 4, S.pa, ped_bytes);
+            tma_store(P.ped_a + (size_t)e0 * N * 4, S.pa2, ped_bytes);
             tma_store(P.ped_b + (size_t)e0 * N * 4, S.pb, ped_bytes);
         }
         if (bulk_obs) {
@@ -772,6 +840,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 tma_store(P.obs_peers[p] + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
         }
         tma_store_commit_and_wait();
+        FSTAMP(8);
     }
     if (!bulk_obs) {             // plain coalesced stores (reset launches, unaligned or ragged tiles)
         for (int w = warp; w < nE; w += T / 32) {
@@ -785,22 +854,6 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
     }
-    // debug taps (tests only): raw cleaned ranges + hit ids for every ray
-    if (P.dbg_ranges || P.dbg_hid) {
-        for (int w = warp; w < nE; w += T / 32) {
-            if (!(S.sc[w * F_WORDS + F_XFLAGS] & XF_ACTIVE)) continue;
-            const size_t base = (size_t)(e0 + w) * NR;
-            for (int j = lane; j < NR; j += 32) {
-                const unsigned long long key = S.keys[(size_t)w * KS + j];
-                const uint32_t lo = (uint32_t)key;
-                const float t = f_of((uint32_t)(key >> 32));
-                const uint8_t h = (lo == 0xFFFFFFFFu) ? CN_HIT_NONE : (lo < 2u ? CN_HIT_WALL : (uint8_t)(lo - 2u));
-                const float rr = (h == CN_HIT_NONE) ? P.max_range : ((t < P.sensor_min_range) ? P.sensor_min_range : t);
-                if (P.dbg_ranges) P.dbg_ranges[base + j] = rr;
-                if (P.dbg_hid) P.dbg_hid[base + j] = h;
-            }
-        }
-    }
 }
 
 }  // namespace
@@ -809,28 +862,30 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L) {
-    const int N = n_peds, NR = n_samples - 1, D = obs_dim, W = tile;
-    if (threads != 256 && threads != 512) return -1;
-    if (W < 1 || W > 32 || (size_t)W * N > (size_t)(threads - 32 * CF_POSE_WARPS)) return -1;
-    if ((size_t)W * N > 0x3FFF || (size_t)W * 4 > 0x3FFF) return -1;        // group-entry / list-entry fields
+    const int N = n_peds, D = obs_dim, W = tile;
+    if (threads != 128 && threads != 256 && threads != 512) return -1;
+    if (W < 1 || W > 32) return -1;
+    if ((size_t)W * N > 0x3FFF) return -1;                                  // group-entry / list-entry fields
+    (void)n_samples;
     L->W = W;
     L->threads = threads;
+    L->plain_store = 0;
     L->magic_n = (N > 1) ? (uint32_t)(((1ull << 32) + (uint64_t)N - 1) / (uint64_t)N) : 0u;
-    L->key_stride = (uint32_t)((NR + 1) & ~1);
     L->cap_wg = (uint32_t)W * 32u;
     L->cap_pg = (uint32_t)W * 24u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_pb = (uint32_t)o;
+    o += (size_t)W * N * 16;                        L->off_pa2 = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
     o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
-    o = up16(o + (size_t)W * D * 4);                L->off_keys = (uint32_t)o;
-    o += (size_t)W * L->key_stride * 8;             L->off_sc = (uint32_t)o;
+    o = up16(o + (size_t)W * D * 4);                L->off_sc = (uint32_t)o;
     o += (size_t)W * F_WORDS * 4;                   L->off_rec = (uint32_t)o;
-    o += (size_t)W * N * 32;                        L->off_pk = (uint32_t)o;
-    o += (size_t)W * N * 8;                         L->off_peers = (uint32_t)o;
-    o += (size_t)W * N * 8;                         L->off_clist = (uint32_t)o;
-    o = up16(o + (size_t)W * N * 2);                L->off_rlist = (uint32_t)o;
+    L->off_pk = L->off_rec;                         /* phase-1 scratch lives where the candidate records go later */
+    L->off_peers = L->off_rec + (uint32_t)((size_t)W * N * 8);
+    o += (size_t)W * N * 32;                        L->off_clist = (uint32_t)o;
+    o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
+    o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_wg = (uint32_t)o;
     o += (size_t)L->cap_wg * 4;                     L->off_pg = (uint32_t)o;
@@ -842,24 +897,21 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
 }
 
 int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, size_t smem_per_sm, cn_flat_layout* L) {
-    // 256-thread CTAs, four per SM: the largest tile whose shared memory allows that, preferring tiles whose row
-    // block can leave by bulk store.  Falls back to 512-thread CTAs, two per SM, for wide worlds.
-    for (int pass = 0; pass < 2; ++pass) {
-        const int threads = pass == 0 ? 256 : 512;
-        const int ctas = 1024 / threads;
-        const size_t budget = smem_per_sm / ctas - 1024;
-        int best = 0;
-        for (int W = 16; W >= 1; --W) {
-            cn_flat_layout t;
-            if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, &t) != 0 || t.total > budget) continue;
-            const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
-            if (!best) best = W;
-            if (bulk) { best = W; break; }
-            if (W < best - 3) break;
-        }
-        if (best >= 4 || (pass == 1 && best >= 1)) return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, L);
+    // 256-thread CTAs, four per SM: the largest tile (<= 16 worlds) whose shared memory allows that, preferring tiles
+    // whose row block can leave by bulk store.
+    const int threads = 256, ctas = 4;
+    const size_t budget = smem_per_sm / ctas - 1024;
+    int best = 0;
+    for (int W = 16; W >= 1; --W) {
+        cn_flat_layout t;
+        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, &t) != 0 || t.total > budget) continue;
+        const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
+        if (!best) best = W;
+        if (bulk) { best = W; break; }
+        if (W < best - 3) break;
     }
-    return -1;
+    if (!best) return -1;
+    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, L);
 }
 
 template <int MODE, int T>
@@ -876,7 +928,14 @@ static cudaError_t launch_flat_t(const cn_kparams& P, const cn_flat_layout& L, c
     return cudaGetLastError();
 }
 
+#ifdef CN_TIMELINE
+extern "C" int cn_debug_set_timeline_flat(unsigned long long* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr));
+}
+#endif
+
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream) {
+    if (L.threads == 128) return mode == 0 ? launch_flat_t<0, 128>(P, L, stream) : launch_flat_t<1, 128>(P, L, stream);
     if (L.threads == 256) return mode == 0 ? launch_flat_t<0, 256>(P, L, stream) : launch_flat_t<1, 256>(P, L, stream);
     return mode == 0 ? launch_flat_t<0, 512>(P, L, stream) : launch_flat_t<1, 512>(P, L, stream);
 }

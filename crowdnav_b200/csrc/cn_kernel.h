@@ -45,12 +45,12 @@ struct cn_kparams {
 /* cn_flat.cu: shared-memory layout of one tile of W worlds (byte offsets), computed once per handle on the host */
 struct cn_flat_layout {
     int W;                      /* worlds per CTA */
-    int threads;                /* threads per CTA: 256 (four CTAs per SM) or 512 (two) */
+    int threads;                /* threads per CTA: 128, 256 or 512 */
+    int plain_store;            /* 1: write the tile back with cooperative 16-byte stores, 0: bulk TMA stores */
     uint32_t magic_n;           /* ceil(2^32 / N): world index of a flat pedestrian index by __umulhi */
-    uint32_t key_stride;        /* 64-bit hit keys per world row (rays rounded up to even) */
     uint32_t cap_wg, cap_pg;    /* capacity of the wall / pedestrian ray-group lists */
-    uint32_t off_pa, off_pb, off_act, off_obs, off_keys, off_sc, off_rec, off_pk, off_peers,
-             off_clist, off_rlist, off_olist, off_wg, off_pg, off_cnt, off_bar;
+    uint32_t off_pa, off_pb, off_pa2, off_act, off_obs, off_sc, off_rec, off_pk, off_peers,
+             off_clist, off_clw, off_rlist, off_olist, off_wg, off_pg, off_cnt, off_bar;
     uint32_t total;             /* dynamic shared memory per CTA */
 };
 int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L);

@@ -1,13 +1,21 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > gpurun_out/s5_pytest.log; cat gpurun_out/s5_pytest.log
-for cfg in "8,256" "6,256" "16,512" "14,512"; do
-  for wl in c2 c3; do
-    CN_FLAT_TILE=$cfg python bench.py --steps 40 --warmup 5 --workload $wl --no-cpu-baseline > gpurun_out/s5_bench_${wl}_${cfg}.json 2> gpurun_out/s5_bench_${wl}_${cfg}.err
+#!/bin/bash
+# A/B harness for the flat step kernel: parity tests, then bench.py over a list of CN_FLAT_TILE="W,threads" settings.
+# usage (on the GPU box): bash profiles/tools/ab.sh <tag> "<cfg> <cfg> ..." "<workload> ..."   cfg = default | W,threads[:plain]
+tag=${1:-ab}; cfgs=${2:-"default"}; wls=${3:-"c2 c3"}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > gpurun_out/${tag}_pytest.log; cat gpurun_out/${tag}_pytest.log
+for cfg in $cfgs; do
+  for wl in $wls; do
+    tile=${cfg%%:*}; store=tma; [[ "$cfg" == *:* ]] && store=${cfg##*:}
+    if [ "$tile" = "default" ]; then unset CN_FLAT_TILE; else export CN_FLAT_TILE=$tile; fi
+    export CN_FLAT_STORE=$store
+    python bench.py --steps 40 --warmup 5 --workload $wl --no-cpu-baseline > gpurun_out/${tag}_bench_${wl}_${cfg}.json 2> gpurun_out/${tag}_bench_${wl}_${cfg}.err
   done
 done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/s5_bench_*.json")):
+python - "$tag" <<'PY'
+import json,glob,sys
+for f in sorted(glob.glob("gpurun_out/%s_bench_*.json" % sys.argv[1])):
     try:
         d=json.load(open(f)); print(f, d["roofline"]["kernel"], round(d["roofline"]["kernel_us"],2), round(d["roofline"]["frac"],4), round(d["roofline"]["l2_warm"]["kernel_us"],2))
-    except Exception as e: print(f, "ERR", e)
+    except Exception as e: print(f, "ERR", e, open(f.replace(".json",".err")).read()[-300:])
 PY
