@@ -119,7 +119,9 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             if (comma) tt = atoi(comma + 1);
             rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, &flat);
         } else {
-            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, (size_t)max_sm, &flat);
+            int n_sms = 0;
+            CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, &flat);
         }
         { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
         if (rc != 0 || flat.total > (size_t)max_smem)

@@ -318,7 +318,11 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
             const float ox = xf + P.mount_x * cy, oy = yf + P.mount_x * sy;
             const float maxr = P.max_range;
             uint32_t wdirty = 0;
+#if defined(CN_COMPACT_CODE)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int face = 0; face < 4; ++face) {      // 0: +x, 1: -x, 2: +y, 3: -y
                 const bool xface = face < 2;
                 const bool pos = (face & 1) == 0;

@@ -20,16 +20,18 @@
  *   phase 0   thread 0 issues the bulk TMA loads of the tile's three state
  *             planes + actions; meanwhile all threads pre-fill the observation
  *             rows with the no-return value (16-byte stores).
- *   phase 1   warps 0-1: lane = WORLD, the pose-only part of get_state /
+ *   phase 1   warps 0-2: lane = WORLD, the pose-only part of get_state /
  *             compute_reward (unicycle, waypoint, heading, distance, reward
- *             shaping, wall spans).  Other warps: item = PEDESTRIAN of the
- *             tile: timers; contact prefilter over packed coordinates; Philox
- *             only for the compacted list of pedestrians that resample (or are
- *             re-spawned) this step; integrate + wall clamp into a second copy
- *             of the position plane (Jacobi on the old one).
- *   phase 2   item = pedestrian: LiDAR candidate test -> compact candidate
- *             lists (per tile and per world); item = candidate: bearing,
- *             angular span, centre ray; every span (wall faces too) is cut into
+ *             shaping, wall spans; warp 2 only the new pose, early, for the
+ *             pedestrian side).  Other warps, concurrently: item = PEDESTRIAN
+ *             of the tile: timers; contact prefilter over packed coordinates;
+ *             Philox only for the compacted list of pedestrians that resample
+ *             (or are re-spawned) this step; integrate + wall clamp into a
+ *             second copy of the position plane (Jacobi on the old one), the
+ *             few pedestrians in contact again as a compacted list; then
+ *   phase 2   (same warps) item = pedestrian: LiDAR candidate test -> compact
+ *             candidate lists (per tile and per world); item = candidate:
+ *             bearing, angular span; every span (wall faces too) is cut into
  *             groups of <= 8 consecutive rays appended to a group list.
  *   phase 3   8 lanes per ray group: ray-disc / ray-face intersection with the
  *             oracle's per-ray arithmetic.  Whether the primitive OWNS the ray
@@ -50,6 +52,10 @@
  * primitives in the oracle's operation order; -fmad=false.  Approximate
  * arithmetic appears only in choosing (padded, conservative) span bounds.
  */
+// This kernel runs every piece of code once per tile: cold loops stay rolled and every ray helper has one call site,
+// which took the SASS from 144 KB to about 90 KB.  Turning the math helpers into real calls as well (CN_NOINLINE_BIG,
+// 76 KB) measured 5 % slower (c2 18.3 vs 17.2 us, c3 37.7 vs 35.9 us) and is left off.
+#define CN_COMPACT_CODE 1
 #include "cn_dev.h"
 
 #define CF_POSE_WARPS 2
@@ -71,13 +77,14 @@ enum {
     F_OVF_FACES,        // wall faces whose ray groups did not fit the group list
     F_NOBJ,             // objects of this world in the K block (entries of its object list)
     F_NCAND,            // LiDAR candidates of this world (entries of its candidate list)
-    F_WORDS = 48
+    F_EXI, F_EYI, F_ETH, F_EOFFX, F_EOFFY,      // new robot pose + sensor offset, published early by warp 2 (= S_XI ... S_OFFY)
+    F_WORDS = 52
 };
 #define XF_ACTIVE 1u    // the world is processed by this launch
 #define XF_RESET  2u    // ... as a reset (MODE 1, or next-step auto-reset)
 #define XF_EGO    4u    // an object's centre range < 0.140 (ENV:1000)
 
-enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_WORDS = 8 };
+enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_NCON, C_WORDS = 8 };
 
 // candidate record (8 words per pedestrian slot).  Phases 2-3: q (sensor-relative centre), bearing, span,
 // owned-ray count, centre ray.  Phase 5 puts the object's CP row for phase 6 into the words nobody else reads
@@ -93,11 +100,14 @@ enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY
 struct Ptrs {
     uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
     uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
-    uint16_t* olist; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
+    uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ int world_of(int idx, int N, uint32_t magic) {
     return (N == 1) ? idx : (int)__umulhi((uint32_t)idx, magic);
@@ -197,7 +207,7 @@ __device__ __forceinline__ bool ped_ray_eval(const cn_kparams& P, const Ptrs& S,
     bool own = true;
     const int j = NR - i;
     if ((sc[S_WDIRTY] >> min(j >> 5, 31)) & 1u) {
-#pragma unroll
+#pragma unroll 1
         for (int face = 0; face < 4; ++face) {
             Span ws; wall_span(sc, face, ws);
             if (!in_span(ws, i)) continue;
@@ -208,6 +218,7 @@ __device__ __forceinline__ bool ped_ray_eval(const cn_kparams& P, const Ptrs& S,
     const int nc = (int)sc[F_NCAND];
     if (nc > 1) {
         const uint8_t* cl = S.clw + w * N;
+#pragma unroll 1
         for (int k = 0; k < nc; ++k) {
             const int n2 = (int)cl[k];
             if (n2 == n) continue;
@@ -246,7 +257,7 @@ __device__ __forceinline__ void cast_wall(const cn_kparams& P, const Ptrs& S, in
     if (tw < 0.0f) return;
     const bool xface = face < 2;
     bool own = true;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 2; ++k) {                               // the faces of the other axis (x faces come first)
         const int f2 = (xface ? 2 : 0) + k;
         Span ws; wall_span(sc, f2, ws);
@@ -256,6 +267,7 @@ __device__ __forceinline__ void cast_wall(const cn_kparams& P, const Ptrs& S, in
     }
     const int nc = (int)sc[F_NCAND];
     const uint8_t* cl = S.clw + w * N;
+#pragma unroll 1
     for (int k = 0; k < nc; ++k) {
         const uint32_t* r2 = S.rec + (w * N + (int)cl[k]) * 8;
         Span s2; unpack_span(r2[Q_SPA], r2[Q_SPB], s2);
@@ -285,7 +297,7 @@ __device__ __forceinline__ void fill16(void* base, int n, uint32_t word, int tid
 __device__ __forceinline__ void copy16_out(void* gdst, const void* ssrc, int n, int t, int nthreads) {
     uint4* g = reinterpret_cast<uint4*>(gdst);
     const uint4* s = reinterpret_cast<const uint4*>(ssrc);
-#pragma unroll 4
+#pragma unroll 1
     for (int i = t; i < n; i += nthreads) g[i] = s[i];
 }
 
@@ -295,6 +307,7 @@ __global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 256 ? 4 : 8))
 cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
     constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
+    FSTAMP(14);
     const int W = L.W, N = P.n_peds, NR = P.n_samples - 1, D = P.d.obs_dim, K = P.k_obstacles;
     const int e0 = blockIdx.x * W;
     const int nE = min(W, P.n_envs - e0);
@@ -315,6 +328,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.clw = reinterpret_cast<uint8_t*>(smem + L.off_clw);
     S.rlist = reinterpret_cast<uint16_t*>(smem + L.off_rlist);
     S.olist = reinterpret_cast<uint16_t*>(smem + L.off_olist);
+    S.mark = smem + L.off_mark;
     S.wg = reinterpret_cast<uint32_t*>(smem + L.off_wg);
     S.pg = reinterpret_cast<uint32_t*>(smem + L.off_pg);
     S.cnt = reinterpret_cast<uint32_t*>(smem + L.off_cnt);
@@ -338,12 +352,15 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             tma_load(S.pa, P.ped_a + (size_t)e0 * N * 4, ped_bytes, S.bar);
             tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
         }
+        FSTAMP(15);
     }
     {
         const float fill = P.d.max_range_r3;                                // a ray with no return, already rounded
         const int tot = nE * D, n4 = tot >> 2;
         fill16<T>(S.obs, n4, u_of(fill), tid);
         if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+#pragma unroll 1
+        for (int i = tid; i < 2 * n_items; i += T) S.peers[i] = 0u;
         if (tid < C_WORDS) S.cnt[tid] = 0u;
         if (tid < nE) {
             uint32_t* sc = S.sc + tid * F_WORDS;
@@ -351,9 +368,11 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             sc[F_NOBJ] = 0u; sc[F_NCAND] = 0u;
         }
         if (P.dbg_ranges || P.dbg_hid) {                                    // debug taps (tests only): "no return" everywhere
+#pragma unroll 1
             for (int w = warp; w < nE; w += T / 32) {
                 if (MODE == 1 && P.mask && P.mask[e0 + w] == 0) continue;
                 const size_t base = (size_t)(e0 + w) * NR;
+#pragma unroll 1
                 for (int j = lane; j < NR; j += 32) {
                     if (P.dbg_ranges) P.dbg_ranges[base + j] = P.max_range;
                     if (P.dbg_hid) P.dbg_hid[base + j] = CN_HIT_NONE;
@@ -361,37 +380,68 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
     }
+    FSTAMP(3);
     __syncthreads();            // fills done, barrier init visible
     FSTAMP(11);
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
 
-    // ---------------------------------------------------------------- phase 1
+    // ---------------------------------------------------------------- phase 1 (+ 2)
     if (warp < CF_POSE_WARPS) {
-        // lane = world: everything get_state / compute_reward derive from the pose alone (cn_dev.h)
+        // lane = world: everything get_state / compute_reward derive from the pose alone (cn_dev.h), shared by two
+        // warps; warp 1 publishes the robot's new pose early for the pedestrian side and goes on
         const int part = warp;
-        for (int w = lane; w < nE; w += 32) {
-            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-            bool run = true, reset_now = (MODE == 1);
+        const int w = lane;
+        const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+        uint32_t* scl = S.sc + w * F_WORDS;
+        float* rowl = S.obs + (size_t)w * D;
+        bool run = false, reset_now = (MODE == 1);
+        PoseIn p; p.xi = 0; p.yi = 0; p.th = 0u; p.v = 0.0f; p.w = 0.0f;
+        int bad = 0;
+        if (w < nE) {
+            run = true;
             if (MODE == 1) run = !P.mask || P.mask[e0 + w] != 0;
             else reset_now = (rob[CN_R_FLAGS] & CN_RF_DONE) && (P.flags & CN_FLAG_AUTO_RESET);
-            uint32_t* scl = S.sc + w * F_WORDS;
-            float* rowl = S.obs + (size_t)w * D;
             if (part == 0) scl[F_XFLAGS] = (run ? XF_ACTIVE : 0u) | ((run && reset_now) ? XF_RESET : 0u);
-            if (!run) continue;
+            if (run) {
+                if (reset_now) { p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; }
+                else p = advance_robot(P, rob, act_smem ? S.act + 2 * w : P.action + 2 * (size_t)(e0 + w), bad);
+            }
+        }
+        if (part == 1) {
+            if (run) {
+                float sy, cy; cn_sincos_bin(p.th, &sy, &cy);
+                scl[F_EXI] = (uint32_t)p.xi; scl[F_EYI] = (uint32_t)p.yi; scl[F_ETH] = p.th;
+                scl[F_EOFFX] = u_of(P.mount_x * cy); scl[F_EOFFY] = u_of(P.mount_x * sy);
+            }
+            __threadfence_block();
+            named_bar_arrive(2, 32 + PED_THREADS);
+        }
+        if (run) {
+            // Z: Env.reset (ENV:1227-1263): spawn pose, waypoint = goal, unrounded previous_* (ENV:1243-1244); otherwise
+            // the episode state carried in the robot record
+            float wpx = P.goal_x, wpy = P.goal_y, pd, ph, ppx = 0.0f, ppy = 0.0f;
+            int stepc = 0;
             if (reset_now) {
-                // Z: Env.reset (ENV:1227-1263): spawn pose, waypoint = goal, unrounded previous_* (ENV:1243-1244)
-                PoseIn p; p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; p.v = 0.0f; p.w = 0.0f;
                 const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
-                const float pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);
-                const float ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
-                pose_scalars(P, p, part, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
+                pd = dist_to_wp(xf, yf, P.goal_x, P.goal_y);
+                ph = heading_to_wp(P, xf, yf, cn_bin2rad(p.th), P.goal_x, P.goal_y);
             } else {
-                int bad;
-                const PoseIn p = advance_robot(P, rob, act_smem ? S.act + 2 * w : P.action + 2 * (size_t)(e0 + w), bad);
-                pose_scalars(P, p, part, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
-                             f_of(rob[CN_R_PHEAD]), f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1,
-                             true, true, bad, scl, rowl);
+                wpx = f_of(rob[CN_R_WPX]); wpy = f_of(rob[CN_R_WPY]);
+                pd = f_of(rob[CN_R_PDIST]); ph = f_of(rob[CN_R_PHEAD]);
+                ppx = f_of(rob[CN_R_PPX]); ppy = f_of(rob[CN_R_PPY]);
+                stepc = (int)rob[CN_R_STEP] + 1;
+            }
+            pose_scalars(P, p, part, wpx, wpy, pd, ph, ppx, ppy, stepc, !reset_now, !reset_now, bad, scl, rowl);
+            if (part == 1) {                                                // this world's wall faces -> ray groups
+#pragma unroll 1
+                for (int face = 0; face < 4; ++face) {
+                    Span sp; wall_span(scl, face, sp);
+                    if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)(w * 4 + face), sp)) {
+                        atomicOr(&scl[F_OVF_FACES], 1u << face);
+                        S.cnt[C_OVF] = 1u;
+                    }
+                }
             }
         }
     } else {
@@ -401,26 +451,56 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         uint4* spa2_4 = reinterpret_cast<uint4*>(S.pa2);
         uint4* spb4 = reinterpret_cast<uint4*>(S.pb);
         const bool auto_reset = (P.flags & CN_FLAG_AUTO_RESET) != 0u;
+        const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
+        const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative contact box
+        const uint32_t lim2 = 2u * (uint32_t)lim_i;
+        uint16_t* slowlist = S.olist;                                       // the object list is not in use before phase 5
 
-        // -- alpha: timers, packed coordinates, who needs random numbers
+        // new position from the effective velocity, frictionless wall clamp, LiDAR candidate test (phase 2a)
+        auto finish_ped = [&](int it, int w, int32_t x0, int32_t y0, float vx, float vy, float vex, float vey) {
+            int32_t nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
+            int32_t ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
+            if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
+            if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
+            if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
+            if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
+            spa2_4[it] = make_uint4((uint32_t)nx, (uint32_t)ny, u_of(vx), u_of(vy));
+            return make_int2(nx, ny);
+        };
+        auto cand_test = [&](int it, int w, int32_t nx, int32_t ny) {
+            uint32_t* sc = S.sc + w * F_WORDS;
+            const float qx = (float)(nx - (int32_t)sc[F_EXI]) * CN_GRID - f_of(sc[F_EOFFX]);
+            const float qy = (float)(ny - (int32_t)sc[F_EYI]) * CN_GRID - f_of(sc[F_EOFFY]);
+            if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
+                const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
+                S.clist[pos] = (uint16_t)it;
+                const uint32_t k = atomicAdd(&sc[F_NCAND], 1u);
+                S.clw[w * N + k] = (uint8_t)(it - w * N);
+            }
+        };
+        auto in_contact = [&](int it, int w, int32_t x0, int32_t y0) {
+            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
+            const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
+            const bool near_robot = (uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2;
+            return near_robot || (S.peers[2 * it] | S.peers[2 * it + 1]) != 0u;
+        };
+
+        // -- A: timers; who draws random numbers; contact prefilter on the old positions
+        //    (each unordered pair once: partner = n + r mod N, r <= N/2)
         for (int it = ptid; it < n_items; it += PED_THREADS) {
             const int w = world_of(it, N, L.magic_n), n = it - w * N;
             const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
             bool active = true, respawn = (MODE == 1);
             if (MODE == 1) active = !P.mask || P.mask[e0 + w] != 0;
             else respawn = (rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset;
-            if (!active) { spa2_4[it] = spa4[it]; continue; }           // untouched world: state goes back as it came
+            if (!active) { spa2_4[it] = spa4[it]; S.mark[it] = 2; continue; }   // untouched world: state goes back as it came
             if (respawn) {
                 const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
                 S.rlist[pos] = (uint16_t)(it | 0x8000);
+                S.mark[it] = 1;
                 continue;
             }
-            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
-            // both coordinates in one word: 14-bit fields at 2^-8 m with a guard bit each (cn_derive bounds the room);
-            // the world's list is stored twice back to back so that "partner (n + r) mod N" is a plain offset
-            const uint32_t pk = (((a.x + 0x20000000u) >> 16) & 0x3FFFu) | ((((a.y + 0x20000000u) >> 16) & 0x3FFFu) << 16);
-            S.pk[2 * w * N + n] = pk; S.pk[2 * w * N + N + n] = pk;
-            S.peers[2 * it] = 0u; S.peers[2 * it + 1] = 0u;
+            uint8_t mk = 0;
             int32_t tm = (int32_t)S.pb[4 * it + 2] - CN_TICKS_PER_STEP;
             if (tm <= 0) {
                 const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + w);
@@ -429,6 +509,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 if (P.beh_kind[b] == CN_BEHAVIOR_RANDOM) {
                     const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
                     S.rlist[pos] = (uint16_t)it;
+                    mk = 1;
                 } else {
                     const float speed = P.beh_speed[b];
                     S.pa[4 * it + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
@@ -436,23 +517,18 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 }
             }
             S.pb[4 * it + 2] = (uint32_t)tm;
-        }
-        named_bar_sync(1, PED_THREADS);
-
-        // -- beta: contact prefilter (each unordered pair once: partner = n + r mod N, r <= N/2) ...
-        for (int it = ptid; it < n_items; it += PED_THREADS) {
-            const int w = world_of(it, N, L.magic_n), n = it - w * N;
-            const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-            if (MODE == 1) continue;                                        // a reset launch moves nobody
-            if ((rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset) continue;
-            const uint32_t* pp = S.pk + 2 * w * N + n;
-            const uint32_t pk_biased = (pp[0] | 0x80008000u) + 0x00400040u;
+            S.mark[it] = mk;
+            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
+            const uint32_t bx = a.x + (uint32_t)lim_i, by = a.y + (uint32_t)lim_i;
+            const uint32_t* pw = S.pa + 4 * w * N;
             const int half = N >> 1;
             uint32_t hits = 0u;
+            int m = n;
 #pragma unroll 5
             for (int r = 1; r <= half; ++r) {
-                const uint32_t d = (pk_biased - pp[r]) & 0xFF80FF80u;       // |dx|, |dy| < 0.25 m
-                hits |= (d == 0x80008000u) ? (1u << (r - 1)) : 0u;
+                m = (m + 1 >= N) ? m + 1 - N : m + 1;
+                const uint2 o = *reinterpret_cast<const uint2*>(pw + 4 * m);
+                hits |= ((bx - o.x) < lim2 && (by - o.y) < lim2) ? (1u << (r - 1)) : 0u;
             }
             while (hits) {                                                  // rare
                 const int r = __ffs(hits); hits &= hits - 1;
@@ -461,7 +537,26 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 atomicOr(&S.peers[2 * (w * N + partner) + (n >> 5)], 1u << (n & 31));
             }
         }
-        // ... and Philox for the compacted list of pedestrians that draw this step
+        // contact masks and the draw list are complete; pose warp 1 has published the robot's new pose
+        FSTAMP(4);
+        named_bar_sync(2, 32 + PED_THREADS);
+
+        // -- B: pedestrians with nothing special: integrate, candidate test.  Contacts go to the slow list.
+        if (MODE == 0) {
+            for (int it = ptid; it < n_items; it += PED_THREADS) {
+                if (S.mark[it] != 0) continue;
+                const int w = world_of(it, N, L.magic_n);
+                const uint4 a = spa4[it];
+                if (in_contact(it, w, (int32_t)a.x, (int32_t)a.y)) {
+                    const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
+                    slowlist[pos] = (uint16_t)it;
+                    continue;
+                }
+                const int2 np = finish_ped(it, w, (int32_t)a.x, (int32_t)a.y, f_of(a.z), f_of(a.w), f_of(a.z), f_of(a.w));
+                cand_test(it, w, np.x, np.y);
+            }
+        }
+        //    ... and the compacted list of pedestrians that draw this step: Philox, then the same
         {
             const int n_res = (int)S.cnt[C_NRES];
             for (int q = ptid; q < n_res; q += PED_THREADS) {
@@ -484,160 +579,147 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     yi = max(yi, P.d.ped_ymin); yi = min(yi, P.d.ped_ymax);
                     spa2_4[idx] = make_uint4((uint32_t)xi, (uint32_t)yi, u_of(0.0f), u_of(0.0f));
                     spb4[idx] = make_uint4(0u, 0u, (uint32_t)((nn + 1) * P.beh_stagger[bb]), 0u);
+                    cand_test(idx, ww, xi, yi);
                 } else {
                     const float speed = P.beh_speed[bb];
-                    S.pa[4 * idx + 2] = u_of(cn_usym(rnd.v[0], speed));
-                    S.pa[4 * idx + 3] = u_of(cn_usym(rnd.v[1], speed));
+                    const float vx = cn_usym(rnd.v[0], speed), vy = cn_usym(rnd.v[1], speed);
+                    const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * idx);
+                    if (in_contact(idx, ww, (int32_t)a.x, (int32_t)a.y)) {
+                        S.pa[4 * idx + 2] = u_of(vx); S.pa[4 * idx + 3] = u_of(vy);
+                        const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
+                        slowlist[pos] = (uint16_t)idx;
+                    } else {
+                        const int2 np = finish_ped(idx, ww, (int32_t)a.x, (int32_t)a.y, vx, vy, vx, vy);
+                        cand_test(idx, ww, np.x, np.y);
+                    }
                 }
             }
         }
         named_bar_sync(1, PED_THREADS);
 
-        // -- gamma: repulsion for the rare pairs found, integrate, frictionless wall clamp
+        // -- C: the few pedestrians with somebody inside the contact box: repulsion (index order, like the oracle)
         if (MODE == 0) {
-            const float rr2 = P.ped_radius + P.ped_radius, rrob = P.ped_radius + P.robot_radius;
-            const int32_t lim_i = (int32_t)((fmaxf(rr2, rrob) + P.rep_cutoff) * CN_INV_GRID) + 64;   // conservative prefilter
-            const uint32_t lim2 = 2u * (uint32_t)lim_i;
-            for (int it = ptid; it < n_items; it += PED_THREADS) {
+            const int n_con = (int)S.cnt[C_NCON];
+            for (int q = ptid; q < n_con; q += PED_THREADS) {
+                const int it = (int)slowlist[q];
                 const int w = world_of(it, N, L.magic_n);
                 const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-                if ((rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset) continue;
                 const uint4 a = spa4[it];
                 const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
-                float vx = f_of(a.z), vy = f_of(a.w);
-                float vex = vx, vey = vy;
-                const uint32_t p0 = S.peers[2 * it], p1 = S.peers[2 * it + 1];
-                if (p0 | p1) {                                              // index order, like the oracle
-                    for (uint32_t pm = p0; pm; pm &= pm - 1) {
-                        const int m = __ffs(pm) - 1;
-                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
-                        add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
-                    }
-                    for (uint32_t pm = p1; pm; pm &= pm - 1) {
-                        const int m = __ffs(pm) + 31;
-                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
-                        add_rep(P, x0, y0, (int32_t)o.x, (int32_t)o.y, rr2, vex, vey);
-                    }
-                }
+                float vex = f_of(a.z), vey = f_of(a.w);
                 const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
-                if ((uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2)
-                    add_rep(P, x0, y0, rxi, ryi, rrob, vex, vey);
-                int32_t nx = x0 + cn_f2i((vex * P.dt) * CN_INV_GRID);
-                int32_t ny = y0 + cn_f2i((vey * P.dt) * CN_INV_GRID);
-                if (nx < P.d.ped_xmin) { nx = P.d.ped_xmin; if (vx < 0.0f) vx = 0.0f; }
-                if (nx > P.d.ped_xmax) { nx = P.d.ped_xmax; if (vx > 0.0f) vx = 0.0f; }
-                if (ny < P.d.ped_ymin) { ny = P.d.ped_ymin; if (vy < 0.0f) vy = 0.0f; }
-                if (ny > P.d.ped_ymax) { ny = P.d.ped_ymax; if (vy > 0.0f) vy = 0.0f; }
-                spa2_4[it] = make_uint4((uint32_t)nx, (uint32_t)ny, u_of(vx), u_of(vy));
+                uint32_t p0 = S.peers[2 * it], p1 = S.peers[2 * it + 1];
+                bool robot_pending = (uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2;
+                while (p0 | p1 | (robot_pending ? 1u : 0u)) {               // pedestrians in index order, then the robot
+                    int32_t ox = rxi, oy = ryi;
+                    float rsum = rrob;
+                    if (p0 | p1) {
+                        int m;
+                        if (p0) { m = __ffs(p0) - 1; p0 &= p0 - 1; } else { m = __ffs(p1) + 31; p1 &= p1 - 1; }
+                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                        ox = (int32_t)o.x; oy = (int32_t)o.y; rsum = rr2;
+                    } else {
+                        robot_pending = false;
+                    }
+                    add_rep(P, x0, y0, ox, oy, rsum, vex, vey);
+                }
+                const int2 np = finish_ped(it, w, x0, y0, f_of(a.z), f_of(a.w), vex, vey);
+                cand_test(it, w, np.x, np.y);
             }
+            // every new position is in pa2, the candidate lists are complete, and nobody needs pa / peers any more
+            // (the candidate records reuse that memory)
+            named_bar_sync(1, PED_THREADS);
+        }
+        FSTAMP(13);
+
+        // ------------------------------------------------------------ phase 2b: bearing, span, ray groups
+        const int n_cand_p = (int)S.cnt[C_NCAND];
+        for (int q = ptid; q < n_cand_p; q += PED_THREADS) {
+            const int slot = (int)S.clist[q];
+            const int w = world_of(slot, N, L.magic_n);
+            const uint32_t* sc = S.sc + w * F_WORDS;
+            uint32_t* rec = S.rec + slot * 8;
+            const uint2 a = *reinterpret_cast<const uint2*>(S.pa2 + 4 * slot);
+            const float qx = (float)((int32_t)a.x - (int32_t)sc[F_EXI]) * CN_GRID - f_of(sc[F_EOFFX]);
+            const float qy = (float)((int32_t)a.y - (int32_t)sc[F_EYI]) * CN_GRID - f_of(sc[F_EOFFY]);
+            const float d2 = fmaf(qx, qx, qy * qy);
+            const uint32_t bearing = cn_rad2bin(cn_atan2(qy, qx));
+            float alpha = 4.0f;                                    // sensor inside / touching the disc: all rays
+            const float rlim = P.ped_radius * 1.001f;
+            if (d2 > rlim * rlim) {
+                const float u = P.ped_radius * rsqrtf(d2) * 1.0001f;   // asin(u) <= u + (pi/2 - 1) u^3
+                alpha = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
+            }
+            const Span sp = make_span(P, bearing - sc[F_ETH], alpha);
+            rec[Q_QX] = u_of(qx); rec[Q_QY] = u_of(qy);
+            rec[Q_BEAR] = bearing;
+            rec[Q_SPA] = (uint32_t)sp.a0 | ((uint32_t)sp.a1 << 16);
+            rec[Q_SPB] = (uint32_t)sp.b0 | ((uint32_t)sp.b1 << 16);
+            rec[Q_CNT] = 0u;
+            rec[Q_CKEY] = 0xFFFFFFFFu;
+            uint32_t misc = 0u;
+            if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
+                misc |= MISC_OVF;
+                S.cnt[C_OVF] = 1u;
+            }
+            rec[Q_MISC] = misc;
         }
     }
     FSTAMP(9);
-    __syncthreads();            // #A: new poses, scalar records, new pedestrian positions
+    __syncthreads();            // #A: scalar records, new pedestrian positions, candidate lists
     FSTAMP(2);
-
-    // ---------------------------------------------------------------- phase 2a
-    for (int it = tid; it < n_items; it += T) {
-        const int w = world_of(it, N, L.magic_n);
-        uint32_t* sc = S.sc + w * F_WORDS;
-        if (!(sc[F_XFLAGS] & XF_ACTIVE)) continue;
-        const uint2 a = *reinterpret_cast<const uint2*>(S.pa2 + 4 * it);
-        const float qx = (float)((int32_t)a.x - (int32_t)sc[S_XI]) * CN_GRID - f_of(sc[S_OFFX]);
-        const float qy = (float)((int32_t)a.y - (int32_t)sc[S_YI]) * CN_GRID - f_of(sc[S_OFFY]);
-        if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
-            const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
-            S.clist[pos] = (uint16_t)it;
-            const uint32_t k = atomicAdd(&sc[F_NCAND], 1u);
-            S.clw[w * N + k] = (uint8_t)(it - w * N);
-            uint32_t* rec = S.rec + it * 8;
-            rec[Q_QX] = u_of(qx); rec[Q_QY] = u_of(qy);
-            rec[Q_SPA] = 1u; rec[Q_SPB] = 1u;                               // empty span until phase 2b
-        }
-    }
-    for (int q = T - 1 - tid; q < nE * 4; q += T) {                         // wall faces, from the far end of the CTA
-        uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
-        if (!(sc[F_XFLAGS] & XF_ACTIVE)) continue;
-        Span sp; wall_span(sc, q & 3, sp);
-        if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)q, sp)) {
-            atomicOr(&sc[F_OVF_FACES], 1u << (q & 3));
-            S.cnt[C_OVF] = 1u;
-        }
-    }
-    __syncthreads();            // #B
-    FSTAMP(3);
     const int n_cand = (int)S.cnt[C_NCAND];
-
-    // ---------------------------------------------------------------- phase 2b
-    for (int q = tid; q < n_cand; q += T) {
-        const int slot = (int)S.clist[q];
-        const int w = world_of(slot, N, L.magic_n);
-        uint32_t* rec = S.rec + slot * 8;
-        const float qx = f_of(rec[Q_QX]), qy = f_of(rec[Q_QY]);
-        const float d2 = fmaf(qx, qx, qy * qy);
-        const uint32_t bearing = cn_rad2bin(cn_atan2(qy, qx));
-        float alpha = 4.0f;                                    // sensor inside / touching the disc: all rays
-        const float rlim = P.ped_radius * 1.001f;
-        if (d2 > rlim * rlim) {
-            const float u = P.ped_radius * rsqrtf(d2) * 1.0001f;   // asin(u) <= u + (pi/2 - 1) u^3
-            alpha = u * fmaf(0.5708f * u, u, 1.0f) + 0.01f;
-        }
-        const uint32_t rel = bearing - S.sc[w * F_WORDS + S_TH];
-        const Span sp = make_span(P, rel, alpha);
-        rec[Q_BEAR] = bearing;
-        rec[Q_SPA] = (uint32_t)sp.a0 | ((uint32_t)sp.a1 << 16);
-        rec[Q_SPB] = (uint32_t)sp.b0 | ((uint32_t)sp.b1 << 16);
-        rec[Q_CNT] = 0u;
-        rec[Q_CKEY] = 0xFFFFFFFFu;
-        uint32_t misc = 0u;
-        if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
-            misc |= MISC_OVF;
-            S.cnt[C_OVF] = 1u;
-        }
-        rec[Q_MISC] = misc;
-    }
-    __syncthreads();            // #C
-    FSTAMP(4);
     const int n_wg = min((int)S.cnt[C_NWG], (int)L.cap_wg);
     const int n_pg = min((int)S.cnt[C_NPG], (int)L.cap_pg);
     const bool overflow = S.cnt[C_OVF] != 0u;
     const int lane8 = tid & 7;
 
     // ---------------------------------------------------------------- phase 3: cast + ownership (L, C: XACRO:148-179, UTL:375-392)
-    for (int gi = tid >> 3; gi < n_wg; gi += T / 8) {
-        const uint32_t ent = S.wg[gi];
-        const int i = group_ray(ent, lane8);
-        if (i >= 0) cast_wall(P, S, e0, (int)(ent >> 14), i);
-    }
-    for (int g0 = warp * 4; g0 < n_pg; g0 += (T / 32) * 4) {                // warp-uniform trip count: ballots inside
-        const int gi = g0 + (lane >> 3);
-        bool owned = false;
-        int slot = 0;
-        if (gi < n_pg) {
-            const uint32_t ent = S.pg[gi];
-            const int i = group_ray(ent, lane8);
-            slot = (int)(ent >> 14);
-            if (i >= 0) owned = cast_ped(P, S, L.magic_n, e0, slot, i);
+    // source -1 is the group list; a source >= 0 is a primitive whose groups did not fit and is walked directly
+    // (one call site for both keeps the code small)
+#pragma unroll 1
+    for (int src = -1; src < (overflow ? nE * 4 : 0); ++src) {
+        int n_groups = n_wg;
+        Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
+        if (src >= 0) {
+            const uint32_t* sc = S.sc + (src >> 2) * F_WORDS;
+            if (!((sc[F_OVF_FACES] >> (src & 3)) & 1u)) continue;
+            wall_span(sc, src & 3, sp);
+            n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
         }
-        const uint32_t bm = __ballot_sync(FULL, owned);
-        const int c = __popc((bm >> (lane & 24)) & 0xFFu);
-        if (lane8 == 0 && c) atomicAdd(&S.rec[slot * 8 + Q_CNT], (uint32_t)c);
-    }
-    if (overflow) {             // primitives whose groups did not fit: the whole CTA walks each of them
-        for (int q = 0; q < nE * 4; ++q) {
-            const uint32_t* sc = S.sc + (q >> 2) * F_WORDS;
-            if (!((sc[F_OVF_FACES] >> (q & 3)) & 1u)) continue;
-            Span sp; wall_span(sc, q & 3, sp);
-            for (int pos = tid; pos < NR; pos += T) { const int i = span_ray(sp, pos); if (i >= 0) cast_wall(P, S, e0, q, i); }
+#pragma unroll 1
+        for (int g = tid >> 3; g < n_groups; g += T / 8) {
+            int q = src, i;
+            if (src < 0) { const uint32_t ent = S.wg[g]; i = group_ray(ent, lane8); q = (int)(ent >> 14); }
+            else i = span_ray(sp, g * 8 + lane8);
+            if (i >= 0) cast_wall(P, S, e0, q, i);
         }
-        for (int q = 0; q < n_cand; ++q) {
-            const int slot = (int)S.clist[q];
-            const uint32_t* rec = S.rec + slot * 8;
+    }
+#pragma unroll 1
+    for (int src = -1; src < (overflow ? n_cand : 0); ++src) {
+        int n_groups = n_pg, slot_src = 0;
+        Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
+        if (src >= 0) {
+            slot_src = (int)S.clist[src];
+            const uint32_t* rec = S.rec + slot_src * 8;
             if (!(rec[Q_MISC] & MISC_OVF)) continue;
-            Span sp; unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
-            for (int pos = tid; pos < NR; pos += T) {
-                const int i = span_ray(sp, pos);
-                if (i >= 0 && cast_ped(P, S, L.magic_n, e0, slot, i)) atomicAdd(&S.rec[slot * 8 + Q_CNT], 1u);
+            unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
+            n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
+        }
+#pragma unroll 1
+        for (int g0 = warp * 4; g0 < n_groups; g0 += (T / 32) * 4) {        // warp-uniform trip count: ballots inside
+            const int g = g0 + (lane >> 3);
+            bool owned = false;
+            int slot = slot_src;
+            if (g < n_groups) {
+                int i;
+                if (src < 0) { const uint32_t ent = S.pg[g]; i = group_ray(ent, lane8); slot = (int)(ent >> 14); }
+                else i = span_ray(sp, g * 8 + lane8);
+                if (i >= 0) owned = cast_ped(P, S, L.magic_n, e0, slot, i);
             }
+            const uint32_t bm = __ballot_sync(FULL, owned);
+            const int c = __popc((bm >> (lane & 24)) & 0xFFu);
+            if (lane8 == 0 && c) atomicAdd(&S.rec[slot * 8 + Q_CNT], (uint32_t)c);
         }
     }
     FSTAMP(10);
@@ -772,6 +854,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             if (n_seen > 0) {                                               // M: ENV:653-654, 998-1005
                 float ego_score = 0.0f, emax = -INFINITY;
                 const int n_obj = (int)sc[F_NOBJ];
+#pragma unroll 1
                 for (int k2 = 0; k2 < n_obj; ++k2) emax = fmaxf(emax, f_of(S.rec[(int)S.olist[w * N + k2] * 8 + O_TTC]));
                 if (n_obj > 0) ego_score = emax;                            // ENV:879
                 uint32_t ego = cnt0 & 0xFFFFu, soc = cnt0 >> 16;
@@ -824,6 +907,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         }
         if (bulk_obs) {
             copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
+#pragma unroll 1
             for (int p = 0; p < P.n_obs_peers; ++p)                         // fused all-gather over NVLink
                 copy16_out(P.obs_peers[p] + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
         }
@@ -836,6 +920,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         if (bulk_obs) {
             tma_store(P.obs + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
             // fused all-gather: the same tile goes straight into every peer's gather buffer over NVLink
+#pragma unroll 1
             for (int p = 0; p < P.n_obs_peers; ++p)
                 tma_store(P.obs_peers[p] + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
         }
@@ -843,14 +928,15 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         FSTAMP(8);
     }
     if (!bulk_obs) {             // plain coalesced stores (reset launches, unaligned or ragged tiles)
+#pragma unroll 1
         for (int w = warp; w < nE; w += T / 32) {
             if (!(S.sc[w * F_WORDS + F_XFLAGS] & XF_ACTIVE)) continue;
             const float* row = S.obs + (size_t)w * D;
-            float* g = P.obs + (size_t)(e0 + w) * D;
-            for (int k = lane; k < D; k += 32) g[k] = row[k];
-            for (int p = 0; p < P.n_obs_peers; ++p) {
-                float* gp = P.obs_peers[p] + (size_t)(e0 + w) * D;
-                for (int k = lane; k < D; k += 32) gp[k] = row[k];
+#pragma unroll 1
+            for (int p = -1; p < P.n_obs_peers; ++p) {                      // -1: this rank's buffer, then the peers'
+                float* g = (p < 0 ? P.obs : P.obs_peers[p]) + (size_t)(e0 + w) * D;
+#pragma unroll 1
+                for (int k = lane; k < D; k += 32) g[k] = row[k];
             }
         }
     }
@@ -875,19 +961,22 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->cap_pg = (uint32_t)W * 24u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
+    /* the candidate records (32 B per pedestrian, phases 2-6) reuse the old-position plane and the phase-1 scratch
+     * behind it (packed coordinates, contact masks), all dead by then */
+    L->off_rec = (uint32_t)o;
+    o += (size_t)W * N * 16;                        L->off_peers = (uint32_t)o;   /* 8 of 16 bytes per pedestrian */
+    L->off_pk = 0;
     o += (size_t)W * N * 16;                        L->off_pb = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_pa2 = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
     o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
     o = up16(o + (size_t)W * D * 4);                L->off_sc = (uint32_t)o;
-    o += (size_t)W * F_WORDS * 4;                   L->off_rec = (uint32_t)o;
-    L->off_pk = L->off_rec;                         /* phase-1 scratch lives where the candidate records go later */
-    L->off_peers = L->off_rec + (uint32_t)((size_t)W * N * 8);
-    o += (size_t)W * N * 32;                        L->off_clist = (uint32_t)o;
+    o += (size_t)W * F_WORDS * 4;                   L->off_clist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
     o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
-    o = up16(o + (size_t)W * N * 2);                L->off_wg = (uint32_t)o;
+    o = up16(o + (size_t)W * N * 2);                L->off_mark = (uint32_t)o;
+    o = up16(o + (size_t)W * N);                    L->off_wg = (uint32_t)o;
     o += (size_t)L->cap_wg * 4;                     L->off_pg = (uint32_t)o;
     o = up16(o + (size_t)L->cap_pg * 4);            L->off_cnt = (uint32_t)o;
     o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
@@ -896,19 +985,26 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     return 0;
 }
 
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, size_t smem_per_sm, cn_flat_layout* L) {
-    // 256-thread CTAs, four per SM: the largest tile (<= 16 worlds) whose shared memory allows that, preferring tiles
-    // whose row block can leave by bulk store.
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, cn_flat_layout* L) {
+    // 256-thread CTAs, four per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk store) that
+    // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
+    // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
     const int threads = 256, ctas = 4;
     const size_t budget = smem_per_sm / ctas - 1024;
-    int best = 0;
+    const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
+    int best = 0; double best_score = -1.0;
     for (int W = 16; W >= 1; --W) {
         cn_flat_layout t;
         if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, &t) != 0 || t.total > budget) continue;
         const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
-        if (!best) best = W;
-        if (bulk) { best = W; break; }
-        if (W < best - 3) break;
+        const long n_cta = ((long)n_envs + W - 1) / W;
+        const long waves = (n_cta + slots - 1) / slots;
+        double score;
+        if (waves == 1) score = 100.0 - W;                      /* one wave: the smaller the tile the better ... */
+        else score = (double)n_cta / (double)(waves * slots) + 0.002 * W;   /* ... else wave fill, then amortisation */
+        if (W < 4) score -= 50.0;                               /* tiny tiles waste the lane = world warps */
+        if (!bulk) score -= 10.0;
+        if (score > best_score) { best_score = score; best = W; }
     }
     if (!best) return -1;
     return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, L);

@@ -50,11 +50,11 @@ struct cn_flat_layout {
     uint32_t magic_n;           /* ceil(2^32 / N): world index of a flat pedestrian index by __umulhi */
     uint32_t cap_wg, cap_pg;    /* capacity of the wall / pedestrian ray-group lists */
     uint32_t off_pa, off_pb, off_pa2, off_act, off_obs, off_sc, off_rec, off_pk, off_peers,
-             off_clist, off_clw, off_rlist, off_olist, off_wg, off_pg, off_cnt, off_bar;
+             off_clist, off_clw, off_rlist, off_olist, off_mark, off_wg, off_pg, off_cnt, off_bar;
     uint32_t total;             /* dynamic shared memory per CTA */
 };
 int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L);
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, size_t smem_per_sm, cn_flat_layout* L);
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, cn_flat_layout* L);
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream);
 
 size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim);

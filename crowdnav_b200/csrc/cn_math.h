@@ -130,7 +130,7 @@ CN_HD_BIG float cn_py_round2(float x) { return cn_div100(cn_round_scaled(x, 100.
  * 45-degree bias); the polynomials are the classic single-precision minimax
  * kernels on [-pi/4, pi/4].
  */
-CN_HD_BIG void cn_sincos_bin(uint32_t a, float* s_out, float* c_out) {
+CN_HD void cn_sincos_bin_body(uint32_t a, float* s_out, float* c_out) {
     uint32_t q = (a + 0x20000000u) >> 30;
     int32_t  r = (int32_t)(a - (q << 30));          /* [-2^29, 2^29) */
     float x = (float)r * CN_BIN2RAD;
@@ -147,6 +147,19 @@ CN_HD_BIG void cn_sincos_bin(uint32_t a, float* s_out, float* c_out) {
     }
 }
 
+#if defined(__CUDACC__) && defined(CN_NOINLINE_BIG)
+/* as a real call the two results travel in registers (a struct by value), not through the stack */
+typedef struct { float s, c; } cn_sincos_t;
+static __host__ __device__ __noinline__ cn_sincos_t cn_sincos_bin_call(uint32_t a) {
+    cn_sincos_t r; cn_sincos_bin_body(a, &r.s, &r.c); return r;
+}
+CN_HD void cn_sincos_bin(uint32_t a, float* s_out, float* c_out) {
+    cn_sincos_t r = cn_sincos_bin_call(a); *s_out = r.s; *c_out = r.c;
+}
+#else
+CN_HD_BIG void cn_sincos_bin(uint32_t a, float* s_out, float* c_out) { cn_sincos_bin_body(a, s_out, c_out); }
+#endif
+
 /* radians -> binary angle, any finite |x| < 2^31 / RAD2BIN handled by int64 wrap */
 CN_HD uint32_t cn_rad2bin(float x) {
     return (uint32_t)(uint64_t)cn_f2ll(x * CN_RAD2BIN);
@@ -155,7 +168,7 @@ CN_HD uint32_t cn_rad2bin(float x) {
 CN_HD float cn_bin2rad(uint32_t a) { return (float)(int32_t)a * CN_BIN2RAD; }
 
 /* sin/cos of a float radian argument (|x| up to a few hundred) */
-CN_HD_BIG void cn_sincos_rad(float x, float* s_out, float* c_out) {
+CN_HD void cn_sincos_rad(float x, float* s_out, float* c_out) {
     float k = rintf(x * CN_INV_TWO_PI);
     float r = fmaf(-k, 6.28318548202514648f, x);        /* hi part of 2*pi (float) */
     r = fmaf(-k, -1.74845553146951715e-07f, r);         /* 2*pi - hi */

@@ -17,7 +17,7 @@ E = cfg.n_envs
 W = env.kernel_tile
 print("kernel", env.kernel_name, "tile", W)
 n_cta = (E + W - 1) // W
-tl = torch.zeros((n_cta * 16, 16), dtype=torch.int64, device="cuda")
+tl = torch.zeros((n_cta * 16 + 16, 16), dtype=torch.int64, device="cuda")
 env.reset()
 a = torch.zeros((E, 2), device="cuda"); a[:, 0] = 0.15; a[:, 1] = torch.rand(E, device="cuda") * 2 - 1
 for _ in range(30):
@@ -25,18 +25,18 @@ for _ in range(30):
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 L.cn_debug_set_timeline_flat.argtypes = [C.c_void_p]
 assert L.cn_debug_set_timeline_flat(C.c_void_p(tl.data_ptr())) == 0
-names = {0: "cta start", 11: "fills done (bar #0)", 1: "tma landed", 9: "phase 1 done (per warp)", 2: "after #A", 3: "after #B (2a)",
-         4: "after #C (2b)", 10: "phase 3 done (per warp)", 5: "after #E", 6: "after #F (5)", 12: "phase 6 done (per warp)",
+names = {14: "kernel entry", 15: "tma issued (thread 0)", 3: "fills done (per warp)", 4: "ped A done (ped warps)", 0: "pointers set up", 11: "fills done (bar #0)", 1: "tma landed", 13: "peds integrated (ped warps)", 9: "phase 1+2 done (per warp)",
+         2: "after #A", 10: "phase 3 done (per warp)", 5: "after #E", 6: "after #F (5)", 12: "phase 6 done (per warp)",
          7: "after #G", 8: "stores drained (thread 0)"}
-order = [0, 11, 1, 9, 2, 3, 4, 10, 5, 6, 12, 7, 8]
+order = [14, 0, 15, 3, 11, 1, 4, 13, 9, 2, 10, 5, 6, 12, 7, 8]
 for it in range(4):
     tl.zero_()
     (flush.fill_(it) if os.environ.get("CN_NOFLUSH") is None else None); torch.cuda.synchronize()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record(); env.step(a); s1.record(); torch.cuda.synchronize()
     t = tl.cpu().numpy().astype(np.int64)
-    t = t[t[:, 0] > 0]
-    t0 = t[:, 0].min()
+    t = t[t[:, 14] > 0]
+    t0 = t[:, 14].min()
     rel = (t - t0) / 1000.0
     span = (t.max() - t0) / 1000.0
     print("iter %d: event %.1f us; kernel span by globaltimer %.1f us; warps stamped %d" % (it, s0.elapsed_time(s1) * 1e3, span, len(t)))
@@ -45,6 +45,6 @@ for it in range(4):
         m = t[:, k] > 0
         if not m.any(): continue
         c = rel[m, k]
-        d = (t[m, k] - t[m, 0]) / 1000.0     # since this warp's CTA start
+        d = (t[m, k] - t[m, 14]) / 1000.0    # since this warp's kernel entry
         print("   %-28s abs: med %6.2f max %6.2f | since CTA start: min %5.2f med %5.2f p90 %5.2f max %5.2f" % (
             names[k], np.median(c), c.max(), d.min(), np.median(d), np.percentile(d, 90), d.max()))
