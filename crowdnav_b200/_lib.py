@@ -83,6 +83,7 @@ def load() -> C.CDLL:
     L.cn_kernel_name.restype = C.c_char_p
     L.cn_kernel_name.argtypes = [vp]
     L.cn_kernel_tile.argtypes = [vp]
+    L.cn_plan_tile.argtypes = [C.POINTER(CnConfig), i32, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]
     _lib = L
     return L
 
@@ -95,6 +96,6 @@ def check(rc: int, what: str) -> None:
 
 ABI_SYMBOLS = [
     "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_gather",
-    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile",
+    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile", "cn_plan_tile",
     "cn_last_error", "cn_abi_version",
 ]

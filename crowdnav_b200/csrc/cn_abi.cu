@@ -291,4 +291,15 @@ int64_t cn_launch_count(const cn_handle* h) { return h ? h->launches : 0; }
 const char* cn_kernel_name(const cn_handle* h) { return (h && !h->use_flat) ? "cn_env_kernel" : "cn_flat_kernel"; }
 int cn_kernel_tile(const cn_handle* h) { return !h ? 0 : (h->use_flat ? h->flat.W : CN_TILE); }
 
+int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes) {
+    if (!cfg || !tile || !threads || !smem_bytes) return fail(CN_ERR_INVALID, "cn_plan_tile: null argument%s", NULL);
+    cn_derived d;
+    if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_plan_tile: config out of range%s", NULL);
+    cn_flat_layout L; memset(&L, 0, sizeof(L));
+    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, &L) != 0)
+        return fail(CN_ERR_UNSUPPORTED, "cn_plan_tile: no tile fits%s", NULL);
+    *tile = L.W; *threads = L.threads; *smem_bytes = L.total;
+    return CN_OK;
+}
+
 }  /* extern "C" */

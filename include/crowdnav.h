@@ -172,6 +172,9 @@ int64_t cn_launch_count(const cn_handle* h);
  * the number of worlds per CTA it uses.  For benchmarks and profiles; results are bit-identical. */
 const char* cn_kernel_name(const cn_handle* h);
 int cn_kernel_tile(const cn_handle* h);
+/* Host-only planning query (no GPU needed): the tile (worlds per CTA), CTA size and dynamic shared memory the default
+ * step kernel would use for this config on a device with n_sms SMs and smem_per_sm bytes of shared memory per SM. */
+int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes);
 
 const char* cn_last_error(void);
 int cn_abi_version(void);

@@ -238,3 +238,34 @@ def test_cuda_graph_capture_of_cn_step():
     torch.cuda.synchronize()
     assert bits_equal(g.obs.cpu().numpy(), o.obs) and bits_equal(g.get_state_blob(), o.blob)
     g.close()
+
+
+@pytest.mark.parametrize("kernel", ["warp", "flat"])
+def test_both_step_kernels_against_the_oracle(kernel, monkeypatch):
+    """The library carries two independent step kernels (cn_flat.cu: compacted work lists, the default;
+    cn_step.cu: one warp per world, CN_KERNEL=warp).  Each must match the oracle bit for bit on a rollout that
+    exercises auto-reset, contacts, walls and the K block -- and therefore each other."""
+    monkeypatch.setenv("CN_KERNEL", kernel)
+    cfg = make_config(n_envs=150, auto_reset=True, layout_jitter=0.05)
+    torch, g, o = _mk(cfg)
+    assert g.kernel_name == {"warp": "cn_env_kernel", "flat": "cn_flat_kernel"}[kernel]
+    g.close()
+    n_done = _rollout(cfg, 120, seed=51)
+    assert n_done > 0
+    n_done = _rollout(baseline_config(4, n_envs=96, auto_reset=True), 40, seed=52)     # 50 pedestrians, 720 rays, K = 16
+
+
+@pytest.mark.parametrize("tile", ["2,256", "5,256", "16,256", "6,128", "20,512"])
+def test_flat_kernel_tile_shapes(tile, monkeypatch):
+    """Tile size / CTA size are launch parameters of the flat kernel, not part of the result: odd tiles (rows leave by
+    plain stores), ragged last tiles, several pedestrian passes per thread, group-list overflow (all worlds start next
+    to two walls in the 3 m room) -- all bit-exact."""
+    monkeypatch.setenv("CN_KERNEL", "flat")
+    monkeypatch.setenv("CN_FLAT_TILE", tile)
+    cfg = make_config(n_envs=77, auto_reset=True, layout_jitter=0.05)
+    torch, g, o = _mk(cfg)
+    assert g.kernel_tile == int(tile.split(",")[0])
+    g.close()
+    _rollout(cfg, 60, seed=53)
+    monkeypatch.setenv("CN_FLAT_STORE", "plain")
+    _rollout(baseline_config(1, n_envs=130, auto_reset=True), 30, seed=54)
