@@ -275,16 +275,18 @@ def main():
         for i in range(n):
             if do_flush:
                 flush.fill_(float(i))
-            s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             a = policy(senv.obs_local) if args.with_policy else ring[i % 16]
             if world > 1:
                 senv.begin_step()
             env.step(a)                 # the kernel (in fused mode it also stores the rows into the peers)
             s1.record()
+            s2 = s1                     # single GPU: the step IS the kernel launch, nothing follows it
             if world > 1:
                 senv.gather()           # ncclAllGather, or just the cross-rank barrier in fused mode
-            s2.record()
+                s2 = torch.cuda.Event(enable_timing=True)
+                s2.record()
             if timed:
                 evs.append((s0, s1, s2))
         # pipelined gather (fused mode): the last barriers finish after the last step's events
