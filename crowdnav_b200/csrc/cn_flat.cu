@@ -84,7 +84,7 @@ enum {
 #define XF_RESET  2u    // ... as a reset (MODE 1, or next-step auto-reset)
 #define XF_EGO    4u    // an object's centre range < 0.140 (ENV:1000)
 
-enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_NCON, C_WORDS = 8 };
+enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_NCON, C_NOBJ, C_WORDS = 8 };
 
 // candidate record (8 words per pedestrian slot).  Phases 2-3: q (sensor-relative centre), bearing, span,
 // owned-ray count, centre ray.  Phase 5 puts the object's CP row for phase 6 into the words nobody else reads
@@ -345,14 +345,21 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         mbar_init(S.bar, 1);
         fence_mbar_init();
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
-        mbar_expect_tx(S.bar, rob_bytes + 2u * ped_bytes + act_bytes);
+        mbar_expect_tx(S.bar, rob_bytes + 3u * ped_bytes + act_bytes);
         if (act_bytes) tma_load(S.act, P.action + 2 * (size_t)e0, act_bytes, S.bar);
         tma_load(S.robot, P.robot + (size_t)e0 * CN_ROBOT_WORDS, rob_bytes, S.bar);
-        if (ped_bytes) {
-            tma_load(S.pa, P.ped_a + (size_t)e0 * N * 4, ped_bytes, S.bar);
-            tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
-        }
+        if (ped_bytes) tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
         FSTAMP(15);
+    }
+    if (warp == 0 && N > 0) {
+        // the old-position plane lands TWICE per world, back to back: "pedestrian (n + r) mod N" of the contact
+        // prefilter is then a plain offset from pedestrian n (lane = world issues its two copies)
+        __syncwarp();                                   // after thread 0's expect_tx
+        for (int w = lane; w < nE; w += 32) {
+            const uint32_t* src = P.ped_a + (size_t)(e0 + w) * N * 4;
+            tma_load(S.pa + (size_t)(2 * w) * N * 4, src, (uint32_t)N * 16u, S.bar);
+            tma_load(S.pa + (size_t)(2 * w + 1) * N * 4, src, (uint32_t)N * 16u, S.bar);
+        }
     }
     {
         const float fill = P.d.max_range_r3;                                // a ray with no return, already rounded
@@ -493,7 +500,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             bool active = true, respawn = (MODE == 1);
             if (MODE == 1) active = !P.mask || P.mask[e0 + w] != 0;
             else respawn = (rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset;
-            if (!active) { spa2_4[it] = spa4[it]; S.mark[it] = 2; continue; }   // untouched world: state goes back as it came
+            if (!active) { spa2_4[it] = spa4[it + w * N]; S.mark[it] = 2; continue; }  // untouched world: state goes back as it came
             if (respawn) {
                 const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
                 S.rlist[pos] = (uint16_t)(it | 0x8000);
@@ -512,26 +519,24 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     mk = 1;
                 } else {
                     const float speed = P.beh_speed[b];
-                    S.pa[4 * it + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
-                    S.pa[4 * it + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
+                    S.pa[4 * (it + w * N) + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
+                    S.pa[4 * (it + w * N) + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
                 }
             }
             S.pb[4 * it + 2] = (uint32_t)tm;
             S.mark[it] = mk;
-            const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
+            const uint32_t* pp = S.pa + 4 * (it + w * N);                   // pedestrian n of the doubled list
+            const uint2 a = *reinterpret_cast<const uint2*>(pp);
             const uint32_t bx = a.x + (uint32_t)lim_i, by = a.y + (uint32_t)lim_i;
-            const uint32_t* pw = S.pa + 4 * w * N;
             const int half = N >> 1;
             uint32_t hits = 0u;
-            int m = n;
 #pragma unroll 5
             for (int r = 1; r <= half; ++r) {
-                m = (m + 1 >= N) ? m + 1 - N : m + 1;
-                const uint2 o = *reinterpret_cast<const uint2*>(pw + 4 * m);
-                hits |= ((bx - o.x) < lim2 && (by - o.y) < lim2) ? (1u << (r - 1)) : 0u;
+                const uint2 o = *reinterpret_cast<const uint2*>(pp + 4 * r);
+                hits = (hits << 1) | (((bx - o.x) < lim2 && (by - o.y) < lim2) ? 1u : 0u);      // round r -> bit half - r
             }
             while (hits) {                                                  // rare
-                const int r = __ffs(hits); hits &= hits - 1;
+                const int r = half + 1 - __ffs(hits); hits &= hits - 1;
                 const int partner = (n + r >= N) ? n + r - N : n + r;
                 atomicOr(&S.peers[2 * it + (partner >> 5)], 1u << (partner & 31));
                 atomicOr(&S.peers[2 * (w * N + partner) + (n >> 5)], 1u << (n & 31));
@@ -546,7 +551,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             for (int it = ptid; it < n_items; it += PED_THREADS) {
                 if (S.mark[it] != 0) continue;
                 const int w = world_of(it, N, L.magic_n);
-                const uint4 a = spa4[it];
+                const uint4 a = spa4[it + w * N];
                 if (in_contact(it, w, (int32_t)a.x, (int32_t)a.y)) {
                     const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
                     slowlist[pos] = (uint16_t)it;
@@ -583,9 +588,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 } else {
                     const float speed = P.beh_speed[bb];
                     const float vx = cn_usym(rnd.v[0], speed), vy = cn_usym(rnd.v[1], speed);
-                    const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * idx);
+                    const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * (idx + ww * N));
                     if (in_contact(idx, ww, (int32_t)a.x, (int32_t)a.y)) {
-                        S.pa[4 * idx + 2] = u_of(vx); S.pa[4 * idx + 3] = u_of(vy);
+                        S.pa[4 * (idx + ww * N) + 2] = u_of(vx); S.pa[4 * (idx + ww * N) + 3] = u_of(vy);
                         const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
                         slowlist[pos] = (uint16_t)idx;
                     } else {
@@ -604,7 +609,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 const int it = (int)slowlist[q];
                 const int w = world_of(it, N, L.magic_n);
                 const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-                const uint4 a = spa4[it];
+                const uint4 a = spa4[it + w * N];
                 const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
                 float vex = f_of(a.z), vey = f_of(a.w);
                 const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
@@ -616,7 +621,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     if (p0 | p1) {
                         int m;
                         if (p0) { m = __ffs(p0) - 1; p0 &= p0 - 1; } else { m = __ffs(p1) + 31; p1 &= p1 - 1; }
-                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (2 * w * N + m));
                         ox = (int32_t)o.x; oy = (int32_t)o.y; rsum = rr2;
                     } else {
                         robot_pending = false;
@@ -797,22 +802,22 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         rec[O_CP] = u_of(cp); rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);   // x, y: ped_b
         const uint32_t k = atomicAdd(&sc[F_NOBJ], 1u);                      // the world's object list (any order)
         S.olist[w * N + k] = (uint16_t)slot;
+        S.rlist[atomicAdd(&S.cnt[C_NOBJ], 1u)] = (uint16_t)slot;            // ... and the tile's (the draw list is long gone)
     }
     __syncthreads();            // #F
     FSTAMP(6);
 
     // ---------------------------------------------------------------- phase 6
     // 6a  K: top-K block (ENV:862-907): stable rank by CP among the world's objects, keep [-K:]; padding is in the row
-    //     (item = object: entry k of world w's list, flattened over the tile)
+    //     (item = object of the tile's compacted object list)
     constexpr int T6 = T - 32;                                              // the last warp does 6c meanwhile
-    for (int q = tid; q < n_items && tid < T6; q += T6) {
-        const int w = world_of(q, N, L.magic_n), k = q - w * N;
+    const int n_obj_tile = (int)S.cnt[C_NOBJ];
+    for (int q = tid; q < n_obj_tile && tid < T6; q += T6) {
+        const int slot = (int)S.rlist[q];
+        const int w = world_of(slot, N, L.magic_n), n = slot - w * N;
         const int n_obj = (int)S.sc[w * F_WORDS + F_NOBJ];
-        if (k >= n_obj) continue;
         const uint16_t* ol = S.olist + w * N;
-        const int slot = (int)ol[k];
         const uint32_t* rec = S.rec + slot * 8;
-        const int n = slot - w * N;
         const float my_cp = f_of(rec[O_CP]);
         int rank = 0;
         for (int k2 = 0; k2 < n_obj; ++k2) {
@@ -968,17 +973,17 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->cap_pg = (uint32_t)W * 24u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
-    /* the candidate records (32 B per pedestrian, phases 2-6) reuse the old-position plane and the phase-1 scratch
-     * behind it (packed coordinates, contact masks), all dead by then */
+    /* the old-position plane is loaded twice per world (2 x 16 B per pedestrian); the candidate records (32 B per
+     * pedestrian, phases 2-6) reuse exactly that memory, dead by then */
     L->off_rec = (uint32_t)o;
-    o += (size_t)W * N * 16;                        L->off_peers = (uint32_t)o;   /* 8 of 16 bytes per pedestrian */
     L->off_pk = 0;
-    o += (size_t)W * N * 16;                        L->off_pb = (uint32_t)o;
+    o += (size_t)W * N * 32;                        L->off_pb = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_pa2 = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
     o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
     o = up16(o + (size_t)W * D * 4);                L->off_sc = (uint32_t)o;
-    o += (size_t)W * F_WORDS * 4;                   L->off_clist = (uint32_t)o;
+    o += (size_t)W * F_WORDS * 4;                   L->off_peers = (uint32_t)o;
+    o += (size_t)W * N * 8;                         L->off_clist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
     o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
