@@ -22,6 +22,7 @@ CN_MAX_PEDS = 64
 CN_MAX_BEHAVIORS = 8
 CN_FLAG_AUTO_RESET = 1
 CN_FLAG_TOPK_HIGHEST = 2
+CN_FLAG_ENV_ORIGINAL = 4     # environment_stage_1_original.py: 363-wide row, goal-relative, its own reward
 CN_BEHAVIOR_RANDOM = 0
 CN_BEHAVIOR_TABLE = 1
 TICKS_PER_STEP = 3
@@ -81,7 +82,9 @@ class CnConfig(C.Structure):
     # -- convenience ---------------------------------------------------------
     @property
     def obs_dim(self) -> int:
-        """(R-1) + 7 + 4K, start_td3_training.py:88."""
+        """(R-1) + 7 + 4K, start_td3_training.py:88; (R-1) + 4 for the original environment's row."""
+        if self.flags & CN_FLAG_ENV_ORIGINAL:
+            return (self.n_samples - 1) + 4
         return (self.n_samples - 1) + 7 + 4 * self.k_obstacles
 
     @property
@@ -205,12 +208,20 @@ def make_config(
     dt: float = 0.15,
     wheel_accel: float = 0.0,
     n_substeps: int = 1,
+    env_original: bool = False,
 ) -> CnConfig:
     """Build a config; defaults are the reference's TRAINING world
     (CFG:1-18, WORLD, put_robot_in_world_training.launch:3-8)."""
     cfg = CnConfig()
     cfg.struct_size = C.sizeof(CnConfig)
     cfg.flags = (CN_FLAG_AUTO_RESET if auto_reset else 0) | (CN_FLAG_TOPK_HIGHEST if topk_highest else 0)
+    if env_original:
+        # environment_stage_1_original.py: row = [ranges | heading, distance to the goal | x, y] (original:315-318), the
+        # heading has no starting_pose term (original:246-260), an episode ends below 0.105 m (original:282)
+        cfg.flags |= CN_FLAG_ENV_ORIGINAL
+        k_obstacles, heading_offset = 0, (0.0, 0.0)
+        if collision_range == 0.12:
+            collision_range = 0.105
     cfg.n_envs, cfg.n_peds, cfg.n_samples, cfg.k_obstacles = n_envs, n_peds, n_samples, k_obstacles
     cfg.max_steps = max_steps
     cfg.env_id_offset = env_id_offset

@@ -83,6 +83,7 @@ int cn_config_default(cn_config* c) {
 
 int cn_obs_dim(const cn_config* c) {
     if (!c) return fail(CN_ERR_INVALID, "cn_obs_dim: null config%s", NULL);
+    if (c->flags & CN_FLAG_ENV_ORIGINAL) return (c->n_samples - 1) + 4;
     return (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
 }
 
@@ -107,6 +108,8 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     const char* kern = getenv("CN_KERNEL");
     const int use_flat = !(kern && strcmp(kern, "warp") == 0);
     cn_flat_layout flat; memset(&flat, 0, sizeof(flat));
+    if (!use_flat && (cfg->flags & CN_FLAG_ENV_ORIGINAL))
+        return fail(CN_ERR_UNSUPPORTED, "cn_create: CN_FLAG_ENV_ORIGINAL needs the default kernel (unset CN_KERNEL)%s", NULL);
     if (use_flat) {
         /* CN_FLAT_TILE=W[,threads] overrides the automatic choice (experiments) */
         const char* tile = getenv("CN_FLAT_TILE");

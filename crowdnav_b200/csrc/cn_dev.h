@@ -258,7 +258,21 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
     const int NR = P.n_samples - 1, K = P.k_obstacles;
     const float xf = (float)p.xi * CN_GRID, yf = (float)p.yi * CN_GRID;
     const float yaw = cn_bin2rad(p.th);
-    if (part == 0) {
+    const bool original = (P.flags & CN_FLAG_ENV_ORIGINAL) != 0u;
+    if (part == 0 && original) {
+        // the ORIGINAL environment (environment_stage_1_original.py:278-322): distance / heading to the goal itself;
+        // compute_reward (original:324-410) reads state[-1], state[-2] -- the robot's y and x (sic) -- as "distance"
+        // and "heading", has no step penalty and no waypoint bonus
+        const float dist = cn_py_round2(dist_to_wp(xf, yf, P.goal_x, P.goal_y));
+        const float head = cn_py_round2(heading_to_wp(P, xf, yf, yaw, P.goal_x, P.goal_y));
+        const float px = cn_py_round3(xf), py = cn_py_round3(yf);
+        sc[S_WPX] = u_of(P.goal_x); sc[S_WPY] = u_of(P.goal_y);
+        sc[S_HEAD] = u_of(head); sc[S_DIST] = u_of(dist);
+        sc[S_NPDIST] = u_of(is_step ? py : prev_dist); sc[S_NPHEAD] = u_of(is_step ? px : prev_head);
+        sc[S_REWARD] = (uint32_t)(is_step ? shaping_reward(px, py, prev_head, prev_dist) + 2 : 0);
+        row[NR + 0] = head; row[NR + 1] = dist;
+    }
+    if (part == 0 && !original) {
         // A: waypoint / distance / heading (ENV:246-265); the refresh target depends only on (pose, goal)
         float nwx, nwy;
         waypoint(P, xf, yf, nwx, nwy);
@@ -304,8 +318,10 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         sc[S_AVEL] = u_of(agent_vel);
         sc[S_BAD] = (uint32_t)bad;
         row[NR + 2] = pcx; row[NR + 3] = pcy;
-        row[NR + 4] = cn_py_round3(yaw);
-        row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
+        if (!original) {
+            row[NR + 4] = cn_py_round3(yaw);
+            row[NR + 5] = cn_py_round3(avx); row[NR + 6] = cn_py_round3(avy);
+        }
     }
     if (part == 1) {
         uint32_t pre = 0;
@@ -344,7 +360,7 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         // K-block padding (ENV:866-876, 895-898): [x, y, 0, 0] with the UNROUNDED pose, then np.around
         const float padx = cn_np_round3(xf), pady = cn_np_round3(yf);
         float* b = row + NR + 7;                                  // 16-B alignment is not guaranteed: scalar stores
-        for (int s = 0; s < K; ++s) { b[4 * s] = padx; b[4 * s + 1] = pady; b[4 * s + 2] = 0.0f; b[4 * s + 3] = 0.0f; }
+        for (int s = 0; s < (original ? 0 : K); ++s) { b[4 * s] = padx; b[4 * s + 1] = pady; b[4 * s + 2] = 0.0f; b[4 * s + 3] = 0.0f; }
     }
 }
 

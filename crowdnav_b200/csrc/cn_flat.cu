@@ -185,7 +185,8 @@ __device__ __forceinline__ float wall_t(const cn_kparams& P, const uint32_t* sc,
 // A ray the primitive owns gets its final value: UTL:375-392 (sensor minimum) + np.around (ENV:1042); ENV:1012 min
 __device__ __forceinline__ void finish_ray(const cn_kparams& P, const Ptrs& S, int w, int e, int j, float t, uint8_t hid) {
     const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
-    S.obs[(size_t)w * P.d.obs_dim + j] = cn_np_round3(rr);
+    // nobonus env: np.around of the whole row (ENV:1042); original env: Python round per ray (original:313)
+    S.obs[(size_t)w * P.d.obs_dim + j] = (P.flags & CN_FLAG_ENV_ORIGINAL) ? cn_py_round3(rr) : cn_np_round3(rr);
     atomicMin(S.sc + w * F_WORDS + F_MINBITS, u_of(rr));
     if (P.dbg_ranges) P.dbg_ranges[(size_t)e * (P.n_samples - 1) + j] = rr;
     if (P.dbg_hid) P.dbg_hid[(size_t)e * (P.n_samples - 1) + j] = hid;

@@ -120,7 +120,8 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->inv_cp_span = (float)(1.0 / ((double)c->max_range - (double)c->collision_range));
     d->max_range_r3 = cn_np_round3(c->max_range);
     if (d->max_range_r3 != c->max_range) return -1;   /* the no-return value must be a whole number of millimetres */
-    d->obs_dim = (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
+    if ((c->flags & CN_FLAG_ENV_ORIGINAL) && c->k_obstacles != 0) return -1;
+    d->obs_dim = (c->flags & CN_FLAG_ENV_ORIGINAL) ? (c->n_samples - 1) + 4 : (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
     {
         double lim = (double)(c->ped_radius + (c->ped_radius > c->robot_radius ? c->ped_radius : c->robot_radius))
                      + c->rep_cutoff + 1e-4;

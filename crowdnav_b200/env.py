@@ -104,3 +104,31 @@ class Env:
     def shutdown(self) -> None:
         """ENV:170-173: publish a zero twist.  Nothing to stop here."""
         return None
+
+
+class EnvOriginal(Env):
+    """``Env`` of turtlebot3_rl_sim/src/environment_stage_1_original.py (the reference's first environment: DQN /
+    tabular drivers, the 363-wide TD3 / DDPG ``trajectory_test`` checkpoints): row = [359 ranges | heading, distance
+    to the goal | x, y], reward = progress terms + terminal (original:324-410), discrete actions 0/1/2 =
+    (0.22, 0) / (0.22, +2) / (0.22, -2) (original:412-425)."""
+
+    def __init__(self, action_dim: int = 2, max_step: int = 200, config: CnConfig | None = None,
+                 device: int | None = None):
+        cfg = config.copy() if config is not None else make_config(env_original=True)
+        if not cfg.flags & 4:
+            raise ValueError("EnvOriginal needs a config made with env_original=True")
+        super().__init__(action_dim, max_step, cfg, device)
+
+    def step(self, action, step_counter, mode: str = "discrete"):
+        if mode == "discrete":
+            if action not in (0, 1, 2):
+                raise ValueError("discrete action must be 0, 1 or 2")
+            action = [0.22, (0.0, 2.0, -2.0)[action]]
+        return super().step(action, step_counter, mode="continuous")
+
+    def get_odometry_data(self):
+        """original:494-496: [round(x, 3), round(y, 3), yaw] of the last get_state."""
+        row = self._venv.obs[0].detach().cpu().numpy()
+        blob = self._venv.get_state_blob()
+        yaw = float(np.float32(np.int32(blob[16 + 2])) * np.float32(1.4629180792671596e-09))
+        return [float(row[-2]), float(row[-1]), yaw]

@@ -51,6 +51,13 @@ typedef enum cn_status {
 #define CN_FLAG_TOPK_HIGHEST    2u  /* keep the K highest-CP objects instead of the
                                        reference's `[-K:]` (= K lowest), ENV:883 */
 
+#define CN_FLAG_ENV_ORIGINAL    4u  /* the reference's ORIGINAL environment (environment_stage_1_original.py, used by its
+                                       DQN / tabular drivers and the 363-wide `trajectory_test` checkpoints): row =
+                                       [R-1 ranges | heading, distance to the GOAL | x, y], no waypoints, no K block
+                                       (k_obstacles must be 0), reward = progress terms + terminal, computed -- like
+                                       the reference does (original:324-326) -- from the row's last two entries.
+                                       Same simulator, same state; served by the default kernel only. */
+
 /* behaviour kinds (crowd_behaviors/simulate_*.py, SURVEY table P') */
 #define CN_BEHAVIOR_RANDOM 0   /* U(-speed, speed)^2 redrawn every period */
 #define CN_BEHAVIOR_TABLE  1   /* fixed per-pedestrian direction table * speed */
@@ -113,7 +120,7 @@ typedef struct cn_handle cn_handle;
  * configs/turtlebot3_world.yaml + the world/xacro constants. */
 int cn_config_default(cn_config* cfg);
 
-/* Observation width (R-1) + 7 + 4K  (start_td3_training.py:88). */
+/* Observation width (R-1) + 7 + 4K  (start_td3_training.py:88); (R-1) + 4 with CN_FLAG_ENV_ORIGINAL. */
 int cn_obs_dim(const cn_config* cfg);
 
 /* Bytes of the opaque state blob for this config (cn_get_blob / cn_set_blob). */

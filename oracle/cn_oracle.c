@@ -236,12 +236,21 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     float yaw = cn_bin2rad(th);
     float wx = f_of(rob[CN_R_WPX]), wy = f_of(rob[CN_R_WPY]);
 
-    /* A: ENV:246-265 */
-    if (step_counter == 1) waypoint(c, xf, yf, &wx, &wy);
-    float dist = cn_py_round2(dist_to_wp(xf, yf, wx, wy));
-    float head = cn_py_round2(heading_to_wp(c, xf, yf, yaw, wx, wy));
-    if (step_counter % 5 == 0 || dist < f_of(rob[CN_R_PDIST])) waypoint(c, xf, yf, &wx, &wy);
-    rob[CN_R_WPX] = u_of(wx); rob[CN_R_WPY] = u_of(wy);
+    const int original = (g->flags & CN_FLAG_ENV_ORIGINAL) != 0;
+    float dist, head;
+    if (original) {
+        /* environment_stage_1_original.py:280-281: distance / heading to the goal itself, no waypoints
+         * (desired_point; the heading has no starting_pose term there: the config carries a zero offset) */
+        dist = cn_py_round2(dist_to_wp(xf, yf, g->goal_x, g->goal_y));
+        head = cn_py_round2(heading_to_wp(c, xf, yf, yaw, g->goal_x, g->goal_y));
+    } else {
+        /* A: ENV:246-265 */
+        if (step_counter == 1) waypoint(c, xf, yf, &wx, &wy);
+        dist = cn_py_round2(dist_to_wp(xf, yf, wx, wy));
+        head = cn_py_round2(heading_to_wp(c, xf, yf, yaw, wx, wy));
+        if (step_counter % 5 == 0 || dist < f_of(rob[CN_R_PDIST])) waypoint(c, xf, yf, &wx, &wy);
+        rob[CN_R_WPX] = u_of(wx); rob[CN_R_WPY] = u_of(wy);
+    }
 
     /* B: ENV:267-268 -- yaw RATE used as an angle (sic) */
     float v = f_of(rob[CN_R_V]), w = f_of(rob[CN_R_W]);
@@ -340,7 +349,7 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     /* K: ENV:862-907.  stable sort by CP descending, keep [-K:], pad */
     float* blk = obs + NR + 7;
     for (int s = 0; s < K; ++s) { blk[4 * s] = xf; blk[4 * s + 1] = yf; blk[4 * s + 2] = 0.0f; blk[4 * s + 3] = 0.0f; }
-    for (int a = 0; a < n_obj; ++a) {
+    for (int a = 0; a < (K > 0 ? n_obj : 0); ++a) {
         int rank = 0;
         for (int b = 0; b < n_obj; ++b) {
             if (b == a) continue;
@@ -369,12 +378,19 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     if (in_goal_box(c, xf, yf)) done = 1;
     if (step_counter >= g->max_steps) done = 1;
 
-    /* O: ENV:1025-1042 */
-    obs[NR + 0] = head; obs[NR + 1] = dist;
-    obs[NR + 2] = p_cur_x; obs[NR + 3] = p_cur_y;
-    obs[NR + 4] = cn_py_round3(yaw);
-    obs[NR + 5] = cn_py_round3(avx); obs[NR + 6] = cn_py_round3(avy);
-    for (int k = 0; k < c->d.obs_dim; ++k) obs[k] = cn_np_round3(obs[k]);
+    if (original) {
+        /* original:309-318: [round(range, 3) ... | heading, distance | round(x, 3), round(y, 3)], Python rounding */
+        for (int j = 0; j < NR; ++j) obs[j] = cn_py_round3(obs[j]);
+        obs[NR + 0] = head; obs[NR + 1] = dist;
+        obs[NR + 2] = p_cur_x; obs[NR + 3] = p_cur_y;
+    } else {
+        /* O: ENV:1025-1042 */
+        obs[NR + 0] = head; obs[NR + 1] = dist;
+        obs[NR + 2] = p_cur_x; obs[NR + 3] = p_cur_y;
+        obs[NR + 4] = cn_py_round3(yaw);
+        obs[NR + 5] = cn_py_round3(avx); obs[NR + 6] = cn_py_round3(avy);
+        for (int k = 0; k < c->d.obs_dim; ++k) obs[k] = cn_np_round3(obs[k]);
+    }
 
     /* ENV:1208 / 991-992: the deque keeps the current rounded pose */
     rob[CN_R_PPX] = u_of(p_cur_x); rob[CN_R_PPY] = u_of(p_cur_y);
@@ -567,11 +583,18 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
 
     /* W: compute_reward (ENV:1046-1162) on the ROUNDED heading / distance */
     const int NR = g->n_samples - 1;
+    const int original = (g->flags & CN_FLAG_ENV_ORIGINAL) != 0;
     float cur_head = obs[NR + 0], cur_dist = obs[NR + 1];
     float prev_head = f_of(rob[CN_R_PHEAD]), prev_dist = f_of(rob[CN_R_PDIST]);
     int reward = shaping_reward(cur_head, cur_dist, prev_head, prev_dist);
     float xf = (float)(int32_t)rob[CN_R_X] * CN_GRID, yf = (float)(int32_t)rob[CN_R_Y] * CN_GRID;
     float wx = f_of(rob[CN_R_WPX]), wy = f_of(rob[CN_R_WPY]);
+    if (original) {
+        /* original:324-326: `current_distance = state[-1]`, `current_heading = state[-2]` -- with the 363-wide row
+         * these are the robot's y and x (sic); step_reward = 0 (original:334), no waypoint bonus */
+        cur_head = obs[NR + 2]; cur_dist = obs[NR + 3];
+        reward = shaping_reward(cur_head, cur_dist, prev_head, prev_dist) + 2;
+    } else
     if (in_box(xf, yf, wx - g->goal_box, wx + g->goal_box, wy - g->goal_box, wy + g->goal_box)) {
         waypoint(c, xf, yf, &wx, &wy);                     /* ENV:1109-1116 */
         reward += 200;

@@ -12,6 +12,8 @@ Fixtures (all small, committed):
   waypoints.npz       utils.get_local_goal_waypoints (through the shapely stand-in)
   td3_actor_k8_ep2500.npz
                       the shipped K=8 TD3 actor's state_dict (checkpoint drop-in fixture)
+  trace_original.npz, trace_original_goal.npz
+                      the same for environment_stage_1_original.Env (CN_FLAG_ENV_ORIGINAL)
   trace_c1.npz, trace_train.npz, trace_goal.npz
                       reference-in-the-loop traces: the reference's Env.reset/step
                       (get_state + compute_reward, unmodified) observing physics
@@ -35,7 +37,7 @@ sys.path.insert(0, HERE)
 from ref_harness import Reference, Scan, _XYZ, _Quat  # noqa: E402
 from crowdnav_b200.config import baseline_config, make_config  # noqa: E402
 from oracle.oracle import OracleEnv  # noqa: E402
-from trace_configs import TRACES, trace_config  # noqa: E402
+from trace_configs import TRACES, TRACES_ORIGINAL, trace_config  # noqa: E402
 
 OUT = os.path.join(HERE, "golden")
 
@@ -161,9 +163,12 @@ def gen_trace(ref, name, cfg, n_steps, seed, params, seek_goal=False):
                            "ref_success", "oracle_obs")}
     state_holder = {}
 
+    original = bool(cfg.flags & 4)         # CN_FLAG_ENV_ORIGINAL: the reference's environment_stage_1_original.Env
+
     def new_episode():
         o.reset()
-        env = ref.make_env(max_step=cfg.max_steps, k_obstacle_count=K)
+        env = (ref.make_env_original(max_step=cfg.max_steps) if original
+               else ref.make_env(max_step=cfg.max_steps, k_obstacle_count=K))
         ref.set_odom(env, *oracle_odom(o))
         state_holder["scan"] = raw_scan_from_oracle(o)
         s = env.reset()
@@ -227,13 +232,18 @@ def gen_actor_fixture():
 
 
 def main():
+    """All fixtures, or only the traces named on the command line (`python tests/gen_golden.py original ...`)."""
     os.makedirs(OUT, exist_ok=True)
-    gen_actor_fixture()
+    only = sys.argv[1:]
     ref = Reference()
-    gen_utils(ref)
-    gen_env_methods(ref)
-    gen_waypoints(ref)
-    for name in TRACES:
+    if not only:
+        gen_actor_fixture()
+        gen_utils(ref)
+        gen_env_methods(ref)
+        gen_waypoints(ref)
+    for name in TRACES + TRACES_ORIGINAL:
+        if only and name not in only:
+            continue
         cfg, params, kw = trace_config(name)
         gen_trace(ref, name, cfg, kw["n_steps"], kw["seed"], params, seek_goal=kw["seek_goal"])
 

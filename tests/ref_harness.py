@@ -243,8 +243,13 @@ class Reference:
                                       # generalised so the 37-sample config can run (identical for 360)
                                       "current_heading = state[359]": "current_heading = state[self.scan_ranges - 1]",
                                       "current_distance = state[360]": "current_distance = state[self.scan_ranges]"})
+            # the reference's first environment (environment_stage_1_original.py), unmodified
+            self.envmod_original = self._load("environment_stage_1_original",
+                                              os.path.join(REF_SRC, "environment_stage_1_original.py"), {})
+            # original:284-286 appends every pose to a CSV under the ROS package path: not part of the path under test
+            self.utils.record_data = lambda *a, **k: None
         finally:
-            for k in ("rospy", "tf", "tf.transformations", "shapely", "shapely.geometry", "shapely.geometry.polygon",
+            for k in ("rospy", "tf", "rospkg", "tf.transformations", "shapely", "shapely.geometry", "shapely.geometry.polygon",
                       "visualization_msgs", "visualization_msgs.msg", "geometry_msgs", "geometry_msgs.msg",
                       "sensor_msgs", "sensor_msgs.msg", "nav_msgs", "nav_msgs.msg", "std_srvs", "std_srvs.srv",
                       "utils"):
@@ -271,6 +276,7 @@ class Reference:
             Time=_Inert(), Duration=_Inert, Rate=_Inert, is_shutdown=lambda: False)
         mod("tf")
         mod("tf.transformations", euler_from_quaternion=_euler_from_quaternion)
+        mod("rospkg", RosPack=lambda: types.SimpleNamespace(get_path=lambda name: "/tmp"))
         mod("shapely")
         mod("shapely.geometry", LineString=_SLineString, Point=_SPoint)
         mod("shapely.geometry.polygon", Polygon=_SPolygon)
@@ -314,6 +320,12 @@ class Reference:
         env.orientation = _Quat(0.0)
         env.linear_twist = _XYZ()
         env.angular_twist = _XYZ()
+        return env
+
+    def make_env_original(self, action_dim=2, max_step=1000):
+        env = self.envmod_original.Env(action_dim=action_dim, max_step=max_step)
+        env.position = _XYZ()
+        env.orientation = _Quat(0.0)
         return env
 
     @staticmethod

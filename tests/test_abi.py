@@ -97,3 +97,14 @@ def test_tile_plan_for_the_baseline_configs(L):
     bad = make_config()
     bad.n_peds = 1000
     assert L.cn_plan_tile(C.byref(bad), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == -1
+
+
+def test_original_env_flag_row_width(L):
+    """CN_FLAG_ENV_ORIGINAL: (R-1) + 4 columns, K must be 0 (library and ctypes mirror agree)."""
+    cfg = make_config(env_original=True)
+    assert cfg.flags & 4 and cfg.k_obstacles == 0
+    assert L.cn_obs_dim(C.byref(cfg)) == 363 == cfg.obs_dim
+    tile, threads, smem = C.c_int(), C.c_int(), C.c_size_t()
+    assert L.cn_plan_tile(C.byref(cfg), 148, 233472, C.byref(tile), C.byref(threads), C.byref(smem)) == 0
+    cfg.k_obstacles = 8
+    assert L.cn_plan_tile(C.byref(cfg), 148, 233472, C.byref(tile), C.byref(threads), C.byref(smem)) == -1

@@ -269,3 +269,29 @@ def test_flat_kernel_tile_shapes(tile, monkeypatch):
     _rollout(cfg, 60, seed=53)
     monkeypatch.setenv("CN_FLAT_STORE", "plain")
     _rollout(baseline_config(1, n_envs=130, auto_reset=True), 30, seed=54)
+
+
+def test_original_env_variant():
+    """CN_FLAG_ENV_ORIGINAL (environment_stage_1_original.py: 363-wide row, goal-relative heading / distance, its own
+    reward): same simulator and state, different observation writer and reward -- bit-exact against the oracle, whose
+    variant is pinned to the reference's own code by tests/golden/trace_original*.npz."""
+    cfg = make_config(n_envs=300, auto_reset=True, layout_jitter=0.05, max_steps=120, env_original=True)
+    assert cfg.obs_dim == 363
+    n_done = _rollout(cfg, 200, seed=61)
+    assert n_done > 0
+    # the 20-pedestrian test room, several tiles, ragged tail
+    big = test_world_20(n_envs=1030, auto_reset=True, layout_jitter=0.05)
+    big.flags |= 4
+    big.k_obstacles = 0
+    big.heading_off_x = big.heading_off_y = 0.0
+    big.collision_range = 0.105
+    assert big.obs_dim == 363
+    _rollout(big, 40, seed=62, check_every=10)
+
+
+def test_original_env_needs_the_default_kernel(monkeypatch):
+    from crowdnav_b200._lib import CrowdNavError
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    monkeypatch.setenv("CN_KERNEL", "warp")
+    with pytest.raises(CrowdNavError):
+        CrowdNavVecEnv(make_config(n_envs=4, env_original=True), device=0)

@@ -21,7 +21,7 @@ import pytest
 
 from oracle.oracle import OracleEnv, lib
 from crowdnav_b200.config import make_config
-from trace_configs import TRACES, trace_config
+from trace_configs import TRACES, TRACES_ORIGINAL, trace_config
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -82,6 +82,51 @@ def test_trace_replay_matches_reference(name):
         # with 1-degree rays the reference's own segmentation sees the same objects as ideal association
         assert occ_equal / occ_rows >= 0.90, "K-block occupancy agrees on only %d/%d rows" % (occ_equal, occ_rows)
         assert len(pos_diffs) > 50 and np.median(pos_diffs) < 0.01, "object points differ: median %g" % np.median(pos_diffs)
+
+
+@pytest.mark.parametrize("name", TRACES_ORIGINAL)
+def test_original_env_trace_replay_matches_reference(name):
+    """CN_FLAG_ENV_ORIGINAL against the reference's environment_stage_1_original.Env in the loop: every one of the
+    363 columns to 1e-6 (float32 representation of the float64 row), reward / done / success exactly -- including the
+    reference's reading of the row's last two entries (x, y) as "heading" and "distance" in compute_reward."""
+    t = np.load(os.path.join(GOLD, "trace_%s.npz" % name))
+    cfg, _, _ = trace_config(name)
+    assert cfg.obs_dim == 363 == t["ref_state"].shape[1]
+    o = OracleEnv(cfg, debug=True)
+    R = cfg.n_samples
+    NR = R - 1
+    rewards = set()
+    for i in range(len(t["action"])):
+        if t["episode_start"][i] > 0:
+            obs = o.reset()[0]
+            rew, done = 0.0, 0
+        else:
+            obs_, r_, d_ = o.step(t["action"][i].astype(np.float32).reshape(1, 2))
+            obs, rew, done = obs_[0], float(r_[0]), int(d_[0])
+        raw = np.full(R, np.inf, dtype=np.float32)
+        hit = o.hit_ids[0] != 0xFF
+        idx = (R - 1) - np.arange(NR)
+        raw[idx[hit]] = o.ranges[0][hit]
+        assert np.array_equal(raw, t["scan"][i]), "row %d: simulator no longer reproduces the recorded scan" % i
+        d = np.abs(obs.astype(np.float64) - t["ref_state"][i])
+        assert d.max() <= 1e-6, "row %d: column %d differs from the reference by %g" % (i, int(d.argmax()), d.max())
+        if t["episode_start"][i] == 0:
+            assert rew == t["ref_reward"][i], "row %d: reward %g vs reference %g" % (i, rew, t["ref_reward"][i])
+            assert done == int(t["ref_done"][i]), "row %d: done differs" % i
+            if done:
+                assert int(o.counters()[0, 0]) == int(t["ref_success"][i]), "row %d: success flag differs" % i
+            rewards.add(rew)
+    assert rewards & {0.0, 1.0, 2.0}, "no progress rewards in the trace"
+
+
+def test_original_env_traces_cover_its_reward_terms():
+    seen = set()
+    for name in TRACES_ORIGINAL:
+        seen |= set(np.load(os.path.join(GOLD, "trace_%s.npz" % name))["ref_reward"].tolist())
+    for r in (0.0, 1.0, 2.0):
+        assert r in seen, "no golden row with reward %g" % r
+    assert seen & {200.0, 201.0, 202.0}, "no successful episode in the original-env traces"
+    assert seen & {-200.0, -199.0, -198.0}, "no failed episode in the original-env traces"
 
 
 def test_traces_cover_all_reward_terms():

@@ -13,7 +13,14 @@ def trace_config(name):
     if name == "goal":     # goal seeking: waypoint (+200) / goal (+200) rewards, success episodes
         cfg = make_config(n_envs=1, auto_reset=False, layout_jitter=0.05, max_steps=400, seed=77)
         return cfg, {"/turtlebot3/scan_ranges": 360}, dict(n_steps=700, seed=13, seek_goal=True)
+    if name == "original":         # environment_stage_1_original.py: 363-wide row, goal-relative, its own reward
+        cfg = make_config(n_envs=1, auto_reset=False, layout_jitter=0.05, max_steps=150, seed=91, env_original=True)
+        return cfg, {"/turtlebot3/scan_ranges": 360}, dict(n_steps=450, seed=14, seek_goal=False)
+    if name == "original_goal":    # ... steered at the goal: success episodes (+200)
+        cfg = make_config(n_envs=1, auto_reset=False, layout_jitter=0.05, max_steps=400, seed=92, env_original=True)
+        return cfg, {"/turtlebot3/scan_ranges": 360}, dict(n_steps=450, seed=15, seek_goal=True)
     raise KeyError(name)
 
 
 TRACES = ("c1", "train", "goal")
+TRACES_ORIGINAL = ("original", "original_goal")
