@@ -259,6 +259,16 @@ def make_config(
     return cfg
 
 
+def realworld_layout_config(**kw) -> CnConfig:
+    """The 370-wide row of the reference's physical-robot environment (environment_stage_1_nobonus_realworld.py:
+    731-744): 359 ranges + 7 + ONE obstacle slot holding the object with the highest collision probability
+    (realworld:674-678) -- i.e. K = 1 with the `highest` selection.  Values are rounded like the simulation
+    environment's row (np.around, ENV:1042); the real-world script leaves the slot unrounded."""
+    kw.setdefault("k_obstacles", 1)
+    kw.setdefault("topk_highest", True)
+    return make_config(**kw)
+
+
 def test_world_20(n_envs: int = 1, behaviors: Sequence[Behavior] | None = None, **kw) -> CnConfig:
     """README test protocol (README.md:60-83): 5 m room, start (1, 0), goal (-2, 2)."""
     kw.setdefault("n_peds", 20)

@@ -295,3 +295,13 @@ def test_original_env_needs_the_default_kernel(monkeypatch):
     monkeypatch.setenv("CN_KERNEL", "warp")
     with pytest.raises(CrowdNavError):
         CrowdNavVecEnv(make_config(n_envs=4, env_original=True), device=0)
+
+
+def test_realworld_370_layout_single_max_cp_slot():
+    """environment_stage_1_nobonus_realworld.py's row: 359 + 7 + one slot with the highest-CP object (K = 1,
+    CN_FLAG_TOPK_HIGHEST).  Bit-exact against the oracle; the slot must never hold a lower-CP object than K = N would."""
+    from crowdnav_b200.config import realworld_layout_config
+    cfg = realworld_layout_config(n_envs=256, auto_reset=True, layout_jitter=0.05, max_steps=150)
+    assert cfg.obs_dim == 370 and cfg.k_obstacles == 1 and cfg.flags & 2
+    n_done = _rollout(cfg, 150, seed=71)
+    assert n_done > 0

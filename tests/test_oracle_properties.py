@@ -112,3 +112,27 @@ def test_blob_is_the_whole_state():
     again = [tuple(x.copy() for x in env.step(a)) for a in acts]
     for f, g in zip(first, again):
         assert all(bits_equal(x, y) for x, y in zip(f, g))
+
+
+def test_realworld_layout_slot_is_the_highest_cp_object():
+    """The 370-wide row (environment_stage_1_nobonus_realworld.py:731-744) carries ONE obstacle: the tracked object
+    with the highest collision probability (realworld:674-678).  K = 1 with the `highest` selection must equal the
+    first slot of a K = N highest-first block, on every row."""
+    from crowdnav_b200.config import make_config, realworld_layout_config
+    E = 48
+    c1 = realworld_layout_config(n_envs=E, auto_reset=True, layout_jitter=0.05)
+    cn = make_config(n_envs=E, auto_reset=True, layout_jitter=0.05, k_obstacles=14, topk_highest=True)
+    assert c1.obs_dim == 370
+    o1, on = OracleEnv(c1), OracleEnv(cn)
+    o1.reset()
+    on.reset()
+    rng = np.random.default_rng(5)
+    occupied = 0
+    for t in range(120):
+        a = np.stack([rng.uniform(0, 0.22, E), rng.uniform(-2, 2, E)], 1).astype(np.float32)
+        b1, r1, d1 = o1.step(a)
+        bn, rn, dn = on.step(a)
+        assert np.array_equal(b1[:, :366], bn[:, :366]) and np.array_equal(r1, rn) and np.array_equal(d1, dn)
+        assert np.array_equal(b1[:, 366:370], bn[:, 366:370])
+        occupied += int((np.abs(b1[:, 366] - b1[:, 361]) > 1e-6).sum())
+    assert occupied > 500, "the slot was hardly ever occupied: nothing tested"
