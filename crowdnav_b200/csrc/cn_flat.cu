@@ -304,7 +304,7 @@ __device__ __forceinline__ void copy16_out(void* gdst, const void* ssrc, int n, 
 
 // ------------------------------------------------------------------- kernel
 template <int MODE, int T>
-__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 256 ? 4 : 8))
+__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? 4 : (T >= 192 ? 6 : 8))))
 cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
     constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -962,7 +962,7 @@ static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L) {
     const int N = n_peds, D = obs_dim, W = tile;
-    if (threads != 128 && threads != 256 && threads != 512) return -1;
+    if (threads != 128 && threads != 192 && threads != 256 && threads != 384 && threads != 512) return -1;
     if (W < 1 || W > 32) return -1;
     if ((size_t)W * N > 0x3FFF) return -1;                                  // group-entry / list-entry fields
     (void)n_samples;
@@ -1045,6 +1045,8 @@ extern "C" int cn_debug_set_timeline_flat(unsigned long long* dev_ptr) {
 
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream) {
     if (L.threads == 128) return mode == 0 ? launch_flat_t<0, 128>(P, L, stream) : launch_flat_t<1, 128>(P, L, stream);
+    if (L.threads == 192) return mode == 0 ? launch_flat_t<0, 192>(P, L, stream) : launch_flat_t<1, 192>(P, L, stream);
+    if (L.threads == 384) return mode == 0 ? launch_flat_t<0, 384>(P, L, stream) : launch_flat_t<1, 384>(P, L, stream);
     if (L.threads == 256) return mode == 0 ? launch_flat_t<0, 256>(P, L, stream) : launch_flat_t<1, 256>(P, L, stream);
     return mode == 0 ? launch_flat_t<0, 512>(P, L, stream) : launch_flat_t<1, 512>(P, L, stream);
 }
