@@ -564,8 +564,10 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         }
         //    ... and the compacted list of pedestrians that draw this step: Philox, then the same
         {
+            // (entry q goes to thread PED_THREADS - 1 - q: the high threads have no pedestrian of their own when the
+            //  tile has fewer pedestrians than threads, so the draws start at once instead of after a plain item)
             const int n_res = (int)S.cnt[C_NRES];
-            for (int q = ptid; q < n_res; q += PED_THREADS) {
+            for (int q = PED_THREADS - 1 - ptid; q < n_res; q += PED_THREADS) {
                 const uint32_t ent = S.rlist[q];
                 const int idx = (int)(ent & 0x7FFFu);
                 const bool respawn = (ent & 0x8000u) != 0u;
