@@ -13,8 +13,8 @@ from .config import CnConfig
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.path.join(_PKG, "libcrowdnav.so")
-SOURCES = ["cn_abi.cu", "cn_step.cu", "cn_flat.cu"]
-HEADERS = ["cn_math.h", "cn_state.h", "cn_kernel.h", "cn_dev.h", os.path.join("..", "..", "include", "crowdnav.h")]
+SOURCES = ["cn_abi.cu", "cn_step.cu", "cn_flat.cu", "cn_faithful.cu"]
+HEADERS = ["cn_math.h", "cn_math64.h", "cn_faithful.h", "cn_faithful_state.h", "cn_state.h", "cn_kernel.h", "cn_dev.h", os.path.join("..", "..", "include", "crowdnav.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only

@@ -23,6 +23,7 @@ CN_MAX_BEHAVIORS = 8
 CN_FLAG_AUTO_RESET = 1
 CN_FLAG_TOPK_HIGHEST = 2
 CN_FLAG_ENV_ORIGINAL = 4     # environment_stage_1_original.py: 363-wide row, goal-relative, its own reward
+CN_FLAG_RISK_FAITHFUL = 8    # K block + safety counters from the reference's own segmentation / tracker (ENV:270-1005), float64
 CN_BEHAVIOR_RANDOM = 0
 CN_BEHAVIOR_TABLE = 1
 TICKS_PER_STEP = 3
@@ -209,12 +210,17 @@ def make_config(
     wheel_accel: float = 0.0,
     n_substeps: int = 1,
     env_original: bool = False,
+    risk_faithful: bool = False,
 ) -> CnConfig:
     """Build a config; defaults are the reference's TRAINING world
     (CFG:1-18, WORLD, put_robot_in_world_training.launch:3-8)."""
     cfg = CnConfig()
     cfg.struct_size = C.sizeof(CnConfig)
     cfg.flags = (CN_FLAG_AUTO_RESET if auto_reset else 0) | (CN_FLAG_TOPK_HIGHEST if topk_highest else 0)
+    if risk_faithful:
+        if env_original:
+            raise ValueError("risk_faithful has no meaning for the original environment (no K block)")
+        cfg.flags |= CN_FLAG_RISK_FAITHFUL
     if env_original:
         # environment_stage_1_original.py: row = [ranges | heading, distance to the goal | x, y] (original:315-318), the
         # heading has no starting_pose term (original:246-260), an episode ends below 0.105 m (original:282)

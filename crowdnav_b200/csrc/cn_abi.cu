@@ -20,6 +20,8 @@ struct cn_handle {
     uint32_t* robot;
     uint32_t* ped_a;
     uint32_t* ped_b;
+    uint32_t* trk;          /* CN_FLAG_RISK_FAITHFUL: tracker plane [E][CNF_WORLD_WORDS], else NULL */
+    float* own_ranges;      /* CN_FLAG_RISK_FAITHFUL: pre-rounding ranges [E][R-1] the step kernel leaves for cn_faithful_kernel */
     float* dbg_ranges;
     uint8_t* dbg_hid;
     int64_t launches;
@@ -31,6 +33,15 @@ static cudaError_t launch_env(const cn_handle* h, cn_kparams& P, int mode, cudaS
     if (h->use_flat) return cn_launch_flat_kernel(P, h->flat, mode, s);
     P.obs_bulk_ok = P.obs_bulk_ok && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;   /* every tile starts 16-B aligned */
     return cn_launch_env_kernel(P, mode, s);
+}
+
+/* the risk_faithful block runs behind the step / reset kernel on the same stream */
+static cudaError_t launch_faithful(cn_handle* h, float* obs, const uint8_t* mask, cudaStream_t s) {
+    if (!h->trk) return cudaSuccess;
+    cudaError_t e = cn_launch_faithful(&h->cfg, h->robot, h->trk, h->dbg_ranges ? h->dbg_ranges : h->own_ranges,
+                                       obs, mask, h->d.obs_dim, s);
+    if (e == cudaSuccess) h->launches += 1;
+    return e;
 }
 
 static thread_local char g_err[512] = "";
@@ -135,6 +146,8 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
     }
 
+    if ((cfg->flags & CN_FLAG_RISK_FAITHFUL) && cn_faithful_smem_bytes(cfg->n_samples - 1) > (size_t)max_smem)
+        return fail(CN_ERR_UNSUPPORTED, "cn_create: risk_faithful scratch does not fit shared memory (reduce n_samples)%s", NULL);
     cn_handle* h = new (std::nothrow) cn_handle();
     if (!h) return fail(CN_ERR_NOMEM, "cn_create: host allocation failed%s", NULL);
     h->cfg = *cfg; h->d = d; h->device = device; h->launches = 0;
@@ -143,14 +156,19 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     const size_t cfg_b = align_up(sizeof(cn_config), 256);
     const size_t rob_b = align_up(cn_robot_words(cfg) * 4, 256);
     const size_t ped_b = align_up(cn_ped_plane_words(cfg) * 4 + 16, 256);
-    h->arena_bytes = cfg_b + rob_b + 2 * ped_b;
+    const bool faithful = (cfg->flags & CN_FLAG_RISK_FAITHFUL) != 0;
+    const size_t trk_b = faithful ? align_up(cn_trk_words(cfg) * 4, 256) : 0;
+    const size_t rng_b = faithful ? align_up((size_t)cfg->n_envs * (size_t)(cfg->n_samples - 1) * 4, 256) : 0;
+    h->arena_bytes = cfg_b + rob_b + 2 * ped_b + trk_b + rng_b;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) { delete h; return fail(CN_ERR_NOMEM, "cn_create: cudaMalloc: %s", cudaGetErrorString(e)); }
     uint8_t* p = (uint8_t*)h->arena;
     h->cfg_dev = (cn_config*)p; p += cfg_b;
     h->robot = (uint32_t*)p; p += rob_b;
     h->ped_a = (uint32_t*)p; p += ped_b;
-    h->ped_b = (uint32_t*)p;
+    h->ped_b = (uint32_t*)p; p += ped_b;
+    h->trk = faithful ? (uint32_t*)p : NULL; p += trk_b;
+    h->own_ranges = faithful ? (float*)p : NULL;
     e = cudaMemset(h->arena, 0, h->arena_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(h->cfg_dev, cfg, sizeof(cn_config), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(h->arena); delete h; return fail(CN_ERR_CUDA, "cn_create: init: %s", cudaGetErrorString(e)); }
@@ -170,7 +188,7 @@ static void pack(const cn_handle* h, cn_kparams* P) {
     const cn_config* c = &h->cfg;
     memset(P, 0, sizeof(*P));
     P->robot = h->robot; P->ped_a = h->ped_a; P->ped_b = h->ped_b;
-    P->dbg_ranges = h->dbg_ranges; P->dbg_hid = h->dbg_hid;
+    P->dbg_ranges = h->dbg_ranges ? h->dbg_ranges : h->own_ranges; P->dbg_hid = h->dbg_hid;
     P->cfg = h->cfg_dev; P->d = h->d;
     P->n_envs = c->n_envs; P->n_peds = c->n_peds; P->n_samples = c->n_samples; P->k_obstacles = c->k_obstacles;
     P->max_steps = c->max_steps; P->env_id_offset = c->env_id_offset; P->n_behaviors = c->n_behaviors;
@@ -194,6 +212,7 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
     P.mask = mask_dev; P.obs = obs_dev; P.obs_bulk_ok = 0;
     CN_CUDA(launch_env(h, P, 1, (cudaStream_t)stream));
     h->launches += 1;
+    CN_CUDA(launch_faithful(h, obs_dev, mask_dev, (cudaStream_t)stream));
     return CN_OK;
 }
 
@@ -206,6 +225,7 @@ int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
     h->launches += 1;
+    CN_CUDA(launch_faithful(h, obs_dev, NULL, (cudaStream_t)stream));
     return CN_OK;
 }
 
@@ -215,6 +235,9 @@ int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float*
         return fail(CN_ERR_INVALID, "cn_step_gather: null argument%s", NULL);
     if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_obs_dev))
         return fail(CN_ERR_INVALID, "cn_step_gather: 0..8 peer buffers%s", NULL);
+    if (h->trk && n_peers > 0)
+        return fail(CN_ERR_UNSUPPORTED, "cn_step_gather: CN_FLAG_RISK_FAITHFUL rewrites the K block after the step kernel; "
+                                        "gather with ncclAllGather instead%s", NULL);
     cn_kparams P; pack(h, &P);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
     bool aligned = (((uintptr_t)obs_dev) & 15u) == 0;
@@ -228,13 +251,15 @@ int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float*
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
     h->launches += 1;
+    CN_CUDA(launch_faithful(h, obs_dev, NULL, (cudaStream_t)stream));
     return CN_OK;
 }
 
 int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream) {
     if (!h || !out_dev) return fail(CN_ERR_INVALID, "cn_get_counters: null argument%s", NULL);
     if (((uintptr_t)out_dev) & 15u) return fail(CN_ERR_INVALID, "cn_get_counters: out_dev must be 16-byte aligned%s", NULL);
-    CN_CUDA(cn_launch_counters(h->robot, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
+    if (h->trk) CN_CUDA(cn_launch_faithful_counters(h->robot, h->trk, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
+    else CN_CUDA(cn_launch_counters(h->robot, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -262,6 +287,7 @@ int cn_get_blob(cn_handle* h, void* host, size_t bytes, void* stream) {
         CN_CUDA(cudaMemcpyAsync(w + rw, h->ped_a, pw * 4, cudaMemcpyDeviceToHost, s));
         CN_CUDA(cudaMemcpyAsync(w + rw + pw, h->ped_b, pw * 4, cudaMemcpyDeviceToHost, s));
     }
+    if (h->trk) CN_CUDA(cudaMemcpyAsync(w + rw + 2 * pw, h->trk, cn_trk_words(&h->cfg) * 4, cudaMemcpyDeviceToHost, s));
     CN_CUDA(cudaStreamSynchronize(s));
     return CN_OK;
 }
@@ -280,6 +306,7 @@ int cn_set_blob(cn_handle* h, const void* host, size_t bytes, void* stream) {
         CN_CUDA(cudaMemcpyAsync(h->ped_a, w + rw, pw * 4, cudaMemcpyHostToDevice, s));
         CN_CUDA(cudaMemcpyAsync(h->ped_b, w + rw + pw, pw * 4, cudaMemcpyHostToDevice, s));
     }
+    if (h->trk) CN_CUDA(cudaMemcpyAsync(h->trk, w + rw + 2 * pw, cn_trk_words(&h->cfg) * 4, cudaMemcpyHostToDevice, s));
     CN_CUDA(cudaStreamSynchronize(s));
     return CN_OK;
 }

@@ -1,0 +1,496 @@
+/*
+ * cn_faithful.h -- the `risk_faithful` perception block (CN_FLAG_RISK_FAITHFUL) for ONE world, as the
+ * device code of cn_faithful.cu: the reference's own LiDAR segmentation, wall / obstacle typing, uuid-dict
+ * tracker, collision cone and top-K block (environment_stage_1_nobonus.py:270-1005) in float64.
+ *
+ * Flat-array design: a world's rays live in a scratch area (shared memory on the device); every per-ray map
+ * (hit points UTL:110-126, gradients ENV:329-347, gradient changes ENV:349-368, neighbour association
+ * UTL:435-448) is strided over `nl` lanes, the order-dependent scans (typing state machine ENV:370-404,
+ * segment walk ENV:443-620, tracker ENV:656-743, ranking ENV:862-907) run on lane 0, the tracked x confirmed
+ * IoU search runs one lane per tracked object and the 64-gon ring of the collision cone (UTL:251-293) one
+ * lane per pair of ring edges.  CNF_SYNC() separates the stages.
+ *
+ * The same source compiles for the host (g++, one "lane": nl = 1, CNF_SYNC a no-op): tests/faithful_host.cpp
+ * runs it on the CPU against the independent CPU restatement kept under oracle/ so that the arithmetic is
+ * checked bit for bit before it ever reaches a GPU.  That harness is a test tool: the product only launches
+ * the kernel.
+ */
+#ifndef CN_FAITHFUL_H
+#define CN_FAITHFUL_H
+
+#include "cn_math64.h"
+#include "cn_faithful_state.h"
+
+#if defined(__CUDACC__)
+#define CNF_FN __device__ __forceinline__
+#define CNF_SYNC() __syncwarp()
+#else
+#define CNF_FN static inline
+#define CNF_SYNC() ((void)0)
+#endif
+
+enum { CNF_T_NONE = 0, CNF_T_W = 1, CNF_T_O = 2 };
+
+/* scratch of one world; all pointers 8-byte aligned where they hold doubles */
+typedef struct cnf_scratch {
+    double*   grad;     /* [n] round(gradient, 3)              */
+    double*   chg;      /* [n] |gradient change|               */
+    int32_t*  hx;       /* [n] hit point, thousandths          */
+    int32_t*  hy;
+    int32_t*  rmm;      /* [n] round(range, 3), thousandths    */
+    int16_t*  src;      /* [n] ray whose record ray i carries  */
+    int16_t*  flat;     /* [n] rays in segment order           */
+    int16_t*  sub;      /* [n + 2] sub-segment offsets         */
+    uint8_t*  gok;      /* [n] gradient defined                */
+    uint8_t*  cok;      /* [n] gradient change defined         */
+    uint8_t*  type;     /* [n] record type                     */
+    uint8_t*  close;    /* [n] a segment closes after ray i    */
+    uint32_t* trk;      /* [CNF_WORLD_WORDS] tracker record    */
+    int32_t*  conf;     /* [CNF_CONF_CAP][4] type, x, y, range */
+    double*   am_val;   /* [CNF_TRK_CAP] best IoU per tracked  */
+    int32_t*  am_idx;   /* [CNF_TRK_CAP]                       */
+    double*   hit;      /* [64][2] ring hits of one probe line */
+    uint8_t*  hitf;     /* [64]                                */
+    int32_t*  misc;     /* [8] scalars shared between lanes    */
+} cnf_scratch;
+
+/* bytes of scratch for n rays (offsets are assigned in this order, doubles first) */
+CN_HD size_t cnf_scratch_bytes(int n) {
+    size_t b = 0;
+    b += 2 * sizeof(double) * (size_t)n;                      /* grad, chg */
+    b += sizeof(double) * CNF_TRK_CAP + sizeof(double) * 128; /* am_val, hit */
+    b += sizeof(uint32_t) * CNF_WORLD_WORDS;                  /* trk (1584 B, keeps 8-byte alignment) */
+    b += 3 * sizeof(int32_t) * (size_t)n;                     /* hx, hy, rmm */
+    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8);
+    b += sizeof(int16_t) * (3 * (size_t)n + 2);
+    b += 4 * (size_t)n + 64;
+    return (b + 15) & ~(size_t)15;
+}
+CN_HD void cnf_scratch_carve(unsigned char* base, int n, cnf_scratch* S) {
+    unsigned char* p = base;
+    S->grad = (double*)p; p += sizeof(double) * (size_t)n;
+    S->chg = (double*)p; p += sizeof(double) * (size_t)n;
+    S->am_val = (double*)p; p += sizeof(double) * CNF_TRK_CAP;
+    S->hit = (double*)p; p += sizeof(double) * 128;
+    S->trk = (uint32_t*)p; p += sizeof(uint32_t) * CNF_WORLD_WORDS;
+    S->hx = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
+    S->hy = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
+    S->rmm = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
+    S->conf = (int32_t*)p; p += sizeof(int32_t) * CNF_CONF_CAP * 4;
+    S->am_idx = (int32_t*)p; p += sizeof(int32_t) * CNF_TRK_CAP;
+    S->misc = (int32_t*)p; p += sizeof(int32_t) * 8;
+    S->src = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
+    S->flat = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
+    S->sub = (int16_t*)p; p += sizeof(int16_t) * ((size_t)n + 2);
+    S->gok = p; p += n; S->cok = p; p += n; S->type = p; p += n; S->close = p; p += n;
+    S->hitf = p;
+}
+
+CNF_FN double cnf_ld64(const uint32_t* w) {
+    unsigned long long u = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+    double d; memcpy(&d, &u, 8); return d;
+}
+CNF_FN void cnf_st64(uint32_t* w, double d) {
+    unsigned long long u; memcpy(&u, &d, 8);
+    w[0] = (uint32_t)u; w[1] = (uint32_t)(u >> 32);
+}
+
+/* UTL:421-448: round(IoU, 3) of two squares of half-size h centred on points given in thousandths */
+CNF_FN double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double h) {
+    const double ax = cn_milli64(axk), ay = cn_milli64(ayk), bx = cn_milli64(bxk), by = cn_milli64(byk);
+    const double ax0 = ax - h, ax1 = ax + h, ay0 = ay - h, ay1 = ay + h;
+    const double bx0 = bx - h, bx1 = bx + h, by0 = by - h, by1 = by + h;
+    const double w = (ax1 < bx1 ? ax1 : bx1) - (ax0 > bx0 ? ax0 : bx0);
+    const double hh = (ay1 < by1 ? ay1 : by1) - (ay0 > by0 ? ay0 : by0);
+    const double inter = (w > 0.0 && hh > 0.0) ? w * hh : 0.0;
+    const double area_a = (ax1 - ax0) * (ay1 - ay0), area_b = (bx1 - bx0) * (by1 - by0);
+    const double uni = area_a + area_b - inter;
+    return cn_py_round3_64(inter / uni);
+}
+
+/* UTL:110-126 for observation ray i: both coordinates in thousandths */
+CNF_FN void cnf_hit_point(const cnf_params* P, double x, double y, double yaw, int i, double r, int32_t* hx, int32_t* hy) {
+    const double ang = ((double)i * P->inc_deg) * CN64_DEG2RAD - yaw;
+    double s, c; cn_sincos64(ang, &s, &c);
+    *hx = (int32_t)cn_py_round3_k64(x + r * c);
+    *hy = (int32_t)cn_py_round3_k64(y + (r * s) * -1.0);
+}
+
+/*
+ * One get_state of the perception block for one world.
+ *   scan32 : cleaned ranges in observation order (UTL:375-392), fp32, `no_return32` where nothing was hit
+ *   step_counter : 0 inside reset (ENV:1245), else the 1-based step
+ *   kblock : 4K floats of the observation row (written by lane 0)
+ *   S.trk must hold the world's tracker record on entry (all lanes see it) and holds the new one on exit.
+ */
+CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, double y, double yaw,
+                      const float* scan32, float no_return32, int step_counter, float* kblock,
+                      int lane, int nl) {
+    const cnf_scratch S = *Sp;
+    const int n = P->n_rays, K = P->k_obstacles;
+    const int32_t max_mm = (int32_t)cn_py_round3_k64(P->max_range);
+
+    /* ---- reset: fresh tracker; bounding_box_size from the ground-truth ring (ENV:286-290, UTL:405-419) ---- */
+    if (step_counter == 0) {
+        for (int k = lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;
+        for (int i = lane; i < n; i += nl) cnf_hit_point(P, x, y, yaw, i, P->max_range, &S.hx[i], &S.hy[i]);
+        CNF_SYNC();
+        for (int i = lane; i < n; i += nl) {
+            const int j = (i == n - 1) ? 0 : i + 1;
+            S.chg[i] = cn_hypot64(cn_milli64(S.hx[i]) - cn_milli64(S.hx[j]), cn_milli64(S.hy[i]) - cn_milli64(S.hy[j]));
+        }
+        CNF_SYNC();
+        if (lane == 0) {
+            double sum = 0.0;
+            for (int i = 0; i < n; ++i) sum += S.chg[i];
+            cnf_st64(S.trk + CNF_H_BBOX, sum / (double)n);
+        }
+        CNF_SYNC();
+    }
+    const double bbox = cnf_ld64(S.trk + CNF_H_BBOX);
+
+    /* ---- per-ray maps ---- */
+    for (int i = lane; i < n; i += nl) {
+        const float r32 = scan32[i];
+        const double r = (r32 >= no_return32) ? P->max_range : (double)r32;
+        cnf_hit_point(P, x, y, yaw, i, r, &S.hx[i], &S.hy[i]);
+        S.rmm[i] = (int32_t)cn_py_round3_k64(r);
+    }
+    CNF_SYNC();
+    for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
+        if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.grad[i] = 0.0; continue; }
+        const int j = (i == n - 1) ? 0 : i + 1;
+        const double dy = cn_milli64(S.hy[i]) - cn_milli64(S.hy[j]);
+        double g = 0.0;
+        if (dy != 0.0) g = (cn_milli64(S.hx[i]) - cn_milli64(S.hx[j])) / dy;
+        S.grad[i] = cn_py_round3_64(g); S.gok[i] = 1;
+    }
+    CNF_SYNC();
+    for (int i = lane; i < n - 1; i += nl) {                   /* ENV:349-368, all but the last ray */
+        if (S.gok[i] && S.gok[i + 1]) { S.chg[i] = fabs(S.grad[i] - S.grad[i + 1]); S.cok[i] = 1; }
+        else { S.chg[i] = 0.0; S.cok[i] = 0; }
+    }
+    CNF_SYNC();
+
+    /* ---- lane 0: the order-dependent walks ---- */
+    if (lane == 0) {
+        /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
+        S.chg[n - 1] = 0.0; S.cok[n - 1] = 0;
+        if (S.gok[n - 1]) {
+            for (int i = n - 2; i >= 0; --i)
+                if (S.gok[i]) { S.chg[n - 1] = S.chg[i]; S.cok[n - 1] = S.cok[i]; break; }
+        }
+        /* typing with the delayed-update counter (ENV:370-404); a record is (type, source ray) */
+        int last_type = CNF_T_NONE, last_src = 0, du = 0;
+        for (int i = 0; i < n; ++i) {
+            int t = CNF_T_NONE, s = i;
+            if (S.cok[i] && i != n - 1) {
+                const double ci = S.chg[i];
+                if (ci == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; }
+                else if (du != 1) {
+                    const int nok = S.cok[i + 1];
+                    const double cn = S.chg[i + 1];
+                    t = CNF_T_O;
+                    if (nok && cn == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; du = 0; }
+                    if (nok) {
+                        if (fabs(ci - cn) == 0.0) { t = CNF_T_W; s = i; last_type = CNF_T_W; last_src = i; du = 0; }
+                        else { t = last_type; s = (last_type == CNF_T_NONE) ? i : last_src; du += 1; }
+                    }
+                } else {
+                    t = CNF_T_O; last_type = CNF_T_O; last_src = i;
+                    if (S.cok[i + 1] && S.chg[i + 1] == 0.0) du = 0;
+                }
+            }
+            S.type[i] = (uint8_t)t; S.src[i] = (int16_t)s;
+        }
+    }
+    CNF_SYNC();
+    /* neighbour association on the records' poses (ENV:443-486) */
+    for (int i = lane; i < n; i += nl) {
+        int cl = 1;
+        if (i != n - 1) {
+            const int a = S.src[i], b = S.src[i + 1];
+            cl = !(cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox) > 0.0);
+        }
+        S.close[i] = (uint8_t)cl;
+    }
+    CNF_SYNC();
+
+    if (lane == 0) {
+        /* segments in the reference's order: first (+ last when they join across the blind spot), then the rest */
+        int nseg = 0, e0 = -1, zb = 0;
+        for (int i = 0; i < n; ++i) if (S.close[i]) { if (e0 < 0) e0 = i; ++nseg; if (i != n - 1) zb = i + 1; }
+        int merged = 0;
+        if (nseg > 1) {
+            const int a = S.src[0], b = S.src[n - 1];
+            merged = cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox * 2.0) > 0.0;     /* ENV:488-504 */
+        }
+        int len = 0, first_len;
+        for (int i = 0; i <= e0; ++i) S.flat[len++] = (int16_t)i;
+        if (merged) for (int i = zb; i < n; ++i) S.flat[len++] = (int16_t)i;
+        first_len = len;
+        { const int stop = merged ? zb : n; for (int i = e0 + 1; i < stop; ++i) S.flat[len++] = (int16_t)i; }
+        /* split every segment that holds a hit at its 0.6 <-> hit transitions (ENV:510-571) */
+        int nsub = 0; S.sub[0] = 0;
+        int b = 0;
+        while (b < len) {
+            int e;
+            if (b == 0) e = first_len;
+            else { e = b; while (!S.close[S.flat[e]]) ++e; ++e; }
+            int any_hit = 0;
+            for (int k = b; k < e; ++k) if (S.rmm[S.src[S.flat[k]]] != max_mm) any_hit = 1;
+            if (!any_hit) S.sub[++nsub] = (int16_t)e;
+            else for (int k = b; k < e; ++k) {
+                int cl = 1;
+                if (k != e - 1) cl = (S.rmm[S.src[S.flat[k]]] == max_mm) != (S.rmm[S.src[S.flat[k + 1]]] == max_mm);
+                if (cl) S.sub[++nsub] = (int16_t)(k + 1);
+            }
+            b = e;
+        }
+        /* confirmation (ENV:573-620, UTL:395-402) */
+        int nconf = 0, n_obst = 0, ego_hit = 0;
+        const double span = P->max_range - P->min_range;
+        for (int s = 0; s < nsub; ++s) {
+            const int sb = S.sub[s], se = S.sub[s + 1], sl = se - sb;
+            int any_hit = 0, n_o = 0, n_w = 0, n_none = 0;
+            for (int k = sb; k < se; ++k) {
+                const int r = S.flat[k];
+                if (S.rmm[S.src[r]] != max_mm) any_hit = 1;
+                const int t = S.type[r];
+                n_o += (t == CNF_T_O); n_w += (t == CNF_T_W); n_none += (t == CNF_T_NONE);
+            }
+            if (!any_hit || sl < 4) continue;
+            const int rc = S.src[S.flat[sb + sl / 2]];
+            const double dctr = cn_milli64(S.rmm[rc]);
+            const double estd = 3.0 + floor(29.0 * (P->max_range - dctr) / span);
+            const double denom = ((double)sl < estd) ? (double)sl : estd;
+            const double score = (double)n_o / denom;
+            const int distinct = (n_o > 0) + (n_w > 0) + (n_none > 0);
+            int t = -1;
+            if (distinct > 1) {
+                if (score >= 0.5) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
+                else if ((double)sl <= estd) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
+                else t = CNF_T_W;
+            } else {
+                const double lim = ((double)nsub < estd) ? (double)nsub : estd;
+                if (!((double)sl <= lim)) t = (n_w > 0) ? CNF_T_W : CNF_T_O;
+            }
+            if (t < 0) continue;
+            if (nconf < CNF_CONF_CAP) {
+                int32_t* c = S.conf + 4 * nconf;
+                c[0] = t; c[1] = S.hx[rc]; c[2] = S.hy[rc]; c[3] = S.rmm[rc];
+                ++nconf;
+            } else S.trk[CNF_H_OVERFLOW] += 1;
+        }
+        for (int c = 0; c < nconf; ++c)
+            if (S.conf[4 * c] == CNF_T_O) { ++n_obst; if (cn_milli64(S.conf[4 * c + 3]) < 0.140) ego_hit = 1; }
+        if (n_obst > 0) S.trk[CNF_H_PRESENT] += 1;              /* ENV:653-654 */
+        S.misc[0] = nconf; S.misc[1] = ego_hit;
+        /* popleft of every tracked deque (ENV:679-682) happens before the IoUs are taken */
+        const int n0 = (int)S.trk[CNF_H_N];
+        if (nconf > 0)
+            for (int i = 0; i < n0; ++i) {
+                uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
+                if (q[CNF_E_NDEQ] > 1u) { q[CNF_E_PX] = q[CNF_E_LX]; q[CNF_E_PY] = q[CNF_E_LY]; q[CNF_E_NDEQ] = 1u; }
+            }
+    }
+    CNF_SYNC();
+
+    /* ---- tracker: best confirmed object per tracked one (ENV:691-703), one lane each ---- */
+    const int nconf = S.misc[0];
+    const int n0 = (int)S.trk[CNF_H_N];
+    if (nconf > 0)
+        for (int i = lane; i < n0; i += nl) {
+            const uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
+            int m = 0; double best = 0.0;
+            for (int c = 0; c < nconf; ++c) {
+                const double v = cnf_iou((int32_t)q[CNF_E_LX], (int32_t)q[CNF_E_LY], S.conf[4 * c + 1], S.conf[4 * c + 2], P->track_half);
+                if (c == 0 || v > best) { best = v; m = c; }
+            }
+            S.am_val[i] = best; S.am_idx[i] = m;
+        }
+    CNF_SYNC();
+
+    if (lane == 0) {
+        uint32_t* E = S.trk + CNF_HDR_WORDS;
+        int n_ent = n0;
+        uint64_t checked = 0;                                    /* CNF_CONF_CAP <= 64 */
+        if (n0 > 0 && nconf == 0) n_ent = 0;                     /* ENV:686-689 */
+        else if (n0 > 0) {
+            /* update / drop in dict order; `len(dict) > i` (ENV:718) lets late unmatched entries survive */
+            uint32_t dead = 0; int n_live = n0;
+            for (int i = 0; i < n0; ++i) {
+                uint32_t* q = E + i * CNF_ENTRY_WORDS;
+                if (S.am_val[i] > 0.0) {
+                    const int32_t* c = S.conf + 4 * S.am_idx[i];
+                    q[CNF_E_PX] = q[CNF_E_LX]; q[CNF_E_PY] = q[CNF_E_LY];
+                    q[CNF_E_LX] = (uint32_t)c[1]; q[CNF_E_LY] = (uint32_t)c[2]; q[CNF_E_DIST] = (uint32_t)c[3];
+                    q[CNF_E_NDEQ] = 2u;
+                    checked |= (uint64_t)1 << S.am_idx[i];
+                } else if (n_live > i) { dead |= 1u << i; --n_live; }
+            }
+            int m = 0;
+            for (int i = 0; i < n0; ++i) {
+                if (dead & (1u << i)) continue;
+                if (m != i) for (int k = 0; k < CNF_ENTRY_WORDS; ++k) E[m * CNF_ENTRY_WORDS + k] = E[i * CNF_ENTRY_WORDS + k];
+                ++m;
+            }
+            n_ent = m;
+        }
+        if (!(n0 > 0 && nconf == 0))
+            for (int c = 0; c < nconf; ++c) {                    /* new tracked objects (ENV:663-671, 725-741) */
+                if (S.conf[4 * c] != CNF_T_O || ((checked >> c) & 1)) continue;
+                if (n_ent >= CNF_TRK_CAP) { S.trk[CNF_H_OVERFLOW] += 1; continue; }
+                uint32_t* q = E + n_ent * CNF_ENTRY_WORDS;
+                q[CNF_E_PX] = q[CNF_E_LX] = (uint32_t)S.conf[4 * c + 1];
+                q[CNF_E_PY] = q[CNF_E_LY] = (uint32_t)S.conf[4 * c + 2];
+                q[CNF_E_DIST] = (uint32_t)S.conf[4 * c + 3]; q[CNF_E_NDEQ] = 1u;
+                cnf_st64(q + CNF_E_SPEED, -1.0); cnf_st64(q + CNF_E_VX, 0.0); cnf_st64(q + CNF_E_VY, 0.0);
+                ++n_ent;
+            }
+        for (int k = n_ent * CNF_ENTRY_WORDS; k < CNF_TRK_CAP * CNF_ENTRY_WORDS; ++k) E[k] = 0u;
+        S.trk[CNF_H_N] = (uint32_t)n_ent;
+        /* speed (ENV:745-760), obstacle velocity and the probe target of the collision cone (ENV:799-815) */
+        const double curx = cn_py_round3_64(x), cury = cn_py_round3_64(y);
+        double vox = curx, voy = cury;
+        for (int i = 0; i < n_ent; ++i) {
+            uint32_t* q = E + i * CNF_ENTRY_WORDS;
+            double cx = 0.0, cy = 0.0;
+            if (q[CNF_E_NDEQ] > 1u) {
+                const double px = cn_milli64((int32_t)q[CNF_E_PX]), py = cn_milli64((int32_t)q[CNF_E_PY]);
+                const double lx = cn_milli64((int32_t)q[CNF_E_LX]), ly = cn_milli64((int32_t)q[CNF_E_LY]);
+                cnf_st64(q + CNF_E_SPEED, cn_hypot64(py - ly, px - lx) / P->dt);
+                if (S.trk[CNF_H_HAVE_PREV]) {
+                    cx = px - lx; cy = py - ly;                  /* last - curr (sic, ENV:806-807) */
+                    cnf_st64(q + CNF_E_VX, cx / P->dt); cnf_st64(q + CNF_E_VY, cy / P->dt);
+                }
+            }
+            vox = curx + cx; voy = cury + cy;                    /* leaks out of the loop (ENV:814-815) */
+        }
+        S.hit[0] = vox; S.hit[1] = voy;                          /* handed to all lanes through memory */
+        S.misc[2] = n_ent;
+    }
+    CNF_SYNC();
+
+    /* ---- collision cone: distance to the r = 0.178 ring along the probe lines (UTL:251-293) ---- */
+    const int n_ent = S.misc[2];
+    const int have_prev = (int)S.trk[CNF_H_HAVE_PREV];
+    const double a0x = cn_milli64((int32_t)S.trk[CNF_H_PPX]), a0y = cn_milli64((int32_t)S.trk[CNF_H_PPY]);
+    if (have_prev && n_ent > 0) {
+        const double a1x = S.hit[0], a1y = S.hit[1];
+        CNF_SYNC();
+        double gradient = 0.0;
+        if (a1y != 0.0) gradient = (a1x - a0x) / a1y - a0y;      /* precedence as written (UTL:261) */
+        const double cb = a0x - (gradient * a0y);
+        const long x_hi = (long)ceil(a0x + 3.5), x_lo = (long)floor(a0x - 3.5);
+        for (int i = 0; i < n_ent; ++i) {
+            const uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
+            const double ox = cn_milli64((int32_t)q[CNF_E_LX]), oy = cn_milli64((int32_t)q[CNF_E_LY]);
+            int have = 0; double dtc = 0.0;
+            for (long x2 = x_hi; x2 > x_lo; --x2) {
+                const double qx = (double)x2, qy = ((double)x2 * gradient) + cb;
+                const double rx = qx - a0x, ry = qy - a0y;
+                for (int k = lane; k < 64; k += nl) {
+                    const int k1 = (k + 1) & 63;
+                    const double ax = ox + P->cp_radius * CNF_RING_COS[k], ay = oy + P->cp_radius * CNF_RING_SIN[k];
+                    const double bx = ox + P->cp_radius * CNF_RING_COS[k1], by = oy + P->cp_radius * CNF_RING_SIN[k1];
+                    const double sx = bx - ax, sy = by - ay;
+                    const double den = rx * sy - ry * sx;
+                    int f = 0;
+                    if (den != 0.0) {
+                        const double t = ((ax - a0x) * sy - (ay - a0y) * sx) / den;
+                        const double u = ((ax - a0x) * ry - (ay - a0y) * rx) / den;
+                        if (0.0 <= t && t <= 1.0 && 0.0 <= u && u <= 1.0) { f = 1; S.hit[2 * k] = a0x + t * rx; S.hit[2 * k + 1] = a0y + t * ry; }
+                    }
+                    S.hitf[k] = (uint8_t)f;
+                }
+                CNF_SYNC();
+                /* every lane resolves the (few) hits identically: no broadcast needed */
+                int nh = 0, i0 = -1, i1 = -1, first[4] = {0, 0, 0, 0}; double k0 = 0.0, k1v = 0.0;
+                for (int k = 0; k < 64; ++k) {
+                    if (!S.hitf[k]) continue;
+                    int dup = 0;
+                    for (int o = 0; o < nh && o < 4; ++o)
+                        if (fabs(S.hit[2 * k] - S.hit[2 * first[o]]) < 1e-12 && fabs(S.hit[2 * k + 1] - S.hit[2 * first[o] + 1]) < 1e-12) { dup = 1; break; }
+                    if (dup) continue;
+                    if (nh < 4) first[nh] = k;
+                    ++nh;
+                    const double dx = S.hit[2 * k] - a0x, dy = S.hit[2 * k + 1] - a0y;
+                    const double key = dx * dx + dy * dy;
+                    if (i0 < 0 || key < k0) { i1 = i0; k1v = k0; i0 = k; k0 = key; }
+                    else if (i1 < 0 || key < k1v) { i1 = k; k1v = key; }
+                }
+                int stop = 0;
+                if (nh == 1) { have = 0; stop = 1; }              /* a Point has no .geoms -> None */
+                else if (nh >= 2) {
+                    const double d0 = cn_hypot64(a0x - S.hit[2 * i0], a0y - S.hit[2 * i0 + 1]);
+                    const double d1 = cn_hypot64(a0x - S.hit[2 * i1], a0y - S.hit[2 * i1 + 1]);
+                    dtc = d0 < d1 ? d0 : d1; have = 1; stop = 1;
+                }
+                CNF_SYNC();                                       /* hit[] is rewritten by the next probe */
+                if (stop) break;
+            }
+            if (lane == 0) { S.am_val[i] = dtc; S.am_idx[i] = have; }
+        }
+    }
+    CNF_SYNC();
+
+    /* ---- lane 0: collision probability, ranking, K block, counters (ENV:765-907, 998-1005) ---- */
+    if (lane == 0) {
+        uint32_t* E = S.trk + CNF_HDR_WORDS;
+        double ego_score = cnf_ld64(S.trk + CNF_H_EGOSCORE);
+        const double curx = cn_py_round3_64(x), cury = cn_py_round3_64(y);
+        for (int s = 0; s < K; ++s) {
+            kblock[4 * s] = (float)cn_np_round3_64(x); kblock[4 * s + 1] = (float)cn_np_round3_64(y);
+            kblock[4 * s + 2] = 0.0f; kblock[4 * s + 3] = 0.0f;
+        }
+        if (have_prev) {
+            const double vx = (curx - a0x) / P->dt, vy = (cury - a0y) / P->dt;     /* UTL:227-236 */
+            const double agent_vel = sqrt(vx * vx + vy * vy);
+            const double obstacle_vel = (n_ent == 0) ? 0.0 : cnf_ld64(E + CNF_E_SPEED);   /* ENV:789-797 */
+            const double resultant = agent_vel - obstacle_vel;
+            const double span = P->max_range - P->min_range;
+            double ego_cur = 0.0, ego_max = 0.0;
+            /* the collision probabilities overwrite am_val in place (the distance is consumed first) */
+            for (int i = 0; i < n_ent; ++i) {
+                const double dist = cn_milli64((int32_t)E[i * CNF_ENTRY_WORDS + CNF_E_DIST]);
+                const double dto = (dist > P->max_range) ? 0.0 : (P->max_range - dist) / span;
+                double cp;
+                if (S.am_idx[i]) {
+                    if (resultant == 0.0) cp = 1.0 * dto;
+                    else {
+                        const double ttc = S.am_val[i] / resultant;
+                        const double qq = 0.15 / ttc;
+                        ego_cur = (1.0 < qq) ? 1.0 : qq;
+                        cp = 0.5 * ego_cur + 0.5 * dto;
+                    }
+                } else { ego_cur = 0.0; cp = 0.5 * 0.0 + 0.5 * dto; }
+                S.am_val[i] = cp;
+                if (i == 0 || ego_cur > ego_max) ego_max = ego_cur;
+            }
+            ego_score = (n_ent == 0) ? 0.0 : ego_max;
+            for (int a = 0; a < (K > 0 ? n_ent : 0); ++a) {       /* stable descending sort, keep [-K:] (ENV:882-883) */
+                int rank = 0;
+                for (int b = 0; b < n_ent; ++b)
+                    if (b != a && (S.am_val[b] > S.am_val[a] || (S.am_val[b] == S.am_val[a] && b < a))) ++rank;
+                const int slot = P->topk_highest ? rank : rank - (n_ent > K ? n_ent - K : 0);
+                if (slot < 0 || slot >= K) continue;
+                const uint32_t* q = E + a * CNF_ENTRY_WORDS;
+                kblock[4 * slot] = (float)cn_np_round3_64(cn_milli64((int32_t)q[CNF_E_LX]));
+                kblock[4 * slot + 1] = (float)cn_np_round3_64(cn_milli64((int32_t)q[CNF_E_LY]));
+                kblock[4 * slot + 2] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VX));
+                kblock[4 * slot + 3] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VY));
+            }
+        }
+        cnf_st64(S.trk + CNF_H_EGOSCORE, ego_score);
+        S.trk[CNF_H_HAVE_PREV] = 1u;
+        S.trk[CNF_H_PPX] = (uint32_t)(int32_t)cn_py_round3_k64(x);
+        S.trk[CNF_H_PPY] = (uint32_t)(int32_t)cn_py_round3_k64(y);
+        if (S.misc[1]) S.trk[CNF_H_EGO] += 1;
+        if (ego_score > 0.4) S.trk[CNF_H_SOCIAL] += 1;
+        if (step_counter == 0) { S.trk[CNF_H_EGO] = 0; S.trk[CNF_H_SOCIAL] = 0; S.trk[CNF_H_PRESENT] = 0; }   /* ENV:1258-1262 */
+    }
+    CNF_SYNC();
+}
+
+#endif /* CN_FAITHFUL_H */

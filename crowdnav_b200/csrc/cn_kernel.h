@@ -62,4 +62,10 @@ cudaError_t cn_launch_env_kernel(const cn_kparams& P, int mode /*0 step, 1 reset
 cudaError_t cn_launch_clear_done(uint32_t* robot, const uint8_t* mask, int E, cudaStream_t stream);
 cudaError_t cn_launch_counters(const uint32_t* robot, int32_t* out, int E, cudaStream_t stream);
 
+/* cn_faithful.cu: the risk_faithful perception block behind the step kernel (CN_FLAG_RISK_FAITHFUL) */
+size_t cn_faithful_smem_bytes(int n_rays);
+cudaError_t cn_launch_faithful(const cn_config* cfg, const uint32_t* robot, uint32_t* trk, const float* ranges,
+                               float* obs, const uint8_t* mask, int obs_dim, cudaStream_t stream);
+cudaError_t cn_launch_faithful_counters(const uint32_t* robot, const uint32_t* trk, int32_t* out, int E, cudaStream_t stream);
+
 #endif

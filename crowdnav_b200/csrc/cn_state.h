@@ -13,13 +13,16 @@
  *   ped_b  [E][N][4] words 16 B / pedestrian: last hit point x, y (f32, 3 dp),
  *                                             resample timer (int32 ticks), flags
  *
- * Blob = 16-word header, then the three planes back to back.
+ * Blob = 16-word header, then the three planes back to back (+ the tracker plane
+ * trk [E][CNF_WORLD_WORDS] of cn_faithful_state.h with CN_FLAG_RISK_FAITHFUL).
  */
 #ifndef CN_STATE_H
 #define CN_STATE_H
 
 #include "../../include/crowdnav.h"
 #include "cn_math.h"
+#include "cn_math64.h"
+#include "cn_faithful_state.h"
 
 /* robot / episode record, word indices */
 enum {
@@ -121,6 +124,7 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->max_range_r3 = cn_np_round3(c->max_range);
     if (d->max_range_r3 != c->max_range) return -1;   /* the no-return value must be a whole number of millimetres */
     if ((c->flags & CN_FLAG_ENV_ORIGINAL) && c->k_obstacles != 0) return -1;
+    if ((c->flags & CN_FLAG_RISK_FAITHFUL) && (c->flags & CN_FLAG_ENV_ORIGINAL)) return -1;
     d->obs_dim = (c->flags & CN_FLAG_ENV_ORIGINAL) ? (c->n_samples - 1) + 4 : (c->n_samples - 1) + 7 + 4 * c->k_obstacles;
     {
         double lim = (double)(c->ped_radius + (c->ped_radius > c->robot_radius ? c->ped_radius : c->robot_radius))
@@ -136,8 +140,24 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
 
 static inline size_t cn_robot_words(const cn_config* c) { return (size_t)c->n_envs * CN_ROBOT_WORDS; }
 static inline size_t cn_ped_plane_words(const cn_config* c) { return (size_t)c->n_envs * (size_t)c->n_peds * 4; }
+static inline size_t cn_trk_words(const cn_config* c) {
+    return (c->flags & CN_FLAG_RISK_FAITHFUL) ? (size_t)c->n_envs * CNF_WORLD_WORDS : 0;
+}
 static inline size_t cn_blob_words(const cn_config* c) {
-    return CN_BLOB_HEADER_WORDS + cn_robot_words(c) + 2 * cn_ped_plane_words(c);
+    return CN_BLOB_HEADER_WORDS + cn_robot_words(c) + 2 * cn_ped_plane_words(c) + cn_trk_words(c);
+}
+/* float64 constants of the risk_faithful block from the (float) config */
+static inline void cnf_params_from_config(const cn_config* c, cnf_params* p) {
+    p->n_rays = c->n_samples - 1;
+    p->k_obstacles = c->k_obstacles;
+    p->topk_highest = (c->flags & CN_FLAG_TOPK_HIGHEST) ? 1 : 0;
+    p->pad_ = 0;
+    p->inc_deg = (double)c->hit_angle_inc_deg;
+    p->max_range = cn_dec64(c->max_range);
+    p->min_range = cn_dec64(c->collision_range);
+    p->dt = cn_dec64(c->dt);
+    p->cp_radius = cn_dec64(c->cp_radius);
+    p->track_half = 0.0505;            /* hard-coded at ENV:689 */
 }
 
 #endif /* CN_STATE_H */

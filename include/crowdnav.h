@@ -58,6 +58,14 @@ typedef enum cn_status {
                                        the reference does (original:324-326) -- from the row's last two entries.
                                        Same simulator, same state; served by the default kernel only. */
 
+#define CN_FLAG_RISK_FAITHFUL   8u  /* the K block and the safety counters come from the reference's OWN perception
+                                       chain -- gradient typing, scan segmentation, segment confirmation, the
+                                       uuid-dict tracker, collision cone (ENV:270-1005), computed in float64 like
+                                       CPython does -- instead of the ideal-association restatement.  A second
+                                       kernel runs behind the step kernel on the same stream; the tracker record
+                                       becomes a 4th plane of the state blob.  Not combinable with
+                                       CN_FLAG_ENV_ORIGINAL or the fused gather of cn_step_gather. */
+
 /* behaviour kinds (crowd_behaviors/simulate_*.py, SURVEY table P') */
 #define CN_BEHAVIOR_RANDOM 0   /* U(-speed, speed)^2 redrawn every period */
 #define CN_BEHAVIOR_TABLE  1   /* fixed per-pedestrian direction table * speed */

@@ -51,6 +51,9 @@ int orc_obs_dim(const orc_ctx* c) { return c->d.obs_dim; }
 static uint32_t* blob_robot(const orc_ctx* c, uint32_t* blob) { return blob + CN_BLOB_HEADER_WORDS; }
 static uint32_t* blob_ped_a(const orc_ctx* c, uint32_t* blob) { return blob_robot(c, blob) + cn_robot_words(&c->cfg); }
 static uint32_t* blob_ped_b(const orc_ctx* c, uint32_t* blob) { return blob_ped_a(c, blob) + cn_ped_plane_words(&c->cfg); }
+static uint32_t* blob_trk(const orc_ctx* c, uint32_t* blob) {
+    return (c->cfg.flags & CN_FLAG_RISK_FAITHFUL) ? blob_ped_b(c, blob) + cn_ped_plane_words(&c->cfg) : NULL;
+}
 
 void orc_init_blob(const orc_ctx* c, uint32_t* blob) {
     memset(blob, 0, orc_blob_bytes(c));
@@ -219,12 +222,16 @@ static float cp_dto(const orc_ctx* c, float d) {
 
 typedef struct { float cp, x, y, vx, vy; int n; } risk_obj;
 
+/* cn_oracle_faithful.c: the reference's own perception block (CN_FLAG_RISK_FAITHFUL) */
+void orf_observe(const cnf_params* p, uint32_t* trk, double x, double y, double yaw, const double* scan,
+                 int step_counter, double* kblock);
+
 /*
  * observe: Env.get_state (ENV:245-1044) for one world, `risk_intended` flavour
  * (SURVEY 8a "deterministic restatement of J/K").  Writes the rounded
  * observation row and returns this step's done conditions (ENV:1011-1023).
  */
-static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t* pb,
+static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t* pb, uint32_t* trk,
                    int step_counter, int have_prev_pose, float* obs,
                    float* dbg_ranges, uint8_t* dbg_hid) {
     const cn_config* g = &c->cfg;
@@ -264,6 +271,17 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
     if (dbg_ranges) memcpy(dbg_ranges, ranges, sizeof(float) * NR);
     float min_scan = INFINITY;
     for (int j = 0; j < NR; ++j) if (ranges[j] < min_scan) min_scan = ranges[j];
+
+    /* CN_FLAG_RISK_FAITHFUL: rows E-K and M as the reference computes them (float64, its own segmentation and
+     * tracker) from the same odometry and cleaned scan; the block below still runs (its state stays in the blob)
+     * but its K block is replaced at the end. */
+    double kfaith[4 * CN_MAX_PEDS];
+    if (trk) {
+        cnf_params fp; cnf_params_from_config(g, &fp);
+        double scan64[1024];
+        for (int j = 0; j < NR; ++j) scan64[j] = (ranges[j] >= g->max_range) ? fp.max_range : (double)ranges[j];
+        orf_observe(&fp, trk, (double)xf, (double)yf, (double)yaw, scan64, step_counter, kfaith);
+    }
 
     /* E-I collapsed by ideal association: an object = a pedestrian hit by >= 4
      * rays (ENV:573); its point = the hit ray nearest its centre line. */
@@ -390,6 +408,7 @@ static int observe(const orc_ctx* c, uint32_t* rob, const uint32_t* pa, uint32_t
         obs[NR + 4] = cn_py_round3(yaw);
         obs[NR + 5] = cn_py_round3(avx); obs[NR + 6] = cn_py_round3(avy);
         for (int k = 0; k < c->d.obs_dim; ++k) obs[k] = cn_np_round3(obs[k]);
+        if (trk) for (int k = 0; k < 4 * K; ++k) obs[NR + 7 + k] = (float)kfaith[k];
     }
 
     /* ENV:1208 / 991-992: the deque keeps the current rounded pose */
@@ -419,7 +438,7 @@ static int shaping_reward(float cur_head, float cur_dist, float prev_head, float
 }
 
 /* ---- Z: Env.reset (ENV:1227-1263) + gazebo/reset_simulation -------------- */
-static void reset_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint32_t* pb, float* obs,
+static void reset_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint32_t* pb, uint32_t* trk, float* obs,
                       float* dbg_ranges, uint8_t* dbg_hid) {
     const cn_config* g = &c->cfg;
     const int N = g->n_peds;
@@ -452,7 +471,7 @@ static void reset_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint
     /* ENV:1243-1244: unrounded */
     rob[CN_R_PDIST] = u_of(dist_to_wp(xf, yf, wx, wy));
     rob[CN_R_PHEAD] = u_of(heading_to_wp(c, xf, yf, cn_bin2rad(c->d.start_th), wx, wy));
-    (void)observe(c, rob, pa, pb, 0, 0, obs, dbg_ranges, dbg_hid);   /* ENV:1246 */
+    (void)observe(c, rob, pa, pb, trk, 0, 0, obs, dbg_ranges, dbg_hid);   /* ENV:1246 */
     rob[CN_R_CNT0] = 0; rob[CN_R_CNT1] = 0;               /* ENV:1260-1262 */
 }
 
@@ -471,7 +490,7 @@ static void add_rep(const orc_ctx* c, int32_t xi, int32_t yi, int32_t xj, int32_
 }
 
 /* ---- S: Env.step (ENV:1164-1225) for one world --------------------------- */
-static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint32_t* pb,
+static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint32_t* pb, uint32_t* trk,
                      const float* action, float* obs, float* reward_out, uint8_t* done_out,
                      float* dbg_ranges, uint8_t* dbg_hid) {
     const cn_config* g = &c->cfg;
@@ -486,7 +505,7 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
      * done = 2 (a transition the trainer must not store).  Every world does exactly one get_state per step. */
     if ((rob[CN_R_FLAGS] & CN_RF_DONE) && (g->flags & CN_FLAG_AUTO_RESET)) {
         uint32_t keep = rob[CN_R_FLAGS] & (CN_RF_SUCCESS | CN_RF_FAILURE);
-        reset_env(c, e, rob, pa, pb, obs, dbg_ranges, dbg_hid);
+        reset_env(c, e, rob, pa, pb, trk, obs, dbg_ranges, dbg_hid);
         rob[CN_R_FLAGS] |= keep;   /* last episode's status stays readable (ENV:1265-1267) */
         *reward_out = 0.0f;
         *done_out = 2;
@@ -578,7 +597,7 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
     }
 
     /* get_state */
-    int done_now = observe(c, rob, pa, pb, step_counter, 1, obs, dbg_ranges, dbg_hid);
+    int done_now = observe(c, rob, pa, pb, trk, step_counter, 1, obs, dbg_ranges, dbg_hid);
     int done = ((rob[CN_R_FLAGS] & CN_RF_DONE) != 0) || done_now;   /* sticky, ENV:1011 */
 
     /* W: compute_reward (ENV:1046-1162) on the ROUNDED heading / distance */
@@ -619,11 +638,12 @@ void orc_reset(const orc_ctx* c, uint32_t* blob, const uint8_t* mask, float* obs
                float* dbg_ranges, uint8_t* dbg_hid) {
     const int E = c->cfg.n_envs, N = c->cfg.n_peds, D = c->d.obs_dim, NR = c->cfg.n_samples - 1;
     uint32_t* rob = blob_robot(c, blob); uint32_t* pa = blob_ped_a(c, blob); uint32_t* pb = blob_ped_b(c, blob);
+    uint32_t* trk = blob_trk(c, blob);
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < E; ++e) {
         if (mask && !mask[e]) continue;
         reset_env(c, e, rob + (size_t)e * CN_ROBOT_WORDS, pa + (size_t)e * N * 4, pb + (size_t)e * N * 4,
-                  obs + (size_t)e * D,
+                  trk ? trk + (size_t)e * CNF_WORLD_WORDS : NULL, obs + (size_t)e * D,
                   dbg_ranges ? dbg_ranges + (size_t)e * NR : NULL, dbg_hid ? dbg_hid + (size_t)e * NR : NULL);
         rob[(size_t)e * CN_ROBOT_WORDS + CN_R_FLAGS] = 0;
     }
@@ -633,10 +653,11 @@ void orc_step(const orc_ctx* c, uint32_t* blob, const float* actions, float* obs
               uint8_t* done, float* dbg_ranges, uint8_t* dbg_hid) {
     const int E = c->cfg.n_envs, N = c->cfg.n_peds, D = c->d.obs_dim, NR = c->cfg.n_samples - 1;
     uint32_t* rob = blob_robot(c, blob); uint32_t* pa = blob_ped_a(c, blob); uint32_t* pb = blob_ped_b(c, blob);
+    uint32_t* trk = blob_trk(c, blob);
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < E; ++e) {
         step_env(c, e, rob + (size_t)e * CN_ROBOT_WORDS, pa + (size_t)e * N * 4, pb + (size_t)e * N * 4,
-                 actions + 2 * (size_t)e, obs + (size_t)e * D, reward + e, done + e,
+                 trk ? trk + (size_t)e * CNF_WORLD_WORDS : NULL, actions + 2 * (size_t)e, obs + (size_t)e * D, reward + e, done + e,
                  dbg_ranges ? dbg_ranges + (size_t)e * NR : NULL, dbg_hid ? dbg_hid + (size_t)e * NR : NULL);
     }
 }
@@ -650,9 +671,15 @@ void orc_clear_done(const orc_ctx* c, uint32_t* blob, const uint8_t* mask) {
 /* [E, 4] int32: success, ego violations, social violations, obstacle-present steps */
 void orc_counters(const orc_ctx* c, const uint32_t* blob, int32_t* out) {
     const uint32_t* rob = blob + CN_BLOB_HEADER_WORDS;
+    const uint32_t* trk = blob_trk(c, (uint32_t*)blob);
     for (int e = 0; e < c->cfg.n_envs; ++e) {
         const uint32_t* r = rob + (size_t)e * CN_ROBOT_WORDS;
         out[4 * e + 0] = (r[CN_R_FLAGS] & CN_RF_SUCCESS) ? 1 : 0;
+        if (trk) {                                          /* CN_FLAG_RISK_FAITHFUL: the tracker record's counters */
+            const uint32_t* t = trk + (size_t)e * CNF_WORLD_WORDS;
+            out[4 * e + 1] = (int32_t)t[CNF_H_EGO]; out[4 * e + 2] = (int32_t)t[CNF_H_SOCIAL]; out[4 * e + 3] = (int32_t)t[CNF_H_PRESENT];
+            continue;
+        }
         out[4 * e + 1] = (int32_t)(r[CN_R_CNT0] & 0xFFFFu);
         out[4 * e + 2] = (int32_t)(r[CN_R_CNT0] >> 16);
         out[4 * e + 3] = (int32_t)(r[CN_R_CNT1] & 0xFFFFu);

@@ -19,7 +19,9 @@ _SO = os.path.join(_HERE, "libcn_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle in-tree (gcc, a second or two)."""
-    srcs = [os.path.join(_HERE, "cn_oracle.c"),
+    srcs = [os.path.join(_HERE, "cn_oracle.c"), os.path.join(_HERE, "cn_oracle_faithful.c"),
+            os.path.join(_HERE, "..", "crowdnav_b200", "csrc", "cn_math64.h"),
+            os.path.join(_HERE, "..", "crowdnav_b200", "csrc", "cn_faithful_state.h"),
             os.path.join(_HERE, "..", "crowdnav_b200", "csrc", "cn_math.h"),
             os.path.join(_HERE, "..", "crowdnav_b200", "csrc", "cn_state.h"),
             os.path.join(_HERE, "..", "include", "crowdnav.h")]
@@ -127,6 +129,12 @@ class OracleEnv:
         n = self.cfg.n_peds
         o = 16 + self.E * 16 + self.E * n * 4
         return self.blob[o:o + self.E * n * 4].reshape(self.E, n, 4)
+
+    def trk(self) -> np.ndarray:
+        """[E, 396] tracker records (CN_FLAG_RISK_FAITHFUL; crowdnav_b200/csrc/cn_faithful_state.h)."""
+        n = self.cfg.n_peds
+        o = 16 + self.E * 16 + 2 * self.E * n * 4
+        return self.blob[o:o + self.E * 396].reshape(self.E, 396)
 
     def robot_pose(self) -> np.ndarray:
         """[E, 3] float64 x, y, yaw decoded from the fixed-point state."""
