@@ -190,6 +190,9 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: 'fused' = the step kernel stores its rows into every peer's gather buffer (symmetric "
                          "memory, NVLink) + a barrier; 'nccl' = separate in-place ncclAllGather after the kernel")
+    ap.add_argument("--risk-faithful", action="store_true",
+                    help="CN_FLAG_RISK_FAITHFUL: K block and counters from the reference's own segmentation / tracker "
+                         "(cn_faithful_kernel runs behind the step kernel: two launches per step); single GPU or --gather nccl")
     ap.add_argument("--with-policy", action="store_true",
                     help="run the TD3 actor forward (torch) inside each step instead of replaying action batches")
     args = ap.parse_args()
@@ -223,9 +226,12 @@ def main():
     wl = args.workload
     per_gpu = args.envs_per_gpu or PER_GPU_ENVS[wl]
     cfg_global = baseline_config(WORKLOADS[wl], n_envs=per_gpu * world, auto_reset=True)
+    if args.risk_faithful:
+        from crowdnav_b200.config import CN_FLAG_RISK_FAITHFUL
+        cfg_global.flags |= CN_FLAG_RISK_FAITHFUL
     gather_mode = "none"
     if world > 1:
-        gather_mode = "fused" if args.gather == "fused" else "collective"
+        gather_mode = "fused" if (args.gather == "fused" and not args.risk_faithful) else "collective"
     try:
         senv = ShardedVecEnv(cfg_global, lambda c, o: CrowdNavVecEnv(c, device=local_rank, obs_out=o), dev,
                              gather=gather_mode if world > 1 else "collective")
@@ -411,6 +417,9 @@ def main():
                                                                   "side stream, 3 rotating buffers",
                                                          "collective": "by one in-place ncclAllGather per step"}[gather_mode])),
                        "l2": l2_text,
+                       "risk_block": ("faithful: the reference's own segmentation / tracker in float64, cn_faithful_kernel "
+                                      "behind the step kernel (2 launches per step)" if args.risk_faithful else
+                                      "intended: ideal association inside the step kernel"),
                        "actions": ("TD3 actor forward inside each step" if args.with_policy else
                                    "ring of 16 batches from a random-init TD3 actor + N(0,1) exploration noise, clipped")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -433,14 +442,14 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"] = cpu_baseline(wl, args.risk_faithful)
         _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(wl: str):
+def cpu_baseline(wl: str, risk_faithful: bool = False):
     """The oracle port on the box's host cores: bounded sample of the same workload."""
     import numpy as np
     from crowdnav_b200.config import baseline_config
@@ -448,6 +457,8 @@ def cpu_baseline(wl: str):
     cores = os.cpu_count() or 1
     n = min(PER_GPU_ENVS[wl], 4096)
     cfg = baseline_config(WORKLOADS[wl], n_envs=n)
+    if risk_faithful:
+        cfg.flags |= 8
     env = OracleEnv(cfg, threads=cores)
     env.reset()
     rng = np.random.default_rng(0)

@@ -26,7 +26,9 @@
 #define CNF_SYNC() __syncwarp()
 #else
 #define CNF_FN static inline
+#ifndef CNF_SYNC            /* a host harness may supply a thread barrier to run the lanes as threads */
 #define CNF_SYNC() ((void)0)
+#endif
 #endif
 
 enum { CNF_T_NONE = 0, CNF_T_W = 1, CNF_T_O = 2 };

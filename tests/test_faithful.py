@@ -88,11 +88,12 @@ def _host_device_lib(tmp_path_factory):
     """g++ build of the device header with one lane (tests/faithful_host.cpp)."""
     out = os.path.join(str(tmp_path_factory.mktemp("faithful_host")), "libfaithful_host.so")
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fPIC", "-shared",
-           "-o", out, os.path.join(HERE, "faithful_host.cpp")]
+           "-pthread", "-o", out, os.path.join(HERE, "faithful_host.cpp")]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     H = C.CDLL(out)
     H.cnfh_observe.argtypes = [C.POINTER(CnfParams), C.c_void_p] + [C.c_double] * 3 + [C.c_void_p, C.c_float, C.c_int,
                                                                                     C.c_void_p]
+    H.cnfh_observe_lanes.argtypes = H.cnfh_observe.argtypes + [C.c_int]
     return H
 
 
@@ -149,6 +150,80 @@ def test_device_code_on_host_equals_oracle(host_device, case):
         check("step %d" % (t + 1))
     assert o.trk()[:, 0].max() > 0 or cfg.n_samples < 100       # objects were tracked
     assert int(o.trk()[:, 7].sum()) == 0
+
+
+def _record_worlds(cfg, T, host_device=None, nl=32):
+    """Step the oracle; per world and step yield what cn_faithful_kernel would read and must produce.  With
+    `host_device`, also run the device code with `nl` lanes as `nl` concurrent threads and compare."""
+    cfg = cfg.copy()
+    cfg.flags |= CN_FLAG_RISK_FAITHFUL
+    o = OracleEnv(cfg, debug=True)
+    E, NR, K = cfg.n_envs, cfg.n_samples - 1, cfg.k_obstacles
+    p = _params(cfg)
+    trk = np.zeros((E, 396), dtype=np.uint32)
+    rng = np.random.default_rng(3)
+    recs = []
+
+    def visit():
+        rw = o.robot_words()
+        for e in range(E):
+            r = rw[e]
+            x = float(np.float32(np.int32(r[0])) * np.float32(2.0 ** -24))
+            y = float(np.float32(np.int32(r[1])) * np.float32(2.0 ** -24))
+            yaw = float(np.float32(np.int32(r[2])) * np.float32(1.4629180792671596e-09))
+            sc = np.ascontiguousarray(o.ranges[e])
+            recs.append((trk[e].copy(), x, y, yaw, sc.copy(), int(r[11]), o.obs[e, NR + 7:].copy(), o.trk()[e].copy()))
+            if host_device is not None:
+                kb = np.zeros(4 * K, dtype=np.float32)
+                host_device.cnfh_observe_lanes(C.byref(p), trk[e].ctypes.data, x, y, yaw, sc.ctypes.data,
+                                               C.c_float(cfg.max_range), int(r[11]), kb.ctypes.data, nl)
+                assert np.array_equal(kb.view(np.uint32), o.obs[e, NR + 7:].view(np.uint32))
+                assert np.array_equal(trk[e], o.trk()[e])
+            else:
+                trk[e] = o.trk()[e]
+
+    o.reset()
+    visit()
+    for t in range(T):
+        o.step(np.stack([np.full(E, 0.22), rng.uniform(-0.5, 0.5, E)], 1).astype(np.float32))
+        visit()
+    return p, recs
+
+
+@pytest.mark.parametrize("nl", [32, 7])
+def test_device_code_with_concurrent_lanes(host_device, nl):
+    """The lanes of the warp as real threads, CNF_SYNC() as a barrier over them: same bits as the oracle."""
+    _record_worlds(baseline_config(1, n_envs=6, auto_reset=True), 40, host_device, nl)
+    _record_worlds(baseline_config(4, n_envs=2, auto_reset=True), 12, host_device, nl)
+
+
+def test_device_code_is_race_free_under_thread_sanitizer(tmp_path):
+    """32 lanes as 32 threads under -fsanitize=thread: every access to the world's scratch must be ordered by a
+    CNF_SYNC().  (Checked once by hand that removing one sync is reported.)"""
+    exe = str(tmp_path / "faithful_tsan")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fsanitize=thread",
+           "-pthread", "-o", exe, os.path.join(HERE, "faithful_host_main.cpp")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime here: " + res.stdout[-200:])
+    cfg = baseline_config(1, n_envs=6, auto_reset=True)
+    p, recs = _record_worlds(cfg, 40)
+    path = str(tmp_path / "records.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([len(recs), cfg.n_samples - 1, cfg.k_obstacles], dtype=np.int32).tobytes())
+        f.write(bytes(p))
+        for trk_in, x, y, yaw, sc, step, kb, trk_out in recs:
+            f.write(trk_in.tobytes())
+            f.write(np.array([x, y, yaw], dtype=np.float64).tobytes())
+            f.write(sc.astype(np.float32).tobytes())
+            f.write(np.array([step], dtype=np.int32).tobytes())
+            f.write(kb.astype(np.float32).tobytes())
+            f.write(trk_out.tobytes())
+    res = subprocess.run([exe, path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if "FATAL: ThreadSanitizer" in res.stdout:
+        pytest.skip("ThreadSanitizer cannot run here: " + res.stdout[-200:])
+    assert "ThreadSanitizer: data race" not in res.stdout, res.stdout[-3000:]
+    assert res.returncode == 0, res.stdout[-2000:]
 
 
 def test_faithful_env_properties():
