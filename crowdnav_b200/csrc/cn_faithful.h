@@ -41,7 +41,6 @@ typedef struct cnf_scratch {
     int32_t*  hy;
     int32_t*  rmm;      /* [n] round(range, 3), thousandths    */
     int16_t*  src;      /* [n] ray whose record ray i carries  */
-    int16_t*  flat;     /* [n] rays in segment order           */
     int16_t*  sub;      /* [n + 2] sub-segment offsets         */
     uint8_t*  gok;      /* [n] gradient defined                */
     uint8_t*  cok;      /* [n] gradient change defined         */
@@ -54,6 +53,7 @@ typedef struct cnf_scratch {
     double*   hit;      /* [64][2] ring hits of one probe line */
     uint8_t*  hitf;     /* [64]                                */
     int32_t*  misc;     /* [8] scalars shared between lanes    */
+    int32_t*  red;      /* [128] per-lane partial reductions   */
 } cnf_scratch;
 
 /* bytes of scratch for n rays (offsets are assigned in this order, doubles first) */
@@ -63,9 +63,10 @@ CN_HD size_t cnf_scratch_bytes(int n) {
     b += sizeof(double) * CNF_TRK_CAP + sizeof(double) * 128; /* am_val, hit */
     b += sizeof(uint32_t) * CNF_WORLD_WORDS;                  /* trk (1584 B, keeps 8-byte alignment) */
     b += 3 * sizeof(int32_t) * (size_t)n;                     /* hx, hy, rmm */
-    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8);
-    b += sizeof(int16_t) * (3 * (size_t)n + 2);
-    b += 4 * (size_t)n + 64;
+    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8 + 128);
+    b += 64;                                                  /* hitf */
+    b += sizeof(int16_t) * (2 * (size_t)n + 2);
+    b += 4 * (size_t)n;
     return (b + 15) & ~(size_t)15;
 }
 CN_HD void cnf_scratch_carve(unsigned char* base, int n, cnf_scratch* S) {
@@ -75,17 +76,17 @@ CN_HD void cnf_scratch_carve(unsigned char* base, int n, cnf_scratch* S) {
     S->am_val = (double*)p; p += sizeof(double) * CNF_TRK_CAP;
     S->hit = (double*)p; p += sizeof(double) * 128;
     S->trk = (uint32_t*)p; p += sizeof(uint32_t) * CNF_WORLD_WORDS;
+    S->hitf = p; p += 64;                                     /* 8-byte aligned: read as 8 words */
     S->hx = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->hy = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->rmm = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->conf = (int32_t*)p; p += sizeof(int32_t) * CNF_CONF_CAP * 4;
     S->am_idx = (int32_t*)p; p += sizeof(int32_t) * CNF_TRK_CAP;
     S->misc = (int32_t*)p; p += sizeof(int32_t) * 8;
+    S->red = (int32_t*)p; p += sizeof(int32_t) * 128;
     S->src = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
-    S->flat = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
     S->sub = (int16_t*)p; p += sizeof(int16_t) * ((size_t)n + 2);
-    S->gok = p; p += n; S->cok = p; p += n; S->type = p; p += n; S->close = p; p += n;
-    S->hitf = p;
+    S->gok = p; p += n; S->cok = p; p += n; S->type = p; p += n; S->close = p;
 }
 
 CNF_FN double cnf_ld64(const uint32_t* w) {
@@ -174,19 +175,40 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
     }
     CNF_SYNC();
 
-    /* ---- lane 0: the order-dependent walks ---- */
-    if (lane == 0) {
-        /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
-        S.chg[n - 1] = 0.0; S.cok[n - 1] = 0;
-        if (S.gok[n - 1]) {
-            for (int i = n - 2; i >= 0; --i)
-                if (S.gok[i]) { S.chg[n - 1] = S.chg[i]; S.cok[n - 1] = S.cok[i]; break; }
+    /* ---- typing (ENV:370-404): only rays with a defined gradient change take part in the state machine, so their
+     * indices are compacted first (lane-chunked, order preserving) and lane 0 walks the short list ---- */
+    const int chunk = (n + nl - 1) / nl;
+    const int c_lo = (lane * chunk < n) ? lane * chunk : n;
+    const int c_hi = (c_lo + chunk < n) ? c_lo + chunk : n;
+    int16_t* cand = S.sub;                                      /* free until the sub-segment offsets are built */
+    {
+        int cnt = 0;
+        for (int i = c_lo; i < c_hi; ++i) {
+            S.type[i] = (uint8_t)CNF_T_NONE; S.src[i] = (int16_t)i;
+            cnt += (i != n - 1 && S.cok[i]);
         }
-        /* typing with the delayed-update counter (ENV:370-404); a record is (type, source ray) */
-        int last_type = CNF_T_NONE, last_src = 0, du = 0;
-        for (int i = 0; i < n; ++i) {
-            int t = CNF_T_NONE, s = i;
-            if (S.cok[i] && i != n - 1) {
+        S.red[lane] = cnt;
+        if (lane == 0) {
+            /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
+            S.chg[n - 1] = 0.0; S.cok[n - 1] = 0;
+            if (S.gok[n - 1]) {
+                for (int i = n - 2; i >= 0; --i)
+                    if (S.gok[i]) { S.chg[n - 1] = S.chg[i]; S.cok[n - 1] = S.cok[i]; break; }
+            }
+        }
+    }
+    CNF_SYNC();
+    {
+        int base = 0, total = 0;
+        for (int l = 0; l < nl; ++l) { const int c = S.red[l]; if (l < lane) base += c; total += c; }
+        for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && S.cok[i]) cand[base++] = (int16_t)i;
+        CNF_SYNC();
+        if (lane == 0) {
+            /* a record is (type, source ray): `_scans_object_type[i] = last_type` hands ray i an EARLIER ray's range and pose */
+            int last_type = CNF_T_NONE, last_src = 0, du = 0;
+            for (int q = 0; q < total; ++q) {
+                const int i = cand[q];
+                int t, s = i;
                 const double ci = S.chg[i];
                 if (ci == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; }
                 else if (du != 1) {
@@ -202,85 +224,123 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
                     t = CNF_T_O; last_type = CNF_T_O; last_src = i;
                     if (S.cok[i + 1] && S.chg[i + 1] == 0.0) du = 0;
                 }
+                S.type[i] = (uint8_t)t; S.src[i] = (int16_t)s;
             }
-            S.type[i] = (uint8_t)t; S.src[i] = (int16_t)s;
         }
     }
     CNF_SYNC();
-    /* neighbour association on the records' poses (ENV:443-486) */
-    for (int i = lane; i < n; i += nl) {
-        int cl = 1;
-        if (i != n - 1) {
-            const int a = S.src[i], b = S.src[i + 1];
-            cl = !(cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox) > 0.0);
+    /* neighbour association on the records' poses (ENV:443-486); does the record carry a hit? */
+    uint8_t* hflag = S.gok;                                     /* gradients are consumed */
+    {
+        int first = n, last = -1, cnt = 0;
+        for (int i = lane; i < n; i += nl) {
+            int cl = 1;
+            if (i != n - 1) {
+                const int a = S.src[i], b = S.src[i + 1];
+                cl = !(cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox) > 0.0);
+            }
+            S.close[i] = (uint8_t)cl;
+            hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
+            if (cl) { ++cnt; if (i < first) first = i; if (i != n - 1 && i > last) last = i; }
         }
-        S.close[i] = (uint8_t)cl;
+        S.red[32 + 3 * lane] = first; S.red[33 + 3 * lane] = last; S.red[34 + 3 * lane] = cnt;
     }
     CNF_SYNC();
-
-    if (lane == 0) {
-        /* segments in the reference's order: first (+ last when they join across the blind spot), then the rest */
-        int nseg = 0, e0 = -1, zb = 0;
-        for (int i = 0; i < n; ++i) if (S.close[i]) { if (e0 < 0) e0 = i; ++nseg; if (i != n - 1) zb = i + 1; }
-        int merged = 0;
-        if (nseg > 1) {
-            const int a = S.src[0], b = S.src[n - 1];
-            merged = cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox * 2.0) > 0.0;     /* ENV:488-504 */
+    /* segments in the reference's order: first (+ last when they join across the blind spot, ENV:488-504), then the
+     * rest.  Position k of that order holds ray flat_of(k); every lane derives the same three scalars. */
+    int e0 = n, zb = 0, nseg = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int f = S.red[32 + 3 * l], z = S.red[33 + 3 * l];
+        if (f < e0) e0 = f;
+        if (z + 1 > zb) zb = z + 1;
+        nseg += S.red[34 + 3 * l];
+    }
+    int merged = 0;
+    if (nseg > 1) {
+        const int a = S.src[0], b = S.src[n - 1];
+        merged = cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox * 2.0) > 0.0;
+    }
+    const int len_a = e0 + 1, len_z = merged ? n - zb : 0;
+#define CNF_FLAT_OF(k) ((k) < len_a ? (k) : ((k) < len_a + len_z ? zb + ((k) - len_a) : (k) - len_z))
+    /* a sub-segment ends where its segment ends or where hit and no-hit records meet (ENV:510-571: a segment
+     * without any hit has no such place, so it stays whole); running counts of 'o' / 'w' records along the order */
+    int16_t* cum_o = (int16_t*)S.grad;                           /* [n + 1] each; the gradients are consumed */
+    int16_t* cum_w = cum_o + (n + 1);
+    uint8_t* subend = S.cok;                                    /* the gradient changes are consumed */
+    CNF_SYNC();                                                 /* red[] and cok[] are about to be reused */
+    {
+        int n_end = 0, n_o = 0, n_w = 0;
+        for (int k = c_lo; k < c_hi; ++k) {
+            const int r = CNF_FLAT_OF(k);
+            int end;
+            if (merged && k < len_a + len_z) end = (k == len_a + len_z - 1);
+            else end = S.close[r];
+            if (!end) { const int r1 = CNF_FLAT_OF(k + 1); end = hflag[r] != hflag[r1]; }
+            subend[k] = (uint8_t)end;
+            n_end += end; n_o += (S.type[r] == CNF_T_O); n_w += (S.type[r] == CNF_T_W);
         }
-        int len = 0, first_len;
-        for (int i = 0; i <= e0; ++i) S.flat[len++] = (int16_t)i;
-        if (merged) for (int i = zb; i < n; ++i) S.flat[len++] = (int16_t)i;
-        first_len = len;
-        { const int stop = merged ? zb : n; for (int i = e0 + 1; i < stop; ++i) S.flat[len++] = (int16_t)i; }
-        /* split every segment that holds a hit at its 0.6 <-> hit transitions (ENV:510-571) */
-        int nsub = 0; S.sub[0] = 0;
-        int b = 0;
-        while (b < len) {
-            int e;
-            if (b == 0) e = first_len;
-            else { e = b; while (!S.close[S.flat[e]]) ++e; ++e; }
-            int any_hit = 0;
-            for (int k = b; k < e; ++k) if (S.rmm[S.src[S.flat[k]]] != max_mm) any_hit = 1;
-            if (!any_hit) S.sub[++nsub] = (int16_t)e;
-            else for (int k = b; k < e; ++k) {
-                int cl = 1;
-                if (k != e - 1) cl = (S.rmm[S.src[S.flat[k]]] == max_mm) != (S.rmm[S.src[S.flat[k + 1]]] == max_mm);
-                if (cl) S.sub[++nsub] = (int16_t)(k + 1);
-            }
-            b = e;
+        S.red[3 * lane] = n_end; S.red[3 * lane + 1] = n_o; S.red[3 * lane + 2] = n_w;
+    }
+    CNF_SYNC();
+    int nsub = 0;
+    {
+        int b_end = 0, b_o = 0, b_w = 0;
+        for (int l = 0; l < nl; ++l) {
+            const int c = S.red[3 * l];
+            if (l < lane) { b_end += c; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
+            nsub += c;
         }
-        /* confirmation (ENV:573-620, UTL:395-402) */
-        int nconf = 0, n_obst = 0, ego_hit = 0;
+        if (lane == 0) { S.sub[0] = 0; cum_o[0] = 0; cum_w[0] = 0; }
+        for (int k = c_lo; k < c_hi; ++k) {
+            const int r = CNF_FLAT_OF(k);
+            b_o += (S.type[r] == CNF_T_O); b_w += (S.type[r] == CNF_T_W);
+            cum_o[k + 1] = (int16_t)b_o; cum_w[k + 1] = (int16_t)b_w;
+            if (subend[k]) S.sub[++b_end] = (int16_t)(k + 1);
+        }
+    }
+    CNF_SYNC();
+    /* confirmation (ENV:573-620, UTL:395-402), one lane per sub-segment; every record of a sub-segment is a hit or
+     * none is, so its first one decides */
+    int32_t* verdict = (int32_t*)S.chg;                          /* [nsub] <= n; the gradient changes are consumed */
+    {
         const double span = P->max_range - P->min_range;
-        for (int s = 0; s < nsub; ++s) {
+        for (int s = lane; s < nsub; s += nl) {
             const int sb = S.sub[s], se = S.sub[s + 1], sl = se - sb;
-            int any_hit = 0, n_o = 0, n_w = 0, n_none = 0;
-            for (int k = sb; k < se; ++k) {
-                const int r = S.flat[k];
-                if (S.rmm[S.src[r]] != max_mm) any_hit = 1;
-                const int t = S.type[r];
-                n_o += (t == CNF_T_O); n_w += (t == CNF_T_W); n_none += (t == CNF_T_NONE);
+            int v = -1;
+            if (sl >= 4 && hflag[CNF_FLAT_OF(sb)]) {
+                const int n_o = cum_o[se] - cum_o[sb], n_w = cum_w[se] - cum_w[sb], n_none = sl - n_o - n_w;
+                const int kc = sb + sl / 2;
+                const int rc = S.src[CNF_FLAT_OF(kc)];
+                const double dctr = cn_milli64(S.rmm[rc]);
+                const double estd = 3.0 + floor(29.0 * (P->max_range - dctr) / span);
+                const double denom = ((double)sl < estd) ? (double)sl : estd;
+                const double score = (double)n_o / denom;
+                const int distinct = (n_o > 0) + (n_w > 0) + (n_none > 0);
+                int t = -1;
+                if (distinct > 1) {
+                    if (score >= 0.5) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
+                    else if ((double)sl <= estd) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
+                    else t = CNF_T_W;
+                } else {
+                    const double lim = ((double)nsub < estd) ? (double)nsub : estd;
+                    if (!((double)sl <= lim)) t = (n_w > 0) ? CNF_T_W : CNF_T_O;
+                }
+                if (t >= 0) v = t | (rc << 8);
             }
-            if (!any_hit || sl < 4) continue;
-            const int rc = S.src[S.flat[sb + sl / 2]];
-            const double dctr = cn_milli64(S.rmm[rc]);
-            const double estd = 3.0 + floor(29.0 * (P->max_range - dctr) / span);
-            const double denom = ((double)sl < estd) ? (double)sl : estd;
-            const double score = (double)n_o / denom;
-            const int distinct = (n_o > 0) + (n_w > 0) + (n_none > 0);
-            int t = -1;
-            if (distinct > 1) {
-                if (score >= 0.5) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
-                else if ((double)sl <= estd) t = (n_o > n_w) ? CNF_T_O : CNF_T_W;
-                else t = CNF_T_W;
-            } else {
-                const double lim = ((double)nsub < estd) ? (double)nsub : estd;
-                if (!((double)sl <= lim)) t = (n_w > 0) ? CNF_T_W : CNF_T_O;
-            }
-            if (t < 0) continue;
+            verdict[s] = v;
+        }
+    }
+#undef CNF_FLAT_OF
+    CNF_SYNC();
+    if (lane == 0) {
+        int nconf = 0, n_obst = 0, ego_hit = 0;
+        for (int s = 0; s < nsub; ++s) {
+            const int v = verdict[s];
+            if (v < 0) continue;
             if (nconf < CNF_CONF_CAP) {
+                const int rc = v >> 8;
                 int32_t* c = S.conf + 4 * nconf;
-                c[0] = t; c[1] = S.hx[rc]; c[2] = S.hy[rc]; c[3] = S.rmm[rc];
+                c[0] = v & 0xFF; c[1] = S.hx[rc]; c[2] = S.hy[rc]; c[3] = S.rmm[rc];
                 ++nconf;
             } else S.trk[CNF_H_OVERFLOW] += 1;
         }
@@ -297,6 +357,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
             }
     }
     CNF_SYNC();
+
 
     /* ---- tracker: best confirmed object per tracked one (ENV:691-703), one lane each ---- */
     const int nconf = S.misc[0];
@@ -350,7 +411,6 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
                 cnf_st64(q + CNF_E_SPEED, -1.0); cnf_st64(q + CNF_E_VX, 0.0); cnf_st64(q + CNF_E_VY, 0.0);
                 ++n_ent;
             }
-        for (int k = n_ent * CNF_ENTRY_WORDS; k < CNF_TRK_CAP * CNF_ENTRY_WORDS; ++k) E[k] = 0u;
         S.trk[CNF_H_N] = (uint32_t)n_ent;
         /* speed (ENV:745-760), obstacle velocity and the probe target of the collision cone (ENV:799-815) */
         const double curx = cn_py_round3_64(x), cury = cn_py_round3_64(y);
@@ -376,6 +436,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
 
     /* ---- collision cone: distance to the r = 0.178 ring along the probe lines (UTL:251-293) ---- */
     const int n_ent = S.misc[2];
+    for (int k = CNF_HDR_WORDS + n_ent * CNF_ENTRY_WORDS + lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;   /* unused entries read as zero */
     const int have_prev = (int)S.trk[CNF_H_HAVE_PREV];
     const double a0x = cn_milli64((int32_t)S.trk[CNF_H_PPX]), a0y = cn_milli64((int32_t)S.trk[CNF_H_PPY]);
     if (have_prev && n_ent > 0) {
@@ -407,20 +468,25 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
                     S.hitf[k] = (uint8_t)f;
                 }
                 CNF_SYNC();
-                /* every lane resolves the (few) hits identically: no broadcast needed */
+                /* every lane resolves the (few) hits identically: no broadcast needed.  Most probes miss the ring:
+                 * the 64 flags are first looked at as 8 words. */
                 int nh = 0, i0 = -1, i1 = -1, first[4] = {0, 0, 0, 0}; double k0 = 0.0, k1v = 0.0;
-                for (int k = 0; k < 64; ++k) {
-                    if (!S.hitf[k]) continue;
-                    int dup = 0;
-                    for (int o = 0; o < nh && o < 4; ++o)
-                        if (fabs(S.hit[2 * k] - S.hit[2 * first[o]]) < 1e-12 && fabs(S.hit[2 * k + 1] - S.hit[2 * first[o] + 1]) < 1e-12) { dup = 1; break; }
-                    if (dup) continue;
-                    if (nh < 4) first[nh] = k;
-                    ++nh;
-                    const double dx = S.hit[2 * k] - a0x, dy = S.hit[2 * k + 1] - a0y;
-                    const double key = dx * dx + dy * dy;
-                    if (i0 < 0 || key < k0) { i1 = i0; k1v = k0; i0 = k; k0 = key; }
-                    else if (i1 < 0 || key < k1v) { i1 = k; k1v = key; }
+                for (int w8 = 0; w8 < 8; ++w8) {
+                    unsigned long long word; memcpy(&word, S.hitf + 8 * w8, 8);
+                    if (word == 0ull) continue;
+                    for (int k = 8 * w8; k < 8 * w8 + 8; ++k) {
+                        if (!S.hitf[k]) continue;
+                        int dup = 0;
+                        for (int o = 0; o < nh && o < 4; ++o)
+                            if (fabs(S.hit[2 * k] - S.hit[2 * first[o]]) < 1e-12 && fabs(S.hit[2 * k + 1] - S.hit[2 * first[o] + 1]) < 1e-12) { dup = 1; break; }
+                        if (dup) continue;
+                        if (nh < 4) first[nh] = k;
+                        ++nh;
+                        const double dx = S.hit[2 * k] - a0x, dy = S.hit[2 * k + 1] - a0y;
+                        const double key = dx * dx + dy * dy;
+                        if (i0 < 0 || key < k0) { i1 = i0; k1v = k0; i0 = k; k0 = key; }
+                        else if (i1 < 0 || key < k1v) { i1 = k; k1v = key; }
+                    }
                 }
                 int stop = 0;
                 if (nh == 1) { have = 0; stop = 1; }              /* a Point has no .geoms -> None */

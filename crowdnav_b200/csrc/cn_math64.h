@@ -69,7 +69,14 @@ CN_HD long long cn_py_round3_k64(double x) {
     return (long long)n + up;
 }
 /* the double CPython returns for that decimal: the correctly rounded k / 1000 */
-CN_HD double cn_milli64(long long k) { return (double)k / 1000.0; }
+CN_HD double cn_milli64(long long k) {
+    const double kd = (double)k;
+    if (k > 33554432ll || k < -33554432ll) return kd / 1000.0;
+    /* Markstein: q = k * RN(1/1000) is within an ulp, one fma correction gives RN(k / 1000) -- the same bits as the
+     * IEEE division for every |k| <= 2^25 (exhaustive check: tests/test_faithful.py) at 3 instructions instead of ~20 */
+    const double q = kd * 0.001;
+    return fma(fma(-q, 1000.0, kd), 0.001, q);
+}
 CN_HD double cn_py_round3_64(double x) { return cn_milli64(cn_py_round3_k64(x)); }
 /* np.around(x, 3) in float64: rint(x * 1000) / 1000 (numpy multiplies, rints, divides) */
 CN_HD double cn_np_round3_64(double x) { return rint(x * 1000.0) / 1000.0; }

@@ -427,3 +427,8 @@ void orf_observe(const cnf_params* p, uint32_t* trk, double x, double y, double 
 void orf_sincos64(const double* a, double* s, double* c, int n) { for (int i = 0; i < n; ++i) cn_sincos64(a[i], s + i, c + i); }
 void orf_round3(const double* x, double* out, int n) { for (int i = 0; i < n; ++i) out[i] = cn_py_round3_64(x[i]); }
 int orf_world_words(void) { return CNF_WORLD_WORDS; }
+long orf_milli_mismatches(long lo, long hi) {
+    long bad = 0;
+    for (long k = lo; k <= hi; ++k) bad += (cn_milli64(k) != (double)k / 1000.0);
+    return bad;
+}

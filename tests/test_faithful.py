@@ -84,6 +84,13 @@ def test_sincos64_and_round3(oracle_lib):
     assert np.array_equal(out[~ties], want[~ties])
 
 
+def test_milli64_is_the_ieee_division(oracle_lib):
+    """cn_milli64 (k / 1000 by one multiplication and two fmas) == the IEEE division for every |k| <= 2^25."""
+    oracle_lib.orf_milli_mismatches.restype = C.c_long
+    oracle_lib.orf_milli_mismatches.argtypes = [C.c_long, C.c_long]
+    assert oracle_lib.orf_milli_mismatches(-(1 << 25) - 1000, (1 << 25) + 1000) == 0
+
+
 def _host_device_lib(tmp_path_factory):
     """g++ build of the device header with one lane (tests/faithful_host.cpp)."""
     out = os.path.join(str(tmp_path_factory.mktemp("faithful_host")), "libfaithful_host.so")
