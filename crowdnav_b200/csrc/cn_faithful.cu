@@ -1,6 +1,6 @@
 /*
- * cn_faithful.cu -- kernel of the `risk_faithful` perception block (CN_FLAG_RISK_FAITHFUL): one warp per world
- * runs cnf_world() (cn_faithful.h) behind the step kernel, on the same stream.  It reads what the step kernel
+ * cn_faithful.cu -- kernel of the `risk_faithful` perception block (CN_FLAG_RISK_FAITHFUL): two warps (64 threads, their own named barrier) per world
+ * run cnf_world() (cn_faithful.h) behind the step kernel, on the same stream.  It reads what the step kernel
  * left in HBM -- the robot record (pose on the integer grid, steps taken: 0 = the world was (re)started by this
  * launch) and the cleaned pre-rounding ranges -- keeps the world's tracker record in shared memory, and
  * overwrites the K block of the observation row (ENV:862-907) and the safety counters (ENV:653-654, 998-1005).
@@ -12,30 +12,31 @@
 #include "cn_kernel.h"
 #include "cn_faithful.h"
 
-#define CNF_WARPS 4
+#define CNF_WORLDS 4            /* worlds per CTA, CNF_LANES (64) threads each */
 
-__global__ void __launch_bounds__(32 * CNF_WARPS)
+__global__ void __launch_bounds__(CNF_LANES * CNF_WORLDS)
 cn_faithful_kernel(cnf_params P, const uint32_t* __restrict__ robot, uint32_t* __restrict__ trk,
                    const float* __restrict__ ranges, float* __restrict__ obs, const uint8_t* __restrict__ mask,
                    int E, int obs_dim, float no_return32, unsigned scratch_bytes) {
     extern __shared__ __align__(16) unsigned char cnf_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * CNF_WARPS + warp;
-    if (e >= E) return;
+    const int wi = threadIdx.x / CNF_LANES, lane = threadIdx.x % CNF_LANES;
+    const int e = blockIdx.x * CNF_WORLDS + wi;
+    const int bar = 1 + wi;                                    /* named barrier of this world's threads */
+    if (e >= E) return;                                        /* whole groups leave together */
     if (mask != nullptr && mask[e] == 0) return;              /* masked reset: untouched worlds keep their tracker */
     cnf_scratch S;
-    cnf_scratch_carve(cnf_smem + (size_t)warp * scratch_bytes, P.n_rays, &S);
+    cnf_scratch_carve(cnf_smem + (size_t)wi * scratch_bytes, P.n_rays, &S);
     const uint32_t* rob = robot + (size_t)e * CN_ROBOT_WORDS;
     uint32_t* g = trk + (size_t)e * CNF_WORLD_WORDS;
-    for (int k = lane; k < CNF_WORLD_WORDS; k += 32) S.trk[k] = g[k];
-    __syncwarp();
+    for (int k = lane; k < CNF_WORLD_WORDS; k += CNF_LANES) S.trk[k] = g[k];
+    CNF_SYNC();
     const double x = (double)((float)(int32_t)rob[CN_R_X] * CN_GRID);
     const double y = (double)((float)(int32_t)rob[CN_R_Y] * CN_GRID);
     const double yaw = (double)cn_bin2rad(rob[CN_R_TH]);
     const int step_counter = (int)rob[CN_R_STEP];
-    cnf_world(&P, &S, x, y, yaw, ranges + (size_t)e * P.n_rays, no_return32, step_counter,
-              obs + (size_t)e * obs_dim + P.n_rays + 7, lane, 32);
-    for (int k = lane; k < CNF_WORLD_WORDS; k += 32) g[k] = S.trk[k];
+    cnf_world(&P, S, x, y, yaw, ranges + (size_t)e * P.n_rays, no_return32, step_counter,
+              obs + (size_t)e * obs_dim + P.n_rays + 7, lane, CNF_LANES, bar);
+    for (int k = lane; k < CNF_WORLD_WORDS; k += CNF_LANES) g[k] = S.trk[k];
 }
 
 /* [E, 4] int32: success (robot record), ego / social violations, obstacle-present steps (tracker record) */
@@ -50,12 +51,12 @@ __global__ void cn_faithful_counters_kernel(const uint32_t* __restrict__ robot, 
     reinterpret_cast<int4*>(out)[e] = v;
 }
 
-size_t cn_faithful_smem_bytes(int n_rays) { return CNF_WARPS * cnf_scratch_bytes(n_rays); }
+size_t cn_faithful_smem_bytes(int n_rays) { return CNF_WORLDS * cnf_scratch_bytes(n_rays); }
 
 cudaError_t cn_launch_faithful(const cn_config* cfg, const uint32_t* robot, uint32_t* trk, const float* ranges,
                                float* obs, const uint8_t* mask, int obs_dim, cudaStream_t stream) {
     cnf_params P; cnf_params_from_config(cfg, &P);
-    const size_t per = cnf_scratch_bytes(P.n_rays), smem = CNF_WARPS * per;
+    const size_t per = cnf_scratch_bytes(P.n_rays), smem = CNF_WORLDS * per;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(cn_faithful_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -63,7 +64,7 @@ cudaError_t cn_launch_faithful(const cn_config* cfg, const uint32_t* robot, uint
         configured = smem;
     }
     const int E = cfg->n_envs;
-    cn_faithful_kernel<<<(E + CNF_WARPS - 1) / CNF_WARPS, 32 * CNF_WARPS, smem, stream>>>(
+    cn_faithful_kernel<<<(E + CNF_WORLDS - 1) / CNF_WORLDS, CNF_LANES * CNF_WORLDS, smem, stream>>>(
         P, robot, trk, ranges, obs, mask, E, obs_dim, cfg->max_range, (unsigned)per);
     return cudaGetLastError();
 }

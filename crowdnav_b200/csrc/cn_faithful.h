@@ -21,9 +21,11 @@
 #include "cn_math64.h"
 #include "cn_faithful_state.h"
 
+#define CNF_LANES 64          /* device: threads (two warps) that share one world */
 #if defined(__CUDACC__)
 #define CNF_FN __device__ __forceinline__
-#define CNF_SYNC() __syncwarp()
+/* the world's CNF_LANES threads meet at their own named barrier (bar = 1 + world index inside the CTA) */
+#define CNF_SYNC() asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(CNF_LANES) : "memory")
 #else
 #define CNF_FN static inline
 #ifndef CNF_SYNC            /* a host harness may supply a thread barrier to run the lanes as threads */
@@ -53,7 +55,7 @@ typedef struct cnf_scratch {
     double*   hit;      /* [64][2] ring hits of one probe line */
     uint8_t*  hitf;     /* [64]                                */
     int32_t*  misc;     /* [8] scalars shared between lanes    */
-    int32_t*  red;      /* [128] per-lane partial reductions   */
+    int32_t*  red;      /* [256] per-lane partial reductions   */
 } cnf_scratch;
 
 /* bytes of scratch for n rays (offsets are assigned in this order, doubles first) */
@@ -63,7 +65,7 @@ CN_HD size_t cnf_scratch_bytes(int n) {
     b += sizeof(double) * CNF_TRK_CAP + sizeof(double) * 128; /* am_val, hit */
     b += sizeof(uint32_t) * CNF_WORLD_WORDS;                  /* trk (1584 B, keeps 8-byte alignment) */
     b += 3 * sizeof(int32_t) * (size_t)n;                     /* hx, hy, rmm */
-    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8 + 128);
+    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8 + 256);
     b += 64;                                                  /* hitf */
     b += sizeof(int16_t) * (2 * (size_t)n + 2);
     b += 4 * (size_t)n;
@@ -83,11 +85,14 @@ CN_HD void cnf_scratch_carve(unsigned char* base, int n, cnf_scratch* S) {
     S->conf = (int32_t*)p; p += sizeof(int32_t) * CNF_CONF_CAP * 4;
     S->am_idx = (int32_t*)p; p += sizeof(int32_t) * CNF_TRK_CAP;
     S->misc = (int32_t*)p; p += sizeof(int32_t) * 8;
-    S->red = (int32_t*)p; p += sizeof(int32_t) * 128;
+    S->red = (int32_t*)p; p += sizeof(int32_t) * 256;
     S->src = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
     S->sub = (int16_t*)p; p += sizeof(int16_t) * ((size_t)n + 2);
     S->gok = p; p += n; S->cok = p; p += n; S->type = p; p += n; S->close = p;
 }
+
+/* k / 1000 for the thousandths this block stores (positions within +-31 m, ranges <= max_range): |k| < 2^25 */
+#define CNF_MILLI(k) cn_milli64_small((int32_t)(k))
 
 CNF_FN double cnf_ld64(const uint32_t* w) {
     unsigned long long u = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
@@ -100,7 +105,7 @@ CNF_FN void cnf_st64(uint32_t* w, double d) {
 
 /* UTL:421-448: round(IoU, 3) of two squares of half-size h centred on points given in thousandths */
 CNF_FN double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double h) {
-    const double ax = cn_milli64(axk), ay = cn_milli64(ayk), bx = cn_milli64(bxk), by = cn_milli64(byk);
+    const double ax = CNF_MILLI(axk), ay = CNF_MILLI(ayk), bx = CNF_MILLI(bxk), by = CNF_MILLI(byk);
     const double ax0 = ax - h, ax1 = ax + h, ay0 = ay - h, ay1 = ay + h;
     const double bx0 = bx - h, bx1 = bx + h, by0 = by - h, by1 = by + h;
     const double w = (ax1 < bx1 ? ax1 : bx1) - (ax0 > bx0 ? ax0 : bx0);
@@ -124,12 +129,13 @@ CNF_FN void cnf_hit_point(const cnf_params* P, double x, double y, double yaw, i
  *   scan32 : cleaned ranges in observation order (UTL:375-392), fp32, `no_return32` where nothing was hit
  *   step_counter : 0 inside reset (ENV:1245), else the 1-based step
  *   kblock : 4K floats of the observation row (written by lane 0)
+ *   lane, nl : this thread's index among the nl threads that share the world; bar: their barrier (device only)
  *   S.trk must hold the world's tracker record on entry (all lanes see it) and holds the new one on exit.
  */
-CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, double y, double yaw,
+CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double y, double yaw,
                       const float* scan32, float no_return32, int step_counter, float* kblock,
-                      int lane, int nl) {
-    const cnf_scratch S = *Sp;
+                      int lane, int nl, int bar) {
+    (void)bar;
     const int n = P->n_rays, K = P->k_obstacles;
     const int32_t max_mm = (int32_t)cn_py_round3_k64(P->max_range);
 
@@ -140,7 +146,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
         CNF_SYNC();
         for (int i = lane; i < n; i += nl) {
             const int j = (i == n - 1) ? 0 : i + 1;
-            S.chg[i] = cn_hypot64(cn_milli64(S.hx[i]) - cn_milli64(S.hx[j]), cn_milli64(S.hy[i]) - cn_milli64(S.hy[j]));
+            S.chg[i] = cn_hypot64(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]));
         }
         CNF_SYNC();
         if (lane == 0) {
@@ -163,9 +169,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
     for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
         if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.grad[i] = 0.0; continue; }
         const int j = (i == n - 1) ? 0 : i + 1;
-        const double dy = cn_milli64(S.hy[i]) - cn_milli64(S.hy[j]);
+        const double dy = CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]);
         double g = 0.0;
-        if (dy != 0.0) g = (cn_milli64(S.hx[i]) - cn_milli64(S.hx[j])) / dy;
+        if (dy != 0.0) g = (CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j])) / dy;
         S.grad[i] = cn_py_round3_64(g); S.gok[i] = 1;
     }
     CNF_SYNC();
@@ -243,17 +249,17 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
             hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
             if (cl) { ++cnt; if (i < first) first = i; if (i != n - 1 && i > last) last = i; }
         }
-        S.red[32 + 3 * lane] = first; S.red[33 + 3 * lane] = last; S.red[34 + 3 * lane] = cnt;
+        S.red[64 + 3 * lane] = first; S.red[65 + 3 * lane] = last; S.red[66 + 3 * lane] = cnt;
     }
     CNF_SYNC();
     /* segments in the reference's order: first (+ last when they join across the blind spot, ENV:488-504), then the
      * rest.  Position k of that order holds ray flat_of(k); every lane derives the same three scalars. */
     int e0 = n, zb = 0, nseg = 0;
     for (int l = 0; l < nl; ++l) {
-        const int f = S.red[32 + 3 * l], z = S.red[33 + 3 * l];
+        const int f = S.red[64 + 3 * l], z = S.red[65 + 3 * l];
         if (f < e0) e0 = f;
         if (z + 1 > zb) zb = z + 1;
-        nseg += S.red[34 + 3 * l];
+        nseg += S.red[66 + 3 * l];
     }
     int merged = 0;
     if (nseg > 1) {
@@ -311,7 +317,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
                 const int n_o = cum_o[se] - cum_o[sb], n_w = cum_w[se] - cum_w[sb], n_none = sl - n_o - n_w;
                 const int kc = sb + sl / 2;
                 const int rc = S.src[CNF_FLAT_OF(kc)];
-                const double dctr = cn_milli64(S.rmm[rc]);
+                const double dctr = CNF_MILLI(S.rmm[rc]);
                 const double estd = 3.0 + floor(29.0 * (P->max_range - dctr) / span);
                 const double denom = ((double)sl < estd) ? (double)sl : estd;
                 const double score = (double)n_o / denom;
@@ -345,7 +351,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
             } else S.trk[CNF_H_OVERFLOW] += 1;
         }
         for (int c = 0; c < nconf; ++c)
-            if (S.conf[4 * c] == CNF_T_O) { ++n_obst; if (cn_milli64(S.conf[4 * c + 3]) < 0.140) ego_hit = 1; }
+            if (S.conf[4 * c] == CNF_T_O) { ++n_obst; if (CNF_MILLI(S.conf[4 * c + 3]) < 0.140) ego_hit = 1; }
         if (n_obst > 0) S.trk[CNF_H_PRESENT] += 1;              /* ENV:653-654 */
         S.misc[0] = nconf; S.misc[1] = ego_hit;
         /* popleft of every tracked deque (ENV:679-682) happens before the IoUs are taken */
@@ -419,8 +425,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
             uint32_t* q = E + i * CNF_ENTRY_WORDS;
             double cx = 0.0, cy = 0.0;
             if (q[CNF_E_NDEQ] > 1u) {
-                const double px = cn_milli64((int32_t)q[CNF_E_PX]), py = cn_milli64((int32_t)q[CNF_E_PY]);
-                const double lx = cn_milli64((int32_t)q[CNF_E_LX]), ly = cn_milli64((int32_t)q[CNF_E_LY]);
+                const double px = CNF_MILLI(q[CNF_E_PX]), py = CNF_MILLI(q[CNF_E_PY]);
+                const double lx = CNF_MILLI(q[CNF_E_LX]), ly = CNF_MILLI(q[CNF_E_LY]);
                 cnf_st64(q + CNF_E_SPEED, cn_hypot64(py - ly, px - lx) / P->dt);
                 if (S.trk[CNF_H_HAVE_PREV]) {
                     cx = px - lx; cy = py - ly;                  /* last - curr (sic, ENV:806-807) */
@@ -438,7 +444,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
     const int n_ent = S.misc[2];
     for (int k = CNF_HDR_WORDS + n_ent * CNF_ENTRY_WORDS + lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;   /* unused entries read as zero */
     const int have_prev = (int)S.trk[CNF_H_HAVE_PREV];
-    const double a0x = cn_milli64((int32_t)S.trk[CNF_H_PPX]), a0y = cn_milli64((int32_t)S.trk[CNF_H_PPY]);
+    const double a0x = CNF_MILLI(S.trk[CNF_H_PPX]), a0y = CNF_MILLI(S.trk[CNF_H_PPY]);
     if (have_prev && n_ent > 0) {
         const double a1x = S.hit[0], a1y = S.hit[1];
         CNF_SYNC();
@@ -448,11 +454,24 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
         const long x_hi = (long)ceil(a0x + 3.5), x_lo = (long)floor(a0x - 3.5);
         for (int i = 0; i < n_ent; ++i) {
             const uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
-            const double ox = cn_milli64((int32_t)q[CNF_E_LX]), oy = cn_milli64((int32_t)q[CNF_E_LY]);
+            const double ox = CNF_MILLI(q[CNF_E_LX]), oy = CNF_MILLI(q[CNF_E_LY]);
             int have = 0; double dtc = 0.0;
             for (long x2 = x_hi; x2 > x_lo; --x2) {
                 const double qx = (double)x2, qy = ((double)x2 * gradient) + cb;
                 const double rx = qx - a0x, ry = qy - a0y;
+                {
+                    /* every vertex of the ring lies on the circle: a probe segment that stays farther than the radius
+                     * (+1e-6, far above round-off) from its centre cannot meet it -- 'LINESTRING EMPTY' without
+                     * testing the 64 edges.  All lanes compute the same bits, so the decision is uniform. */
+                    const double len2 = rx * rx + ry * ry;
+                    if (len2 > 0.0) {
+                        double tp = ((ox - a0x) * rx + (oy - a0y) * ry) / len2;
+                        tp = tp < 0.0 ? 0.0 : (tp > 1.0 ? 1.0 : tp);
+                        const double ex = ox - (a0x + tp * rx), ey = oy - (a0y + tp * ry);
+                        const double rm = P->cp_radius * 1.000001;
+                        if (ex * ex + ey * ey > rm * rm) continue;
+                    }
+                }
                 for (int k = lane; k < 64; k += nl) {
                     const int k1 = (k + 1) & 63;
                     const double ax = ox + P->cp_radius * CNF_RING_COS[k], ay = oy + P->cp_radius * CNF_RING_SIN[k];
@@ -521,7 +540,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
             double ego_cur = 0.0, ego_max = 0.0;
             /* the collision probabilities overwrite am_val in place (the distance is consumed first) */
             for (int i = 0; i < n_ent; ++i) {
-                const double dist = cn_milli64((int32_t)E[i * CNF_ENTRY_WORDS + CNF_E_DIST]);
+                const double dist = CNF_MILLI(E[i * CNF_ENTRY_WORDS + CNF_E_DIST]);
                 const double dto = (dist > P->max_range) ? 0.0 : (P->max_range - dist) / span;
                 double cp;
                 if (S.am_idx[i]) {
@@ -544,8 +563,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch* Sp, double x, doub
                 const int slot = P->topk_highest ? rank : rank - (n_ent > K ? n_ent - K : 0);
                 if (slot < 0 || slot >= K) continue;
                 const uint32_t* q = E + a * CNF_ENTRY_WORDS;
-                kblock[4 * slot] = (float)cn_np_round3_64(cn_milli64((int32_t)q[CNF_E_LX]));
-                kblock[4 * slot + 1] = (float)cn_np_round3_64(cn_milli64((int32_t)q[CNF_E_LY]));
+                kblock[4 * slot] = (float)cn_np_round3_64(CNF_MILLI(q[CNF_E_LX]));
+                kblock[4 * slot + 1] = (float)cn_np_round3_64(CNF_MILLI(q[CNF_E_LY]));
                 kblock[4 * slot + 2] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VX));
                 kblock[4 * slot + 3] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VY));
             }

@@ -77,6 +77,12 @@ CN_HD double cn_milli64(long long k) {
     const double q = kd * 0.001;
     return fma(fma(-q, 1000.0, kd), 0.001, q);
 }
+/* the same for a caller that guarantees |k| <= 2^25 */
+CN_HD double cn_milli64_small(int32_t k) {
+    const double kd = (double)k;
+    const double q = kd * 0.001;
+    return fma(fma(-q, 1000.0, kd), 0.001, q);
+}
 CN_HD double cn_py_round3_64(double x) { return cn_milli64(cn_py_round3_k64(x)); }
 /* np.around(x, 3) in float64: rint(x * 1000) / 1000 (numpy multiplies, rints, divides) */
 CN_HD double cn_np_round3_64(double x) { return rint(x * 1000.0) / 1000.0; }

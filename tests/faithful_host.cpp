@@ -27,7 +27,7 @@ void cnfh_observe(const cnf_params* P, uint32_t* trk, double x, double y, double
     cnf_scratch S;
     cnf_scratch_carve(base, P->n_rays, &S);
     memcpy(S.trk, trk, sizeof(uint32_t) * CNF_WORLD_WORDS);
-    cnf_world(P, &S, x, y, yaw, scan32, no_return32, step_counter, kblock, 0, 1);
+    cnf_world(P, S, x, y, yaw, scan32, no_return32, step_counter, kblock, 0, 1, 0);
     memcpy(trk, S.trk, sizeof(uint32_t) * CNF_WORLD_WORDS);
     free(base);
 }
@@ -47,7 +47,7 @@ void cnfh_observe_lanes(const cnf_params* P, uint32_t* trk, double x, double y, 
     for (int lane = 0; lane < nl; ++lane)
         th.emplace_back([&, lane]() {
             cnfh_bar = &bar;
-            cnf_world(P, &S, x, y, yaw, scan32, no_return32, step_counter, kblock, lane, nl);
+            cnf_world(P, S, x, y, yaw, scan32, no_return32, step_counter, kblock, lane, nl, 0);
             cnfh_bar = nullptr;
         });
     for (auto& t : th) t.join();

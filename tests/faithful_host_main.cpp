@@ -1,5 +1,5 @@
-// Race check of the risk_faithful device code: replays recorded worlds (written by tests/test_faithful.py) with 32
-// "lanes" as 32 threads and compares with the recorded oracle results.  Built with -fsanitize=thread, any access
+// Race check of the risk_faithful device code: replays recorded worlds (written by tests/test_faithful.py) with 64
+// "lanes" as 64 threads and compares with the recorded oracle results.  Built with -fsanitize=thread, any access
 // to the shared scratch that is not ordered by a CNF_SYNC() shows up as a data race.
 //   usage: faithful_host_main <records.bin>      exit code = mismatching records (ThreadSanitizer reports on stderr)
 #include <cstdio>
@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
             fread(scan.data(), 4, n, f) != (size_t)n || fread(&step, 4, 1, f) != 1 ||
             fread(want_kb.data(), 4, 4 * K, f) != (size_t)(4 * K) ||
             fread(want_trk.data(), 4, CNF_WORLD_WORDS, f) != (size_t)CNF_WORLD_WORDS) return 2;
-        cnfh_observe_lanes(&P, trk.data(), pose[0], pose[1], pose[2], scan.data(), (float)0.6f, step, kb.data(), 32);
+        cnfh_observe_lanes(&P, trk.data(), pose[0], pose[1], pose[2], scan.data(), (float)0.6f, step, kb.data(), 64);
         if (memcmp(kb.data(), want_kb.data(), 16 * K) != 0 || memcmp(trk.data(), want_trk.data(), 4 * CNF_WORLD_WORDS) != 0) ++bad;
     }
     fclose(f);

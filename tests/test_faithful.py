@@ -159,7 +159,7 @@ def test_device_code_on_host_equals_oracle(host_device, case):
     assert int(o.trk()[:, 7].sum()) == 0
 
 
-def _record_worlds(cfg, T, host_device=None, nl=32):
+def _record_worlds(cfg, T, host_device=None, nl=64):
     """Step the oracle; per world and step yield what cn_faithful_kernel would read and must produce.  With
     `host_device`, also run the device code with `nl` lanes as `nl` concurrent threads and compare."""
     cfg = cfg.copy()
@@ -197,7 +197,7 @@ def _record_worlds(cfg, T, host_device=None, nl=32):
     return p, recs
 
 
-@pytest.mark.parametrize("nl", [32, 7])
+@pytest.mark.parametrize("nl", [64, 32, 7])
 def test_device_code_with_concurrent_lanes(host_device, nl):
     """The lanes of the warp as real threads, CNF_SYNC() as a barrier over them: same bits as the oracle."""
     _record_worlds(baseline_config(1, n_envs=6, auto_reset=True), 40, host_device, nl)
@@ -205,7 +205,7 @@ def test_device_code_with_concurrent_lanes(host_device, nl):
 
 
 def test_device_code_is_race_free_under_thread_sanitizer(tmp_path):
-    """32 lanes as 32 threads under -fsanitize=thread: every access to the world's scratch must be ordered by a
+    """64 lanes as 64 threads under -fsanitize=thread: every access to the world's scratch must be ordered by a
     CNF_SYNC().  (Checked once by hand that removing one sync is reported.)"""
     exe = str(tmp_path / "faithful_tsan")
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fsanitize=thread",
