@@ -35,60 +35,59 @@
 
 enum { CNF_T_NONE = 0, CNF_T_W = 1, CNF_T_O = 2 };
 
-/* scratch of one world; all pointers 8-byte aligned where they hold doubles */
+/* scratch of one world (12.5 KB at 359 rays); later stages reuse arrays the earlier ones have consumed */
 typedef struct cnf_scratch {
-    double*   grad;     /* [n] round(gradient, 3)              */
-    double*   chg;      /* [n] |gradient change|               */
+    int32_t*  gk;       /* [n + 1] round(gradient, 3) in thousandths; then cum_o, cum_w: int16 [n + 1] each */
     int32_t*  hx;       /* [n] hit point, thousandths          */
     int32_t*  hy;
     int32_t*  rmm;      /* [n] round(range, 3), thousandths    */
     int16_t*  src;      /* [n] ray whose record ray i carries  */
-    int16_t*  sub;      /* [n + 2] sub-segment offsets         */
-    uint8_t*  gok;      /* [n] gradient defined                */
-    uint8_t*  cok;      /* [n] gradient change defined         */
-    uint8_t*  type;     /* [n] record type                     */
-    uint8_t*  close;    /* [n] a segment closes after ray i    */
+    int16_t*  sub;      /* [n + 2] candidate rays of the typing walk; then sub-segment offsets */
+    uint8_t*  gok;      /* [nb] gradient defined; then: the ray's record carries a hit */
+    uint8_t*  close;    /* [nb] a segment closes after ray i   */
+    uint8_t*  subend;   /* [nb] a sub-segment ends at position k; with type[]: the verdicts, int16 [n] */
+    uint8_t*  type;     /* [nb] record type                    */
     uint32_t* trk;      /* [CNF_WORLD_WORDS] tracker record    */
     int32_t*  conf;     /* [CNF_CONF_CAP][4] type, x, y, range */
-    double*   am_val;   /* [CNF_TRK_CAP] best IoU per tracked  */
+    double*   am_val;   /* [CNF_TRK_CAP] best IoU per tracked; then distance to collision; then CP */
     int32_t*  am_idx;   /* [CNF_TRK_CAP]                       */
     double*   hit;      /* [64][2] ring hits of one probe line */
+    int32_t*  red;      /* [256] per-lane partial sums: the same 1 KB as hit[], used before the collision cone */
     uint8_t*  hitf;     /* [64]                                */
     int32_t*  misc;     /* [8] scalars shared between lanes    */
-    int32_t*  red;      /* [256] per-lane partial reductions   */
 } cnf_scratch;
 
-/* bytes of scratch for n rays (offsets are assigned in this order, doubles first) */
+/* bytes of scratch for n rays (carved in this order: 8-byte items first) */
 CN_HD size_t cnf_scratch_bytes(int n) {
+    const size_t nb = ((size_t)n + 1) & ~(size_t)1;
     size_t b = 0;
-    b += 2 * sizeof(double) * (size_t)n;                      /* grad, chg */
-    b += sizeof(double) * CNF_TRK_CAP + sizeof(double) * 128; /* am_val, hit */
-    b += sizeof(uint32_t) * CNF_WORLD_WORDS;                  /* trk (1584 B, keeps 8-byte alignment) */
-    b += 3 * sizeof(int32_t) * (size_t)n;                     /* hx, hy, rmm */
-    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8 + 256);
+    b += sizeof(double) * CNF_TRK_CAP + sizeof(double) * 128; /* am_val, hit / red */
+    b += sizeof(uint32_t) * CNF_WORLD_WORDS;                  /* trk: 1584 B, keeps 8-byte alignment */
     b += 64;                                                  /* hitf */
-    b += sizeof(int16_t) * (2 * (size_t)n + 2);
-    b += 4 * (size_t)n;
+    b += sizeof(int32_t) * ((size_t)n + 1);                   /* gk */
+    b += 3 * sizeof(int32_t) * (size_t)n;                     /* hx, hy, rmm */
+    b += sizeof(int32_t) * (CNF_CONF_CAP * 4 + CNF_TRK_CAP + 8);
+    b += sizeof(int16_t) * (2 * (size_t)n + 2);               /* src, sub */
+    b += 4 * nb;
     return (b + 15) & ~(size_t)15;
 }
 CN_HD void cnf_scratch_carve(unsigned char* base, int n, cnf_scratch* S) {
+    const size_t nb = ((size_t)n + 1) & ~(size_t)1;
     unsigned char* p = base;
-    S->grad = (double*)p; p += sizeof(double) * (size_t)n;
-    S->chg = (double*)p; p += sizeof(double) * (size_t)n;
     S->am_val = (double*)p; p += sizeof(double) * CNF_TRK_CAP;
-    S->hit = (double*)p; p += sizeof(double) * 128;
+    S->hit = (double*)p; S->red = (int32_t*)p; p += sizeof(double) * 128;
     S->trk = (uint32_t*)p; p += sizeof(uint32_t) * CNF_WORLD_WORDS;
     S->hitf = p; p += 64;                                     /* 8-byte aligned: read as 8 words */
+    S->gk = (int32_t*)p; p += sizeof(int32_t) * ((size_t)n + 1);
     S->hx = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->hy = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->rmm = (int32_t*)p; p += sizeof(int32_t) * (size_t)n;
     S->conf = (int32_t*)p; p += sizeof(int32_t) * CNF_CONF_CAP * 4;
     S->am_idx = (int32_t*)p; p += sizeof(int32_t) * CNF_TRK_CAP;
     S->misc = (int32_t*)p; p += sizeof(int32_t) * 8;
-    S->red = (int32_t*)p; p += sizeof(int32_t) * 256;
     S->src = (int16_t*)p; p += sizeof(int16_t) * (size_t)n;
     S->sub = (int16_t*)p; p += sizeof(int16_t) * ((size_t)n + 2);
-    S->gok = p; p += n; S->cok = p; p += n; S->type = p; p += n; S->close = p;
+    S->gok = p; p += nb; S->close = p; p += nb; S->subend = p; p += nb; S->type = p;   /* subend + type: 2-byte aligned */
 }
 
 /* k / 1000 for the thousandths this block stores (positions within +-31 m, ranges <= max_range): |k| < 2^25 */
@@ -144,14 +143,12 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         for (int k = lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;
         for (int i = lane; i < n; i += nl) cnf_hit_point(P, x, y, yaw, i, P->max_range, &S.hx[i], &S.hy[i]);
         CNF_SYNC();
-        for (int i = lane; i < n; i += nl) {
-            const int j = (i == n - 1) ? 0 : i + 1;
-            S.chg[i] = cn_hypot64(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]));
-        }
-        CNF_SYNC();
-        if (lane == 0) {
+        if (lane == 0) {                                       /* summed in ray order, like sum() does */
             double sum = 0.0;
-            for (int i = 0; i < n; ++i) sum += S.chg[i];
+            for (int i = 0; i < n; ++i) {
+                const int j = (i == n - 1) ? 0 : i + 1;
+                sum += cn_hypot64(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]));
+            }
             cnf_st64(S.trk + CNF_H_BBOX, sum / (double)n);
         }
         CNF_SYNC();
@@ -167,19 +164,19 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     }
     CNF_SYNC();
     for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
-        if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.grad[i] = 0.0; continue; }
+        if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.gk[i] = 0; continue; }
         const int j = (i == n - 1) ? 0 : i + 1;
         const double dy = CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]);
         double g = 0.0;
         if (dy != 0.0) g = (CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j])) / dy;
-        S.grad[i] = cn_py_round3_64(g); S.gok[i] = 1;
+        S.gk[i] = (int32_t)cn_py_round3_k64(g); S.gok[i] = 1;   /* |g| <= 1.2 m / 1 mm: fits easily */
     }
     CNF_SYNC();
-    for (int i = lane; i < n - 1; i += nl) {                   /* ENV:349-368, all but the last ray */
-        if (S.gok[i] && S.gok[i + 1]) { S.chg[i] = fabs(S.grad[i] - S.grad[i + 1]); S.cok[i] = 1; }
-        else { S.chg[i] = 0.0; S.cok[i] = 0; }
-    }
-    CNF_SYNC();
+    /* the change of gradient of ray i < n-1 (ENV:349-368) is defined when rays i and i+1 both have a gradient; it is
+     * recomputed where needed from the two rounded gradients (the same doubles round() returned) */
+#define CNF_G(i) cn_milli64((long long)S.gk[i])
+#define CNF_CHG_OK(i) (S.gok[i] && S.gok[(i) + 1])
+#define CNF_CHG(i) fabs(CNF_G(i) - CNF_G((i) + 1))
 
     /* ---- typing (ENV:370-404): only rays with a defined gradient change take part in the state machine, so their
      * indices are compacted first (lane-chunked, order preserving) and lane 0 walks the short list ---- */
@@ -191,35 +188,36 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         int cnt = 0;
         for (int i = c_lo; i < c_hi; ++i) {
             S.type[i] = (uint8_t)CNF_T_NONE; S.src[i] = (int16_t)i;
-            cnt += (i != n - 1 && S.cok[i]);
+            cnt += (i != n - 1 && CNF_CHG_OK(i));
         }
         S.red[lane] = cnt;
-        if (lane == 0) {
-            /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
-            S.chg[n - 1] = 0.0; S.cok[n - 1] = 0;
-            if (S.gok[n - 1]) {
-                for (int i = n - 2; i >= 0; --i)
-                    if (S.gok[i]) { S.chg[n - 1] = S.chg[i]; S.cok[n - 1] = S.cok[i]; break; }
-            }
-        }
     }
     CNF_SYNC();
     {
-        int base = 0, total = 0;
-        for (int l = 0; l < nl; ++l) { const int c = S.red[l]; if (l < lane) base += c; total += c; }
-        for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && S.cok[i]) cand[base++] = (int16_t)i;
+        int base = 0;
+        for (int l = 0; l < lane; ++l) base += S.red[l];
+        for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && CNF_CHG_OK(i)) cand[base++] = (int16_t)i;
+        if (lane == nl - 1) S.misc[3] = base;                   /* the last lane ends at the total */
         CNF_SYNC();
         if (lane == 0) {
+            const int total = S.misc[3];
+            /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
+            int last_ok = 0; double last_val = 0.0;
+            if (S.gok[n - 1]) {
+                for (int i = n - 2; i >= 0; --i)
+                    if (S.gok[i]) { last_ok = CNF_CHG_OK(i); if (last_ok) last_val = CNF_CHG(i); break; }
+            }
             /* a record is (type, source ray): `_scans_object_type[i] = last_type` hands ray i an EARLIER ray's range and pose */
             int last_type = CNF_T_NONE, last_src = 0, du = 0;
             for (int q = 0; q < total; ++q) {
                 const int i = cand[q];
                 int t, s = i;
-                const double ci = S.chg[i];
+                const double ci = CNF_CHG(i);
+                const int nok = (i + 1 == n - 1) ? last_ok : CNF_CHG_OK(i + 1);
+                double cn = 0.0;
+                if (nok) cn = (i + 1 == n - 1) ? last_val : CNF_CHG(i + 1);
                 if (ci == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; }
                 else if (du != 1) {
-                    const int nok = S.cok[i + 1];
-                    const double cn = S.chg[i + 1];
                     t = CNF_T_O;
                     if (nok && cn == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; du = 0; }
                     if (nok) {
@@ -228,12 +226,15 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                     }
                 } else {
                     t = CNF_T_O; last_type = CNF_T_O; last_src = i;
-                    if (S.cok[i + 1] && S.chg[i + 1] == 0.0) du = 0;
+                    if (nok && cn == 0.0) du = 0;
                 }
                 S.type[i] = (uint8_t)t; S.src[i] = (int16_t)s;
             }
         }
     }
+#undef CNF_G
+#undef CNF_CHG_OK
+#undef CNF_CHG
     CNF_SYNC();
     /* neighbour association on the records' poses (ENV:443-486); does the record carry a hit? */
     uint8_t* hflag = S.gok;                                     /* gradients are consumed */
@@ -249,18 +250,19 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
             if (cl) { ++cnt; if (i < first) first = i; if (i != n - 1 && i > last) last = i; }
         }
-        S.red[64 + 3 * lane] = first; S.red[65 + 3 * lane] = last; S.red[66 + 3 * lane] = cnt;
+        S.red[lane] = first; S.red[64 + lane] = last; S.red[128 + lane] = cnt;
     }
     CNF_SYNC();
-    /* segments in the reference's order: first (+ last when they join across the blind spot, ENV:488-504), then the
-     * rest.  Position k of that order holds ray flat_of(k); every lane derives the same three scalars. */
-    int e0 = n, zb = 0, nseg = 0;
-    for (int l = 0; l < nl; ++l) {
-        const int f = S.red[64 + 3 * l], z = S.red[65 + 3 * l];
-        if (f < e0) e0 = f;
-        if (z + 1 > zb) zb = z + 1;
-        nseg += S.red[66 + 3 * l];
+    for (int q = lane; q < 3; q += nl) {                        /* min / max / sum of the partials, one lane each */
+        int v = (q == 0) ? n : (q == 1 ? -1 : 0);
+        for (int l = 0; l < nl; ++l) {
+            const int c = S.red[64 * q + l];
+            if (q == 0) { if (c < v) v = c; } else if (q == 1) { if (c > v) v = c; } else v += c;
+        }
+        S.misc[4 + q] = v;
     }
+    CNF_SYNC();
+    const int e0 = S.misc[4], zb = S.misc[5] + 1, nseg = S.misc[6];
     int merged = 0;
     if (nseg > 1) {
         const int a = S.src[0], b = S.src[n - 1];
@@ -270,10 +272,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
 #define CNF_FLAT_OF(k) ((k) < len_a ? (k) : ((k) < len_a + len_z ? zb + ((k) - len_a) : (k) - len_z))
     /* a sub-segment ends where its segment ends or where hit and no-hit records meet (ENV:510-571: a segment
      * without any hit has no such place, so it stays whole); running counts of 'o' / 'w' records along the order */
-    int16_t* cum_o = (int16_t*)S.grad;                           /* [n + 1] each; the gradients are consumed */
+    int16_t* cum_o = (int16_t*)S.gk;                             /* [n + 1] each; the gradients are consumed */
     int16_t* cum_w = cum_o + (n + 1);
-    uint8_t* subend = S.cok;                                    /* the gradient changes are consumed */
-    CNF_SYNC();                                                 /* red[] and cok[] are about to be reused */
+    uint8_t* subend = S.subend;
     {
         int n_end = 0, n_o = 0, n_w = 0;
         for (int k = c_lo; k < c_hi; ++k) {
@@ -288,14 +289,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.red[3 * lane] = n_end; S.red[3 * lane + 1] = n_o; S.red[3 * lane + 2] = n_w;
     }
     CNF_SYNC();
-    int nsub = 0;
     {
         int b_end = 0, b_o = 0, b_w = 0;
-        for (int l = 0; l < nl; ++l) {
-            const int c = S.red[3 * l];
-            if (l < lane) { b_end += c; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
-            nsub += c;
-        }
+        for (int l = 0; l < lane; ++l) { b_end += S.red[3 * l]; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
         if (lane == 0) { S.sub[0] = 0; cum_o[0] = 0; cum_w[0] = 0; }
         for (int k = c_lo; k < c_hi; ++k) {
             const int r = CNF_FLAT_OF(k);
@@ -303,11 +299,13 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             cum_o[k + 1] = (int16_t)b_o; cum_w[k + 1] = (int16_t)b_w;
             if (subend[k]) S.sub[++b_end] = (int16_t)(k + 1);
         }
+        if (lane == nl - 1) S.misc[3] = b_end;                  /* the last lane ends at the total */
     }
     CNF_SYNC();
+    const int nsub = S.misc[3];
     /* confirmation (ENV:573-620, UTL:395-402), one lane per sub-segment; every record of a sub-segment is a hit or
      * none is, so its first one decides */
-    int32_t* verdict = (int32_t*)S.chg;                          /* [nsub] <= n; the gradient changes are consumed */
+    int16_t* verdict = (int16_t*)S.subend;                       /* [nsub] <= n over subend[] + type[], both consumed */
     {
         const double span = P->max_range - P->min_range;
         for (int s = lane; s < nsub; s += nl) {
@@ -331,9 +329,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                     const double lim = ((double)nsub < estd) ? (double)nsub : estd;
                     if (!((double)sl <= lim)) t = (n_w > 0) ? CNF_T_W : CNF_T_O;
                 }
-                if (t >= 0) v = t | (rc << 8);
+                if (t >= 0) v = t | (rc << 2);                   /* rc < 1024 */
             }
-            verdict[s] = v;
+            verdict[s] = (int16_t)v;
         }
     }
 #undef CNF_FLAT_OF
@@ -344,9 +342,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             const int v = verdict[s];
             if (v < 0) continue;
             if (nconf < CNF_CONF_CAP) {
-                const int rc = v >> 8;
+                const int rc = v >> 2;
                 int32_t* c = S.conf + 4 * nconf;
-                c[0] = v & 0xFF; c[1] = S.hx[rc]; c[2] = S.hy[rc]; c[3] = S.rmm[rc];
+                c[0] = v & 3; c[1] = S.hx[rc]; c[2] = S.hy[rc]; c[3] = S.rmm[rc];
                 ++nconf;
             } else S.trk[CNF_H_OVERFLOW] += 1;
         }
