@@ -14,7 +14,7 @@
 
 #define CNF_WORLDS 4            /* worlds per CTA, CNF_LANES (64) threads each */
 
-__global__ void __launch_bounds__(CNF_LANES * CNF_WORLDS)
+__global__ void __launch_bounds__(CNF_LANES * CNF_WORLDS, 4)
 cn_faithful_kernel(cnf_params P, const uint32_t* __restrict__ robot, uint32_t* __restrict__ trk,
                    const float* __restrict__ ranges, float* __restrict__ obs, const uint8_t* __restrict__ mask,
                    int E, int obs_dim, float no_return32, unsigned scratch_bytes) {

@@ -174,7 +174,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     CNF_SYNC();
     /* the change of gradient of ray i < n-1 (ENV:349-368) is defined when rays i and i+1 both have a gradient; it is
      * recomputed where needed from the two rounded gradients (the same doubles round() returned) */
-#define CNF_G(i) cn_milli64((long long)S.gk[i])
+#define CNF_G(i) cn_milli64_small(S.gk[i])          /* |gradient| <= 1.2 m / 1 mm = 1200 */
 #define CNF_CHG_OK(i) (S.gok[i] && S.gok[(i) + 1])
 #define CNF_CHG(i) fabs(CNF_G(i) - CNF_G((i) + 1))
 
