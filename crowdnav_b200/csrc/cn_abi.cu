@@ -138,6 +138,9 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, &flat);
         }
         { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
+        /* programmatic dependent launch is opt-in (CN_PDL=1): measured on B200 it helps back-to-back stream launches
+         * (c2 23.2 -> 20.6 us per step) but not the graph-replayed step (11.8 -> 12.8 us), see DESIGN.md 4.4 */
+        { const char* pd = getenv("CN_PDL"); flat.pdl = (pd && strcmp(pd, "1") == 0) ? 1 : 0; }
         if (rc != 0 || flat.total > (size_t)max_smem)
             return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
     } else {

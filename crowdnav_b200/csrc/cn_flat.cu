@@ -342,9 +342,18 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     const bool act_smem = (MODE == 0) && P.act_bulk_ok && (W % 2) == 0 && (nE % 2) == 0;
 
     // ---------------------------------------------------------------- phase 0
+    // Programmatic dependent launch (only when the launch carries the attribute, CN_PDL=1; otherwise both instructions
+    // are no-ops): the NEXT launch on the stream (the next step) may start scheduling its CTAs as
+    // soon as every CTA of this one has got here -- they take the SM slots this grid's CTAs free one by one -- while
+    // this launch itself touches no global memory before the grid in front of it has completed and flushed
+    // (griddepcontrol.wait).  What is hidden is the launch gap and the CTA start-up between back-to-back steps.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         mbar_init(S.bar, 1);
         fence_mbar_init();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
         mbar_expect_tx(S.bar, rob_bytes + 3u * ped_bytes + act_bytes);
         if (act_bytes) tma_load(S.act, P.action + 2 * (size_t)e0, act_bytes, S.bar);
@@ -1035,8 +1044,17 @@ static cudaError_t launch_flat_t(const cn_kparams& P, const cn_flat_layout& L, c
         attr_smem = L.total;
     }
     const int grid = (P.n_envs + L.W - 1) / L.W;
-    k<<<grid, T, L.total, stream>>>(P, L);
-    return cudaGetLastError();
+    if (!L.pdl) {
+        k<<<grid, T, L.total, stream>>>(P, L);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)T); cfg.dynamicSmemBytes = L.total; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, P, L);
 }
 
 #ifdef CN_TIMELINE

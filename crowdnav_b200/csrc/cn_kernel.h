@@ -47,6 +47,7 @@ struct cn_flat_layout {
     int W;                      /* worlds per CTA */
     int threads;                /* threads per CTA: 128, 256 or 512 */
     int plain_store;            /* 1: write the tile back with cooperative 16-byte stores, 0: bulk TMA stores */
+    int pdl;                    /* 1: launch with programmatic stream serialization (back-to-back steps overlap their start-up) */
     uint32_t magic_n;           /* ceil(2^32 / N): world index of a flat pedestrian index by __umulhi */
     uint32_t cap_wg, cap_pg;    /* capacity of the wall / pedestrian ray-group lists */
     uint32_t off_pa, off_pb, off_pa2, off_act, off_obs, off_sc, off_rec, off_pk, off_peers,
