@@ -116,3 +116,37 @@ def test_fused_gather_is_refused():
                              C.c_void_p(g.reward.data_ptr()), C.c_void_p(g.done.data_ptr()), g._stream())
     assert rc == -4 and b"RISK_FAITHFUL" in _lib.load().cn_last_error()
     g.close()
+
+
+def test_duck_type_and_evaluation_harness_with_the_faithful_block():
+    """The single-env `Env` duck type and the README evaluation protocol run on the reference's own perception
+    block: same row width, counters read from the tracker record, scores like ENV:1269-1283."""
+    import os
+    from crowdnav_b200.env import Env
+    from crowdnav_b200.evaluate import evaluate, scenario_config, summarize
+    from crowdnav_b200.rollout import load_reference_actor
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    from oracle.oracle import OracleEnv
+    cfg = make_config(risk_faithful=True)
+    env = Env(action_dim=2, max_step=60, config=cfg)
+    ocfg = cfg.copy()
+    ocfg.n_envs, ocfg.max_steps = 1, 60
+    ocfg.flags &= ~1
+    o = OracleEnv(ocfg)
+    s = env.reset()
+    o.reset()
+    env.done = False
+    assert s.shape == (398,) and np.array_equal(s.astype(np.float32), o.obs[0])
+    for t in range(40):
+        a = [0.2, 0.3 if t % 7 else -0.4]
+        s, r, d = env.step(a, t + 1, mode="continuous")
+        oo, orr, od = o.step(np.array([a], dtype=np.float32))
+        assert np.array_equal(s.astype(np.float32), oo[0]) and r == orr[0] and d == bool(od[0])
+        if d:
+            break
+    assert list(env._counts()) == [int(v) for v in o.counters()[0, 1:]]
+    actor = load_reference_actor(os.path.join(os.path.dirname(__file__), "golden", "td3_actor_k8_ep2500.npz"), "cuda")
+    venv = CrowdNavVecEnv(scenario_config("crossing", 8, n_envs=256, max_steps=300, risk_faithful=True), device=0)
+    rows = evaluate(venv, actor, 300)
+    sm = summarize(rows)
+    assert len(rows) == 300 and sm["mean_steps"] <= 300 and sm["ego_safety"] <= 1.0 and sm["social_safety"] <= 1.0
