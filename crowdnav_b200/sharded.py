@@ -58,6 +58,10 @@ class ShardedVecEnv:
         self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
         self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
         self.gather_mode = gather if self.world > 1 else "none"
+        if self.gather_mode == "fused" and (cfg_global.flags & 8):
+            # CN_FLAG_RISK_FAITHFUL: cn_faithful_kernel rewrites the K block after the step kernel has already sent
+            # its rows to the peers, so cn_step_gather refuses peers in that mode
+            raise ValueError("risk_faithful worlds gather with gather='collective' (ncclAllGather), not 'fused'")
         self._symm = None
         if self.gather_mode == "fused":
             # Gather buffers in symmetric memory: every rank can address every peer's copy, so the step kernel

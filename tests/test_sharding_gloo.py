@@ -61,11 +61,15 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, E, steps, q):
+def _worker(rank, world, port, E, steps, q, flags=0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         cfg = baseline_config(3, n_envs=E)
+        cfg.flags |= flags
+        if flags & 8:                       # risk_faithful rows cannot leave through the fused gather
+            with pytest.raises(ValueError):
+                ShardedVecEnv(cfg, lambda c, o: _OracleStepper(c, o), torch.device("cpu"), gather="fused")
         senv = ShardedVecEnv(cfg, lambda c, o: _OracleStepper(c, o), torch.device("cpu"))
         rng = np.random.default_rng(123)
         acts = [random_actions(rng, E) for _ in range(steps)]
@@ -80,20 +84,23 @@ def _worker(rank, world, port, E, steps, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_gather_equals_single_process():
+@pytest.mark.parametrize("flags", [0, 8], ids=["risk_intended", "risk_faithful"])
+def test_two_rank_gather_equals_single_process(flags):
     """Same seeds on 1 vs 2 ranks give bit-identical concatenated observations."""
     E, steps, world = 12, 25, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, E, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, E, steps, q, flags)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    ref = OracleEnv(baseline_config(3, n_envs=E))
+    ref_cfg = baseline_config(3, n_envs=E)
+    ref_cfg.flags |= flags
+    ref = OracleEnv(ref_cfg)
     rng = np.random.default_rng(123)
     acts = [random_actions(rng, E) for _ in range(steps)]
     want = [ref.reset().copy()]
