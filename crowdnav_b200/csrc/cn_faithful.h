@@ -24,10 +24,14 @@
 #define CNF_LANES 64          /* device: threads (two warps) that share one world */
 #if defined(__CUDACC__)
 #define CNF_FN __device__ __forceinline__
+/* the float64 helpers are real calls on the device: inlined everywhere the kernel was 290 KB of SASS and its warps
+ * stalled on instruction fetch more than on anything else (ncu: no_instruction 3.0 per issue) */
+#define CNF_FN_BIG static __device__ __noinline__
 /* the world's CNF_LANES threads meet at their own named barrier (bar = 1 + world index inside the CTA) */
 #define CNF_SYNC() asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(CNF_LANES) : "memory")
 #else
 #define CNF_FN static inline
+#define CNF_FN_BIG static inline
 #ifndef CNF_SYNC            /* a host harness may supply a thread barrier to run the lanes as threads */
 #define CNF_SYNC() ((void)0)
 #endif
@@ -103,7 +107,17 @@ CNF_FN void cnf_st64(uint32_t* w, double d) {
 }
 
 /* UTL:421-448: round(IoU, 3) of two squares of half-size h centred on points given in thousandths */
-CNF_FN double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double h) {
+CNF_FN_BIG long long cnf_round3k(double x) { return cn_py_round3_k64(x); }
+CNF_FN_BIG double cnf_div(double a, double b) { return a / b; }            /* one copy of the ~25-instruction IEEE division */
+CNF_FN_BIG double cnf_hypot(double a, double b) { return cn_hypot64(a, b); }
+CNF_FN_BIG double cnf_np_round3(double x) { return cn_np_round3_64(x); }
+#if defined(__CUDACC__)
+#define CNF_ROLLED _Pragma("unroll 1")       /* keep the loops rolled: the kernel is bound by instruction fetch */
+#else
+#define CNF_ROLLED
+#endif
+
+CNF_FN_BIG double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double h) {
     const double ax = CNF_MILLI(axk), ay = CNF_MILLI(ayk), bx = CNF_MILLI(bxk), by = CNF_MILLI(byk);
     const double ax0 = ax - h, ax1 = ax + h, ay0 = ay - h, ay1 = ay + h;
     const double bx0 = bx - h, bx1 = bx + h, by0 = by - h, by1 = by + h;
@@ -112,15 +126,18 @@ CNF_FN double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double
     const double inter = (w > 0.0 && hh > 0.0) ? w * hh : 0.0;
     const double area_a = (ax1 - ax0) * (ay1 - ay0), area_b = (bx1 - bx0) * (by1 - by0);
     const double uni = area_a + area_b - inter;
-    return cn_py_round3_64(inter / uni);
+    return cn_milli64(cn_py_round3_k64(cnf_div(inter, uni)));
 }
 
 /* UTL:110-126 for observation ray i: both coordinates in thousandths */
-CNF_FN void cnf_hit_point(const cnf_params* P, double x, double y, double yaw, int i, double r, int32_t* hx, int32_t* hy) {
-    const double ang = ((double)i * P->inc_deg) * CN64_DEG2RAD - yaw;
+typedef struct { int32_t x, y; } cnf_pt;
+CNF_FN_BIG cnf_pt cnf_hit_point(double inc_deg, double x, double y, double yaw, int i, double r) {
+    const double ang = ((double)i * inc_deg) * CN64_DEG2RAD - yaw;
     double s, c; cn_sincos64(ang, &s, &c);
-    *hx = (int32_t)cn_py_round3_k64(x + r * c);
-    *hy = (int32_t)cn_py_round3_k64(y + (r * s) * -1.0);
+    cnf_pt o;
+    o.x = (int32_t)cn_py_round3_k64(x + r * c);
+    o.y = (int32_t)cn_py_round3_k64(y + (r * s) * -1.0);
+    return o;
 }
 
 /*
@@ -136,40 +153,41 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                       int lane, int nl, int bar) {
     (void)bar;
     const int n = P->n_rays, K = P->k_obstacles;
-    const int32_t max_mm = (int32_t)cn_py_round3_k64(P->max_range);
+    const int32_t max_mm = (int32_t)cnf_round3k(P->max_range);
 
     /* ---- reset: fresh tracker; bounding_box_size from the ground-truth ring (ENV:286-290, UTL:405-419) ---- */
     if (step_counter == 0) {
-        for (int k = lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;
-        for (int i = lane; i < n; i += nl) cnf_hit_point(P, x, y, yaw, i, P->max_range, &S.hx[i], &S.hy[i]);
+        CNF_ROLLED for (int k = lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;
+        CNF_ROLLED for (int i = lane; i < n; i += nl) { const cnf_pt h = cnf_hit_point(P->inc_deg, x, y, yaw, i, P->max_range); S.hx[i] = h.x; S.hy[i] = h.y; }
         CNF_SYNC();
         if (lane == 0) {                                       /* summed in ray order, like sum() does */
             double sum = 0.0;
-            for (int i = 0; i < n; ++i) {
+            CNF_ROLLED for (int i = 0; i < n; ++i) {
                 const int j = (i == n - 1) ? 0 : i + 1;
-                sum += cn_hypot64(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]));
+                sum += cnf_hypot(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]));
             }
-            cnf_st64(S.trk + CNF_H_BBOX, sum / (double)n);
+            cnf_st64(S.trk + CNF_H_BBOX, cnf_div(sum, (double)n));
         }
         CNF_SYNC();
     }
     const double bbox = cnf_ld64(S.trk + CNF_H_BBOX);
 
     /* ---- per-ray maps ---- */
-    for (int i = lane; i < n; i += nl) {
+    CNF_ROLLED for (int i = lane; i < n; i += nl) {
         const float r32 = scan32[i];
         const double r = (r32 >= no_return32) ? P->max_range : (double)r32;
-        cnf_hit_point(P, x, y, yaw, i, r, &S.hx[i], &S.hy[i]);
-        S.rmm[i] = (int32_t)cn_py_round3_k64(r);
+        const cnf_pt h = cnf_hit_point(P->inc_deg, x, y, yaw, i, r);
+        S.hx[i] = h.x; S.hy[i] = h.y;
+        S.rmm[i] = (int32_t)cnf_round3k(r);
     }
     CNF_SYNC();
-    for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
+    CNF_ROLLED for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
         if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.gk[i] = 0; continue; }
         const int j = (i == n - 1) ? 0 : i + 1;
         const double dy = CNF_MILLI(S.hy[i]) - CNF_MILLI(S.hy[j]);
         double g = 0.0;
-        if (dy != 0.0) g = (CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j])) / dy;
-        S.gk[i] = (int32_t)cn_py_round3_k64(g); S.gok[i] = 1;   /* |g| <= 1.2 m / 1 mm: fits easily */
+        if (dy != 0.0) g = cnf_div(CNF_MILLI(S.hx[i]) - CNF_MILLI(S.hx[j]), dy);
+        S.gk[i] = (int32_t)cnf_round3k(g); S.gok[i] = 1;   /* |g| <= 1.2 m / 1 mm: fits easily */
     }
     CNF_SYNC();
     /* the change of gradient of ray i < n-1 (ENV:349-368) is defined when rays i and i+1 both have a gradient; it is
@@ -186,7 +204,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     int16_t* cand = S.sub;                                      /* free until the sub-segment offsets are built */
     {
         int cnt = 0;
-        for (int i = c_lo; i < c_hi; ++i) {
+        CNF_ROLLED for (int i = c_lo; i < c_hi; ++i) {
             S.type[i] = (uint8_t)CNF_T_NONE; S.src[i] = (int16_t)i;
             cnt += (i != n - 1 && CNF_CHG_OK(i));
         }
@@ -195,8 +213,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     CNF_SYNC();
     {
         int base = 0;
-        for (int l = 0; l < lane; ++l) base += S.red[l];
-        for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && CNF_CHG_OK(i)) cand[base++] = (int16_t)i;
+        CNF_ROLLED for (int l = 0; l < lane; ++l) base += S.red[l];
+        CNF_ROLLED for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && CNF_CHG_OK(i)) cand[base++] = (int16_t)i;
         if (lane == nl - 1) S.misc[3] = base;                   /* the last lane ends at the total */
         CNF_SYNC();
         if (lane == 0) {
@@ -204,12 +222,12 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
             int last_ok = 0; double last_val = 0.0;
             if (S.gok[n - 1]) {
-                for (int i = n - 2; i >= 0; --i)
+                CNF_ROLLED for (int i = n - 2; i >= 0; --i)
                     if (S.gok[i]) { last_ok = CNF_CHG_OK(i); if (last_ok) last_val = CNF_CHG(i); break; }
             }
             /* a record is (type, source ray): `_scans_object_type[i] = last_type` hands ray i an EARLIER ray's range and pose */
             int last_type = CNF_T_NONE, last_src = 0, du = 0;
-            for (int q = 0; q < total; ++q) {
+            CNF_ROLLED for (int q = 0; q < total; ++q) {
                 const int i = cand[q];
                 int t, s = i;
                 const double ci = CNF_CHG(i);
@@ -240,7 +258,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     uint8_t* hflag = S.gok;                                     /* gradients are consumed */
     {
         int first = n, last = -1, cnt = 0;
-        for (int i = lane; i < n; i += nl) {
+        CNF_ROLLED for (int i = lane; i < n; i += nl) {
             int cl = 1;
             if (i != n - 1) {
                 const int a = S.src[i], b = S.src[i + 1];
@@ -253,9 +271,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.red[lane] = first; S.red[64 + lane] = last; S.red[128 + lane] = cnt;
     }
     CNF_SYNC();
-    for (int q = lane; q < 3; q += nl) {                        /* min / max / sum of the partials, one lane each */
+    CNF_ROLLED for (int q = lane; q < 3; q += nl) {                        /* min / max / sum of the partials, one lane each */
         int v = (q == 0) ? n : (q == 1 ? -1 : 0);
-        for (int l = 0; l < nl; ++l) {
+        CNF_ROLLED for (int l = 0; l < nl; ++l) {
             const int c = S.red[64 * q + l];
             if (q == 0) { if (c < v) v = c; } else if (q == 1) { if (c > v) v = c; } else v += c;
         }
@@ -277,7 +295,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     uint8_t* subend = S.subend;
     {
         int n_end = 0, n_o = 0, n_w = 0;
-        for (int k = c_lo; k < c_hi; ++k) {
+        CNF_ROLLED for (int k = c_lo; k < c_hi; ++k) {
             const int r = CNF_FLAT_OF(k);
             int end;
             if (merged && k < len_a + len_z) end = (k == len_a + len_z - 1);
@@ -291,9 +309,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     CNF_SYNC();
     {
         int b_end = 0, b_o = 0, b_w = 0;
-        for (int l = 0; l < lane; ++l) { b_end += S.red[3 * l]; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
+        CNF_ROLLED for (int l = 0; l < lane; ++l) { b_end += S.red[3 * l]; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
         if (lane == 0) { S.sub[0] = 0; cum_o[0] = 0; cum_w[0] = 0; }
-        for (int k = c_lo; k < c_hi; ++k) {
+        CNF_ROLLED for (int k = c_lo; k < c_hi; ++k) {
             const int r = CNF_FLAT_OF(k);
             b_o += (S.type[r] == CNF_T_O); b_w += (S.type[r] == CNF_T_W);
             cum_o[k + 1] = (int16_t)b_o; cum_w[k + 1] = (int16_t)b_w;
@@ -308,7 +326,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     int16_t* verdict = (int16_t*)S.subend;                       /* [nsub] <= n over subend[] + type[], both consumed */
     {
         const double span = P->max_range - P->min_range;
-        for (int s = lane; s < nsub; s += nl) {
+        CNF_ROLLED for (int s = lane; s < nsub; s += nl) {
             const int sb = S.sub[s], se = S.sub[s + 1], sl = se - sb;
             int v = -1;
             if (sl >= 4 && hflag[CNF_FLAT_OF(sb)]) {
@@ -316,9 +334,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 const int kc = sb + sl / 2;
                 const int rc = S.src[CNF_FLAT_OF(kc)];
                 const double dctr = CNF_MILLI(S.rmm[rc]);
-                const double estd = 3.0 + floor(29.0 * (P->max_range - dctr) / span);
+                const double estd = 3.0 + floor(cnf_div(29.0 * (P->max_range - dctr), span));
                 const double denom = ((double)sl < estd) ? (double)sl : estd;
-                const double score = (double)n_o / denom;
+                const double score = cnf_div((double)n_o, denom);
                 const int distinct = (n_o > 0) + (n_w > 0) + (n_none > 0);
                 int t = -1;
                 if (distinct > 1) {
@@ -338,7 +356,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     CNF_SYNC();
     if (lane == 0) {
         int nconf = 0, n_obst = 0, ego_hit = 0;
-        for (int s = 0; s < nsub; ++s) {
+        CNF_ROLLED for (int s = 0; s < nsub; ++s) {
             const int v = verdict[s];
             if (v < 0) continue;
             if (nconf < CNF_CONF_CAP) {
@@ -348,14 +366,14 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 ++nconf;
             } else S.trk[CNF_H_OVERFLOW] += 1;
         }
-        for (int c = 0; c < nconf; ++c)
+        CNF_ROLLED for (int c = 0; c < nconf; ++c)
             if (S.conf[4 * c] == CNF_T_O) { ++n_obst; if (CNF_MILLI(S.conf[4 * c + 3]) < 0.140) ego_hit = 1; }
         if (n_obst > 0) S.trk[CNF_H_PRESENT] += 1;              /* ENV:653-654 */
         S.misc[0] = nconf; S.misc[1] = ego_hit;
         /* popleft of every tracked deque (ENV:679-682) happens before the IoUs are taken */
         const int n0 = (int)S.trk[CNF_H_N];
         if (nconf > 0)
-            for (int i = 0; i < n0; ++i) {
+            CNF_ROLLED for (int i = 0; i < n0; ++i) {
                 uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
                 if (q[CNF_E_NDEQ] > 1u) { q[CNF_E_PX] = q[CNF_E_LX]; q[CNF_E_PY] = q[CNF_E_LY]; q[CNF_E_NDEQ] = 1u; }
             }
@@ -367,10 +385,10 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     const int nconf = S.misc[0];
     const int n0 = (int)S.trk[CNF_H_N];
     if (nconf > 0)
-        for (int i = lane; i < n0; i += nl) {
+        CNF_ROLLED for (int i = lane; i < n0; i += nl) {
             const uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
             int m = 0; double best = 0.0;
-            for (int c = 0; c < nconf; ++c) {
+            CNF_ROLLED for (int c = 0; c < nconf; ++c) {
                 const double v = cnf_iou((int32_t)q[CNF_E_LX], (int32_t)q[CNF_E_LY], S.conf[4 * c + 1], S.conf[4 * c + 2], P->track_half);
                 if (c == 0 || v > best) { best = v; m = c; }
             }
@@ -386,7 +404,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         else if (n0 > 0) {
             /* update / drop in dict order; `len(dict) > i` (ENV:718) lets late unmatched entries survive */
             uint32_t dead = 0; int n_live = n0;
-            for (int i = 0; i < n0; ++i) {
+            CNF_ROLLED for (int i = 0; i < n0; ++i) {
                 uint32_t* q = E + i * CNF_ENTRY_WORDS;
                 if (S.am_val[i] > 0.0) {
                     const int32_t* c = S.conf + 4 * S.am_idx[i];
@@ -397,15 +415,17 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 } else if (n_live > i) { dead |= 1u << i; --n_live; }
             }
             int m = 0;
-            for (int i = 0; i < n0; ++i) {
+            CNF_ROLLED for (int i = 0; i < n0; ++i) {
                 if (dead & (1u << i)) continue;
-                if (m != i) for (int k = 0; k < CNF_ENTRY_WORDS; ++k) E[m * CNF_ENTRY_WORDS + k] = E[i * CNF_ENTRY_WORDS + k];
+                if (m != i) {
+                    CNF_ROLLED for (int k = 0; k < CNF_ENTRY_WORDS; ++k) E[m * CNF_ENTRY_WORDS + k] = E[i * CNF_ENTRY_WORDS + k];
+                }
                 ++m;
             }
             n_ent = m;
         }
         if (!(n0 > 0 && nconf == 0))
-            for (int c = 0; c < nconf; ++c) {                    /* new tracked objects (ENV:663-671, 725-741) */
+            CNF_ROLLED for (int c = 0; c < nconf; ++c) {                    /* new tracked objects (ENV:663-671, 725-741) */
                 if (S.conf[4 * c] != CNF_T_O || ((checked >> c) & 1)) continue;
                 if (n_ent >= CNF_TRK_CAP) { S.trk[CNF_H_OVERFLOW] += 1; continue; }
                 uint32_t* q = E + n_ent * CNF_ENTRY_WORDS;
@@ -417,18 +437,18 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             }
         S.trk[CNF_H_N] = (uint32_t)n_ent;
         /* speed (ENV:745-760), obstacle velocity and the probe target of the collision cone (ENV:799-815) */
-        const double curx = cn_py_round3_64(x), cury = cn_py_round3_64(y);
+        const double curx = cn_milli64(cnf_round3k(x)), cury = cn_milli64(cnf_round3k(y));
         double vox = curx, voy = cury;
-        for (int i = 0; i < n_ent; ++i) {
+        CNF_ROLLED for (int i = 0; i < n_ent; ++i) {
             uint32_t* q = E + i * CNF_ENTRY_WORDS;
             double cx = 0.0, cy = 0.0;
             if (q[CNF_E_NDEQ] > 1u) {
                 const double px = CNF_MILLI(q[CNF_E_PX]), py = CNF_MILLI(q[CNF_E_PY]);
                 const double lx = CNF_MILLI(q[CNF_E_LX]), ly = CNF_MILLI(q[CNF_E_LY]);
-                cnf_st64(q + CNF_E_SPEED, cn_hypot64(py - ly, px - lx) / P->dt);
+                cnf_st64(q + CNF_E_SPEED, cnf_div(cnf_hypot(py - ly, px - lx), P->dt));
                 if (S.trk[CNF_H_HAVE_PREV]) {
                     cx = px - lx; cy = py - ly;                  /* last - curr (sic, ENV:806-807) */
-                    cnf_st64(q + CNF_E_VX, cx / P->dt); cnf_st64(q + CNF_E_VY, cy / P->dt);
+                    cnf_st64(q + CNF_E_VX, cnf_div(cx, P->dt)); cnf_st64(q + CNF_E_VY, cnf_div(cy, P->dt));
                 }
             }
             vox = curx + cx; voy = cury + cy;                    /* leaks out of the loop (ENV:814-815) */
@@ -440,21 +460,21 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
 
     /* ---- collision cone: distance to the r = 0.178 ring along the probe lines (UTL:251-293) ---- */
     const int n_ent = S.misc[2];
-    for (int k = CNF_HDR_WORDS + n_ent * CNF_ENTRY_WORDS + lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;   /* unused entries read as zero */
+    CNF_ROLLED for (int k = CNF_HDR_WORDS + n_ent * CNF_ENTRY_WORDS + lane; k < CNF_WORLD_WORDS; k += nl) S.trk[k] = 0u;   /* unused entries read as zero */
     const int have_prev = (int)S.trk[CNF_H_HAVE_PREV];
     const double a0x = CNF_MILLI(S.trk[CNF_H_PPX]), a0y = CNF_MILLI(S.trk[CNF_H_PPY]);
     if (have_prev && n_ent > 0) {
         const double a1x = S.hit[0], a1y = S.hit[1];
         CNF_SYNC();
         double gradient = 0.0;
-        if (a1y != 0.0) gradient = (a1x - a0x) / a1y - a0y;      /* precedence as written (UTL:261) */
+        if (a1y != 0.0) gradient = cnf_div(a1x - a0x, a1y) - a0y;      /* precedence as written (UTL:261) */
         const double cb = a0x - (gradient * a0y);
         const long x_hi = (long)ceil(a0x + 3.5), x_lo = (long)floor(a0x - 3.5);
-        for (int i = 0; i < n_ent; ++i) {
+        CNF_ROLLED for (int i = 0; i < n_ent; ++i) {
             const uint32_t* q = S.trk + CNF_HDR_WORDS + i * CNF_ENTRY_WORDS;
             const double ox = CNF_MILLI(q[CNF_E_LX]), oy = CNF_MILLI(q[CNF_E_LY]);
             int have = 0; double dtc = 0.0;
-            for (long x2 = x_hi; x2 > x_lo; --x2) {
+            CNF_ROLLED for (long x2 = x_hi; x2 > x_lo; --x2) {
                 const double qx = (double)x2, qy = ((double)x2 * gradient) + cb;
                 const double rx = qx - a0x, ry = qy - a0y;
                 {
@@ -463,14 +483,14 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                      * testing the 64 edges.  All lanes compute the same bits, so the decision is uniform. */
                     const double len2 = rx * rx + ry * ry;
                     if (len2 > 0.0) {
-                        double tp = ((ox - a0x) * rx + (oy - a0y) * ry) / len2;
+                        double tp = cnf_div((ox - a0x) * rx + (oy - a0y) * ry, len2);
                         tp = tp < 0.0 ? 0.0 : (tp > 1.0 ? 1.0 : tp);
                         const double ex = ox - (a0x + tp * rx), ey = oy - (a0y + tp * ry);
                         const double rm = P->cp_radius * 1.000001;
                         if (ex * ex + ey * ey > rm * rm) continue;
                     }
                 }
-                for (int k = lane; k < 64; k += nl) {
+                CNF_ROLLED for (int k = lane; k < 64; k += nl) {
                     const int k1 = (k + 1) & 63;
                     const double ax = ox + P->cp_radius * CNF_RING_COS[k], ay = oy + P->cp_radius * CNF_RING_SIN[k];
                     const double bx = ox + P->cp_radius * CNF_RING_COS[k1], by = oy + P->cp_radius * CNF_RING_SIN[k1];
@@ -478,8 +498,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                     const double den = rx * sy - ry * sx;
                     int f = 0;
                     if (den != 0.0) {
-                        const double t = ((ax - a0x) * sy - (ay - a0y) * sx) / den;
-                        const double u = ((ax - a0x) * ry - (ay - a0y) * rx) / den;
+                        const double t = cnf_div((ax - a0x) * sy - (ay - a0y) * sx, den);
+                        const double u = cnf_div((ax - a0x) * ry - (ay - a0y) * rx, den);
                         if (0.0 <= t && t <= 1.0 && 0.0 <= u && u <= 1.0) { f = 1; S.hit[2 * k] = a0x + t * rx; S.hit[2 * k + 1] = a0y + t * ry; }
                     }
                     S.hitf[k] = (uint8_t)f;
@@ -488,13 +508,13 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 /* every lane resolves the (few) hits identically: no broadcast needed.  Most probes miss the ring:
                  * the 64 flags are first looked at as 8 words. */
                 int nh = 0, i0 = -1, i1 = -1, first[4] = {0, 0, 0, 0}; double k0 = 0.0, k1v = 0.0;
-                for (int w8 = 0; w8 < 8; ++w8) {
+                CNF_ROLLED for (int w8 = 0; w8 < 8; ++w8) {
                     unsigned long long word; memcpy(&word, S.hitf + 8 * w8, 8);
                     if (word == 0ull) continue;
-                    for (int k = 8 * w8; k < 8 * w8 + 8; ++k) {
+                    CNF_ROLLED for (int k = 8 * w8; k < 8 * w8 + 8; ++k) {
                         if (!S.hitf[k]) continue;
                         int dup = 0;
-                        for (int o = 0; o < nh && o < 4; ++o)
+                        CNF_ROLLED for (int o = 0; o < nh && o < 4; ++o)
                             if (fabs(S.hit[2 * k] - S.hit[2 * first[o]]) < 1e-12 && fabs(S.hit[2 * k + 1] - S.hit[2 * first[o] + 1]) < 1e-12) { dup = 1; break; }
                         if (dup) continue;
                         if (nh < 4) first[nh] = k;
@@ -508,8 +528,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 int stop = 0;
                 if (nh == 1) { have = 0; stop = 1; }              /* a Point has no .geoms -> None */
                 else if (nh >= 2) {
-                    const double d0 = cn_hypot64(a0x - S.hit[2 * i0], a0y - S.hit[2 * i0 + 1]);
-                    const double d1 = cn_hypot64(a0x - S.hit[2 * i1], a0y - S.hit[2 * i1 + 1]);
+                    const double d0 = cnf_hypot(a0x - S.hit[2 * i0], a0y - S.hit[2 * i0 + 1]);
+                    const double d1 = cnf_hypot(a0x - S.hit[2 * i1], a0y - S.hit[2 * i1 + 1]);
                     dtc = d0 < d1 ? d0 : d1; have = 1; stop = 1;
                 }
                 CNF_SYNC();                                       /* hit[] is rewritten by the next probe */
@@ -524,28 +544,28 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     if (lane == 0) {
         uint32_t* E = S.trk + CNF_HDR_WORDS;
         double ego_score = cnf_ld64(S.trk + CNF_H_EGOSCORE);
-        const double curx = cn_py_round3_64(x), cury = cn_py_round3_64(y);
-        for (int s = 0; s < K; ++s) {
-            kblock[4 * s] = (float)cn_np_round3_64(x); kblock[4 * s + 1] = (float)cn_np_round3_64(y);
+        const double curx = cn_milli64(cnf_round3k(x)), cury = cn_milli64(cnf_round3k(y));
+        CNF_ROLLED for (int s = 0; s < K; ++s) {
+            kblock[4 * s] = (float)cnf_np_round3(x); kblock[4 * s + 1] = (float)cnf_np_round3(y);
             kblock[4 * s + 2] = 0.0f; kblock[4 * s + 3] = 0.0f;
         }
         if (have_prev) {
-            const double vx = (curx - a0x) / P->dt, vy = (cury - a0y) / P->dt;     /* UTL:227-236 */
+            const double vx = cnf_div(curx - a0x, P->dt), vy = cnf_div(cury - a0y, P->dt);     /* UTL:227-236 */
             const double agent_vel = sqrt(vx * vx + vy * vy);
             const double obstacle_vel = (n_ent == 0) ? 0.0 : cnf_ld64(E + CNF_E_SPEED);   /* ENV:789-797 */
             const double resultant = agent_vel - obstacle_vel;
             const double span = P->max_range - P->min_range;
             double ego_cur = 0.0, ego_max = 0.0;
             /* the collision probabilities overwrite am_val in place (the distance is consumed first) */
-            for (int i = 0; i < n_ent; ++i) {
+            CNF_ROLLED for (int i = 0; i < n_ent; ++i) {
                 const double dist = CNF_MILLI(E[i * CNF_ENTRY_WORDS + CNF_E_DIST]);
-                const double dto = (dist > P->max_range) ? 0.0 : (P->max_range - dist) / span;
+                const double dto = (dist > P->max_range) ? 0.0 : cnf_div(P->max_range - dist, span);
                 double cp;
                 if (S.am_idx[i]) {
                     if (resultant == 0.0) cp = 1.0 * dto;
                     else {
-                        const double ttc = S.am_val[i] / resultant;
-                        const double qq = 0.15 / ttc;
+                        const double ttc = cnf_div(S.am_val[i], resultant);
+                        const double qq = cnf_div(0.15, ttc);
                         ego_cur = (1.0 < qq) ? 1.0 : qq;
                         cp = 0.5 * ego_cur + 0.5 * dto;
                     }
@@ -554,23 +574,23 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                 if (i == 0 || ego_cur > ego_max) ego_max = ego_cur;
             }
             ego_score = (n_ent == 0) ? 0.0 : ego_max;
-            for (int a = 0; a < (K > 0 ? n_ent : 0); ++a) {       /* stable descending sort, keep [-K:] (ENV:882-883) */
+            CNF_ROLLED for (int a = 0; a < (K > 0 ? n_ent : 0); ++a) {       /* stable descending sort, keep [-K:] (ENV:882-883) */
                 int rank = 0;
-                for (int b = 0; b < n_ent; ++b)
+                CNF_ROLLED for (int b = 0; b < n_ent; ++b)
                     if (b != a && (S.am_val[b] > S.am_val[a] || (S.am_val[b] == S.am_val[a] && b < a))) ++rank;
                 const int slot = P->topk_highest ? rank : rank - (n_ent > K ? n_ent - K : 0);
                 if (slot < 0 || slot >= K) continue;
                 const uint32_t* q = E + a * CNF_ENTRY_WORDS;
-                kblock[4 * slot] = (float)cn_np_round3_64(CNF_MILLI(q[CNF_E_LX]));
-                kblock[4 * slot + 1] = (float)cn_np_round3_64(CNF_MILLI(q[CNF_E_LY]));
-                kblock[4 * slot + 2] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VX));
-                kblock[4 * slot + 3] = (float)cn_np_round3_64(cnf_ld64(q + CNF_E_VY));
+                kblock[4 * slot] = (float)cnf_np_round3(CNF_MILLI(q[CNF_E_LX]));
+                kblock[4 * slot + 1] = (float)cnf_np_round3(CNF_MILLI(q[CNF_E_LY]));
+                kblock[4 * slot + 2] = (float)cnf_np_round3(cnf_ld64(q + CNF_E_VX));
+                kblock[4 * slot + 3] = (float)cnf_np_round3(cnf_ld64(q + CNF_E_VY));
             }
         }
         cnf_st64(S.trk + CNF_H_EGOSCORE, ego_score);
         S.trk[CNF_H_HAVE_PREV] = 1u;
-        S.trk[CNF_H_PPX] = (uint32_t)(int32_t)cn_py_round3_k64(x);
-        S.trk[CNF_H_PPY] = (uint32_t)(int32_t)cn_py_round3_k64(y);
+        S.trk[CNF_H_PPX] = (uint32_t)(int32_t)cnf_round3k(x);
+        S.trk[CNF_H_PPY] = (uint32_t)(int32_t)cnf_round3k(y);
         if (S.misc[1]) S.trk[CNF_H_EGO] += 1;
         if (ego_score > 0.4) S.trk[CNF_H_SOCIAL] += 1;
         if (step_counter == 0) { S.trk[CNF_H_EGO] = 0; S.trk[CNF_H_SOCIAL] = 0; S.trk[CNF_H_PRESENT] = 0; }   /* ENV:1258-1262 */
