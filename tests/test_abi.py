@@ -41,6 +41,23 @@ def test_struct_layout_and_pure_entry_points(L):
     assert L.cn_abi_version() == 1
 
 
+def test_risk_faithful_flag_in_the_abi(L):
+    """CN_FLAG_RISK_FAITHFUL: same row width, the blob grows by one tracker record (396 words) per world, the flag
+    is refused together with the original environment (which has no K block)."""
+    from crowdnav_b200.config import CN_FLAG_RISK_FAITHFUL
+    hdr = open(os.path.join(ROOT, "include", "crowdnav.h")).read()
+    assert int(re.search(r"#define CN_FLAG_RISK_FAITHFUL\s+(\d+)u", hdr).group(1)) == CN_FLAG_RISK_FAITHFUL == 8
+    base, fa = make_config(n_envs=5), make_config(n_envs=5, risk_faithful=True)
+    assert fa.flags & 8 and L.cn_obs_dim(C.byref(fa)) == L.cn_obs_dim(C.byref(base)) == 398
+    assert L.cn_blob_bytes(C.byref(fa)) == L.cn_blob_bytes(C.byref(base)) + 5 * 396 * 4
+    with pytest.raises(ValueError):
+        make_config(env_original=True, risk_faithful=True)
+    bad = make_config(env_original=True)
+    bad.flags |= 8
+    h = C.c_void_p()
+    assert L.cn_create(C.byref(bad), 0, C.byref(h)) == -1
+
+
 def test_errors_are_codes_not_crashes(L):
     h = C.c_void_p()
     bad = make_config()
