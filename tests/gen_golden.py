@@ -34,7 +34,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from ref_harness import Reference, Scan, _XYZ, _Quat  # noqa: E402
+from ref_harness import DEFAULT_PARAMS, Reference, Scan, _XYZ, _Quat  # noqa: E402
 from crowdnav_b200.config import baseline_config, make_config  # noqa: E402
 from oracle.oracle import OracleEnv  # noqa: E402
 from trace_configs import TRACES, TRACES_ORIGINAL, trace_config  # noqa: E402
@@ -155,6 +155,8 @@ def oracle_odom(o: OracleEnv):
 
 def gen_trace(ref, name, cfg, n_steps, seed, params, seek_goal=False):
     """Reference Env in the loop, physics from the oracle's simulator."""
+    ref.params.clear()
+    ref.params.update(DEFAULT_PARAMS)       # every trace starts from the YAML defaults
     ref.params.update(params)
     o = OracleEnv(cfg, debug=True)
     rng = np.random.default_rng(seed)

@@ -14,12 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
-from ref_harness import Reference, Scan      # noqa: E402
+from ref_harness import DEFAULT_PARAMS, Reference, Scan      # noqa: E402
 from trace_configs import TRACES, trace_config   # noqa: E402
 
 
 def replay(ref, name):
     cfg, params, _ = trace_config(name)
+    ref.params.clear()
+    ref.params.update(DEFAULT_PARAMS)       # every trace starts from the YAML defaults
     ref.params.update(params)
     z = np.load(os.path.join(HERE, "golden", "trace_%s.npz" % name))
     n = len(z["odom"])

@@ -38,7 +38,7 @@ def _params(cfg, inc_deg=None):
                      round(float(cfg.cp_radius), 6), 0.0505)
 
 
-@pytest.mark.parametrize("name", ["c1", "train", "goal"])
+@pytest.mark.parametrize("name", ["c1", "train", "goal", "test20"])
 def test_oracle_matches_reference_traces(oracle_lib, name):
     L = oracle_lib
     L.orf_observe.argtypes = [C.POINTER(CnfParams), C.c_void_p] + [C.c_double] * 3 + [C.c_void_p, C.c_int, C.c_void_p]
