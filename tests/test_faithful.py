@@ -233,6 +233,74 @@ def test_device_code_is_race_free_under_thread_sanitizer(tmp_path):
     assert res.returncode == 0, res.stdout[-2000:]
 
 
+def _synth_scan(rng, n, kind):
+    """Synthetic cleaned scans the simulator rarely produces: blobs, walls with objects in front, salt-and-pepper
+    returns, and (kind 3) more small objects than the tracker / confirmed-list capacities."""
+    s = np.full(n, 0.6, np.float32)
+    if kind == 0:
+        for _ in range(rng.integers(0, 12)):
+            c, w, d = rng.integers(0, n), rng.integers(1, 40), rng.uniform(0.09, 0.59)
+            idx = (c + np.arange(w)) % n
+            s[idx] = np.minimum(s[idx], (d + rng.normal(0, 0.002, w) + 0.05 * ((np.arange(w) - w / 2) / w) ** 2).astype(np.float32))
+    elif kind == 1:
+        for _ in range(rng.integers(1, 3)):
+            t0, d, th = rng.uniform(0, 2 * np.pi), rng.uniform(0.1, 0.55), np.arange(n) * (2 * np.pi / n)
+            c = np.cos(th - t0)
+            s = np.minimum(s, np.where(c > 0.05, d / np.maximum(c, 1e-3), 9.0).astype(np.float32))
+        for _ in range(rng.integers(0, 6)):
+            c, w, d = rng.integers(0, n), rng.integers(3, 25), rng.uniform(0.09, 0.5)
+            idx = (c + np.arange(w)) % n
+            s[idx] = np.minimum(s[idx], np.float32(d))
+    elif kind == 2:
+        m = rng.uniform(size=n) < rng.uniform(0.1, 0.9)
+        s[m] = rng.uniform(0.08, 0.6, m.sum()).astype(np.float32)
+        if rng.uniform() < 0.5:
+            s = np.round(s, 2)
+    else:
+        i = 0
+        while i < n - 6:
+            w = rng.integers(4, 7)
+            s[i:i + w] = np.float32(rng.uniform(0.15, 0.55)) + rng.normal(0, 0.0005, w).astype(np.float32)
+            i += w + rng.integers(1, 4)
+    return np.clip(s, np.float32(0.08), np.float32(0.6)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,K,nl", [(359, 8, 1), (36, 3, 1), (720, 16, 1), (1024, 64, 1), (359, 8, 64)])
+def test_device_code_fuzz_on_synthetic_scans(oracle_lib, host_device, n, K, nl):
+    """Oracle vs device code (host build) on scan sequences far outside what the simulator produces, including more
+    objects than the capacities (the overflow handling must agree too): K block and tracker record bit for bit."""
+    L = oracle_lib
+    L.orf_observe.argtypes = [C.POINTER(CnfParams), C.c_void_p] + [C.c_double] * 3 + [C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(n + K + nl)
+    p = CnfParams(n, K, int(K == 3), 0, 1.0 if n == 359 else 360.0 / n, 0.6, 0.12, 0.15, 0.178, 0.0505)
+    overflow = tracked = 0
+    for ep in range(8 if nl == 1 else 2):
+        ta, tb = np.zeros(396, np.uint32), np.zeros(396, np.uint32)
+        x, y, yaw = rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-3.1, 3.1)
+        kind = ep % 4
+        base = _synth_scan(rng, n, kind)
+        for t in range(30 if nl == 1 else 10):
+            base = _synth_scan(rng, n, kind) if (kind == 3 or rng.uniform() < 0.3) else np.roll(base, rng.integers(-2, 3))
+            sc = np.clip(base + rng.normal(0, 0.001, n).astype(np.float32) * (base < 0.6), np.float32(0.08), np.float32(0.6))
+            sc = sc.astype(np.float32)
+            s64 = np.where(sc >= np.float32(0.6), 0.6, sc.astype(np.float64))
+            ka, kb = np.zeros(4 * K), np.zeros(4 * K, np.float32)
+            L.orf_observe(C.byref(p), ta.ctypes.data, x, y, yaw, s64.ctypes.data, t, ka.ctypes.data)
+            host_device.cnfh_observe_lanes(C.byref(p), tb.ctypes.data, x, y, yaw, sc.ctypes.data, C.c_float(0.6), t,
+                                           kb.ctypes.data, nl)
+            assert np.array_equal(ka.astype(np.float32).view(np.uint32), kb.view(np.uint32)), (ep, t, ka, kb)
+            assert np.array_equal(ta, tb), (ep, t, np.nonzero(ta != tb)[0][:10])
+            v = rng.uniform(0, 0.22)
+            x = float(np.float32(x + v * 0.15 * np.cos(yaw)))
+            y = float(np.float32(y + v * 0.15 * np.sin(yaw)))
+            yaw = float(np.float32(yaw + rng.uniform(-0.3, 0.3)))
+            tracked = max(tracked, int(ta[0]))
+        overflow += int(ta[7])
+    assert tracked > 2
+    if n >= 359 and nl == 1:
+        assert overflow > 0 and tracked == 32                    # the capacity paths were exercised
+
+
 def test_faithful_env_properties():
     """The flag only replaces the K block and the counters: every other column, reward, done and the three base
     planes of the state are those of the default (`risk_intended`) environment."""
