@@ -129,6 +129,8 @@ def run_reference(args):
     n_envs = PER_GPU_ENVS[wl] * args.gpus
     sample_envs = min(n_envs, 4096)          # bounded sample: one step of <= 4096 worlds
     cfg = baseline_config(WORKLOADS[wl], n_envs=sample_envs)
+    if getattr(args, "risk_faithful", False):
+        cfg.flags |= 8                       # CN_FLAG_RISK_FAITHFUL: the same arm with the reference's own perception block
     env = OracleEnv(cfg, threads=cores)
     env.reset()
     rng = np.random.default_rng(0)
