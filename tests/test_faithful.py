@@ -23,6 +23,7 @@ from trace_configs import trace_config
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"      # the distro compiler, like oracle/Makefile
 
 
 class CnfParams(C.Structure):      # crowdnav_b200/csrc/cn_faithful_state.h
@@ -94,7 +95,7 @@ def test_milli64_is_the_ieee_division(oracle_lib):
 def _host_device_lib(tmp_path_factory):
     """g++ build of the device header with one lane (tests/faithful_host.cpp)."""
     out = os.path.join(str(tmp_path_factory.mktemp("faithful_host")), "libfaithful_host.so")
-    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fPIC", "-shared",
+    cmd = [GXX, "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fPIC", "-shared",
            "-pthread", "-o", out, os.path.join(HERE, "faithful_host.cpp")]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     H = C.CDLL(out)
@@ -208,7 +209,7 @@ def test_device_code_is_race_free_under_thread_sanitizer(tmp_path):
     """64 lanes as 64 threads under -fsanitize=thread: every access to the world's scratch must be ordered by a
     CNF_SYNC().  (Checked once by hand that removing one sync is reported.)"""
     exe = str(tmp_path / "faithful_tsan")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fsanitize=thread",
+    cmd = [GXX, "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2", "-fsanitize=thread",
            "-pthread", "-o", exe, os.path.join(HERE, "faithful_host_main.cpp")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
