@@ -13,6 +13,7 @@ files.  Citations are paths under /root/reference:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Iterable, Sequence
 
@@ -262,6 +263,34 @@ def make_config(
     if behaviors is None:
         behaviors = [behavior_random(0.2, 0.1 * n_peds + 0.1)]   # CROWD:48,144
     cfg.set_behaviors(behaviors)
+    return cfg
+
+
+def config_from_rosparams(params, **kw) -> CnConfig:
+    """The reference's rosparam YAML (configs/turtlebot3_world.yaml, loaded under /turtlebot3 by
+    launch/start_td3_training.launch:6-9 and read at ENV:71-90) -> a CnConfig.
+
+    `params` is a path to such a YAML file or the already parsed mapping (with or without the `turtlebot3:` namespace
+    level).  Keys used: scan_ranges -> n_samples, max_scan_range, min_scan_range -> collision_range (README.md:60-62
+    sets it to 0.0 for evaluation), desired_pose -> goal, starting_pose -> the offset ENV:223-224 adds in the heading.
+    The three discrete-action speeds (CFG:2-4) stay attributes of `Env`.  Everything else -- room, robot spawn pose,
+    pedestrians, K -- comes from `kw` / make_config's defaults, as in the reference it comes from the world and launch files."""
+    if isinstance(params, (str, bytes, os.PathLike)):
+        import yaml
+        with open(params) as fp:
+            params = yaml.safe_load(fp)
+    params = dict(params.get("turtlebot3", params))
+    if "desired_pose" in params:
+        kw.setdefault("goal", (float(params["desired_pose"]["x"]), float(params["desired_pose"]["y"])))
+    if "starting_pose" in params:
+        kw.setdefault("heading_offset", (float(params["starting_pose"]["x"]), float(params["starting_pose"]["y"])))
+    if "scan_ranges" in params:
+        kw.setdefault("n_samples", int(params["scan_ranges"]))
+    if "min_scan_range" in params:
+        kw.setdefault("collision_range", float(params["min_scan_range"]))
+    cfg = make_config(**kw)
+    if "max_scan_range" in params:
+        cfg.max_range = float(params["max_scan_range"])
     return cfg
 
 

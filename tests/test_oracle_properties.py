@@ -1,5 +1,7 @@
 """Size-independent properties of the env-step (run on the oracle; the GPU suite repeats the
 sharding / determinism ones on the device at full BASELINE sizes)."""
+import os
+
 import numpy as np
 from hypothesis import given, settings, strategies as st
 
@@ -136,3 +138,22 @@ def test_realworld_layout_slot_is_the_highest_cp_object():
         assert np.array_equal(b1[:, 366:370], bn[:, 366:370])
         occupied += int((np.abs(b1[:, 366] - b1[:, 361]) > 1e-6).sum())
     assert occupied > 500, "the slot was hardly ever occupied: nothing tested"
+
+
+def test_config_from_the_reference_rosparam_yaml(tmp_path):
+    """configs/turtlebot3_world.yaml -> CnConfig (ENV:71-90); the README's evaluation edits (README.md:60-71) too."""
+    from crowdnav_b200.config import ROOM_5M, config_from_rosparams, make_config
+    text = ("turtlebot3: #namespace\n    linear_forward_speed: 0.5\n    scan_ranges: 360\n    max_scan_range: 0.6\n"
+            "    min_scan_range: 0.12\n    desired_pose:\n      x: -1.0\n      y: 1.0\n      z: 0.0\n"
+            "    starting_pose:\n      x: 0.75\n      y: -0.75\n      z: 0.0\n")
+    p = tmp_path / "turtlebot3_world.yaml"
+    p.write_text(text)
+    a, b = config_from_rosparams(str(p)), make_config()
+    assert bytes(a) == bytes(b)                                   # the defaults ARE that file
+    ev = config_from_rosparams({"scan_ranges": 360, "max_scan_range": 0.6, "min_scan_range": 0.0,
+                                "desired_pose": {"x": -2.0, "y": 2.0, "z": 0.0}, "starting_pose": {"x": 1.0, "y": 0.0, "z": 0.0}},
+                               room=ROOM_5M, start=(1.0, 0.0, 3.14))
+    assert (ev.goal_x, ev.goal_y, ev.collision_range, ev.heading_off_x, ev.heading_off_y) == (-2.0, 2.0, 0.0, 1.0, 0.0)
+    ref = "/root/reference/turtlebot3_rl_sim/src/configs/turtlebot3_world.yaml"
+    if os.path.exists(ref):
+        assert bytes(config_from_rosparams(ref)) == bytes(b)
