@@ -51,6 +51,12 @@ __global__ void cn_faithful_counters_kernel(const uint32_t* __restrict__ robot, 
     reinterpret_cast<int4*>(out)[e] = v;
 }
 
+#ifdef CN_TIMELINE
+extern "C" int cn_debug_set_timeline_faithful(unsigned long long* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(cnf_timeline, &dev_ptr, sizeof(dev_ptr));
+}
+#endif
+
 size_t cn_faithful_smem_bytes(int n_rays) { return CNF_WORLDS * cnf_scratch_bytes(n_rays); }
 
 cudaError_t cn_launch_faithful(const cn_config* cfg, const uint32_t* robot, uint32_t* trk, const float* ranges,

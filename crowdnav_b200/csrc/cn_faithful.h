@@ -37,6 +37,15 @@
 #endif
 #endif
 
+/* debug builds only (-DCN_TIMELINE): %globaltimer stamps per world, 16 slots (profiles/tools/timeline_faithful.py) */
+#if defined(__CUDACC__) && defined(CN_TIMELINE)
+__device__ unsigned long long* cnf_timeline = nullptr;
+#define CNF_STAMP(k) do { if (lane == 0 && cnf_timeline) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    cnf_timeline[((size_t)blockIdx.x * (blockDim.x / CNF_LANES) + threadIdx.x / CNF_LANES) * 16 + (k)] = t_; } } while (0)
+#else
+#define CNF_STAMP(k) do { } while (0)
+#endif
+
 enum { CNF_T_NONE = 0, CNF_T_W = 1, CNF_T_O = 2 };
 
 /* scratch of one world (12.5 KB at 359 rays); later stages reuse arrays the earlier ones have consumed */
@@ -152,6 +161,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                       const float* scan32, float no_return32, int step_counter, float* kblock,
                       int lane, int nl, int bar) {
     (void)bar;
+    CNF_STAMP(0);
     const int n = P->n_rays, K = P->k_obstacles;
     const int32_t max_mm = (int32_t)cnf_round3k(P->max_range);
 
@@ -181,6 +191,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.rmm[i] = (int32_t)cnf_round3k(r);
     }
     CNF_SYNC();
+    CNF_STAMP(1);
     CNF_ROLLED for (int i = lane; i < n; i += nl) {                       /* ENV:329-347 */
         if (S.rmm[i] == max_mm) { S.gok[i] = 0; S.gk[i] = 0; continue; }
         const int j = (i == n - 1) ? 0 : i + 1;
@@ -190,6 +201,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.gk[i] = (int32_t)cnf_round3k(g); S.gok[i] = 1;   /* |g| <= 1.2 m / 1 mm: fits easily */
     }
     CNF_SYNC();
+    CNF_STAMP(2);
     /* the change of gradient of ray i < n-1 (ENV:349-368) is defined when rays i and i+1 both have a gradient; it is
      * recomputed where needed from the two rounded gradients (the same doubles round() returned) */
 #define CNF_G(i) cn_milli64_small(S.gk[i])          /* |gradient| <= 1.2 m / 1 mm = 1200 */
@@ -211,6 +223,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.red[lane] = cnt;
     }
     CNF_SYNC();
+    CNF_STAMP(3);
     {
         int base = 0;
         CNF_ROLLED for (int l = 0; l < lane; ++l) base += S.red[l];
@@ -254,6 +267,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
 #undef CNF_CHG_OK
 #undef CNF_CHG
     CNF_SYNC();
+    CNF_STAMP(4);
     /* neighbour association on the records' poses (ENV:443-486); does the record carry a hit? */
     uint8_t* hflag = S.gok;                                     /* gradients are consumed */
     {
@@ -271,6 +285,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.red[lane] = first; S.red[64 + lane] = last; S.red[128 + lane] = cnt;
     }
     CNF_SYNC();
+    CNF_STAMP(5);
     CNF_ROLLED for (int q = lane; q < 3; q += nl) {                        /* min / max / sum of the partials, one lane each */
         int v = (q == 0) ? n : (q == 1 ? -1 : 0);
         CNF_ROLLED for (int l = 0; l < nl; ++l) {
@@ -280,6 +295,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.misc[4 + q] = v;
     }
     CNF_SYNC();
+    CNF_STAMP(6);
     const int e0 = S.misc[4], zb = S.misc[5] + 1, nseg = S.misc[6];
     int merged = 0;
     if (nseg > 1) {
@@ -307,6 +323,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.red[3 * lane] = n_end; S.red[3 * lane + 1] = n_o; S.red[3 * lane + 2] = n_w;
     }
     CNF_SYNC();
+    CNF_STAMP(7);
     {
         int b_end = 0, b_o = 0, b_w = 0;
         CNF_ROLLED for (int l = 0; l < lane; ++l) { b_end += S.red[3 * l]; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
@@ -320,6 +337,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         if (lane == nl - 1) S.misc[3] = b_end;                  /* the last lane ends at the total */
     }
     CNF_SYNC();
+    CNF_STAMP(8);
     const int nsub = S.misc[3];
     /* confirmation (ENV:573-620, UTL:395-402), one lane per sub-segment; every record of a sub-segment is a hit or
      * none is, so its first one decides */
@@ -354,6 +372,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     }
 #undef CNF_FLAT_OF
     CNF_SYNC();
+    CNF_STAMP(9);
     if (lane == 0) {
         int nconf = 0, n_obst = 0, ego_hit = 0;
         CNF_ROLLED for (int s = 0; s < nsub; ++s) {
@@ -379,6 +398,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             }
     }
     CNF_SYNC();
+    CNF_STAMP(10);
 
 
     /* ---- tracker: best confirmed object per tracked one (ENV:691-703), one lane each ---- */
@@ -395,6 +415,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             S.am_val[i] = best; S.am_idx[i] = m;
         }
     CNF_SYNC();
+    CNF_STAMP(11);
 
     if (lane == 0) {
         uint32_t* E = S.trk + CNF_HDR_WORDS;
@@ -457,6 +478,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         S.misc[2] = n_ent;
     }
     CNF_SYNC();
+    CNF_STAMP(12);
 
     /* ---- collision cone: distance to the r = 0.178 ring along the probe lines (UTL:251-293) ---- */
     const int n_ent = S.misc[2];
@@ -539,6 +561,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         }
     }
     CNF_SYNC();
+    CNF_STAMP(13);
 
     /* ---- lane 0: collision probability, ranking, K block, counters (ENV:765-907, 998-1005) ---- */
     if (lane == 0) {
@@ -596,6 +619,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         if (step_counter == 0) { S.trk[CNF_H_EGO] = 0; S.trk[CNF_H_SOCIAL] = 0; S.trk[CNF_H_PRESENT] = 0; }   /* ENV:1258-1262 */
     }
     CNF_SYNC();
+    CNF_STAMP(14);
 }
 
 #endif /* CN_FAITHFUL_H */
