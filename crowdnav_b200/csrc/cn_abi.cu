@@ -24,10 +24,40 @@ struct cn_handle {
     float* own_ranges;      /* CN_FLAG_RISK_FAITHFUL: pre-rounding ranges [E][R-1] the step kernel leaves for cn_faithful_kernel */
     float* dbg_ranges;
     uint8_t* dbg_hid;
+    unsigned int* gather_timeouts;  /* device word: bounded waits of the fused gather that gave up */
     int64_t launches;
     int use_flat;           /* 1: cn_flat.cu (compacted work lists, default), 0: cn_step.cu (warp per world; CN_KERNEL=warp) */
     cn_flat_layout flat;
+    cn_kparams base;        /* everything of cn_kparams that does not change between calls, packed once (repack()) */
 };
+
+/* Every entry point runs with the handle's device current and puts the caller's device back on return:
+ * one process may hold handles on several GPUs. */
+struct cn_device_guard {
+    int prev, dev;
+    explicit cn_device_guard(int d) : prev(-1), dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~cn_device_guard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember the largest value
+ * configured for (kernel slot, device) -- not one process-wide static per kernel. */
+#include <mutex>
+static std::mutex g_attr_mu;
+static size_t g_attr[CN_ATTR_SLOTS][CN_ATTR_MAX_DEVICES];
+cudaError_t cn_ensure_smem_attr(const void* func, int slot, size_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (slot < 0 || slot >= CN_ATTR_SLOTS || dev < 0 || dev >= CN_ATTR_MAX_DEVICES) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (smem <= g_attr[slot][dev] && g_attr[slot][dev] != 0) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) g_attr[slot][dev] = smem;
+    return e;
+}
 
 static cudaError_t launch_env(const cn_handle* h, cn_kparams& P, int mode, cudaStream_t s) {
     if (h->use_flat) return cn_launch_flat_kernel(P, h->flat, mode, s);
@@ -43,6 +73,8 @@ static cudaError_t launch_faithful(cn_handle* h, float* obs, const uint8_t* mask
     if (e == cudaSuccess) h->launches += 1;
     return e;
 }
+
+static void repack(cn_handle* h);
 
 static thread_local char g_err[512] = "";
 
@@ -113,7 +145,7 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     int ndev = 0;
     CN_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(CN_ERR_INVALID, "cn_create: no such device%s", NULL);
-    CN_CUDA(cudaSetDevice(device));
+    cn_device_guard guard(device);           /* the caller's current device is put back on return */
     int max_smem = 0;
     CN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const char* kern = getenv("CN_KERNEL");
@@ -162,7 +194,7 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     const bool faithful = (cfg->flags & CN_FLAG_RISK_FAITHFUL) != 0;
     const size_t trk_b = faithful ? align_up(cn_trk_words(cfg) * 4, 256) : 0;
     const size_t rng_b = faithful ? align_up((size_t)cfg->n_envs * (size_t)(cfg->n_samples - 1) * 4, 256) : 0;
-    h->arena_bytes = cfg_b + rob_b + 2 * ped_b + trk_b + rng_b;
+    h->arena_bytes = cfg_b + rob_b + 2 * ped_b + trk_b + rng_b + 256;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) { delete h; return fail(CN_ERR_NOMEM, "cn_create: cudaMalloc: %s", cudaGetErrorString(e)); }
     uint8_t* p = (uint8_t*)h->arena;
@@ -171,28 +203,35 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     h->ped_a = (uint32_t*)p; p += ped_b;
     h->ped_b = (uint32_t*)p; p += ped_b;
     h->trk = faithful ? (uint32_t*)p : NULL; p += trk_b;
-    h->own_ranges = faithful ? (float*)p : NULL;
+    h->own_ranges = faithful ? (float*)p : NULL; p += rng_b;
+    h->gather_timeouts = (unsigned int*)p;
     e = cudaMemset(h->arena, 0, h->arena_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(h->cfg_dev, cfg, sizeof(cn_config), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(h->arena); delete h; return fail(CN_ERR_CUDA, "cn_create: init: %s", cudaGetErrorString(e)); }
+    repack(h);
     *out = h;
     return CN_OK;
 }
 
 int cn_destroy(cn_handle* h) {
     if (!h) return CN_OK;
-    cudaSetDevice(h->device);
+    cn_device_guard guard(h->device);
     cudaFree(h->arena);
     delete h;
     return CN_OK;
 }
 
-static void pack(const cn_handle* h, cn_kparams* P) {
+}  /* extern "C" */
+
+/* the call-invariant part of cn_kparams, built once per handle (and again when the debug taps change) */
+static void repack(cn_handle* h) {
     const cn_config* c = &h->cfg;
+    cn_kparams* P = &h->base;
     memset(P, 0, sizeof(*P));
     P->robot = h->robot; P->ped_a = h->ped_a; P->ped_b = h->ped_b;
     P->dbg_ranges = h->dbg_ranges ? h->dbg_ranges : h->own_ranges; P->dbg_hid = h->dbg_hid;
     P->cfg = h->cfg_dev; P->d = h->d;
+    P->gather_timeouts = h->gather_timeouts;
     P->n_envs = c->n_envs; P->n_peds = c->n_peds; P->n_samples = c->n_samples; P->k_obstacles = c->k_obstacles;
     P->max_steps = c->max_steps; P->env_id_offset = c->env_id_offset; P->n_behaviors = c->n_behaviors;
     P->n_substeps = c->n_substeps;
@@ -209,9 +248,12 @@ static void pack(const cn_handle* h, cn_kparams* P) {
     }
 }
 
+extern "C" {
+
 int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     if (!h || !obs_dev) return fail(CN_ERR_INVALID, "cn_reset: null argument%s", NULL);
-    cn_kparams P; pack(h, &P);
+    cn_device_guard guard(h->device);
+    cn_kparams P = h->base;
     P.mask = mask_dev; P.obs = obs_dev; P.obs_bulk_ok = 0;
     CN_CUDA(launch_env(h, P, 1, (cudaStream_t)stream));
     h->launches += 1;
@@ -219,16 +261,43 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
     return CN_OK;
 }
 
+/* one step launch (+ the risk_faithful kernel) with the handle's device already current */
+static int step_once(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peers, int n_peers,
+                     float* reward_dev, uint8_t* done_dev, cudaStream_t stream) {
+    cn_kparams P = h->base;
+    P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
+    bool aligned = (((uintptr_t)obs_dev) & 15u) == 0;
+    for (int p = 0; p < n_peers; ++p) {
+        P.obs_peers[p] = peers[p];
+        aligned = aligned && (((uintptr_t)peers[p]) & 15u) == 0;
+    }
+    P.n_obs_peers = n_peers;
+    P.obs_bulk_ok = aligned;
+    P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
+    CN_CUDA(launch_env(h, P, 0, stream));
+    h->launches += 1;
+    CN_CUDA(launch_faithful(h, obs_dev, NULL, stream));
+    return CN_OK;
+}
+
 int cn_step(cn_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
     if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
         return fail(CN_ERR_INVALID, "cn_step: null argument%s", NULL);
-    cn_kparams P; pack(h, &P);
-    P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
-    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0;
-    P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
-    CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
-    h->launches += 1;
-    CN_CUDA(launch_faithful(h, obs_dev, NULL, (cudaStream_t)stream));
+    cn_device_guard guard(h->device);
+    return step_once(h, action_dev, obs_dev, NULL, 0, reward_dev, done_dev, (cudaStream_t)stream);
+}
+
+int cn_step_n(cn_handle* h, int n_steps, const float* action_dev, size_t action_stride, float* obs_dev,
+              float* reward_dev, uint8_t* done_dev, size_t out_stride, void* stream) {
+    if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_step_n: null argument%s", NULL);
+    if (n_steps < 0) return fail(CN_ERR_INVALID, "cn_step_n: n_steps < 0%s", NULL);
+    cn_device_guard guard(h->device);
+    for (int i = 0; i < n_steps; ++i) {
+        int rc = step_once(h, action_dev + (size_t)i * action_stride, obs_dev, NULL, 0,
+                           reward_dev + (size_t)i * out_stride, done_dev + (size_t)i * out_stride, (cudaStream_t)stream);
+        if (rc != CN_OK) return rc;
+    }
     return CN_OK;
 }
 
@@ -241,26 +310,128 @@ int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float*
     if (h->trk && n_peers > 0)
         return fail(CN_ERR_UNSUPPORTED, "cn_step_gather: CN_FLAG_RISK_FAITHFUL rewrites the K block after the step kernel; "
                                         "gather with ncclAllGather instead%s", NULL);
-    cn_kparams P; pack(h, &P);
+    for (int p = 0; p < n_peers; ++p)
+        if (!peer_obs_dev[p]) return fail(CN_ERR_INVALID, "cn_step_gather: null peer buffer%s", NULL);
+    cn_device_guard guard(h->device);
+    return step_once(h, action_dev, obs_dev, peer_obs_dev, n_peers, reward_dev, done_dev, (cudaStream_t)stream);
+}
+
+int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peer_obs_dev,
+                          unsigned long long* const* peer_arrive_dev, int n_peers, float* obs_mc_dev,
+                          unsigned long long* arrive_mc_dev, unsigned long long* arrive_local_dev, int n_ranks,
+                          int rank, int wait_back, float* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_step_gather_signal: null argument%s", NULL);
+    if (!h->use_flat) return fail(CN_ERR_UNSUPPORTED, "cn_step_gather_signal: default (flat) kernel only%s", NULL);
+    if (h->trk) return fail(CN_ERR_UNSUPPORTED, "cn_step_gather_signal: CN_FLAG_RISK_FAITHFUL rewrites the K block after "
+                                                "the step kernel; gather with ncclAllGather instead%s", NULL);
+    const bool mc = obs_mc_dev != NULL;
+    if (mc != (arrive_mc_dev != NULL)) return fail(CN_ERR_INVALID, "cn_step_gather_signal: obs_mc_dev and arrive_mc_dev go together%s", NULL);
+    if (!mc && (n_peers < 1 || n_peers > 8 || !peer_obs_dev || !peer_arrive_dev))
+        return fail(CN_ERR_INVALID, "cn_step_gather_signal: 1..8 peers (or multicast addresses)%s", NULL);
+    if (!arrive_local_dev || wait_back < 0) return fail(CN_ERR_INVALID, "cn_step_gather_signal: arrive_local_dev / wait_back%s", NULL);
+    if (n_ranks < 2 || n_ranks > 32 || rank < 0 || rank >= n_ranks) return fail(CN_ERR_INVALID, "cn_step_gather_signal: 2..32 ranks, 0 <= rank < n_ranks%s", NULL);
+    if (mc && (((uintptr_t)obs_mc_dev) & 15u)) return fail(CN_ERR_INVALID, "cn_step_gather_signal: obs_mc_dev must be 16-byte aligned%s", NULL);
+    cn_device_guard guard(h->device);
+    cn_kparams P = h->base;
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
     bool aligned = (((uintptr_t)obs_dev) & 15u) == 0;
-    for (int p = 0; p < n_peers; ++p) {
-        if (!peer_obs_dev[p]) return fail(CN_ERR_INVALID, "cn_step_gather: null peer buffer%s", NULL);
-        P.obs_peers[p] = peer_obs_dev[p];
-        aligned = aligned && (((uintptr_t)peer_obs_dev[p]) & 15u) == 0;
+    if (mc) {
+        P.obs_mc = obs_mc_dev; P.arrive_mc = arrive_mc_dev;
+    } else {
+        for (int p = 0; p < n_peers; ++p) {
+            if (!peer_obs_dev[p] || !peer_arrive_dev[p]) return fail(CN_ERR_INVALID, "cn_step_gather_signal: null peer pointer%s", NULL);
+            P.obs_peers[p] = peer_obs_dev[p]; P.arrive_peers[p] = peer_arrive_dev[p];
+            aligned = aligned && (((uintptr_t)peer_obs_dev[p]) & 15u) == 0;
+        }
+        P.n_obs_peers = n_peers;
     }
-    P.n_obs_peers = n_peers;
+    P.arrive_local = arrive_local_dev; P.arrive_back = wait_back; P.arrive_slots = n_ranks; P.arrive_self = rank;
+    P.ctas_per_step = (unsigned int)cn_kernel_ctas(h);
     P.obs_bulk_ok = aligned;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
     h->launches += 1;
-    CN_CUDA(launch_faithful(h, obs_dev, NULL, (cudaStream_t)stream));
+    return CN_OK;
+}
+
+int cn_gather_wait(cn_handle* h, const unsigned long long* arrive_local_dev, int n_ranks, int rank, void* stream) {
+    if (!h || !arrive_local_dev) return fail(CN_ERR_INVALID, "cn_gather_wait: null argument%s", NULL);
+    if (n_ranks < 2 || n_ranks > 32 || rank < 0 || rank >= n_ranks) return fail(CN_ERR_INVALID, "cn_gather_wait: 2..32 ranks, 0 <= rank < n_ranks%s", NULL);
+    cn_device_guard guard(h->device);
+    CN_CUDA(cn_launch_gather_wait(arrive_local_dev, n_ranks, rank, h->gather_timeouts, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_gather_timeouts(cn_handle* h, unsigned int* out_host, void* stream) {
+    if (!h || !out_host) return fail(CN_ERR_INVALID, "cn_gather_timeouts: null argument%s", NULL);
+    cn_device_guard guard(h->device);
+    CN_CUDA(cudaMemcpyAsync(out_host, h->gather_timeouts, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return CN_OK;
+}
+
+/* ---- n steps as one CUDA graph (no torch needed for graph-replayed rollouts of open-loop action batches) */
+struct cn_graph {
+    cn_handle* h;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int n_steps;
+    int launches_per_replay;
+};
+
+int cn_graph_create(cn_handle* h, int n_steps, const float* action_dev, size_t action_stride, float* obs_dev,
+                    float* reward_dev, uint8_t* done_dev, size_t out_stride, cn_graph** out) {
+    if (!h || !out || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_graph_create: null argument%s", NULL);
+    *out = NULL;
+    if (n_steps < 1) return fail(CN_ERR_INVALID, "cn_graph_create: n_steps < 1%s", NULL);
+    cn_device_guard guard(h->device);
+    cudaStream_t cap;
+    CN_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    const int64_t before = h->launches;
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail(CN_ERR_CUDA, "cn_graph_create: begin capture: %s", cudaGetErrorString(e)); }
+    int rc = cn_step_n(h, n_steps, action_dev, action_stride, obs_dev, reward_dev, done_dev, out_stride, cap);
+    cudaGraph_t g = NULL;
+    e = cudaStreamEndCapture(cap, &g);
+    const int per_replay = (int)(h->launches - before);
+    h->launches = before;                               /* captured, not launched */
+    cudaStreamDestroy(cap);
+    if (rc != CN_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess || !g) return fail(CN_ERR_CUDA, "cn_graph_create: end capture: %s", cudaGetErrorString(e));
+    cudaGraphExec_t ex = NULL;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(CN_ERR_CUDA, "cn_graph_create: instantiate: %s", cudaGetErrorString(e)); }
+    cn_graph* G = new (std::nothrow) cn_graph();
+    if (!G) { cudaGraphExecDestroy(ex); cudaGraphDestroy(g); return fail(CN_ERR_NOMEM, "cn_graph_create: host allocation failed%s", NULL); }
+    G->h = h; G->graph = g; G->exec = ex; G->n_steps = n_steps; G->launches_per_replay = per_replay;
+    *out = G;
+    return CN_OK;
+}
+
+int cn_graph_launch(cn_graph* g, void* stream) {
+    if (!g) return fail(CN_ERR_INVALID, "cn_graph_launch: null graph%s", NULL);
+    cn_device_guard guard(g->h->device);
+    CN_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    g->h->launches += g->launches_per_replay;
+    return CN_OK;
+}
+
+int cn_graph_destroy(cn_graph* g) {
+    if (!g) return CN_OK;
+    cn_device_guard guard(g->h->device);
+    cudaGraphExecDestroy(g->exec);
+    cudaGraphDestroy(g->graph);
+    delete g;
     return CN_OK;
 }
 
 int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream) {
     if (!h || !out_dev) return fail(CN_ERR_INVALID, "cn_get_counters: null argument%s", NULL);
     if (((uintptr_t)out_dev) & 15u) return fail(CN_ERR_INVALID, "cn_get_counters: out_dev must be 16-byte aligned%s", NULL);
+    cn_device_guard guard(h->device);
     if (h->trk) CN_CUDA(cn_launch_faithful_counters(h->robot, h->trk, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
     else CN_CUDA(cn_launch_counters(h->robot, out_dev, h->cfg.n_envs, (cudaStream_t)stream));
     h->launches += 1;
@@ -269,6 +440,7 @@ int cn_get_counters(cn_handle* h, int32_t* out_dev, void* stream) {
 
 int cn_clear_done(cn_handle* h, const uint8_t* mask_dev, void* stream) {
     if (!h) return fail(CN_ERR_INVALID, "cn_clear_done: null handle%s", NULL);
+    cn_device_guard guard(h->device);
     CN_CUDA(cn_launch_clear_done(h->robot, mask_dev, h->cfg.n_envs, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
@@ -277,12 +449,10 @@ int cn_clear_done(cn_handle* h, const uint8_t* mask_dev, void* stream) {
 int cn_get_blob(cn_handle* h, void* host, size_t bytes, void* stream) {
     if (!h || !host) return fail(CN_ERR_INVALID, "cn_get_blob: null argument%s", NULL);
     if (bytes != cn_blob_words(&h->cfg) * 4) return fail(CN_ERR_INVALID, "cn_get_blob: size mismatch%s", NULL);
+    cn_device_guard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t* w = (uint32_t*)host;
-    memset(w, 0, CN_BLOB_HEADER_WORDS * 4);
-    w[0] = CN_BLOB_MAGIC; w[1] = CN_ABI_VERSION;
-    w[2] = (uint32_t)h->cfg.n_envs; w[3] = (uint32_t)h->cfg.n_peds;
-    w[4] = (uint32_t)h->cfg.n_samples; w[5] = (uint32_t)h->cfg.k_obstacles;
+    cn_blob_header(&h->cfg, w);
     w += CN_BLOB_HEADER_WORDS;
     const size_t rw = cn_robot_words(&h->cfg), pw = cn_ped_plane_words(&h->cfg);
     CN_CUDA(cudaMemcpyAsync(w, h->robot, rw * 4, cudaMemcpyDeviceToHost, s));
@@ -299,8 +469,15 @@ int cn_set_blob(cn_handle* h, const void* host, size_t bytes, void* stream) {
     if (!h || !host) return fail(CN_ERR_INVALID, "cn_set_blob: null argument%s", NULL);
     if (bytes != cn_blob_words(&h->cfg) * 4) return fail(CN_ERR_INVALID, "cn_set_blob: size mismatch%s", NULL);
     const uint32_t* w = (const uint32_t*)host;
-    if (w[0] != CN_BLOB_MAGIC || w[2] != (uint32_t)h->cfg.n_envs || w[3] != (uint32_t)h->cfg.n_peds)
-        return fail(CN_ERR_INVALID, "cn_set_blob: blob does not match this handle%s", NULL);
+    {
+        /* a blob is only accepted by a handle of the same shape, layout version and risk-block mode */
+        uint32_t want[CN_BLOB_HEADER_WORDS];
+        cn_blob_header(&h->cfg, want);
+        if (memcmp(w, want, sizeof(want)) != 0)
+            return fail(CN_ERR_INVALID, "cn_set_blob: blob header does not match this handle (magic, layout version, "
+                                        "n_envs, n_peds, n_samples, k_obstacles, risk-block mode, tracker record size)%s", NULL);
+    }
+    cn_device_guard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     w += CN_BLOB_HEADER_WORDS;
     const size_t rw = cn_robot_words(&h->cfg), pw = cn_ped_plane_words(&h->cfg);
@@ -317,12 +494,18 @@ int cn_set_blob(cn_handle* h, const void* host, size_t bytes, void* stream) {
 int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev) {
     if (!h) return fail(CN_ERR_INVALID, "cn_set_debug_taps: null handle%s", NULL);
     h->dbg_ranges = ranges_dev; h->dbg_hid = hit_ids_dev;
+    repack(h);
     return CN_OK;
 }
 
 int64_t cn_launch_count(const cn_handle* h) { return h ? h->launches : 0; }
 const char* cn_kernel_name(const cn_handle* h) { return (h && !h->use_flat) ? "cn_env_kernel" : "cn_flat_kernel"; }
 int cn_kernel_tile(const cn_handle* h) { return !h ? 0 : (h->use_flat ? h->flat.W : CN_TILE); }
+int cn_kernel_ctas(const cn_handle* h) {
+    if (!h) return 0;
+    const int W = h->use_flat ? h->flat.W : CN_TILE;
+    return (h->cfg.n_envs + W - 1) / W;
+}
 
 int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes) {
     if (!cfg || !tile || !threads || !smem_bytes) return fail(CN_ERR_INVALID, "cn_plan_tile: null argument%s", NULL);

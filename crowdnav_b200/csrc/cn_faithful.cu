@@ -63,11 +63,9 @@ cudaError_t cn_launch_faithful(const cn_config* cfg, const uint32_t* robot, uint
                                float* obs, const uint8_t* mask, int obs_dim, cudaStream_t stream) {
     cnf_params P; cnf_params_from_config(cfg, &P);
     const size_t per = cnf_scratch_bytes(P.n_rays), smem = CNF_WORLDS * per;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cn_faithful_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = cn_ensure_smem_attr(reinterpret_cast<const void*>(cn_faithful_kernel), 14, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int E = cfg->n_envs;
     cn_faithful_kernel<<<(E + CNF_WORLDS - 1) / CNF_WORLDS, CNF_LANES * CNF_WORLDS, smem, stream>>>(

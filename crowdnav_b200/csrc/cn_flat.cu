@@ -302,6 +302,57 @@ __device__ __forceinline__ void copy16_out(void* gdst, const void* ssrc, int n, 
     for (int i = t; i < n; i += nthreads) g[i] = s[i];
 }
 
+// ---- fused all-gather: system-scope signalling and NVSwitch multicast stores
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_red_release_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+// wait (bounded) until *ctr >= target; false = gave up
+__device__ __forceinline__ bool wait_arrivals(const unsigned long long* ctr, unsigned long long target) {
+    if (ld_acquire_sys(ctr) >= target) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(ctr) < target) {
+        __nanosleep(64);
+        if (globaltimer_ns() - t0 > CN_GATHER_WAIT_NS) return false;
+    }
+    return true;
+}
+// n 16-byte elements from shared memory to a multicast address: ONE store instruction per element, the switch
+// replicates it into every rank's buffer
+__device__ __forceinline__ void copy16_out_mc(void* mcdst, const void* ssrc, int n, int t, int nthreads) {
+    const float4* s = reinterpret_cast<const float4*>(ssrc);
+    float4* g = reinterpret_cast<float4*>(mcdst);
+#pragma unroll 1
+    for (int i = t; i < n; i += nthreads) {
+        const float4 v = s[i];
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(g + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+// the tile's [nE, D] block of rows into every peer's gather buffer.  CTA b starts with peer b mod n: at any moment
+// the CTAs of one GPU are spread over all its NVLink destinations, and (with the host listing the peers from
+// rank + 1 on) the GPUs do not gang up on one receiver.
+__device__ __forceinline__ void push_rows_to_peers(const cn_kparams& P, const float* srows, size_t row0, int n16, int tid, int T) {
+    if (P.obs_mc) { copy16_out_mc(P.obs_mc + row0, srows, n16, tid, T); return; }
+    const int np = P.n_obs_peers;
+    int p = (np > 1) ? (int)(blockIdx.x % (unsigned)np) : 0;
+#pragma unroll 1
+    for (int k = 0; k < np; ++k) {
+        copy16_out(P.obs_peers[p] + row0, srows, n16, tid, T);
+        p = (p + 1 == np) ? 0 : p + 1;
+    }
+}
+
 // ------------------------------------------------------------------- kernel
 template <int MODE, int T>
 __global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? 4 : (T >= 192 ? 6 : 8))))
@@ -911,23 +962,33 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 
     // ---------------------------------------------------------------- phase 7: write-back
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
+    const bool gather = (MODE == 0) && (P.n_obs_peers > 0 || P.obs_mc != nullptr);
+    if (gather && P.arrive_back > 0 && tid < P.arrive_slots && tid != P.arrive_self) {
+        // Which step is this?  This rank's OWN slot counts its CTAs: every CTA of the earlier steps has added 1 (stream
+        // order), the CTAs of this step add theirs at the very end, so t = own / CTAs-per-step.  The buffer about to be
+        // overwritten on the peers was read by them before they launched step t - arrive_back, whose arrivals -- slot s
+        // of OUR array, thread s polls source rank s -- we wait for (normally there long before this point).  Device-
+        // side counting keeps a captured graph of steps correct on every replay.
+        const unsigned long long own = ld_acquire_sys(P.arrive_local + P.arrive_self);
+        const unsigned long long t = own / P.ctas_per_step;
+        if (t >= (unsigned long long)P.arrive_back) {
+            const unsigned long long target = (t - (unsigned long long)P.arrive_back + 1ull) * P.ctas_per_step;
+            if (!wait_arrivals(P.arrive_local + tid, target) && P.gather_timeouts) atomicAdd(P.gather_timeouts, 1u);
+        }
+    }
     FSTAMP(12);
     __syncthreads();             // #G
     FSTAMP(7);
     const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
     if (L.plain_store) {
         // cooperative 16-byte stores: nothing to wait for, the CTA's slot is free as soon as they are issued
+        if (bulk_obs && gather) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);   // NVLink first
         copy16_out(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, (int)(rob_bytes >> 4), tid, T);
         if (ped_bytes) {
             copy16_out(P.ped_a + (size_t)e0 * N * 4, S.pa2, n_items, tid, T);
             copy16_out(P.ped_b + (size_t)e0 * N * 4, S.pb, n_items, tid, T);
         }
-        if (bulk_obs) {
-            copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
-#pragma unroll 1
-            for (int p = 0; p < P.n_obs_peers; ++p)                         // fused all-gather over NVLink
-                copy16_out(P.obs_peers[p] + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
-        }
+        if (bulk_obs) copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
     } else {
         if (tid == 0) {
             tma_store(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, rob_bytes);
@@ -940,12 +1001,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         }
         // fused all-gather: the same block of rows goes straight into every peer's gather buffer over NVLink, as plain
         // 16-byte stores from all threads (measured at 2 GPUs: 32.4 us per step against 36.7 us with bulk stores, whose
-        // completion the CTA would have to wait for)
-        if (bulk_obs) {
-#pragma unroll 1
-            for (int p = 0; p < P.n_obs_peers; ++p)
-                copy16_out(P.obs_peers[p] + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
-        }
+        // completion the CTA would have to wait for), or as multimem stores the switch replicates
+        if (bulk_obs && gather) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);
         if (tid == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             FSTAMP(8);
@@ -957,11 +1014,30 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             if (!(S.sc[w * F_WORDS + F_XFLAGS] & XF_ACTIVE)) continue;
             const float* row = S.obs + (size_t)w * D;
 #pragma unroll 1
-            for (int p = -1; p < P.n_obs_peers; ++p) {                      // -1: this rank's buffer, then the peers'
+            for (int p = -1; p < (P.obs_mc ? 0 : P.n_obs_peers); ++p) {     // -1: this rank's buffer, then the peers'
                 float* g = (p < 0 ? P.obs : P.obs_peers[p]) + (size_t)(e0 + w) * D;
 #pragma unroll 1
                 for (int k = lane; k < D; k += 32) g[k] = row[k];
             }
+            if (MODE == 0 && P.obs_mc) {
+                float* g = P.obs_mc + (size_t)(e0 + w) * D;
+#pragma unroll 1
+                for (int k = lane; k < D; k += 32)
+                    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(g + k), "f"(row[k]) : "memory");
+            }
+        }
+    }
+    if (gather && (P.arrive_mc != nullptr || P.arrive_peers[0] != nullptr)) {
+        // signal: every thread's stores into the peers are ordered before the barrier, the barrier before thread p's
+        // system-scope release; the peer's acquire load of its counter then sees the rows (the pattern of a grid sync)
+        __syncthreads();
+        if (P.arrive_mc) {                                          // (reaches this rank's own slot too)
+            if (tid == 0) { __threadfence_system(); multimem_red_release_sys_add(P.arrive_mc, 1ull); }
+        } else if (tid < P.n_obs_peers) {
+            __threadfence_system();
+            red_release_sys_add(P.arrive_peers[tid], 1ull);
+        } else if (tid == 32) {
+            red_release_sys_add(P.arrive_local + P.arrive_self, 1ull);
         }
     }
 }
@@ -1037,11 +1113,10 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
 template <int MODE, int T>
 static cudaError_t launch_flat_t(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream) {
     auto k = cn_flat_kernel<MODE, T>;
-    static size_t attr_smem = 0;
-    if (L.total > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    {
+        constexpr int ti = (T == 128) ? 0 : (T == 192) ? 1 : (T == 256) ? 2 : (T == 384) ? 3 : 4;
+        cudaError_t e = cn_ensure_smem_attr(reinterpret_cast<const void*>(k), MODE * 5 + ti, L.total);
         if (e != cudaSuccess) return e;
-        attr_smem = L.total;
     }
     const int grid = (P.n_envs + L.W - 1) / L.W;
     if (!L.pdl) {
@@ -1062,6 +1137,21 @@ extern "C" int cn_debug_set_timeline_flat(unsigned long long* dev_ptr) {
     return (int)cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr));
 }
 #endif
+
+// thread s watches source rank s: hold the stream until every other rank's slot of this rank's arrival counters has
+// caught up with this rank's own step count (every CTA of that rank's latest step has stored its rows here and signalled); bounded, a lost peer is counted instead of hanging the GPU
+__global__ void cn_gather_wait_kernel(const unsigned long long* counters, int n_slots, int self_slot, unsigned int* timeouts) {
+    const int s = (int)threadIdx.x;
+    // this rank's own slot = CTAs of all its steps so far (they have completed: stream order); equal shards, so the
+    // same number of arrivals is due from every other rank
+    const unsigned long long target = ld_acquire_sys(counters + self_slot);
+    if (s < n_slots && s != self_slot && !wait_arrivals(counters + s, target) && timeouts) atomicAdd(timeouts, 1u);
+}
+cudaError_t cn_launch_gather_wait(const unsigned long long* counters, int n_slots, int self_slot,
+                                  unsigned int* timeouts, cudaStream_t stream) {
+    cn_gather_wait_kernel<<<1, 32, 0, stream>>>(counters, n_slots, self_slot, timeouts);
+    return cudaGetLastError();
+}
 
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream) {
     if (L.threads == 128) return mode == 0 ? launch_flat_t<0, 128>(P, L, stream) : launch_flat_t<1, 128>(P, L, stream);

@@ -24,6 +24,20 @@ struct cn_kparams {
     uint8_t* dbg_hid;
     float* obs_peers[8];        /* fused all-gather: this rank's row block inside each PEER's [E_total, D] buffer */
     int n_obs_peers;
+    /* fused all-gather with in-kernel signalling (cn_step_gather_signal; flat kernel only).  Every rank owns an array of
+     * 64-bit arrival counters, one slot per SOURCE rank.  After its rows have been stored into a peer, every CTA adds 1
+     * to its own slot of that peer's array (release, system scope); before the first store into the peers the CTA waits
+     * until every other rank's slot of THIS rank's array has reached arrive_wait (the peers are done with the buffer
+     * about to be overwritten).  obs_mc / arrive_mc: NVSwitch multicast addresses (multimem.st / .red), one store
+     * reaches every rank's buffer -- used instead of the unicast lists when non-NULL. */
+    unsigned long long* arrive_peers[8];   /* peer p's array, already offset to this rank's slot */
+    unsigned long long* arrive_local;      /* this rank's array [arrive_slots]; its OWN slot counts this rank's CTAs */
+    int arrive_slots, arrive_self;
+    int arrive_back;                       /* wait for the peers' step (t - arrive_back); 0 = no wait */
+    unsigned int ctas_per_step;
+    float* obs_mc;
+    unsigned long long* arrive_mc;
+    unsigned int* gather_timeouts;  /* device counter: waits given up after CN_GATHER_WAIT_NS (diagnostics, never hangs the GPU) */
     const cn_config* cfg;       /* device copy */
     cn_derived d;
     int n_envs, n_peds, n_samples, k_obstacles, max_steps, env_id_offset, n_behaviors, n_substeps;
@@ -58,8 +72,18 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
 int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, cn_flat_layout* L);
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream);
 
+/* cn_abi.cu: raise cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the CURRENT device to at least `smem`
+ * (the attribute is per device; the table is keyed by (slot, device) and guarded by a mutex).  Slots: 0-9 flat
+ * kernel (mode * 5 + CTA-size index), 10-13 warp kernel (NPL, mode), 14 risk_faithful kernel. */
+#define CN_ATTR_SLOTS 16
+#define CN_ATTR_MAX_DEVICES 64
+cudaError_t cn_ensure_smem_attr(const void* func, int slot, size_t smem);
+
 size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim);
 cudaError_t cn_launch_env_kernel(const cn_kparams& P, int mode /*0 step, 1 reset*/, cudaStream_t stream);
+cudaError_t cn_launch_gather_wait(const unsigned long long* counters, int n_slots, int self_slot,
+                                  unsigned int* timeouts, cudaStream_t stream);
+#define CN_GATHER_WAIT_NS 2000000000ull   /* a peer that is 2 s late is treated as lost: count it and go on */
 cudaError_t cn_launch_clear_done(uint32_t* robot, const uint8_t* mask, int E, cudaStream_t stream);
 cudaError_t cn_launch_counters(const uint32_t* robot, int32_t* out, int E, cudaStream_t stream);
 

@@ -146,6 +146,16 @@ static inline size_t cn_trk_words(const cn_config* c) {
 static inline size_t cn_blob_words(const cn_config* c) {
     return CN_BLOB_HEADER_WORDS + cn_robot_words(c) + 2 * cn_ped_plane_words(c) + cn_trk_words(c);
 }
+/* 16-word blob header: shape, layout version and the mode bits that change what the planes mean.  cn_set_blob
+ * accepts a blob only when all of it matches the handle. */
+static inline void cn_blob_header(const cn_config* c, uint32_t* w) {
+    for (int i = 0; i < CN_BLOB_HEADER_WORDS; ++i) w[i] = 0u;
+    w[0] = CN_BLOB_MAGIC; w[1] = CN_ABI_VERSION;
+    w[2] = (uint32_t)c->n_envs; w[3] = (uint32_t)c->n_peds;
+    w[4] = (uint32_t)c->n_samples; w[5] = (uint32_t)c->k_obstacles;
+    w[6] = c->flags & (CN_FLAG_RISK_FAITHFUL | CN_FLAG_ENV_ORIGINAL);
+    w[7] = (c->flags & CN_FLAG_RISK_FAITHFUL) ? (uint32_t)CNF_WORLD_WORDS : 0u;
+}
 /* float64 constants of the risk_faithful block from the (float) config */
 static inline void cnf_params_from_config(const cn_config* c, cnf_params* p) {
     p->n_rays = c->n_samples - 1;

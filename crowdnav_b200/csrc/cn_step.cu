@@ -729,12 +729,9 @@ size_t cn_kernel_smem_bytes(int n_peds, int n_samples, int obs_dim) {
 template <int NPL, int MODE>
 static cudaError_t launch_t(const cn_kparams& P, size_t smem, cudaStream_t stream) {
     auto k = cn_env_kernel<NPL, MODE>;
-    static bool attr_set = false;
-    static size_t attr_smem = 0;
-    if (!attr_set || smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = cn_ensure_smem_attr(reinterpret_cast<const void*>(k), 10 + (NPL - 1) * 2 + MODE, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true; attr_smem = smem;
     }
     const int grid = (P.n_envs + CN_TILE - 1) / CN_TILE;
     k<<<grid, CN_CTA_THREADS, smem, stream>>>(P);

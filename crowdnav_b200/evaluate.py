@@ -51,38 +51,55 @@ def scenario_config(behavior: str, n_peds: int, fast: bool = False, n_envs: int 
 
 @torch.no_grad()
 def evaluate(env, actor, n_episodes: int, max_launches: int = 100000) -> List[Dict[str, float]]:
-    """Run `actor` greedily (no exploration noise: README "learning = False") until n_episodes have finished.
+    """Run `actor` greedily (no exploration noise: README "learning = False") for n_episodes episodes.
 
-    `env` is a CrowdNavVecEnv built with auto_reset.  Returns one dict per finished episode with the CSV columns."""
+    `env` is a CrowdNavVecEnv built with auto_reset.  Every world gets a fixed QUOTA of ceil(n_episodes / E)
+    episodes: exactly its first `quota` episodes are recorded, later ones are ignored, and the run lasts until every
+    world has met its quota.  (Keeping "the first n episodes to finish" across auto-resetting parallel worlds would
+    over-represent short episodes -- under this protocol short means success -- and cut the time-outs off.)
+    Returns one dict per recorded episode with the CSV columns, ordered by world, then by episode; the list has
+    quota * E >= n_episodes entries so that no world is favoured."""
     E, dev = env.E, env.device
+    quota = max(1, -(-n_episodes // E))
     obs = env.reset().clone()
     ret = torch.zeros(E, device=dev)
     length = torch.zeros(E, device=dev)
-    rows: List[Dict[str, float]] = []
+    n_rec = torch.zeros(E, dtype=torch.int64, device=dev)           # episodes recorded per world
+    # per (world, episode slot): success, ego, social, present, return, length
+    table = torch.zeros((E, quota, 6), dtype=torch.float32, device=dev)
     dt = float(env.cfg.dt)
-    for _ in range(max_launches):
+    world_idx = torch.arange(E, device=dev)
+    for it in range(max_launches):
         nobs, r, d = env.step(actor(obs).contiguous())
         live = d != 2
         ret += torch.where(live, r, torch.zeros_like(r))
         length += live.float()
-        ended = torch.nonzero(d == 1).flatten()
-        if ended.numel():
-            c = env.counters()[ended].float().cpu()            # success, ego, social, obstacle-present
-            rr, ll = ret[ended].cpu(), length[ended].cpu()
-            for k in range(ended.numel()):
-                succ, ego, soc, pres = (float(x) for x in c[k])
-                # ENV:1269-1283; the reference divides by zero when no obstacle was ever seen -- reported as 1.0 here
-                rows.append({"episode_number": len(rows) + 1, "success_episode": bool(succ), "failure_episode": not bool(succ),
-                             "episode_reward": float(rr[k]), "episode_step": int(ll[k]),
-                             "ego_safety_score": 1.0 - ego / pres if pres > 0 else 1.0,
-                             "social_safety_score": 1.0 - soc / pres if pres > 0 else 1.0,
-                             "timelapse": float(ll[k]) * dt})
-            ret[ended] = 0.0
-            length[ended] = 0.0
-            if len(rows) >= n_episodes:
-                break
+        ended = d == 1
+        c = env.counters().float()                                  # success, ego, social, obstacle-present
+        rec = ended & (n_rec < quota)
+        slot = n_rec.clamp(max=quota - 1)
+        row = torch.cat([c, ret.unsqueeze(1), length.unsqueeze(1)], 1)
+        cur = table[world_idx, slot]
+        table[world_idx, slot] = torch.where(rec.unsqueeze(1), row, cur)
+        n_rec += rec.to(torch.int64)
+        ret.masked_fill_(ended, 0.0)
+        length.masked_fill_(ended, 0.0)
         obs = nobs.clone()
-    return rows[:n_episodes]
+        if (it & 15) == 15 and bool((n_rec >= quota).all()):        # one read-back every 16 launches
+            break
+    t = table.cpu()
+    done_n = n_rec.cpu()
+    rows: List[Dict[str, float]] = []
+    for w in range(E):
+        for k in range(int(done_n[w])):
+            succ, ego, soc, pres, rr, ll = (float(x) for x in t[w, k])
+            # ENV:1269-1283; the reference divides by zero when no obstacle was ever seen -- reported as 1.0 here
+            rows.append({"episode_number": len(rows) + 1, "success_episode": bool(succ), "failure_episode": not bool(succ),
+                         "episode_reward": rr, "episode_step": int(ll),
+                         "ego_safety_score": 1.0 - ego / pres if pres > 0 else 1.0,
+                         "social_safety_score": 1.0 - soc / pres if pres > 0 else 1.0,
+                         "timelapse": ll * dt})
+    return rows
 
 
 def write_csv(rows: Sequence[Dict[str, float]], path: str) -> None:

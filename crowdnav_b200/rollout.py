@@ -11,9 +11,12 @@ batch-wise, everything resident on the GPU:
     `load_reference_actor` reads the reference's `torch.save(state_dict)` checkpoints
     (or the npz fixture made from one) unchanged.
   * `explore`                 -- Gaussian exploration sigma = 1, clipped to the action box (TD3:67-78, 209-215).
-  * `ReplayRing`              -- tensor ring buffer; rows whose step was an auto-reset (done == 2) are dropped.
+  * `SACActor`                -- the reference's SAC policy network (sac.py:43-106), same checkpoint layout.
+  * `ReplayRing`              -- tensor ring buffer; rows whose step was an auto-reset (done == 2) are dropped;
+                                 device-side cursor, no host synchronisation.
   * `TD3Learner`              -- twin critics, target smoothing, delayed policy update (TD3:225-285).
-  * `collect`                 -- batched rollout loop over CrowdNavVecEnv.
+  * `collect`                 -- batched rollout loop over CrowdNavVecEnv, statistics accumulated on the device.
+  * `rollout_throughput`      -- env-steps/s of policy + env + replay (+ learner) for bench.py.
 
 PyTorch only; the env step underneath is the CUDA library.
 """
@@ -86,38 +89,86 @@ def explore(action: torch.Tensor, sigma: float = 1.0, generator: torch.Generator
 
 
 class ReplayRing:
-    """Device-resident ring buffer replacing the Python-list ReplayBuffer (TD3:19-37)."""
+    """Device-resident ring buffer replacing the Python-list ReplayBuffer (TD3:19-37).
+
+    No host synchronisation anywhere: the write cursor and the fill level are device tensors, a vectorised step is
+    appended with one scatter per field (rows that carry no transition go to a spare trash row), and `sample` draws
+    its indices on the device.  `len()` is the only call that reads the fill level back."""
 
     def __init__(self, capacity: int, obs_dim: int, device: torch.device):
-        self.capacity, self.size, self.pos = capacity, 0, 0
-        self.state = torch.empty((capacity, obs_dim), dtype=torch.float32, device=device)
-        self.next_state = torch.empty((capacity, obs_dim), dtype=torch.float32, device=device)
-        self.action = torch.empty((capacity, 2), dtype=torch.float32, device=device)
-        self.reward = torch.empty((capacity, 1), dtype=torch.float32, device=device)
-        self.done = torch.empty((capacity, 1), dtype=torch.float32, device=device)
+        self.capacity = capacity
+        # row `capacity` is the trash row: scatter target of the rows that are dropped
+        self.state = torch.zeros((capacity + 1, obs_dim), dtype=torch.float32, device=device)
+        self.next_state = torch.zeros((capacity + 1, obs_dim), dtype=torch.float32, device=device)
+        self.action = torch.zeros((capacity + 1, 2), dtype=torch.float32, device=device)
+        self.reward = torch.zeros((capacity + 1, 1), dtype=torch.float32, device=device)
+        self.done = torch.zeros((capacity + 1, 1), dtype=torch.float32, device=device)
+        self._pos = torch.zeros((), dtype=torch.int64, device=device)      # next slot to write
+        self._size = torch.zeros((), dtype=torch.int64, device=device)     # valid rows
 
-    def add_batch(self, state, action, reward, next_state, done) -> int:
-        """Append the transitions of one vectorised step; auto-reset rows (done == 2) carry no transition."""
+    def add_batch(self, state, action, reward, next_state, done) -> None:
+        """Append the transitions of one vectorised step; auto-reset rows (done == 2) carry no transition.  When one
+        batch holds more transitions than the ring, only the last `capacity` of them are kept (every slot is then
+        written exactly once, so the five fields of a slot always belong to the same transition)."""
         keep = done != 2
-        n = int(keep.sum().item())
-        if n == 0:
-            return 0
-        idx = (self.pos + torch.arange(n, device=state.device)) % self.capacity
-        self.state[idx] = state[keep]
-        self.next_state[idx] = next_state[keep]
-        self.action[idx] = action[keep]
-        self.reward[idx] = reward[keep].unsqueeze(1)
-        self.done[idx] = (done[keep] == 1).float().unsqueeze(1)
-        self.pos = (self.pos + n) % self.capacity
-        self.size = min(self.size + n, self.capacity)
-        return n
+        order = torch.cumsum(keep.to(torch.int64), 0) - 1            # rank of each kept row among the kept rows
+        n = order[-1] + 1
+        keep = keep & (order >= n - self.capacity)
+        idx = torch.where(keep, (self._pos + order) % self.capacity, torch.full_like(order, self.capacity))
+        self.state[idx] = state
+        self.next_state[idx] = next_state
+        self.action[idx] = action
+        self.reward[idx] = reward.unsqueeze(1)
+        self.done[idx] = (done == 1).float().unsqueeze(1)
+        self._pos.copy_((self._pos + n) % self.capacity)
+        self._size.copy_(torch.clamp(self._size + n, max=self.capacity))
 
     def sample(self, batch_size: int, generator: torch.Generator | None = None):
-        idx = torch.randint(0, self.size, (batch_size,), device=self.state.device, generator=generator)
+        u = torch.rand((batch_size,), device=self.state.device, generator=generator)
+        idx = (u * self._size.clamp(min=1).to(torch.float32)).to(torch.int64).clamp_(max=self.capacity - 1)
         return self.state[idx], self.action[idx], self.reward[idx], self.next_state[idx], self.done[idx]
+
+    @property
+    def pos(self) -> int:
+        return int(self._pos.item())
+
+    @property
+    def size(self) -> int:
+        return int(self._size.item())
 
     def __len__(self) -> int:
         return self.size
+
+
+class SACActor(nn.Module):
+    """The reference's SAC policy network (sac.py:43-106): shared trunk, mean / log-std heads, action =
+    (sigmoid(tanh(z)[0]) * max_lin_vel, tanh(tanh(z)[1]) * max_ang_vel) with z ~ N(mean, std) -- the double squashing is
+    the reference's (sac.py:97-101).  Attribute names match so its `torch.save(state_dict)` checkpoints load."""
+
+    def __init__(self, num_inputs: int, num_actions: int = 2, hidden_size: int = 256, max_lin_vel: float = MAX_LIN_VEL,
+                 max_ang_vel: float = MAX_ANG_VEL, init_w: float = 3e-3, log_std_min: float = -20.0, log_std_max: float = 2.0):
+        super().__init__()
+        self.log_std_min, self.log_std_max = log_std_min, log_std_max
+        self.linear1 = nn.Linear(num_inputs, hidden_size)
+        self.linear2 = nn.Linear(hidden_size, hidden_size)
+        self.mean_linear = nn.Linear(hidden_size, num_actions)
+        self.log_std_linear = nn.Linear(hidden_size, num_actions)
+        for lin in (self.mean_linear, self.log_std_linear):
+            lin.weight.data.uniform_(-init_w, init_w)
+            lin.bias.data.uniform_(-init_w, init_w)
+        self.max_lin_vel, self.max_ang_vel = max_lin_vel, max_ang_vel
+
+    def heads(self, state: torch.Tensor):
+        x = F.relu(self.linear1(state))
+        x = F.relu(self.linear2(x))
+        return self.mean_linear(x), torch.clamp(self.log_std_linear(x), self.log_std_min, self.log_std_max)
+
+    def forward(self, state: torch.Tensor, generator: torch.Generator | None = None, deterministic: bool = False) -> torch.Tensor:
+        """A sampled action per row (sac.py:92-103 `get_action`); deterministic=True uses z = mean."""
+        mean, log_std = self.heads(state)
+        z = mean if deterministic else mean + log_std.exp() * torch.randn(mean.shape, device=mean.device, generator=generator)
+        a = torch.tanh(z)
+        return torch.stack([torch.sigmoid(a[:, 0]) * self.max_lin_vel, torch.tanh(a[:, 1]) * self.max_ang_vel], dim=1)
 
 
 class TD3Learner:
@@ -141,20 +192,19 @@ class TD3Learner:
             for p, tp in zip(net.parameters(), target.parameters()):
                 tp.mul_(1.0 - self.tau).add_(p, alpha=self.tau)
 
-    def learn(self, batch) -> Dict[str, float]:
+    def learn(self, batch) -> Dict[str, torch.Tensor]:
         state, action, reward, next_state, done = batch
         with torch.no_grad():
             na = self.t_actor(next_state)
             noise = (torch.randn_like(na) * self.noise_std).clamp(-self.noise_clip, self.noise_clip)
-            na = na + noise
-            na = torch.stack([na[:, 0].clamp(0.0, MAX_LIN_VEL), na[:, 1].clamp(-MAX_ANG_VEL, MAX_ANG_VEL)], 1)
+            na = na + noise                       # TD3:247-250: the smoothed target action is NOT clipped to the action box
             tq = torch.min(self.t_critic1(next_state, na), self.t_critic2(next_state, na))
             target = reward + (1.0 - done) * self.gamma * tq
         l1 = F.mse_loss(self.critic1(state, action), target)
         l2 = F.mse_loss(self.critic2(state, action), target)
         self.opt_c1.zero_grad(set_to_none=True); l1.backward(); self.opt_c1.step()
         self.opt_c2.zero_grad(set_to_none=True); l2.backward(); self.opt_c2.step()
-        out = {"critic1": float(l1.detach()), "critic2": float(l2.detach())}
+        out = {"critic1": l1.detach(), "critic2": l2.detach()}      # device scalars: no host sync in the update
         self.updates += 1
         if self.updates % self.policy_update == 0:
             la = -self.critic1(state, self.actor(state)).mean()
@@ -162,24 +212,30 @@ class TD3Learner:
             self._soft(self.actor, self.t_actor)
             self._soft(self.critic1, self.t_critic1)
             self._soft(self.critic2, self.t_critic2)
-            out["actor"] = float(la.detach())
+            out["actor"] = la.detach()
         return out
 
 
 @torch.no_grad()
 def collect(env, actor: nn.Module, steps: int, sigma: float = 0.0, replay: ReplayRing | None = None,
-            generator: torch.Generator | None = None) -> Dict[str, float]:
+            generator: torch.Generator | None = None, learner: "TD3Learner | None" = None, learn_every: int = 0,
+            batch_size: int = 256) -> Dict[str, float]:
     """Run `steps` vectorised env steps of `env` (a CrowdNavVecEnv with auto-reset) under `actor`.
 
-    Returns episode statistics in the reference's terms (UTL:53-64): episodes finished, successes, mean
-    undiscounted return per finished episode, mean length."""
+    Nothing in the loop synchronises with the host: episode statistics are accumulated on the device and read once
+    at the end.  With `learner` and `learn_every` > 0 a TD3 update on a replay mini-batch follows every
+    `learn_every`-th env step (TD3DRV:128-133: the reference learns once per env step).
+
+    Returns episode statistics in the reference's terms (UTL:53-64) over the episodes that FINISHED inside the
+    window -- episodes finished, successes, mean undiscounted return and length -- plus, separately, the episodes the
+    window cut off (`censored`, with their partial mean return / length): a fixed window over-represents short
+    episodes, so success rates from `collect` are not comparable with evaluate()'s per-world quota."""
     E, dev = env.E, env.device
     obs = env.obs.clone()
     ret = torch.zeros(E, device=dev)
     length = torch.zeros(E, device=dev)
-    n_eps = n_succ = 0
-    sum_ret = sum_len = 0.0
-    for _ in range(steps):
+    acc = torch.zeros(4, dtype=torch.float64, device=dev)       # episodes, successes, sum of returns, sum of lengths
+    for t in range(steps):
         a = actor(obs)
         a = explore(a, sigma, generator) if sigma > 0 else a.contiguous()
         nobs, r, d = env.step(a)
@@ -189,14 +245,44 @@ def collect(env, actor: nn.Module, steps: int, sigma: float = 0.0, replay: Repla
         ret += torch.where(live, r, torch.zeros_like(r))
         length += live.float()
         ended = d == 1
-        if ended.any():
-            succ = env.counters()[:, 0] == 1
-            n_eps += int(ended.sum())
-            n_succ += int((ended & succ).sum())
-            sum_ret += float(ret[ended].sum())
-            sum_len += float(length[ended].sum())
-            ret[ended] = 0.0
-            length[ended] = 0.0
+        succ = env.counters()[:, 0] == 1                         # one tiny kernel, no read-back
+        e64 = ended.to(torch.float64)
+        acc += torch.stack([e64.sum(), (ended & succ).to(torch.float64).sum(), (ret.double() * e64).sum(),
+                            (length.double() * e64).sum()])
+        ret.masked_fill_(ended, 0.0)
+        length.masked_fill_(ended, 0.0)
         obs = nobs.clone()
-    return {"episodes": n_eps, "successes": n_succ, "success_rate": n_succ / max(n_eps, 1),
-            "mean_return": sum_ret / max(n_eps, 1), "mean_length": sum_len / max(n_eps, 1)}
+        if learner is not None and learn_every > 0 and replay is not None and (t + 1) % learn_every == 0:
+            with torch.enable_grad():
+                learner.learn(replay.sample(batch_size, generator))
+    running = length > 0
+    tail = torch.stack([running.double().sum(), (ret.double() * running).sum(), (length.double() * running).sum()])
+    n_eps, n_succ, sum_ret, sum_len = (float(x) for x in acc.cpu())
+    n_cens, c_ret, c_len = (float(x) for x in tail.cpu())
+    return {"episodes": int(n_eps), "successes": int(n_succ), "success_rate": n_succ / max(n_eps, 1.0),
+            "mean_return": sum_ret / max(n_eps, 1.0), "mean_length": sum_len / max(n_eps, 1.0),
+            "censored": int(n_cens), "censored_mean_return": c_ret / max(n_cens, 1.0),
+            "censored_mean_length": c_len / max(n_cens, 1.0)}
+
+
+def rollout_throughput(env, policy: nn.Module, steps: int, warmup: int = 5, learn: bool = False, sigma: float = 1.0,
+                       capacity: int = 1 << 18, batch_size: int = 256) -> Dict[str, float]:
+    """env-steps/s of the whole rollout loop -- policy forward (torch) -> env step (CUDA library) -> replay append
+    (-> one TD3 update per env step, TD3DRV:128-133) -- timed on the device with one event pair around `steps`
+    iterations; no host synchronisation inside the loop."""
+    dev = env.device
+    replay = ReplayRing(capacity, env.D, dev)
+    learner = TD3Learner(env.D, dev) if learn else None
+    if learner is not None:
+        policy = learner.actor
+    kw = dict(sigma=sigma, replay=replay, learner=learner, learn_every=1 if learn else 0, batch_size=batch_size)
+    collect(env, policy, warmup, **kw)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    collect(env, policy, steps, **kw)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return {"value": env.E * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps, "steps": steps,
+            "learn": bool(learn), "updates": learner.updates if learner else 0, "replay_rows": len(replay)}

@@ -7,7 +7,9 @@ streams are keyed by GLOBAL env id (cn_config.env_id_offset), so results do not
 depend on G.  The one collective is what BASELINE.json's north_star asks for:
 an all-gather of the observation tensor so every rank (learner replicas) sees
 all E rows.  The step kernel writes straight into this rank's slice of the
-gather buffer and the all-gather runs in place (NCCL over NVLink / NVSwitch).
+gather buffer and either the all-gather runs in place (NCCL over NVLink /
+NVSwitch) or -- the default on GPUs -- the step kernel itself stores its rows
+into every peer's buffer and signals them (see ShardedVecEnv).
 """
 from __future__ import annotations
 
@@ -44,6 +46,27 @@ class ShardedVecEnv:
     `make_local(cfg_local, obs_slice)` builds the rank's stepper: on a GPU box it
     is ``CrowdNavVecEnv(cfg_local, obs_out=obs_slice)``; the CPU gloo tests pass
     a stand-in with the same reset()/step() surface.
+
+    gather modes (world > 1):
+
+    ``"collective"``    the step kernel writes this rank's slice of the [E, D] buffer, then one in-place
+                        ``all_gather_into_tensor`` (ncclAllGather) on the stepping stream.
+    ``"fused"``         cn_step_gather_signal: the gather buffers and one array of arrival counters per rank live in
+                        symmetric memory (peer-mapped over NVLink); the step kernel stores every tile of rows into all
+                        peers' buffers itself and then signals each peer's counter -- data AND synchronisation of the
+                        collective are inside the one kernel, nothing else is launched per step, and a sequence of
+                        steps is graph-capturable.  ``wait_gathered()`` enqueues a one-warp kernel that holds the
+                        stream until all rows of the latest step have arrived.  THREE buffers rotate: step t writes
+                        buffer t % 3 on every rank, which a peer may have been reading as step t-3's result; that
+                        peer finished reading before it launched step t-2 (stream order), and its step-t-2 CTAs
+                        signalling THIS rank is what the kernel of step t waits for before its first remote store.
+                        All step counting happens on the device (a rank's own counter slot), so a CUDA graph of
+                        3k such steps can be replayed any number of times.
+    ``"fused_mc"``      the same with NVSwitch multicast: one ``multimem.st`` per 16 bytes reaches every rank's buffer
+                        (egress 1x instead of (world-1)x), signal by ``multimem.red``.  Needs multicast-capable
+                        symmetric memory; raises if the handle has no multicast pointer.
+    ``"fused_barrier"`` round 1's variant, kept for A/B: peer stores from the kernel (cn_step_gather) + a torch
+                        symmetric-memory barrier on a high-priority side stream.
     """
 
     def __init__(self, cfg_global: CnConfig, make_local: Callable, device: torch.device,
@@ -53,53 +76,96 @@ class ShardedVecEnv:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if cfg_global.n_envs % self.world != 0:
             raise ValueError("all_gather_into_tensor needs equal shards: n_envs %% world_size must be 0")
+        if gather not in ("collective", "fused", "fused_mc", "fused_barrier", "none"):
+            raise ValueError("unknown gather mode %r" % gather)
         self.cfg_global = cfg_global.copy()
         self.cfg_local = local_config(cfg_global, self.rank, self.world)
         self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
         self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
         self.gather_mode = gather if self.world > 1 else "none"
-        if self.gather_mode == "fused" and (cfg_global.flags & 8):
+        self.fused = self.gather_mode.startswith("fused")
+        if self.fused and (cfg_global.flags & 8):
             # CN_FLAG_RISK_FAITHFUL: cn_faithful_kernel rewrites the K block after the step kernel has already sent
             # its rows to the peers, so cn_step_gather refuses peers in that mode
             raise ValueError("risk_faithful worlds gather with gather='collective' (ncclAllGather), not 'fused'")
         self._symm = None
-        if self.gather_mode == "fused":
-            # Gather buffers in symmetric memory: every rank can address every peer's copy, so the step kernel
-            # stores its rows into all of them itself (bulk TMA stores over NVLink) -- no collective launch.
-            # What is left of the collective is a cross-rank barrier ("every shard of step t has landed"); it runs
-            # on a side stream, off the stepping stream's critical path.  THREE buffers rotate: the kernel of
-            # step t writes buffer t % 3 on every rank, which a slow peer may still be reading from step t-3; that
-            # peer finished reading before it launched step t-2, which is what barrier t-2 certifies -- so the
-            # stepping stream only ever waits for a barrier issued two steps earlier.
+        self._t = 0                              # fused steps issued so far
+        if self.fused:
+            import ctypes as C
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else dist.group.WORLD
-            self._bufs, self._symm, self._peers = [], [], []
+            self._bufs, self._symm, self._peers, self._mc = [], [], [], []
+            # peers in ring order starting at rank + 1: at any moment the ranks' stores are headed for DIFFERENT
+            # GPUs (ascending order from 0 would aim every rank at GPU 0 first, then GPU 1, ...)
+            order = [(self.rank + 1 + k) % self.world for k in range(self.world - 1)]
+            off = self.lo * self.D * 4
             for _ in range(3):
                 buf = symm_mem.empty((self.E, self.D), dtype=torch.float32, device=device)
                 buf.zero_()
                 hdl = symm_mem.rendezvous(buf, grp)
-                off = self.lo * self.D * 4
                 self._bufs.append(buf)
                 self._symm.append(hdl)
-                self._peers.append([int(p) + off for r, p in enumerate(hdl.buffer_ptrs) if r != self.rank])
+                ptrs = [int(hdl.buffer_ptrs[r]) + off for r in order]
+                self._peers.append((C.c_void_p * len(ptrs))(*ptrs))
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                self._mc.append(mc + off if mc else 0)
+            # arrival counters: one 64-bit slot per SOURCE rank (padded to 32 slots)
+            self._arrive = symm_mem.empty((32,), dtype=torch.int64, device=device)
+            self._arrive.zero_()
+            ah = symm_mem.rendezvous(self._arrive, grp)
+            self._arrive_hdl = ah
+            aptrs = [int(ah.buffer_ptrs[r]) + 8 * self.rank for r in order]
+            self._arrive_peers = (C.c_void_p * len(aptrs))(*aptrs)
+            amc = int(getattr(ah, "multicast_ptr", 0) or 0)
+            self._arrive_mc = amc + 8 * self.rank if amc else 0
+            if self.gather_mode == "fused_mc" and not (amc and all(self._mc)):
+                raise RuntimeError("gather='fused_mc' needs multicast-capable symmetric memory (multicast_ptr is 0)")
+            self.multicast_available = bool(amc and all(self._mc))
+            torch.cuda.synchronize(device)
+            ah.barrier(channel=0)                # everyone's counters are zero before anyone signals
             self._cur = 0
-            self._comm = torch.cuda.Stream(device=device, priority=-1)   # barrier kernels jump the queue
-            self._ready = [None, None, None]                # event: barrier of the step that wrote buffer i is done
+            self._comm = torch.cuda.Stream(device=device, priority=-1)   # fused_barrier: barrier kernels jump the queue
+            self._ready = [None, None, None]     # fused_barrier: event "barrier of the step that wrote buffer i is done"
             self.obs_all = self._bufs[0]
         else:
             self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
         self.obs_local = self.obs_all[self.lo:self.hi]          # contiguous row block
         self.env = make_local(self.cfg_local, self.obs_local)
-        if self.gather_mode == "fused":
-            self.env.set_obs_peers(self._peers[0])
+        if self.gather_mode == "fused_barrier":
+            self.env.set_obs_peers(list(self._peers[0]))
+
+    def step_local(self, actions_local: torch.Tensor, env=None):
+        """Rotate the gather buffer and launch this rank's step (with the fused gather where enabled) on the current
+        stream.  `env`: a replica of the local shard (same config) to step instead of self.env -- bench.py rotates
+        several so that their state is cold in L2.  Returns the stepper's (obs_local, reward, done)."""
+        env = self.env if env is None else env
+        if self.gather_mode in ("fused", "fused_mc"):
+            self._cur = (self._cur + 1) % 3
+            self.obs_all = self._bufs[self._cur]
+            self.obs_local = self.obs_all[self.lo:self.hi]
+            env.obs = self.obs_local
+            mc = self.gather_mode == "fused_mc"
+            env.step_gather_signal(actions_local, self._peers[self._cur], self._arrive_peers, self.world - 1,
+                                   self._mc[self._cur] if mc else 0, self._arrive_mc if mc else 0,
+                                   self._arrive.data_ptr(), self.world, self.rank, 2)
+            self._t += 1
+            return env.obs, env.reward, env.done
+        if self.gather_mode == "fused_barrier":
+            self.begin_step()
+            env.obs = self.obs_local
+            env.set_obs_peers(list(self._peers[self._cur]))
+        elif env is not self.env:
+            env.obs = self.obs_local
+        return env.step(actions_local)
 
     def gather(self) -> torch.Tensor:
         """Make obs_all complete on every rank.  'collective': an in-place all-gather of the rows (sendbuf =
-        recvbuf + rank * count) on the stepping stream.  'fused': the kernels already wrote every peer's copy; the
-        cross-rank barrier is enqueued on the side stream -- call wait_gathered() before reading other ranks' rows."""
+        recvbuf + rank * count) on the stepping stream.  'fused' / 'fused_mc': nothing to launch -- the kernels wrote
+        every peer's copy and signalled; 'fused_barrier': the cross-rank barrier is enqueued on the side stream.
+        In the fused modes call wait_gathered() before reading other ranks' rows."""
         if self.gather_mode == "collective":
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
-        elif self.gather_mode == "fused":
+        elif self.gather_mode == "fused_barrier":
             main = torch.cuda.current_stream(self.obs_all.device)
             done = torch.cuda.Event()
             done.record(main)
@@ -113,13 +179,16 @@ class ShardedVecEnv:
 
     def wait_gathered(self) -> torch.Tensor:
         """Order the current stream behind the arrival of every rank's rows of the latest step."""
-        if self.gather_mode == "fused" and self._ready[self._cur] is not None:
+        if self.gather_mode in ("fused", "fused_mc") and self._t > 0:
+            self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
+        elif self.gather_mode == "fused_barrier" and self._ready[self._cur] is not None:
             torch.cuda.current_stream(self.obs_all.device).wait_event(self._ready[self._cur])
         return self.obs_all
 
     def reset(self) -> torch.Tensor:
+        self.env.obs = self.obs_local
         self.env.reset()
-        if self.gather_mode == "fused":
+        if self.fused:
             # cn_reset writes the local rows only: publish them once with the collective
             self._symm[self._cur].barrier(channel=0)
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
@@ -128,19 +197,32 @@ class ShardedVecEnv:
         return self.gather()
 
     def begin_step(self) -> None:
-        """Fused mode: rotate to the next gather buffer (see __init__) once its previous readers are done."""
-        if self.gather_mode == "fused":
+        """fused_barrier mode: rotate to the next gather buffer once its previous readers are done."""
+        if self.gather_mode == "fused_barrier":
             self._cur = (self._cur + 1) % 3
             guard = self._ready[(self._cur + 1) % 3]         # barrier of two steps ago
             if guard is not None:
                 torch.cuda.current_stream(self.obs_all.device).wait_event(guard)
             self.obs_all = self._bufs[self._cur]
             self.obs_local = self.obs_all[self.lo:self.hi]
-            self.env.obs = self.obs_local
-            self.env.set_obs_peers(self._peers[self._cur])
+
+    def step_host(self, actions_local):
+        """The sharded step through HOST buffers (bench.py's e2e leg for N > 1): pinned H2D of this rank's actions, the
+        step (+ gather), arrival of every rank's rows certified, D2H of the local obs / reward / done, stream sync."""
+        env = self.env
+        env._host_buffers()
+        env._h_act.numpy()[...] = actions_local
+        env._d_act.copy_(env._h_act, non_blocking=True)
+        _, reward, done = self.step_local(env._d_act)
+        self.gather()
+        self.wait_gathered()
+        env._h_obs.copy_(self.obs_local, non_blocking=True)
+        env._h_rew.copy_(reward, non_blocking=True)
+        env._h_done.copy_(done, non_blocking=True)
+        torch.cuda.current_stream(self.obs_all.device).synchronize()
+        return env._h_obs.numpy(), env._h_rew.numpy(), env._h_done.numpy()
 
     def step(self, actions_local: torch.Tensor):
-        self.begin_step()
-        _, reward, done = self.env.step(actions_local)
+        _, reward, done = self.step_local(actions_local)
         self.gather()
         return self.obs_all, reward, done

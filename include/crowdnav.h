@@ -16,7 +16,10 @@
  *     void*); no hidden synchronisation, graph-capturable.
  *   - return 0 on success, a negative cn_status otherwise; message via
  *     cn_last_error().  No C++ exception crosses the boundary.
- *   - a handle is bound to one device; calls on one handle are not re-entrant.
+ *   - a handle is bound to one device: every entry point makes that device
+ *     current for the duration of the call and puts the caller's device back,
+ *     so one process may drive handles on several GPUs.  Calls on one handle
+ *     are not re-entrant.
  */
 #ifndef CROWDNAV_H
 #define CROWDNAV_H
@@ -30,7 +33,7 @@ extern "C" {
 
 #define CN_MAX_PEDS       64
 #define CN_MAX_BEHAVIORS  8
-#define CN_ABI_VERSION    1
+#define CN_ABI_VERSION    2
 
 /* words (4 B) per env in the three state planes */
 #define CN_ROBOT_WORDS    16
@@ -153,14 +156,63 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
 int cn_step(cn_handle* h, const float* action_dev, float* obs_dev,
             float* reward_dev, uint8_t* done_dev, void* stream);
 
+/* n_steps control periods back to back (n_steps launches enqueued by ONE call: open-loop action batches, action
+ * repeat / frame skip, benchmarks).  Step i reads action_dev + i * action_stride (floats; 0 = the same batch every
+ * step, 2 * E = a [n_steps, E, 2] array) and writes reward_dev + i * out_stride, done_dev + i * out_stride
+ * (elements; 0 = overwrite, E = [n_steps, E] arrays); obs_dev [E, D] holds the rows of the LAST step. */
+int cn_step_n(cn_handle* h, int n_steps, const float* action_dev, size_t action_stride, float* obs_dev,
+              float* reward_dev, uint8_t* done_dev, size_t out_stride, void* stream);
+
+/* The same n_steps launches captured once into a CUDA graph owned by the library: cn_graph_launch replays them with
+ * one driver call (no per-launch host cost, no torch needed).  The buffers are baked into the graph and must stay
+ * valid until cn_graph_destroy; the handle must outlive the graph. */
+typedef struct cn_graph cn_graph;
+int cn_graph_create(cn_handle* h, int n_steps, const float* action_dev, size_t action_stride, float* obs_dev,
+                    float* reward_dev, uint8_t* done_dev, size_t out_stride, cn_graph** out);
+int cn_graph_launch(cn_graph* g, void* stream);
+int cn_graph_destroy(cn_graph* g);
+
 /* cn_step with the observation all-gather FUSED into the kernel (multi-GPU, one process per GPU):
  * besides obs_dev (this rank's [E, D] row block inside its own [E_total, D] gather buffer) the kernel
  * stores every tile of rows into the same row block of each peer's gather buffer -- peer-mapped device
- * pointers (CUDA IPC / symmetric memory), already offset to this rank's first row -- with bulk TMA stores
- * over NVLink.  The caller orders consumers behind the launch with a cross-rank barrier.  Replaces the
- * ncclAllGather SURVEY.md 8(e) puts after the step.  n_peers <= 8 (0 = plain cn_step). */
+ * pointers (CUDA IPC / symmetric memory), already offset to this rank's first row -- with 16-byte stores
+ * over NVLink, in the order the caller lists the peers (list them starting at rank + 1 so that the ranks do not
+ * all write to the same GPU at once).  The local rows leave by bulk TMA store.  The caller orders consumers behind
+ * the launch with a cross-rank barrier.  Replaces the ncclAllGather SURVEY.md 8(e) puts after the step.
+ * n_peers <= 8 (0 = plain cn_step). */
 int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peer_obs_dev, int n_peers,
                    float* reward_dev, uint8_t* done_dev, void* stream);
+
+/* cn_step_gather with the collective's SYNCHRONISATION fused in as well: nothing but the step kernel runs per step.
+ * Every rank owns an array of n_ranks 64-bit arrival counters (zeroed once), one slot per SOURCE rank, in memory its
+ * peers can address.  All step counting is done on the device, so a captured CUDA graph of such steps stays correct
+ * on every replay.
+ *   peer_arrive_dev[p]  peer-mapped address of THIS rank's slot in peer p's array: after a CTA's rows have been
+ *                       stored into peer p it adds 1 there (release, system scope); it also adds 1 to this rank's own
+ *                       slot of its own array, which therefore counts the rank's own progress.  A rank holds all rows
+ *                       of its latest step once every other slot has caught up with its own slot (equal shards);
+ *                       cn_gather_wait holds a stream until then.
+ *   arrive_local_dev, n_ranks, rank, wait_back   before its first store into the peers a CTA of step t (t = own slot
+ *                       / cn_kernel_ctas()) waits until every other rank's slot shows all arrivals of that rank's step
+ *                       t - wait_back (0 = no wait).  With three gather buffers in rotation pass 2: "everyone has
+ *                       launched step t-2, so everyone is done reading the buffer step t overwrites".
+ *   obs_mc_dev, arrive_mc_dev      optional NVSwitch MULTICAST addresses of this rank's row block / of this rank's
+ *                       slot (CUDA multicast objects, e.g. torch symmetric memory's multicast_ptr): when non-NULL the
+ *                       rows leave as multimem.st and the signal as multimem.red -- one store, the switch replicates
+ *                       it into every rank's buffer, this rank's included -- and the unicast lists are ignored.
+ * Waits are bounded (2 s): a lost peer is counted (cn_gather_timeouts) instead of hanging the GPU.
+ * Default kernel only; not with CN_FLAG_RISK_FAITHFUL. */
+int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peer_obs_dev,
+                          unsigned long long* const* peer_arrive_dev, int n_peers, float* obs_mc_dev,
+                          unsigned long long* arrive_mc_dev, unsigned long long* arrive_local_dev, int n_ranks,
+                          int rank, int wait_back, float* reward_dev, uint8_t* done_dev, void* stream);
+/* Hold `stream` until every other rank's slot of arrive_local_dev[n_ranks] has caught up with this rank's own slot
+ * (one small kernel; bounded like the in-kernel wait). */
+int cn_gather_wait(cn_handle* h, const unsigned long long* arrive_local_dev, int n_ranks, int rank, void* stream);
+/* Number of bounded gather waits that gave up since cn_create (0 in a healthy run).  Synchronous on `stream`. */
+int cn_gather_timeouts(cn_handle* h, unsigned int* out_host, void* stream);
+/* CTAs one step launch of this handle consists of (= arrivals per peer per step). */
+int cn_kernel_ctas(const cn_handle* h);
 
 /* Per-env counters [E, 4] int32: success, ego violations, social violations,
  * obstacle-present steps.  Replaces get_episode_status / get_*_violation_status

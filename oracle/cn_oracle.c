@@ -57,9 +57,7 @@ static uint32_t* blob_trk(const orc_ctx* c, uint32_t* blob) {
 
 void orc_init_blob(const orc_ctx* c, uint32_t* blob) {
     memset(blob, 0, orc_blob_bytes(c));
-    blob[0] = CN_BLOB_MAGIC; blob[1] = CN_ABI_VERSION;
-    blob[2] = (uint32_t)c->cfg.n_envs; blob[3] = (uint32_t)c->cfg.n_peds;
-    blob[4] = (uint32_t)c->cfg.n_samples; blob[5] = (uint32_t)c->cfg.k_obstacles;
+    cn_blob_header(&c->cfg, blob);
 }
 
 static float f_of(uint32_t u) { return cn_bits2f(u); }

@@ -38,7 +38,7 @@ def test_struct_layout_and_pure_entry_points(L):
               "waypoint_radius", "goal_box"):
         assert getattr(cfg, f) == getattr(py, f), f
     assert L.cn_blob_bytes(C.byref(cfg)) == 4 * (16 + 16 + 2 * 14 * 4)
-    assert L.cn_abi_version() == 1
+    assert L.cn_abi_version() == 2
 
 
 def test_risk_faithful_flag_in_the_abi(L):

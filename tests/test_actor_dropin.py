@@ -53,14 +53,14 @@ def test_shipped_actor_rollout_on_gpu_and_td3_update():
     env.reset()
     replay = ReplayRing(200_000, env.D, dev)
     stats = collect(env, actor, 400, sigma=0.0, replay=replay)
-    assert stats["episodes"] > 3000
+    assert stats["episodes"] > 3000 and stats["censored"] <= 4096
     assert 0.35 <= stats["success_rate"] <= 0.85, stats
     assert len(replay) == 200_000
     s, a, r, s2, d = replay.sample(128)
     assert s.shape == (128, 398) and set(torch.unique(d).tolist()) <= {0.0, 1.0}
     learner = TD3Learner(env.D, dev)
     losses = [learner.learn(replay.sample(128)) for _ in range(6)]
-    assert all(np.isfinite(v) for l in losses for v in l.values()) and any("actor" in l for l in losses)
+    assert all(np.isfinite(float(v)) for l in losses for v in l.values()) and any("actor" in l for l in losses)
     # exploration (TD3:67-78) keeps actions inside the box
     noisy = collect(env, actor, 20, sigma=1.0)
     assert noisy["episodes"] >= 0
