@@ -234,7 +234,7 @@ class Bench:
         except Exception as exc:                       # symmetric memory / multicast unavailable: say so, fall back
             if not self.gather_mode.startswith("fused"):
                 raise
-            nxt = "fused" if self.gather_mode == "fused_mc" else "collective"
+            nxt = "fused" if self.gather_mode in ("fused_mc", "fused_async") else "collective"
             self.fallback = "%s unavailable (%s); using %s" % (self.gather_mode, str(exc).splitlines()[0][:160], nxt)
             if self.rank == 0:
                 print(self.fallback, file=sys.stderr)
@@ -417,7 +417,23 @@ class Bench:
             torch.cuda.synchronize()
             ok = ok and bool(torch.equal(senv.obs_all[flo:fhi], fobs)) and bool(torch.equal(senv.obs_all[senv.lo:senv.hi], mine.obs))
             self.barrier()                                      # nobody runs ahead while a peer still compares
-        timeouts = mine.gather_timeouts if senv.gather_mode in ("fused", "fused_mc") else 0
+        if senv.gather_mode == "fused_async":
+            # ... and the pipelined path proper: rows forwarded by the NEXT step's kernel, no flush in between
+            prev_f = None
+            for s in range(steps):
+                u = torch.rand((self.E_total, 2), device=self.dev, generator=gen)
+                act = torch.stack([u[:, 0] * 0.22, u[:, 1] * 4.0 - 2.0], 1).contiguous()
+                senv.step_local(act[senv.lo:senv.hi].contiguous(), env=mine)
+                got_prev = senv.wait_pushed()
+                fobs, _, _ = other.step(act[flo:fhi].contiguous())
+                torch.cuda.synchronize()
+                if prev_f is not None:
+                    ok = ok and bool(torch.equal(got_prev[flo:fhi], prev_f))
+                prev_f = fobs.clone()
+                self.barrier()
+            ok = ok and bool(torch.equal(senv.wait_gathered()[flo:fhi], prev_f))
+            self.barrier()
+        timeouts = (mine.gather_timeouts + senv.env.gather_timeouts) if senv.fused else 0
         flag = torch.tensor([1 if (ok and timeouts == 0) else 0], dtype=torch.int64, device=self.dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         mine.close()
@@ -433,7 +449,7 @@ def measure(args, wl, per_gpu, gather_mode, K, warmup, full=True):
     out = {"bench": B}
     graph_ms, ginfo = B.graph_timed(K, warmup, gather=True)
     out["graph_ms"], out["ginfo"] = B.max_over_ranks([graph_ms])[0], ginfo
-    out["launches_per_rank"] = K + (1 if (world > 1 and B.gather_mode.startswith("fused") and B.gather_mode != "fused_barrier") else 0)
+    out["launches_per_rank"] = K + {"fused": 1, "fused_mc": 1, "fused_async": 2}.get(B.gather_mode if world > 1 else "", 0)
     if world > 1:
         none_ms, _ = B.graph_timed(K, warmup, gather=False)
         out["none_ms"] = B.max_over_ranks([none_ms])[0]
@@ -455,15 +471,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "fused_mc", "fused_barrier", "nccl"],
-                    help="N>1: 'fused' = the step kernel stores its rows into every peer's gather buffer (symmetric "
-                         "memory, NVLink) and signals the peers' arrival counters -- no other launch per step; "
-                         "'fused_mc' = the same with NVSwitch multicast (multimem.st / multimem.red); 'fused_barrier' = "
-                         "round 1's peer stores + torch symmetric-memory barrier on a side stream; "
-                         "'nccl' = separate in-place ncclAllGather after the kernel")
+    ap.add_argument("--gather", default="fused_async", choices=["fused_async", "fused", "fused_mc", "nccl"],
+                    help="N>1: 'fused_async' = pipelined fused gather: the kernel of step t+1 forwards the rows of step t to "
+                         "every peer (bulk TMA through a staging tile) under its own compute and signals the peers' arrival "
+                         "counters; one push-only launch flushes the last step; 'fused' = the step kernel stores its OWN rows "
+                         "into every peer at its end and signals -- no other launch per step; 'fused_mc' = the same with "
+                         "NVSwitch multicast (multimem.st / multimem.red); 'nccl' = separate in-place ncclAllGather after the kernel")
     ap.add_argument("--risk-faithful", action="store_true",
                     help="CN_FLAG_RISK_FAITHFUL: K block and counters from the reference's own segmentation / tracker "
                          "(cn_faithful_kernel runs behind the step kernel: two launches per step); single GPU or --gather nccl")
+    ap.add_argument("--skip-verify", action="store_true", help="diagnostics: do not run the gather self-check")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline_c3 / configs3 / rollout_td3 / verification extras")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -509,7 +526,7 @@ def main():
 
     # --- N > 1: prove the gather (single-GPU batch == gathered rows) before anything else is reported
     gather_verified, gather_check = None, None
-    if world > 1 and not args.risk_faithful:
+    if world > 1 and not args.risk_faithful and not args.skip_verify:
         gather_verified, gather_check = B.verify_gather()
 
     # --- e2e through the public host-buffer API: per step pinned H2D of the actions, the kernel, D2H of obs / reward /
@@ -598,8 +615,11 @@ def main():
                      "step counting, no other launch per step" % world,
             "fused_mc": "env-id sharding x%d; obs all-gather fused into the step kernel with NVSwitch multicast: one "
                         "multimem.st per 16 bytes reaches every rank's buffer, signal by multimem.red; 3 rotating buffers" % world,
-            "fused_barrier": "env-id sharding x%d; peer stores from the step kernel + torch symmetric-memory barrier on a "
-                             "side stream (round 1's variant)" % world,
+            "fused_async": "env-id sharding x%d; obs all-gather fused into the step kernels and PIPELINED: the kernel of step t+1 "
+                           "forwards the rows of step t (bulk TMA load into a staging tile, bulk TMA stores into every peer's "
+                           "symmetric-memory buffer, peer order rotated per rank and per CTA) under its own compute and signals "
+                           "the peers' arrival counters; the timed graph ends with one push-only launch for the last step and "
+                           "the arrival wait, so all K steps' rows have landed on every rank inside the timed region" % world,
             "collective": "env-id sharding x%d; one in-place ncclAllGather per step" % world}[B.gather_mode]
         line = {
             "metric": "env-steps/s", "value": E_total / (ms_per_step * 1e-3), "unit": "env-steps/s",

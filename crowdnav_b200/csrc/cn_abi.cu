@@ -163,16 +163,18 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             int tw = atoi(tile), tt = 256;
             const char* comma = strchr(tile, ',');
             if (comma) tt = atoi(comma + 1);
-            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, &flat);
+            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &flat);
         } else {
             int n_sms = 0;
             CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
-            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, &flat);
+            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm,
+                                   (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &flat);
         }
         { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
         /* programmatic dependent launch is opt-in (CN_PDL=1): measured on B200 it helps back-to-back stream launches
          * (c2 23.2 -> 20.6 us per step) but not the graph-replayed step (11.8 -> 12.8 us), see DESIGN.md 4.4 */
         { const char* pd = getenv("CN_PDL"); flat.pdl = (pd && strcmp(pd, "1") == 0) ? 1 : 0; }
+        { const char* gd = getenv("CN_GATHER_DEBUG"); flat.gather_debug = gd ? atoi(gd) : 0; }   /* timing diagnostics only */
         if (rc != 0 || flat.total > (size_t)max_smem)
             return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
     } else {
@@ -231,7 +233,7 @@ static void repack(cn_handle* h) {
     P->robot = h->robot; P->ped_a = h->ped_a; P->ped_b = h->ped_b;
     P->dbg_ranges = h->dbg_ranges ? h->dbg_ranges : h->own_ranges; P->dbg_hid = h->dbg_hid;
     P->cfg = h->cfg_dev; P->d = h->d;
-    P->gather_timeouts = h->gather_timeouts;
+    P->gather_timeouts = h->gather_timeouts; P->gather_done = h->gather_timeouts + 1;
     P->n_envs = c->n_envs; P->n_peds = c->n_peds; P->n_samples = c->n_samples; P->k_obstacles = c->k_obstacles;
     P->max_steps = c->max_steps; P->env_id_offset = c->env_id_offset; P->n_behaviors = c->n_behaviors;
     P->n_substeps = c->n_substeps;
@@ -351,6 +353,63 @@ int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev,
     P.obs_bulk_ok = aligned;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+/* common argument checks + parameter block of the two pipelined-gather entry points */
+static int pack_push(cn_handle* h, const char* who, cn_kparams* P, const float* push_src_dev, float* const* push_peer_dev,
+                     unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
+                     int n_ranks, int rank, int wait_back) {
+    if (!h->use_flat) return fail(CN_ERR_UNSUPPORTED, "%s: default (flat) kernel only", who);
+    if (h->trk) return fail(CN_ERR_UNSUPPORTED, "%s: not with CN_FLAG_RISK_FAITHFUL (gather with ncclAllGather instead)", who);
+    if (!push_src_dev || !push_peer_dev || !peer_arrive_dev || !arrive_local_dev || n_peers < 1 || n_peers > 8 || wait_back < 0)
+        return fail(CN_ERR_INVALID, "%s: null argument / 1..8 peers", who);
+    if (n_ranks < 2 || n_ranks > 32 || rank < 0 || rank >= n_ranks) return fail(CN_ERR_INVALID, "%s: 2..32 ranks, 0 <= rank < n_ranks", who);
+    *P = h->base;
+    bool aligned = (((uintptr_t)push_src_dev) & 15u) == 0;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!push_peer_dev[p] || !peer_arrive_dev[p]) return fail(CN_ERR_INVALID, "%s: null peer pointer", who);
+        P->push_peers[p] = push_peer_dev[p]; P->arrive_peers[p] = peer_arrive_dev[p];
+        aligned = aligned && (((uintptr_t)push_peer_dev[p]) & 15u) == 0;
+    }
+    P->push_src = push_src_dev; P->n_push_peers = n_peers; P->push_bulk_ok = aligned ? 1 : 0;
+    P->arrive_local = arrive_local_dev; P->arrive_back = wait_back; P->arrive_slots = n_ranks; P->arrive_self = rank;
+    P->ctas_per_step = (unsigned int)cn_kernel_ctas(h);
+    return CN_OK;
+}
+
+int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, const float* push_src_dev,
+                         float* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
+                         unsigned long long* arrive_local_dev, int n_ranks, int rank, int wait_back,
+                         float* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
+        return fail(CN_ERR_INVALID, "cn_step_gather_async: null argument%s", NULL);
+    if (!(h->cfg.flags & CN_FLAG_GATHER_STAGE))
+        return fail(CN_ERR_INVALID, "cn_step_gather_async: create the handle with CN_FLAG_GATHER_STAGE%s", NULL);
+    cn_kparams P;
+    int rc = pack_push(h, "cn_step_gather_async", &P, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers, arrive_local_dev,
+                       n_ranks, rank, wait_back);
+    if (rc != CN_OK) return rc;
+    cn_device_guard guard(h->device);
+    P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
+    P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0;
+    P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
+    CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_gather_flush(cn_handle* h, const float* push_src_dev, float* const* push_peer_dev,
+                    unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
+                    int n_ranks, int rank, int wait_back, void* stream) {
+    if (!h) return fail(CN_ERR_INVALID, "cn_gather_flush: null handle%s", NULL);
+    cn_kparams P;
+    int rc = pack_push(h, "cn_gather_flush", &P, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers, arrive_local_dev,
+                       n_ranks, rank, wait_back);
+    if (rc != CN_OK) return rc;
+    cn_device_guard guard(h->device);
+    CN_CUDA(cn_launch_push_kernel(P, h->flat, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -512,7 +571,8 @@ int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile,
     cn_derived d;
     if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_plan_tile: config out of range%s", NULL);
     cn_flat_layout L; memset(&L, 0, sizeof(L));
-    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, &L) != 0)
+    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm,
+                          (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &L) != 0)
         return fail(CN_ERR_UNSUPPORTED, "cn_plan_tile: no tile fits%s", NULL);
     *tile = L.W; *threads = L.threads; *smem_bytes = L.total;
     return CN_OK;

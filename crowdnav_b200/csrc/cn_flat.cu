@@ -100,7 +100,7 @@ enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY
 struct Ptrs {
     uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
     uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
-    uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar;
+    uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar; float* stage;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -308,11 +308,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// (relaxed: the caller has just executed ONE system-scope fence for all of its signals -- fence + relaxed atomic is
+//  the release pattern; a .release on every atomic would repeat the fence per peer)
+__device__ __forceinline__ void red_relaxed_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void multimem_red_release_sys_add(unsigned long long* p, unsigned long long v) {
-    asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void multimem_red_relaxed_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
@@ -327,6 +329,39 @@ __device__ __forceinline__ bool wait_arrivals(const unsigned long long* ctr, uns
     }
     return true;
 }
+// Before a CTA overwrites a gather buffer on the peers: which step is this?  This rank's OWN slot counts the CTAs of
+// its completed launches -- the last CTA of a launch adds the launch's CTA count at the very end (signal_peers) -- so
+// t = own / CTAs-per-launch.  The buffer about to be overwritten was read by the peers before they launched step
+// t - arrive_back, whose arrivals (slot s of OUR array; the calling thread polls source rank `slot`) we wait for;
+// normally they are there long before.  Device-side counting keeps a captured graph of steps correct on every replay.
+__device__ __forceinline__ void guard_peer_buffers(const cn_kparams& P, int slot) {
+    if (P.arrive_back <= 0 || slot >= P.arrive_slots || slot == P.arrive_self) return;
+    const unsigned long long own = ld_acquire_sys(P.arrive_local + P.arrive_self);
+    const unsigned long long t = own / P.ctas_per_step;
+    if (t < (unsigned long long)P.arrive_back) return;
+    const unsigned long long target = (t - (unsigned long long)P.arrive_back + 1ull) * P.ctas_per_step;
+    if (!wait_arrivals(P.arrive_local + slot, target) && P.gather_timeouts) atomicAdd(P.gather_timeouts, 1u);
+}
+// ... and after its rows have reached the peers.  ONE system-scope release per launch, not one per CTA (512 CTAs each
+// fencing at system scope and hitting the peer's counter cost 17 us per step on two B200s -- profiles/r02): thread 0 of
+// every CTA makes the CTA's stores (ordered before this call by a CTA barrier, or completed bulk stores of its own)
+// performed with a GPU-scope fence and counts the CTA on a device-local word; the CTA that finds itself last fences
+// at system scope and adds the whole launch's CTA count to this rank's slot on every peer and to its own slot.
+// Causality: CTA i's stores -> its gpu-scope fence + atomic -> the last CTA's atomic (same scope) -> its sys-scope
+// release -> the peer's acquire load.
+__device__ __forceinline__ void signal_peers(const cn_kparams& P, int n_peers, int tid) {
+    if (tid != 0) return;
+    __threadfence();
+    const unsigned int ctas = P.ctas_per_step;
+    if (atomicAdd(P.gather_done, 1u) + 1u != ctas) return;
+    *P.gather_done = 0u;                                 // the next launch starts after this one has completed
+    __threadfence_system();
+    if (P.arrive_mc) { multimem_red_relaxed_sys_add(P.arrive_mc, (unsigned long long)ctas); return; }   // own slot included
+#pragma unroll 1
+    for (int p = 0; p < n_peers; ++p) red_relaxed_sys_add(P.arrive_peers[p], (unsigned long long)ctas);
+    red_relaxed_sys_add(P.arrive_local + P.arrive_self, (unsigned long long)ctas);
+}
+
 // n 16-byte elements from shared memory to a multicast address: ONE store instruction per element, the switch
 // replicates it into every rank's buffer
 __device__ __forceinline__ void copy16_out_mc(void* mcdst, const void* ssrc, int n, int t, int nthreads) {
@@ -385,6 +420,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.pg = reinterpret_cast<uint32_t*>(smem + L.off_pg);
     S.cnt = reinterpret_cast<uint32_t*>(smem + L.off_cnt);
     S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    S.stage = reinterpret_cast<float*>(smem + L.off_stage);
 
     FSTAMP(0);
     const int n_items = nE * N;                       // pedestrians of the tile
@@ -399,12 +435,21 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // this launch itself touches no global memory before the grid in front of it has completed and flushed
     // (griddepcontrol.wait).  What is hidden is the launch gap and the CTA start-up between back-to-back steps.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // pipelined fused gather: the rows of the PREVIOUS step (in this rank's gather buffer) go to the peers under this
+    // step's compute -- bulk load into the staging tile now, bulk stores to every peer as soon as it has landed
+    const bool push = (MODE == 0) && P.n_push_peers > 0;
+    const bool push_bulk = push && L.off_stage != 0u && P.push_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
     if (tid == 0) {
         mbar_init(S.bar, 1);
+        mbar_init(S.bar + 1, 1);
         fence_mbar_init();
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
+        if (push_bulk) {
+            mbar_expect_tx(S.bar + 1, (uint32_t)((size_t)nE * D * 4));
+            tma_load(S.stage, P.push_src + (size_t)e0 * D, (uint32_t)((size_t)nE * D * 4), S.bar + 1);
+        }
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
         mbar_expect_tx(S.bar, rob_bytes + 3u * ped_bytes + act_bytes);
         if (act_bytes) tma_load(S.act, P.action + 2 * (size_t)e0, act_bytes, S.bar);
@@ -453,6 +498,20 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     FSTAMP(11);
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
+    if (push_bulk && warp == 0) {
+        if (!(L.gather_debug & 1)) guard_peer_buffers(P, lane);     // lane s polls source rank s (normally one L2 hit)
+        __syncwarp();
+        if (tid == 0 && !(L.gather_debug & 4)) {
+            mbar_wait(S.bar + 1, 0);
+            int p = (P.n_push_peers > 1) ? (int)(blockIdx.x % (unsigned)P.n_push_peers) : 0;   // CTAs start at different peers
+#pragma unroll 1
+            for (int k = 0; k < P.n_push_peers; ++k) {
+                tma_store(P.push_peers[p] + (size_t)e0 * D, S.stage, (uint32_t)((size_t)nE * D * 4));
+                p = (p + 1 == P.n_push_peers) ? 0 : p + 1;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
 
     // ---------------------------------------------------------------- phase 1 (+ 2)
     if (warp < CF_POSE_WARPS) {
@@ -963,26 +1022,14 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // ---------------------------------------------------------------- phase 7: write-back
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
     const bool gather = (MODE == 0) && (P.n_obs_peers > 0 || P.obs_mc != nullptr);
-    if (gather && P.arrive_back > 0 && tid < P.arrive_slots && tid != P.arrive_self) {
-        // Which step is this?  This rank's OWN slot counts its CTAs: every CTA of the earlier steps has added 1 (stream
-        // order), the CTAs of this step add theirs at the very end, so t = own / CTAs-per-step.  The buffer about to be
-        // overwritten on the peers was read by them before they launched step t - arrive_back, whose arrivals -- slot s
-        // of OUR array, thread s polls source rank s -- we wait for (normally there long before this point).  Device-
-        // side counting keeps a captured graph of steps correct on every replay.
-        const unsigned long long own = ld_acquire_sys(P.arrive_local + P.arrive_self);
-        const unsigned long long t = own / P.ctas_per_step;
-        if (t >= (unsigned long long)P.arrive_back) {
-            const unsigned long long target = (t - (unsigned long long)P.arrive_back + 1ull) * P.ctas_per_step;
-            if (!wait_arrivals(P.arrive_local + tid, target) && P.gather_timeouts) atomicAdd(P.gather_timeouts, 1u);
-        }
-    }
+    if ((gather || (push && !push_bulk)) && tid < 32 && !(L.gather_debug & 1)) guard_peer_buffers(P, tid);
     FSTAMP(12);
     __syncthreads();             // #G
     FSTAMP(7);
     const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
     if (L.plain_store) {
         // cooperative 16-byte stores: nothing to wait for, the CTA's slot is free as soon as they are issued
-        if (bulk_obs && gather) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);   // NVLink first
+        if (bulk_obs && gather && !(L.gather_debug & 4)) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);   // NVLink first
         copy16_out(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, (int)(rob_bytes >> 4), tid, T);
         if (ped_bytes) {
             copy16_out(P.ped_a + (size_t)e0 * N * 4, S.pa2, n_items, tid, T);
@@ -1002,7 +1049,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         // fused all-gather: the same block of rows goes straight into every peer's gather buffer over NVLink, as plain
         // 16-byte stores from all threads (measured at 2 GPUs: 32.4 us per step against 36.7 us with bulk stores, whose
         // completion the CTA would have to wait for), or as multimem stores the switch replicates
-        if (bulk_obs && gather) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);
+        if (bulk_obs && gather && !(L.gather_debug & 4)) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);
         if (tid == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             FSTAMP(8);
@@ -1031,14 +1078,28 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         // signal: every thread's stores into the peers are ordered before the barrier, the barrier before thread p's
         // system-scope release; the peer's acquire load of its counter then sees the rows (the pattern of a grid sync)
         __syncthreads();
-        if (P.arrive_mc) {                                          // (reaches this rank's own slot too)
-            if (tid == 0) { __threadfence_system(); multimem_red_release_sys_add(P.arrive_mc, 1ull); }
-        } else if (tid < P.n_obs_peers) {
-            __threadfence_system();
-            red_release_sys_add(P.arrive_peers[tid], 1ull);
-        } else if (tid == 32) {
-            red_release_sys_add(P.arrive_local + P.arrive_self, 1ull);
+        if (!(L.gather_debug & 2)) signal_peers(P, P.n_obs_peers, tid);
+    }
+    if (push) {
+        if (push_bulk) {
+            // thread 0 issued the bulk stores of the old rows at the start of the kernel: they have had the whole step
+            // to drain; wait for their completion (not just for the reads of the staging tile), then signal
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+        } else {
+            // ragged or unaligned tile: forward the old rows with plain loads / stores from all threads
+#pragma unroll 1
+            for (int p = 0; p < P.n_push_peers; ++p) {
+                const float* src = P.push_src + (size_t)e0 * D;
+                float* dst = P.push_peers[p] + (size_t)e0 * D;
+#pragma unroll 1
+                for (int k = tid; k < nE * D; k += T) dst[k] = src[k];
+            }
         }
+        __syncthreads();
+        if (!(L.gather_debug & 2)) signal_peers(P, P.n_push_peers, tid);
     }
 }
 
@@ -1047,7 +1108,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 // ------------------------------------------------------------- host side
 static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L) {
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, cn_flat_layout* L) {
     const int N = n_peds, D = obs_dim, W = tile;
     if (threads != 128 && threads != 192 && threads != 256 && threads != 384 && threads != 512) return -1;
     if (W < 1 || W > 32) return -1;
@@ -1081,11 +1142,13 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o = up16(o + (size_t)L->cap_pg * 4);            L->off_cnt = (uint32_t)o;
     o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
     o += 16;
+    L->off_stage = 0;
+    if (stage) { o = up16(o); L->off_stage = (uint32_t)o; o = up16(o + (size_t)W * D * 4); }
     L->total = (uint32_t)o;
     return 0;
 }
 
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, cn_flat_layout* L) {
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, cn_flat_layout* L) {
     // 256-thread CTAs, four per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk store) that
     // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
     // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
@@ -1095,7 +1158,7 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
     int best = 0; double best_score = -1.0;
     for (int W = 16; W >= 1; --W) {
         cn_flat_layout t;
-        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, &t) != 0 || t.total > budget) continue;
+        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, &t) != 0 || t.total > budget) continue;
         const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
         const long n_cta = ((long)n_envs + W - 1) / W;
         const long waves = (n_cta + slots - 1) / slots;
@@ -1107,7 +1170,7 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
         if (score > best_score) { best_score = score; best = W; }
     }
     if (!best) return -1;
-    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, L);
+    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, L);
 }
 
 template <int MODE, int T>
@@ -1150,6 +1213,40 @@ __global__ void cn_gather_wait_kernel(const unsigned long long* counters, int n_
 cudaError_t cn_launch_gather_wait(const unsigned long long* counters, int n_slots, int self_slot,
                                   unsigned int* timeouts, cudaStream_t stream) {
     cn_gather_wait_kernel<<<1, 32, 0, stream>>>(counters, n_slots, self_slot, timeouts);
+    return cudaGetLastError();
+}
+
+// Push-only launch of the pipelined gather: the rows of the LATEST step, which no later step kernel will forward.
+// Same tiling, same guard and signal as the step kernel, so the arrival counting does not care which of the two
+// delivered a step's rows.
+__global__ void __launch_bounds__(256) cn_push_kernel(const __grid_constant__ cn_kparams P, int W) {
+    const int D = P.d.obs_dim, tid = (int)threadIdx.x;
+    const int e0 = (int)blockIdx.x * W, nE = min(W, P.n_envs - e0);
+    if (tid < 32) guard_peer_buffers(P, tid);
+    __syncthreads();
+    const size_t row0 = (size_t)e0 * D;
+    const bool vec = P.push_bulk_ok && (row0 % 4 == 0) && (((size_t)nE * D) % 4 == 0);
+    int p = (P.n_push_peers > 1) ? (int)(blockIdx.x % (unsigned)P.n_push_peers) : 0;
+#pragma unroll 1
+    for (int k = 0; k < P.n_push_peers; ++k) {
+        const float* src = P.push_src + row0;
+        float* dst = P.push_peers[p] + row0;
+        if (vec) {
+            const int n4 = (nE * D) >> 2;
+#pragma unroll 4
+            for (int i = tid; i < n4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < nE * D; i += 256) dst[i] = src[i];
+        }
+        p = (p + 1 == P.n_push_peers) ? 0 : p + 1;
+    }
+    __syncthreads();
+    signal_peers(P, P.n_push_peers, tid);
+}
+cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream) {
+    const int grid = (P.n_envs + L.W - 1) / L.W;
+    cn_push_kernel<<<grid, 256, 0, stream>>>(P, L.W);
     return cudaGetLastError();
 }
 

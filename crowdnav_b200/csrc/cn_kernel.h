@@ -37,6 +37,15 @@ struct cn_kparams {
     unsigned int ctas_per_step;
     float* obs_mc;
     unsigned long long* arrive_mc;
+    /* pipelined variant (cn_step_gather_async): the kernel of step t+1 forwards the rows of step t -- push_src, this
+     * rank's row block of the previous gather buffer -- to the peers (push_peers) at its START: thread 0 of every CTA
+     * bulk-loads its tile of old rows into a staging tile and bulk-stores it into every peer, so the transfer runs
+     * under the step's compute; arrivals are signalled at the end of the kernel.  Needs CN_FLAG_GATHER_STAGE. */
+    const float* push_src;
+    float* push_peers[8];
+    int n_push_peers;
+    int push_bulk_ok;               /* push_src and every push peer are 16-B aligned */
+    unsigned int* gather_done;      /* device word: CTAs of the running launch whose rows have reached the peers (the last one signals) */
     unsigned int* gather_timeouts;  /* device counter: waits given up after CN_GATHER_WAIT_NS (diagnostics, never hangs the GPU) */
     const cn_config* cfg;       /* device copy */
     cn_derived d;
@@ -66,10 +75,14 @@ struct cn_flat_layout {
     uint32_t cap_wg, cap_pg;    /* capacity of the wall / pedestrian ray-group lists */
     uint32_t off_pa, off_pb, off_pa2, off_act, off_obs, off_sc, off_rec, off_pk, off_peers,
              off_clist, off_clw, off_rlist, off_olist, off_mark, off_wg, off_pg, off_cnt, off_bar;
+    int gather_debug;           /* diagnostics (CN_GATHER_DEBUG): 1 no guard wait, 2 no arrival signal, 4 no row transfer */
+    uint32_t off_stage;         /* CN_FLAG_GATHER_STAGE: [W, D] floats for the previous step's rows on their way to the peers; else 0 */
     uint32_t total;             /* dynamic shared memory per CTA */
 };
-int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, cn_flat_layout* L);
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, cn_flat_layout* L);
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, cn_flat_layout* L);
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, cn_flat_layout* L);
+/* push-only launch of the pipelined gather (the rows of the LAST step, which no later step kernel will forward) */
+cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream);
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream);
 
 /* cn_abi.cu: raise cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the CURRENT device to at least `smem`

@@ -39,6 +39,9 @@ def local_config(cfg_global: CnConfig, rank: int, world: int) -> CnConfig:
     return cfg
 
 
+GATHER_MODES = ("collective", "fused", "fused_mc", "fused_async", "none")
+
+
 class ShardedVecEnv:
     """E worlds over `world` ranks; step() returns the local (obs, reward, done)
     views and leaves the gathered [E, D] observation in ``self.obs_all``.
@@ -65,8 +68,14 @@ class ShardedVecEnv:
     ``"fused_mc"``      the same with NVSwitch multicast: one ``multimem.st`` per 16 bytes reaches every rank's buffer
                         (egress 1x instead of (world-1)x), signal by ``multimem.red``.  Needs multicast-capable
                         symmetric memory; raises if the handle has no multicast pointer.
-    ``"fused_barrier"`` round 1's variant, kept for A/B: peer stores from the kernel (cn_step_gather) + a torch
-                        symmetric-memory barrier on a high-priority side stream.
+    ``"fused_async"``   cn_step_gather_async, the PIPELINED fused gather: the kernel of step t+1 forwards the rows of
+                        step t to the peers at its start (bulk load into a staging tile, bulk stores to every peer), so
+                        the NVLink transfer runs under the next step's compute instead of behind the step that
+                        produced the rows.  ``step_local()`` therefore leaves the rows of the step it has just launched
+                        un-forwarded; ``wait_gathered()`` flushes them with a push-only launch (cn_gather_flush) and
+                        waits, ``wait_pushed()`` only waits for what the step kernels have forwarded so far (all rows
+                        of the step BEFORE the latest one, in ``obs_all_prev``).  Rows of step t must be consumed
+                        before step t+2 is launched.  Local handles are created with CN_FLAG_GATHER_STAGE.
     """
 
     def __init__(self, cfg_global: CnConfig, make_local: Callable, device: torch.device,
@@ -76,20 +85,22 @@ class ShardedVecEnv:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if cfg_global.n_envs % self.world != 0:
             raise ValueError("all_gather_into_tensor needs equal shards: n_envs %% world_size must be 0")
-        if gather not in ("collective", "fused", "fused_mc", "fused_barrier", "none"):
+        if gather not in GATHER_MODES:
             raise ValueError("unknown gather mode %r" % gather)
         self.cfg_global = cfg_global.copy()
-        self.cfg_local = local_config(cfg_global, self.rank, self.world)
-        self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
-        self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
         self.gather_mode = gather if self.world > 1 else "none"
         self.fused = self.gather_mode.startswith("fused")
+        self.cfg_local = local_config(cfg_global, self.rank, self.world)
+        if self.gather_mode == "fused_async":
+            self.cfg_local.flags |= 16            # CN_FLAG_GATHER_STAGE
+        self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
+        self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
         if self.fused and (cfg_global.flags & 8):
             # CN_FLAG_RISK_FAITHFUL: cn_faithful_kernel rewrites the K block after the step kernel has already sent
-            # its rows to the peers, so cn_step_gather refuses peers in that mode
+            # its rows to the peers, so the fused entry points refuse that mode
             raise ValueError("risk_faithful worlds gather with gather='collective' (ncclAllGather), not 'fused'")
         self._symm = None
-        self._t = 0                              # fused steps issued so far
+        self._pending = False                    # fused_async: the latest step's rows have not been forwarded yet
         if self.fused:
             import ctypes as C
             import torch.distributed._symmetric_memory as symm_mem
@@ -124,65 +135,70 @@ class ShardedVecEnv:
             torch.cuda.synchronize(device)
             ah.barrier(channel=0)                # everyone's counters are zero before anyone signals
             self._cur = 0
-            self._comm = torch.cuda.Stream(device=device, priority=-1)   # fused_barrier: barrier kernels jump the queue
-            self._ready = [None, None, None]     # fused_barrier: event "barrier of the step that wrote buffer i is done"
             self.obs_all = self._bufs[0]
+            self.obs_all_prev = self._bufs[0]
         else:
             self.obs_all = torch.zeros((self.E, self.D), dtype=torch.float32, device=device)
         self.obs_local = self.obs_all[self.lo:self.hi]          # contiguous row block
         self.env = make_local(self.cfg_local, self.obs_local)
-        if self.gather_mode == "fused_barrier":
-            self.env.set_obs_peers(list(self._peers[0]))
 
     def step_local(self, actions_local: torch.Tensor, env=None):
         """Rotate the gather buffer and launch this rank's step (with the fused gather where enabled) on the current
         stream.  `env`: a replica of the local shard (same config) to step instead of self.env -- bench.py rotates
         several so that their state is cold in L2.  Returns the stepper's (obs_local, reward, done)."""
         env = self.env if env is None else env
-        if self.gather_mode in ("fused", "fused_mc"):
+        if self.fused:
+            prev = self._cur
             self._cur = (self._cur + 1) % 3
+            self.obs_all_prev = self._bufs[prev]
             self.obs_all = self._bufs[self._cur]
             self.obs_local = self.obs_all[self.lo:self.hi]
             env.obs = self.obs_local
-            mc = self.gather_mode == "fused_mc"
-            env.step_gather_signal(actions_local, self._peers[self._cur], self._arrive_peers, self.world - 1,
-                                   self._mc[self._cur] if mc else 0, self._arrive_mc if mc else 0,
-                                   self._arrive.data_ptr(), self.world, self.rank, 2)
-            self._t += 1
+            if self.gather_mode == "fused_async":
+                if self._pending:
+                    env.step_gather_async(actions_local, self._bufs[prev][self.lo:self.hi].data_ptr(), self._peers[prev],
+                                          self._arrive_peers, self.world - 1, self._arrive.data_ptr(), self.world, self.rank, 2)
+                else:
+                    env.step(actions_local)      # nothing to forward (first step, or the rows were flushed)
+                self._pending = True
+            else:
+                mc = self.gather_mode == "fused_mc"
+                env.step_gather_signal(actions_local, self._peers[self._cur], self._arrive_peers, self.world - 1,
+                                       self._mc[self._cur] if mc else 0, self._arrive_mc if mc else 0,
+                                       self._arrive.data_ptr(), self.world, self.rank, 2)
             return env.obs, env.reward, env.done
-        if self.gather_mode == "fused_barrier":
-            self.begin_step()
-            env.obs = self.obs_local
-            env.set_obs_peers(list(self._peers[self._cur]))
-        elif env is not self.env:
+        if env is not self.env:
             env.obs = self.obs_local
         return env.step(actions_local)
 
     def gather(self) -> torch.Tensor:
         """Make obs_all complete on every rank.  'collective': an in-place all-gather of the rows (sendbuf =
-        recvbuf + rank * count) on the stepping stream.  'fused' / 'fused_mc': nothing to launch -- the kernels wrote
-        every peer's copy and signalled; 'fused_barrier': the cross-rank barrier is enqueued on the side stream.
-        In the fused modes call wait_gathered() before reading other ranks' rows."""
+        recvbuf + rank * count) on the stepping stream.  Fused modes: nothing to launch here -- the kernels write
+        every peer's copy and signal; call wait_gathered() before reading other ranks' rows."""
         if self.gather_mode == "collective":
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
-        elif self.gather_mode == "fused_barrier":
-            main = torch.cuda.current_stream(self.obs_all.device)
-            done = torch.cuda.Event()
-            done.record(main)
-            self._comm.wait_event(done)
-            with torch.cuda.stream(self._comm):
-                self._symm[self._cur].barrier(channel=0)
-                ev = torch.cuda.Event()
-                ev.record(self._comm)
-            self._ready[self._cur] = ev
         return self.obs_all
 
-    def wait_gathered(self) -> torch.Tensor:
-        """Order the current stream behind the arrival of every rank's rows of the latest step."""
-        if self.gather_mode in ("fused", "fused_mc") and self._t > 0:
+    def flush_gather(self) -> None:
+        """fused_async: forward the rows of the latest step now (push-only launch) instead of with the next step."""
+        if self.gather_mode == "fused_async" and self._pending:
+            self.env.gather_flush(self.obs_local.data_ptr(), self._peers[self._cur], self._arrive_peers, self.world - 1,
+                                  self._arrive.data_ptr(), self.world, self.rank, 2)
+            self._pending = False
+
+    def wait_pushed(self) -> torch.Tensor:
+        """Order the current stream behind the arrival of everything the peers' kernels have forwarded so far: with
+        'fused_async' that is every row of the step before the latest one (obs_all_prev); in the other fused modes the
+        latest step itself."""
+        if self.fused:
             self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
-        elif self.gather_mode == "fused_barrier" and self._ready[self._cur] is not None:
-            torch.cuda.current_stream(self.obs_all.device).wait_event(self._ready[self._cur])
+        return self.obs_all_prev if (self.gather_mode == "fused_async" and self._pending) else self.obs_all
+
+    def wait_gathered(self) -> torch.Tensor:
+        """Order the current stream behind the arrival of every rank's rows of the LATEST step."""
+        if self.fused:
+            self.flush_gather()
+            self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
         return self.obs_all
 
     def reset(self) -> torch.Tensor:
@@ -193,18 +209,9 @@ class ShardedVecEnv:
             self._symm[self._cur].barrier(channel=0)
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
             self._symm[self._cur].barrier(channel=0)
+            self._pending = False
             return self.obs_all
         return self.gather()
-
-    def begin_step(self) -> None:
-        """fused_barrier mode: rotate to the next gather buffer once its previous readers are done."""
-        if self.gather_mode == "fused_barrier":
-            self._cur = (self._cur + 1) % 3
-            guard = self._ready[(self._cur + 1) % 3]         # barrier of two steps ago
-            if guard is not None:
-                torch.cuda.current_stream(self.obs_all.device).wait_event(guard)
-            self.obs_all = self._bufs[self._cur]
-            self.obs_local = self.obs_all[self.lo:self.hi]
 
     def step_host(self, actions_local):
         """The sharded step through HOST buffers (bench.py's e2e leg for N > 1): pinned H2D of this rank's actions, the
@@ -223,6 +230,8 @@ class ShardedVecEnv:
         return env._h_obs.numpy(), env._h_rew.numpy(), env._h_done.numpy()
 
     def step(self, actions_local: torch.Tensor):
+        """One strict step: launches it and the gather ('collective'); in the fused modes call wait_gathered() before
+        reading other ranks' rows of obs_all."""
         _, reward, done = self.step_local(actions_local)
         self.gather()
         return self.obs_all, reward, done

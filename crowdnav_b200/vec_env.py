@@ -144,6 +144,25 @@ class CrowdNavVecEnv:
             _lib.check(rc, "cn_step_gather_signal")
         return self.obs, self.reward, self.done
 
+    def step_gather_async(self, actions: torch.Tensor, push_src: int, push_peers, peer_arrive, n_peers: int,
+                          arrive_local: int, n_ranks: int, rank: int, wait_back: int = 2):
+        """cn_step_gather_async (see include/crowdnav.h): this step's kernel forwards the PREVIOUS step's rows
+        (push_src) to the peers under its own compute.  Handle created with CN_FLAG_GATHER_STAGE."""
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
+                or actions.numel() != 2 * self.E:
+            raise ValueError("actions must be a contiguous float32 [E, 2] tensor on %s" % self.device)
+        rc = self._L.cn_step_gather_async(self._h, actions.data_ptr(), self.obs.data_ptr(), push_src, push_peers, peer_arrive,
+                                          n_peers, arrive_local, n_ranks, rank, wait_back, self.reward.data_ptr(),
+                                          self.done.data_ptr(), self._stream())
+        if rc != 0:
+            _lib.check(rc, "cn_step_gather_async")
+        return self.obs, self.reward, self.done
+
+    def gather_flush(self, push_src: int, push_peers, peer_arrive, n_peers: int, arrive_local: int, n_ranks: int,
+                     rank: int, wait_back: int = 2) -> None:
+        _lib.check(self._L.cn_gather_flush(self._h, push_src, push_peers, peer_arrive, n_peers, arrive_local, n_ranks, rank,
+                                           wait_back, self._stream()), "cn_gather_flush")
+
     def gather_wait(self, arrive_local: int, n_ranks: int, rank: int) -> None:
         _lib.check(self._L.cn_gather_wait(self._h, arrive_local, n_ranks, rank, self._stream()), "cn_gather_wait")
 

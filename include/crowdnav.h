@@ -69,6 +69,9 @@ typedef enum cn_status {
                                        becomes a 4th plane of the state blob.  Not combinable with
                                        CN_FLAG_ENV_ORIGINAL or the fused gather of cn_step_gather. */
 
+#define CN_FLAG_GATHER_STAGE    16u /* reserve a staging tile per CTA for cn_step_gather_async (the pipelined fused
+                                       all-gather).  Costs [tile, D] floats of shared memory per CTA; no effect on results. */
+
 /* behaviour kinds (crowd_behaviors/simulate_*.py, SURVEY table P') */
 #define CN_BEHAVIOR_RANDOM 0   /* U(-speed, speed)^2 redrawn every period */
 #define CN_BEHAVIOR_TABLE  1   /* fixed per-pedestrian direction table * speed */
@@ -187,11 +190,13 @@ int cn_step_gather(cn_handle* h, const float* action_dev, float* obs_dev, float*
  * Every rank owns an array of n_ranks 64-bit arrival counters (zeroed once), one slot per SOURCE rank, in memory its
  * peers can address.  All step counting is done on the device, so a captured CUDA graph of such steps stays correct
  * on every replay.
- *   peer_arrive_dev[p]  peer-mapped address of THIS rank's slot in peer p's array: after a CTA's rows have been
- *                       stored into peer p it adds 1 there (release, system scope); it also adds 1 to this rank's own
- *                       slot of its own array, which therefore counts the rank's own progress.  A rank holds all rows
- *                       of its latest step once every other slot has caught up with its own slot (equal shards);
- *                       cn_gather_wait holds a stream until then.
+ *   peer_arrive_dev[p]  peer-mapped address of THIS rank's slot in peer p's array.  Every CTA makes its stores
+ *                       performed (GPU-scope fence) and counts itself on a device-local word; the LAST CTA of the
+ *                       launch then adds cn_kernel_ctas() to that slot on every peer with one system-scope release --
+ *                       one signal per launch, not per CTA -- and to this rank's own slot of its own array, which
+ *                       therefore counts the rank's own progress.  A rank holds all rows of its latest step once every
+ *                       other slot has caught up with its own slot (equal shards); cn_gather_wait holds a stream
+ *                       until then.
  *   arrive_local_dev, n_ranks, rank, wait_back   before its first store into the peers a CTA of step t (t = own slot
  *                       / cn_kernel_ctas()) waits until every other rank's slot shows all arrivals of that rank's step
  *                       t - wait_back (0 = no wait).  With three gather buffers in rotation pass 2: "everyone has
@@ -206,6 +211,22 @@ int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev,
                           unsigned long long* const* peer_arrive_dev, int n_peers, float* obs_mc_dev,
                           unsigned long long* arrive_mc_dev, unsigned long long* arrive_local_dev, int n_ranks,
                           int rank, int wait_back, float* reward_dev, uint8_t* done_dev, void* stream);
+/* The PIPELINED fused all-gather: the kernel of step t+1 forwards the rows of step t.  At its start every CTA bulk-loads
+ * its tile of the previous step's rows (push_src_dev: this rank's row block of the PREVIOUS gather buffer) into a
+ * staging tile and bulk-stores it into every peer (push_peer_dev[p]: the same row block of peer p's copy of that
+ * buffer), so the NVLink transfer runs under the step's compute instead of behind it; the arrival counters (as in
+ * cn_step_gather_signal, slot per source rank, device-side step counting, wait_back) are signalled at the end of the
+ * kernel.  Every rank therefore holds all rows of step t once the kernel of step t+1 -- or cn_gather_flush, the
+ * push-only launch for the rows of the last step -- has run on every rank (cn_gather_wait).  The first step after a
+ * reset has nothing to forward: use cn_step.  Handle created with CN_FLAG_GATHER_STAGE; default kernel only; not with
+ * CN_FLAG_RISK_FAITHFUL. */
+int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, const float* push_src_dev,
+                         float* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
+                         unsigned long long* arrive_local_dev, int n_ranks, int rank, int wait_back,
+                         float* reward_dev, uint8_t* done_dev, void* stream);
+int cn_gather_flush(cn_handle* h, const float* push_src_dev, float* const* push_peer_dev,
+                    unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
+                    int n_ranks, int rank, int wait_back, void* stream);
 /* Hold `stream` until every other rank's slot of arrive_local_dev[n_ranks] has caught up with this rank's own slot
  * (one small kernel; bounded like the in-kernel wait). */
 int cn_gather_wait(cn_handle* h, const unsigned long long* arrive_local_dev, int n_ranks, int rank, void* stream);

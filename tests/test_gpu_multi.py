@@ -52,7 +52,24 @@ def _worker(rank, world, port, mode, E, steps, q):
             dist.barrier()
             if not (torch.equal(obs_all, fo) and torch.equal(r, fr[senv.lo:senv.hi]) and torch.equal(d, fd[senv.lo:senv.hi])):
                 bad += 1
-        if mode in ("fused", "fused_mc"):
+        if mode == "fused_async":
+            # pipelined semantics: after the kernel of step t+1 (no flush) every rank holds all rows of step t
+            prev_full = None
+            for t in range(9):
+                a = torch.from_numpy(random_actions(rng, E)).to(dev)
+                senv.step_local(a[senv.lo:senv.hi].contiguous())
+                got_prev = senv.wait_pushed()
+                fo, _, _ = full.step(a)
+                torch.cuda.synchronize()
+                dist.barrier()
+                if prev_full is not None and not torch.equal(got_prev, prev_full):
+                    bad += 1
+                prev_full = fo.clone()
+            if not torch.equal(senv.wait_gathered(), prev_full):        # flush: the latest step
+                bad += 1
+            torch.cuda.synchronize()
+            dist.barrier()
+        if mode in ("fused", "fused_mc", "fused_async"):
             # the same steps as ONE CUDA graph, replayed twice: the step counting of the fused gather lives on the
             # device, so every replay must wait for / signal the right steps (6 steps = two turns of the 3 buffers)
             acts = [torch.from_numpy(random_actions(rng, E)).to(dev) for _ in range(6)]
@@ -78,7 +95,7 @@ def _worker(rank, world, port, mode, E, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_mc", "fused_barrier", "collective"])
+@pytest.mark.parametrize("mode", ["fused", "fused_mc", "fused_async", "collective"])
 def test_two_gpu_gather_equals_single_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
