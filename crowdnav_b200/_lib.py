@@ -12,7 +12,8 @@ from .config import CnConfig
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
-SO_PATH = os.path.join(_PKG, "libcrowdnav.so")
+# CN_LIB: an alternative build of the library next to the default one (profiling / A-B experiments only)
+SO_PATH = os.path.join(_PKG, os.environ.get("CN_LIB", "libcrowdnav.so"))
 SOURCES = ["cn_abi.cu", "cn_step.cu", "cn_flat.cu", "cn_faithful.cu"]
 HEADERS = ["cn_math.h", "cn_math64.h", "cn_faithful.h", "cn_faithful_state.h", "cn_state.h", "cn_kernel.h", "cn_dev.h", os.path.join("..", "..", "include", "crowdnav.h")]
 

@@ -201,6 +201,25 @@ __device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
     return m;
 }
 
+// rays that can see wall face `face` (0: +x, 1: -x, 2: +y, 3: -y) from the sensor origin (ox, oy) at yaw th, when the
+// face is within range: acos(u) <= (pi/2) sqrt(1-u); the chunks of the row they touch are OR-ed into `chunks`
+__device__ __forceinline__ Span face_span(const cn_kparams& P, float ox, float oy, uint32_t th, int face, uint32_t& chunks) {
+    const bool xface = face < 2;
+    const bool pos = (face & 1) == 0;
+    const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
+    const float o = xface ? ox : oy;
+    const float Dw = pos ? (wall - o) : (o - wall);
+    const float maxr = P.max_range;
+    Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
+    if (Dw > 0.0f && Dw <= maxr * 1.0001f) {
+        const uint32_t normal = xface ? (pos ? 0u : 0x80000000u) : (pos ? 0x40000000u : 0xC0000000u);
+        const float alpha = CN_PIO2 * sqrtf(fmaxf(1.0f - Dw / maxr, 0.0f)) + 0.02f;
+        sp = make_span(P, normal - th, alpha);
+        chunks |= span_chunks(sp, P.n_samples - 1);
+    }
+    return sp;
+}
+
 // ------------------------------------------------------------------ phase A
 // The part of Env.step / get_state / compute_reward that depends on the pose
 // alone, for ONE world held by the calling thread.  `part` selects a slice of
@@ -211,7 +230,33 @@ __device__ __forceinline__ uint32_t span_chunks(const Span& s, int NR) {
 //   sc    : the world's scalar record      row : the world's observation row
 struct PoseIn { int32_t xi, yi; uint32_t th; float v, w; };
 
-__device__ __forceinline__ PoseIn advance_robot(const cn_kparams& P, const uint32_t* rob, const float* action, int& bad) {
+// Body contact of the robot (only with d.robot_contact: collision_range < robot_radius, the README test protocol's
+// min_scan_range 0.0 -- otherwise the LiDAR threshold ends the episode before the body touches anything and the pose
+// is integrated freely, as in the reference-in-the-loop traces).  One kinematic sub-step from (xi, yi) to the
+// candidate (nx, ny): the centre stays robot_radius off the inner wall faces, and a sub-step that would bring the
+// centre closer to a pedestrian (position at the START of the control period, like the pedestrians see the robot)
+// while inside robot_radius + ped_radius of it is not taken; the heading still turns.
+__device__ __forceinline__ void robot_contact_step(const cn_kparams& P, const uint32_t* peds, int n_peds,
+                                                   int32_t xi, int32_t yi, int32_t& nx, int32_t& ny) {
+    nx = min(max(nx, P.d.rob_xmin), P.d.rob_xmax);
+    ny = min(max(ny, P.d.rob_ymin), P.d.rob_ymax);
+    bool blocked = false;
+#pragma unroll 1
+    for (int n = 0; n < n_peds; ++n) {
+        const int32_t px = (int32_t)peds[4 * n], py = (int32_t)peds[4 * n + 1];
+        const float dxn = (float)(nx - px) * CN_GRID, dyn = (float)(ny - py) * CN_GRID;
+        const float d2n = fmaf(dxn, dxn, dyn * dyn);
+        if (d2n < P.d.rob_ped_r2) {
+            const float dxo = (float)(xi - px) * CN_GRID, dyo = (float)(yi - py) * CN_GRID;
+            if (d2n < fmaf(dxo, dxo, dyo * dyo)) blocked = true;
+        }
+    }
+    if (blocked) { nx = xi; ny = yi; }
+}
+
+// peds_old: the world's pedestrian plane A as it was at the start of the step ([n_peds][4] words: x, y, vx, vy)
+__device__ __forceinline__ PoseIn advance_robot(const cn_kparams& P, const uint32_t* rob, const float* action, int& bad,
+                                                const uint32_t* peds_old, int n_peds) {
     // T2 (ENV:1190-1192), sanitised; R: unicycle, midpoint rule (FAKE:109-118, 156-167)
     float av = action[0], aw = action[1];
     bad = 0;
@@ -243,8 +288,10 @@ __device__ __forceinline__ PoseIn advance_robot(const cn_kparams& P, const uint3
         const int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
         const uint32_t mid = p.th + (uint32_t)(dth_bin >> 1);
         float sm, cm; cn_sincos_bin(mid, &sm, &cm);
-        p.xi += cn_f2i((ds * cm) * CN_INV_GRID);
-        p.yi += cn_f2i((ds * sm) * CN_INV_GRID);
+        int32_t nx = p.xi + cn_f2i((ds * cm) * CN_INV_GRID);
+        int32_t ny = p.yi + cn_f2i((ds * sm) * CN_INV_GRID);
+        if (P.d.robot_contact) robot_contact_step(P, peds_old, n_peds, p.xi, p.yi, nx, ny);
+        p.xi = nx; p.yi = ny;
         p.th += (uint32_t)dth_bin;
     }
     p.v = v_body; p.w = w_body;
@@ -328,11 +375,11 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
         if (in_goal_box(P, xf, yf)) pre |= 1u;                    // ENV:1017
         if (step_counter >= P.max_steps) pre |= 2u;               // ENV:1021
         sc[S_PRE] = pre;
-        // walls in range of the sensor: the rays that can see each face.  acos(u) <= (pi/2) sqrt(1-u)
+#if !defined(CN_WALLS_BY_LANE)
+        // walls in range of the sensor: the rays that can see each face
         {
             float sy, cy; cn_sincos_bin(p.th, &sy, &cy);
             const float ox = xf + P.mount_x * cy, oy = yf + P.mount_x * sy;
-            const float maxr = P.max_range;
             uint32_t wdirty = 0;
 #if defined(CN_COMPACT_CODE)
 #pragma unroll 1
@@ -340,23 +387,13 @@ __device__ __forceinline__ void pose_scalars(const cn_kparams& P, const PoseIn& 
 #pragma unroll
 #endif
             for (int face = 0; face < 4; ++face) {      // 0: +x, 1: -x, 2: +y, 3: -y
-                const bool xface = face < 2;
-                const bool pos = (face & 1) == 0;
-                const float wall = xface ? (pos ? P.room_xmax : P.room_xmin) : (pos ? P.room_ymax : P.room_ymin);
-                const float o = xface ? ox : oy;
-                const float Dw = pos ? (wall - o) : (o - wall);
-                Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
-                if (Dw > 0.0f && Dw <= maxr * 1.0001f) {
-                    const uint32_t normal = xface ? (pos ? 0u : 0x80000000u) : (pos ? 0x40000000u : 0xC0000000u);
-                    const float alpha = CN_PIO2 * sqrtf(fmaxf(1.0f - Dw / maxr, 0.0f)) + 0.02f;
-                    sp = make_span(P, normal - p.th, alpha);
-                    wdirty |= span_chunks(sp, NR);
-                }
+                const Span sp = face_span(P, ox, oy, p.th, face, wdirty);
                 sc[S_WSPAN + 4 * face + 0] = (uint32_t)sp.a0; sc[S_WSPAN + 4 * face + 1] = (uint32_t)sp.a1;
                 sc[S_WSPAN + 4 * face + 2] = (uint32_t)sp.b0; sc[S_WSPAN + 4 * face + 3] = (uint32_t)sp.b1;
             }
             sc[S_WDIRTY] = wdirty;
         }
+#endif
         // K-block padding (ENV:866-876, 895-898): [x, y, 0, 0] with the UNROUNDED pose, then np.around
         const float padx = cn_np_round3(xf), pady = cn_np_round3(yf);
         float* b = row + NR + 7;                                  // 16-B alignment is not guaranteed: scalar stores

@@ -56,9 +56,16 @@
 // which took the SASS from 144 KB to about 90 KB.  Turning the math helpers into real calls as well (CN_NOINLINE_BIG,
 // 76 KB) measured 5 % slower (c2 18.3 vs 17.2 us, c3 37.7 vs 35.9 us) and is left off.
 #define CN_COMPACT_CODE 1
+#define CN_WALLS_BY_LANE 1      // pose_scalars leaves the wall faces to the kernel: one lane per (world, face)
 #include "cn_dev.h"
 
 #define CF_POSE_WARPS 2
+#ifndef CN_FLAT_CTAS_PER_SM
+// resident 256-thread CTAs per SM the kernel is compiled (register cap: 45 registers, no spills) and tiled for.
+// Measured on B200 (profiles/r02/ctas_per_sm_ab.txt): 4 -> 5 is neutral at c2 / c3 and 10 % faster at c5; 6 (40 registers)
+// leaves the 20-pedestrian configs with tiles too small for the lane = world warps.
+#define CN_FLAT_CTAS_PER_SM 5
+#endif
 
 #ifdef CN_TIMELINE
 // debug builds only: %globaltimer stamps per (CTA, warp), 16 slots each (profiles/tools/timeline_flat.py)
@@ -89,9 +96,9 @@ enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_NCON, C_NOBJ, C_WORDS = 8 };
 // candidate record (8 words per pedestrian slot).  Phases 2-3: q (sensor-relative centre), bearing, span,
 // owned-ray count, centre ray.  Phase 5 puts the object's CP row for phase 6 into the words nobody else reads
 // (q and the span stay: another candidate's occluded-centre search may still need them).
-enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_MISC, Q_CKEY };  // Q_MISC: overflow << 31
+enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_MISC, Q_CKEY };
 enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY: min centre-ray key over the owned rays
-#define MISC_OVF 0x80000000u
+#define MARK_OVF 3           // S.mark[slot] of a candidate whose ray groups did not fit the group list
 
 // ray-group entry: up to 8 consecutive scan indices of one primitive
 //   bits 0-2 count - 1, bits 3-13 first index, bits 14-31 primitive (pedestrian slot, or world * 4 + face)
@@ -100,7 +107,7 @@ enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY
 struct Ptrs {
     uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
     uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
-    uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar; float* stage;
+    uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar; float* stage; uint32_t* strips;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -183,13 +190,21 @@ __device__ __forceinline__ float wall_t(const cn_kparams& P, const uint32_t* sc,
 }
 
 // A ray the primitive owns gets its final value: UTL:375-392 (sensor minimum) + np.around (ENV:1042); ENV:1012 min
-__device__ __forceinline__ void finish_ray(const cn_kparams& P, const Ptrs& S, int w, int e, int j, float t, uint8_t hid) {
+// (returns the cleaned range's bit pattern: the caller folds the minimum over its ray group before touching the
+//  world's min(scan) word -- one shared-memory atomic per group of 8 rays instead of one per ray)
+__device__ __forceinline__ uint32_t finish_ray(const cn_kparams& P, const Ptrs& S, int w, int e, int j, float t, uint8_t hid) {
     const float rr = (t < P.sensor_min_range) ? P.sensor_min_range : t;
     // nobonus env: np.around of the whole row (ENV:1042); original env: Python round per ray (original:313)
     S.obs[(size_t)w * P.d.obs_dim + j] = (P.flags & CN_FLAG_ENV_ORIGINAL) ? cn_py_round3(rr) : cn_np_round3(rr);
-    atomicMin(S.sc + w * F_WORDS + F_MINBITS, u_of(rr));
     if (P.dbg_ranges) P.dbg_ranges[(size_t)e * (P.n_samples - 1) + j] = rr;
     if (P.dbg_hid) P.dbg_hid[(size_t)e * (P.n_samples - 1) + j] = hid;
+    return u_of(rr);
+}
+// minimum over the 8 lanes of a ray group (every lane of the warp calls it)
+__device__ __forceinline__ uint32_t group_min8(uint32_t v) {
+    v = min(v, __shfl_xor_sync(FULL, v, 1));
+    v = min(v, __shfl_xor_sync(FULL, v, 2));
+    return min(v, __shfl_xor_sync(FULL, v, 4));
 }
 
 // Does pedestrian n of world w return ray i, and is it the primitive the oracle would report (walls first, then
@@ -233,29 +248,27 @@ __device__ __forceinline__ bool ped_ray_eval(const cn_kparams& P, const Ptrs& S,
     return own;
 }
 // phase 3, one ray of a pedestrian's span; returns true when the pedestrian owns it
-__device__ __forceinline__ bool cast_ped(const cn_kparams& P, const Ptrs& S, uint32_t magic, int e0, int slot, int i) {
-    const int N = P.n_peds;
-    const int w = world_of(slot, N, magic), n = slot - w * N;
+__device__ __forceinline__ bool cast_ped(const cn_kparams& P, const Ptrs& S, int e0, int w, int n, int slot, int i,
+                                         uint32_t& rbits, uint32_t& ckey) {
     float t; uint32_t ang;
     if (!ped_ray_eval(P, S, w, n, slot, i, t, ang)) return false;
-    finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, t, (uint8_t)n);
+    rbits = finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, t, (uint8_t)n);
     // centre ray (ENV:577 collapsed by ideal association): the owned ray nearest the pedestrian's centre line, in the
     // oracle's order -- smaller |ray angle - bearing| first (sign in the low bit).  Distinct rays have distinct keys
-    // (adjacent rays are inc_bin >> 2 apart), so the minimum key identifies the ray; phase 5 decodes it.
-    uint32_t* rec = S.rec + slot * 8;
-    const int32_t delta = (int32_t)(ang - rec[Q_BEAR]);
+    // (adjacent rays are inc_bin >> 2 apart), so the minimum key identifies the ray; risk_candidate decodes it.
+    const int32_t delta = (int32_t)(ang - S.rec[slot * 8 + Q_BEAR]);
     const uint32_t ad = (delta < 0) ? (0u - (uint32_t)delta) : (uint32_t)delta;
-    atomicMin(&rec[Q_CKEY], (ad & ~1u) | (delta < 0 ? 1u : 0u));
+    ckey = (ad & ~1u) | (delta < 0 ? 1u : 0u);
     return true;
 }
 // phase 3, one ray of a wall face's span
-__device__ __forceinline__ void cast_wall(const cn_kparams& P, const Ptrs& S, int e0, int q, int i) {
+__device__ __forceinline__ uint32_t cast_wall(const cn_kparams& P, const Ptrs& S, int e0, int q, int i) {
     const int N = P.n_peds;
     const int w = q >> 2, face = q & 3;
     const uint32_t* sc = S.sc + w * F_WORDS;
     float sn, co; cn_sincos_bin(sc[S_TH] + (uint32_t)i * P.d.inc_bin, &sn, &co);
     const float tw = wall_t(P, sc, face, sn, co);
-    if (tw < 0.0f) return;
+    if (tw < 0.0f) return 0xFFFFFFFFu;
     const bool xface = face < 2;
     bool own = true;
 #pragma unroll 1
@@ -276,22 +289,20 @@ __device__ __forceinline__ void cast_wall(const cn_kparams& P, const Ptrs& S, in
         const float t2 = ped_t(P, f_of(r2[Q_QX]), f_of(r2[Q_QY]), sn, co);
         if (t2 >= 0.0f && t2 < tw) own = false;
     }
-    if (own) finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, tw, CN_HIT_WALL);
+    return own ? finish_ray(P, S, w, e0 + w, (P.n_samples - 1) - i, tw, CN_HIT_WALL) : 0xFFFFFFFFu;
 }
 
-// n 16-byte elements of shared memory, strided over the CTA
+// n 16-byte elements of shared memory, strided over the CTA: four predicated stores per trip (one trip at c2)
 template <int T>
 __device__ __forceinline__ void fill16(void* base, int n, uint32_t word, int tid) {
     uint32_t a = smem_u32(base) + (uint32_t)tid * 16u;
-    int i = tid;
-    for (; i + 3 * T < n; i += 4 * T, a += 64u * T) {
+#pragma unroll 1
+    for (int i = tid; i < n; i += 4 * T, a += 64u * T) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(word) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 16u * T), "r"(word) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 32u * T), "r"(word) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 48u * T), "r"(word) : "memory");
+        if (i + T < n) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 16u * T), "r"(word) : "memory");
+        if (i + 2 * T < n) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 32u * T), "r"(word) : "memory");
+        if (i + 3 * T < n) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 48u * T), "r"(word) : "memory");
     }
-    for (; i < n; i += T, a += 16u * T)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(word) : "memory");
 }
 
 // n 16-byte elements from shared to global memory, strided over `nthreads` threads (fire-and-forget stores)
@@ -388,17 +399,98 @@ __device__ __forceinline__ void push_rows_to_peers(const cn_kparams& P, const fl
     }
 }
 
+// ---- phase 5, E-J for ONE candidate whose rays have all been cast (ENV:568-860): centre ray, hit point, tracker,
+// collision cone, CP; the object joins its world's and the tile's object lists.
+__device__ __forceinline__ void risk_candidate(const cn_kparams& P, const Ptrs& S, uint32_t magic, int slot) {
+    const int N = P.n_peds, NR = P.n_samples - 1;
+    uint32_t* rec = S.rec + slot * 8;
+    if (rec[Q_CNT] < 4u) return;                                      // ENV:573: fewer than 4 rays is no object
+    const int w = world_of(slot, N, magic), n = slot - w * N;
+    uint32_t* sc = S.sc + w * F_WORDS;
+    const uint32_t th = sc[S_TH];
+    // decode the centre ray from its key: ray angle = bearing +- |delta|, scan index = angle / inc (exact to rounding)
+    const uint32_t ckey = rec[Q_CKEY];
+    const uint32_t adk = ckey & ~1u;
+    const uint32_t rel2 = (rec[Q_BEAR] - th) + ((ckey & 1u) ? (0u - adk) : adk);
+    const int istar = (int)fmaf((float)rel2, P.d.inv_inc_bin, 0.5f);
+    const int jstar = NR - istar;
+    float t_raw;
+    {
+        float sn, co; cn_sincos_bin(th + (uint32_t)istar * P.d.inc_bin, &sn, &co);
+        t_raw = ped_t(P, f_of(rec[Q_QX]), f_of(rec[Q_QY]), sn, co);     // the same arithmetic as in phase 3
+    }
+    const float xf = f_of(sc[S_XF]), yf = f_of(sc[S_YF]);
+    const float d_raw = (t_raw < P.sensor_min_range) ? P.sensor_min_range : t_raw;
+    const float d3 = cn_py_round3(d_raw);                               // ENV:324,384
+    float sa, ca; cn_sincos_bin((uint32_t)jstar * P.d.hit_inc_bin - th, &sa, &ca);     // C2: UTL:110-126
+    const float hx = cn_py_round3(xf + d_raw * ca);
+    const float hy = cn_py_round3(yf + (d_raw * sa) * -1.0f);
+    // H/I: tracker with ideal association (ENV:656-760)
+    float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
+    if (S.pb[4 * slot + 3] & CN_PF_TRACKED) {
+        chx = f_of(S.pb[4 * slot + 0]) - hx; chy = f_of(S.pb[4 * slot + 1]) - hy;      // last - curr (sic), ENV:806-807
+        speed = sqrtf(fmaf(chy, chy, chx * chx)) * P.d.inv_dt;
+        ovx = chx * P.d.inv_dt; ovy = chy * P.d.inv_dt;
+    }
+    S.pb[4 * slot + 0] = u_of(hx); S.pb[4 * slot + 1] = u_of(hy);
+    atomicOr(&sc[F_CONF0 + (n >> 5)], 1u << (n & 31));
+    if (d3 < 0.140f) atomicOr(&sc[F_XFLAGS], XF_EGO);                   // ENV:1000
+    if (sc[F_XFLAGS] & XF_RESET) return;                              // ENV:769: no previous pose at step 0
+    // J: collision cone (ENV:765-860, UTL:251-293 as a true ray-circle test)
+    const float pcx = f_of(sc[S_PCX]), pcy = f_of(sc[S_PCY]);
+    const float ppx = f_of(sc[S_PPX]), ppy = f_of(sc[S_PPY]);
+    const float agent_vel = f_of(sc[S_AVEL]);
+    const float tx = pcx + chx, ty = pcy + chy;
+    float ux = tx - ppx, uy = ty - ppy;
+    const float Ln = sqrtf(fmaf(ux, ux, uy * uy));
+    bool have_dtc = false; float dtc = 0.0f;
+    if (Ln > 0.0f) {
+        const float invL = 1.0f / Ln;
+        ux = ux * invL; uy = uy * invL;
+        const float wx_ = hx - ppx, wy_ = hy - ppy;
+        const float b = fmaf(wx_, ux, wy_ * uy);
+        const float h = fmaf(wx_, uy, -(wy_ * ux));
+        const float disc = fmaf(-h, h, P.d.cp_r2);
+        if (disc > 0.0f) {
+            const float t = b - sqrtf(disc);
+            if (t > 0.0f) { have_dtc = true; dtc = t; }
+        }
+    }
+    const float resultant = agent_vel - speed;
+    float cp_ttc = 0.0f, cp;
+    const float dto = cp_dto(P, d3);
+    if (have_dtc && resultant == 0.0f) {
+        cp = dto;
+    } else {
+        if (have_dtc) {
+            const float qq = (0.15f * resultant) / dtc;
+            cp_ttc = (qq < 1.0f) ? qq : 1.0f;
+        }
+        cp = 0.5f * cp_ttc + 0.5f * dto;
+    }
+    rec[O_CP] = u_of(cp); rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);   // x, y: ped_b
+    const uint32_t k = atomicAdd(&sc[F_NOBJ], 1u);                      // the world's object list (any order)
+    S.olist[w * N + k] = (uint16_t)slot;
+    S.rlist[atomicAdd(&S.cnt[C_NOBJ], 1u)] = (uint16_t)slot;            // ... and the tile's (the draw list is long gone)
+}
+
 // ------------------------------------------------------------------- kernel
 template <int MODE, int T>
-__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? 4 : (T >= 192 ? 6 : 8))))
+__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? CN_FLAT_CTAS_PER_SM : (T >= 192 ? 6 : 8))))
 cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
     constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
     FSTAMP(14);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {                                     // first thing: the bulk loads below cannot be issued before this
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+        mbar_init(bar, 1);
+        if (L.off_stage != 0u) mbar_init(bar + 1, 1);
+        fence_mbar_init();
+    }
     const int W = L.W, N = P.n_peds, NR = P.n_samples - 1, D = P.d.obs_dim, K = P.k_obstacles;
     const int e0 = blockIdx.x * W;
     const int nE = min(W, P.n_envs - e0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     Ptrs S;
     S.robot = reinterpret_cast<uint32_t*>(smem);
@@ -421,6 +513,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.cnt = reinterpret_cast<uint32_t*>(smem + L.off_cnt);
     S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     S.stage = reinterpret_cast<float*>(smem + L.off_stage);
+    S.strips = reinterpret_cast<uint32_t*>(smem + L.off_strips);
 
     FSTAMP(0);
     const int n_items = nE * N;                       // pedestrians of the tile
@@ -439,11 +532,6 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // step's compute -- bulk load into the staging tile now, bulk stores to every peer as soon as it has landed
     const bool push = (MODE == 0) && P.n_push_peers > 0;
     const bool push_bulk = push && L.off_stage != 0u && P.push_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
-    if (tid == 0) {
-        mbar_init(S.bar, 1);
-        mbar_init(S.bar + 1, 1);
-        fence_mbar_init();
-    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         if (push_bulk) {
@@ -451,29 +539,31 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             tma_load(S.stage, P.push_src + (size_t)e0 * D, (uint32_t)((size_t)nE * D * 4), S.bar + 1);
         }
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
-        mbar_expect_tx(S.bar, rob_bytes + 3u * ped_bytes + act_bytes);
+        mbar_expect_tx(S.bar, rob_bytes + 2u * ped_bytes + act_bytes);
         if (act_bytes) tma_load(S.act, P.action + 2 * (size_t)e0, act_bytes, S.bar);
         tma_load(S.robot, P.robot + (size_t)e0 * CN_ROBOT_WORDS, rob_bytes, S.bar);
-        if (ped_bytes) tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
+        if (ped_bytes) {
+            tma_load(S.pa, P.ped_a + (size_t)e0 * N * 4, ped_bytes, S.bar);
+            tma_load(S.pb, P.ped_b + (size_t)e0 * N * 4, ped_bytes, S.bar);
+        }
         FSTAMP(15);
     }
-    if (warp == 0 && N > 0) {
-        // the old-position plane lands TWICE per world, back to back: "pedestrian (n + r) mod N" of the contact
-        // prefilter is then a plain offset from pedestrian n (lane = world issues its two copies)
-        __syncwarp();                                   // after thread 0's expect_tx
-        for (int w = lane; w < nE; w += 32) {
-            const uint32_t* src = P.ped_a + (size_t)(e0 + w) * N * 4;
-            tma_load(S.pa + (size_t)(2 * w) * N * 4, src, (uint32_t)N * 16u, S.bar);
-            tma_load(S.pa + (size_t)(2 * w + 1) * N * 4, src, (uint32_t)N * 16u, S.bar);
-        }
-    }
     {
-        const float fill = P.d.max_range_r3;                                // a ray with no return, already rounded
-        const int tot = nE * D, n4 = tot >> 2;
-        fill16<T>(S.obs, n4, u_of(fill), tid);
-        if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+        {
+            // every ray starts as "no return" (already rounded); the fill runs under the latency of the bulk loads.
+            // (Tried: a bulk copy of a constant tile instead -- 15 % fewer instructions at c2 but the tile lands 0.3 us
+            //  later and the step is latency-bound: 11.5 vs 11.2 us.)
+            const float fill = P.d.max_range_r3;
+            const int tot = nE * D, n4 = tot >> 2;
+            fill16<T>(S.obs, n4, u_of(fill), tid);
+            if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+        }
+        {                                                                   // contact-prefilter strips: all empty
+            const int n16 = (nE * 64 * (int)L.strip_words) >> 2;
+            uint4* z = reinterpret_cast<uint4*>(S.strips);
 #pragma unroll 1
-        for (int i = tid; i < 2 * n_items; i += T) S.peers[i] = 0u;
+            for (int i = tid; i < n16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (tid < C_WORDS) S.cnt[tid] = 0u;
         if (tid < nE) {
             uint32_t* sc = S.sc + tid * F_WORDS;
@@ -532,7 +622,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             if (part == 0) scl[F_XFLAGS] = (run ? XF_ACTIVE : 0u) | ((run && reset_now) ? XF_RESET : 0u);
             if (run) {
                 if (reset_now) { p.xi = P.d.start_xi; p.yi = P.d.start_yi; p.th = P.d.start_th; }
-                else p = advance_robot(P, rob, act_smem ? S.act + 2 * w : P.action + 2 * (size_t)(e0 + w), bad);
+                else p = advance_robot(P, rob, act_smem ? S.act + 2 * w : P.action + 2 * (size_t)(e0 + w), bad,
+                                       S.pa + (size_t)w * N * 4, N);
             }
         }
         if (part == 1) {
@@ -560,14 +651,26 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 stepc = (int)rob[CN_R_STEP] + 1;
             }
             pose_scalars(P, p, part, wpx, wpy, pd, ph, ppx, ppy, stepc, !reset_now, !reset_now, bad, scl, rowl);
-            if (part == 1) {                                                // this world's wall faces -> ray groups
+            if (part == 1) scl[S_WDIRTY] = 0u;
+        }
+        if (part == 1) {
+            // the walls in range of the sensor, one lane per (world, face) instead of four faces in a row per world:
+            // the rays that can see the face (span), the chunks of the row they touch, the span's ray groups
+            const uint32_t run_mask = __ballot_sync(FULL, run);
+            __syncwarp();                                                   // the lanes' scalar records
 #pragma unroll 1
-                for (int face = 0; face < 4; ++face) {
-                    Span sp; wall_span(scl, face, sp);
-                    if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)(w * 4 + face), sp)) {
-                        atomicOr(&scl[F_OVF_FACES], 1u << face);
-                        S.cnt[C_OVF] = 1u;
-                    }
+            for (int q = lane; q < 4 * nE; q += 32) {
+                const int wq = q >> 2, face = q & 3;
+                if (!((run_mask >> wq) & 1u)) continue;
+                uint32_t* sq = S.sc + wq * F_WORDS;
+                uint32_t chunks = 0u;
+                const Span sp = face_span(P, f_of(sq[S_XF]) + f_of(sq[S_OFFX]), f_of(sq[S_YF]) + f_of(sq[S_OFFY]), sq[S_TH], face, chunks);
+                sq[S_WSPAN + 4 * face + 0] = (uint32_t)sp.a0; sq[S_WSPAN + 4 * face + 1] = (uint32_t)sp.a1;
+                sq[S_WSPAN + 4 * face + 2] = (uint32_t)sp.b0; sq[S_WSPAN + 4 * face + 3] = (uint32_t)sp.b1;
+                if (chunks) atomicOr(&sq[S_WDIRTY], chunks);
+                if (!push_groups(S.wg, &S.cnt[C_NWG], (int)L.cap_wg, (uint32_t)q, sp)) {
+                    atomicOr(&sq[F_OVF_FACES], 1u << face);
+                    S.cnt[C_OVF] = 1u;
                 }
             }
         }
@@ -605,22 +708,52 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 S.clw[w * N + k] = (uint8_t)(it - w * N);
             }
         };
-        auto in_contact = [&](int it, int w, int32_t x0, int32_t y0) {
+        // Contact prefilter.  Each axis is cut into 32 strips (modulo) at least as wide as the contact box; strip masks
+        // hold one bit per pedestrian of the world.  Whoever can be inside pedestrian n's box sits in one of the three
+        // strips around n's on BOTH axes: (x strips) & (y strips) leaves the few pedestrians to test exactly -- instead
+        // of N / 2 box tests per pedestrian.  Any superset of the true contacts gives the same result (a partner
+        // outside the cut-off adds exactly nothing), and the masks come out symmetric like the pairwise test's.
+        const int sw = (int)L.strip_words;                                  // words per strip mask: 1 (N <= 32) or 2
+        const int sshift = P.d.strip_shift;
+        auto strip_of = [&](int32_t c, int32_t origin) { return (int)(((uint32_t)(c - origin)) >> sshift) & 31; };
+        auto contact_masks = [&](int w, int n, int32_t x0, int32_t y0, uint32_t& m0, uint32_t& m1) {
+            const uint32_t* xm = S.strips + (size_t)w * 64 * sw;
+            const uint32_t* ym = xm + 32 * sw;
+            const int sx = strip_of(x0, P.d.ped_xmin), sy = strip_of(y0, P.d.ped_ymin);
+            const int xa = ((sx + 31) & 31) * sw, xb = sx * sw, xc = ((sx + 1) & 31) * sw;
+            const int ya = ((sy + 31) & 31) * sw, yb = sy * sw, yc = ((sy + 1) & 31) * sw;
+            uint32_t c0 = (xm[xa] | xm[xb] | xm[xc]) & (ym[ya] | ym[yb] | ym[yc]);
+            uint32_t c1 = 0u;
+            if (sw == 2) c1 = (xm[xa + 1] | xm[xb + 1] | xm[xc + 1]) & (ym[ya + 1] | ym[yb + 1] | ym[yc + 1]);
+            if (n < 32) c0 &= ~(1u << n); else c1 &= ~(1u << (n - 32));
+            m0 = 0u; m1 = 0u;
+            const uint32_t bx = (uint32_t)x0 + (uint32_t)lim_i, by = (uint32_t)y0 + (uint32_t)lim_i;
+            while (c0 | c1) {                                               // usually nobody
+                int m;
+                if (c0) { m = __ffs(c0) - 1; c0 &= c0 - 1; } else { m = __ffs(c1) + 31; c1 &= c1 - 1; }
+                const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
+                if ((bx - o.x) < lim2 && (by - o.y) < lim2) { if (m < 32) m0 |= 1u << m; else m1 |= 1u << (m - 32); }
+            }
+        };
+        auto near_robot = [&](int w, int32_t x0, int32_t y0) {
             const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
             const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
-            const bool near_robot = (uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2;
-            return near_robot || (S.peers[2 * it] | S.peers[2 * it + 1]) != 0u;
+            return (uint32_t)(x0 - rxi + lim_i) < lim2 && (uint32_t)(y0 - ryi + lim_i) < lim2;
+        };
+        // pedestrian `it` has somebody inside its contact box: remember who, queue it for the repulsion pass
+        auto to_slow_list = [&](int it, uint32_t m0, uint32_t m1) {
+            S.peers[2 * it] = m0; S.peers[2 * it + 1] = m1;
+            slowlist[atomicAdd(&S.cnt[C_NCON], 1u)] = (uint16_t)it;
         };
 
-        // -- A: timers; who draws random numbers; contact prefilter on the old positions
-        //    (each unordered pair once: partner = n + r mod N, r <= N/2)
+        // -- A: timers; who draws random numbers; every pedestrian enters its strips (old positions)
         for (int it = ptid; it < n_items; it += PED_THREADS) {
             const int w = world_of(it, N, L.magic_n), n = it - w * N;
             const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
             bool active = true, respawn = (MODE == 1);
             if (MODE == 1) active = !P.mask || P.mask[e0 + w] != 0;
             else respawn = (rob[CN_R_FLAGS] & CN_RF_DONE) && auto_reset;
-            if (!active) { spa2_4[it] = spa4[it + w * N]; S.mark[it] = 2; continue; }  // untouched world: state goes back as it came
+            if (!active) { spa2_4[it] = spa4[it]; S.mark[it] = 2; continue; }  // untouched world: state goes back as it came
             if (respawn) {
                 const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
                 S.rlist[pos] = (uint16_t)(it | 0x8000);
@@ -639,27 +772,18 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     mk = 1;
                 } else {
                     const float speed = P.beh_speed[b];
-                    S.pa[4 * (it + w * N) + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
-                    S.pa[4 * (it + w * N) + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
+                    S.pa[4 * it + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
+                    S.pa[4 * it + 3] = u_of(__ldg(&P.cfg->behavior_table[b][n][1]) * speed);
                 }
             }
             S.pb[4 * it + 2] = (uint32_t)tm;
             S.mark[it] = mk;
-            const uint32_t* pp = S.pa + 4 * (it + w * N);                   // pedestrian n of the doubled list
-            const uint2 a = *reinterpret_cast<const uint2*>(pp);
-            const uint32_t bx = a.x + (uint32_t)lim_i, by = a.y + (uint32_t)lim_i;
-            const int half = N >> 1;
-            uint32_t hits = 0u;
-#pragma unroll 5
-            for (int r = 1; r <= half; ++r) {
-                const uint2 o = *reinterpret_cast<const uint2*>(pp + 4 * r);
-                hits = (hits << 1) | (((bx - o.x) < lim2 && (by - o.y) < lim2) ? 1u : 0u);      // round r -> bit half - r
-            }
-            while (hits) {                                                  // rare
-                const int r = half + 1 - __ffs(hits); hits &= hits - 1;
-                const int partner = (n + r >= N) ? n + r - N : n + r;
-                atomicOr(&S.peers[2 * it + (partner >> 5)], 1u << (partner & 31));
-                atomicOr(&S.peers[2 * (w * N + partner) + (n >> 5)], 1u << (n & 31));
+            if (MODE == 0) {
+                const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
+                uint32_t* xm = S.strips + (size_t)w * 64 * sw;
+                const uint32_t bit = 1u << (n & 31);
+                atomicOr(xm + strip_of((int32_t)a.x, P.d.ped_xmin) * sw + (n >> 5), bit);
+                atomicOr(xm + 32 * sw + strip_of((int32_t)a.y, P.d.ped_ymin) * sw + (n >> 5), bit);
             }
         }
         // contact masks and the draw list are complete; pose warp 1 has published the robot's new pose
@@ -671,12 +795,10 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             for (int it = ptid; it < n_items; it += PED_THREADS) {
                 if (S.mark[it] != 0) continue;
                 const int w = world_of(it, N, L.magic_n);
-                const uint4 a = spa4[it + w * N];
-                if (in_contact(it, w, (int32_t)a.x, (int32_t)a.y)) {
-                    const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
-                    slowlist[pos] = (uint16_t)it;
-                    continue;
-                }
+                const uint4 a = spa4[it];
+                uint32_t m0, m1;
+                contact_masks(w, it - w * N, (int32_t)a.x, (int32_t)a.y, m0, m1);
+                if ((m0 | m1) != 0u || near_robot(w, (int32_t)a.x, (int32_t)a.y)) { to_slow_list(it, m0, m1); continue; }
                 const int2 np = finish_ped(it, w, (int32_t)a.x, (int32_t)a.y, f_of(a.z), f_of(a.w), f_of(a.z), f_of(a.w));
                 cand_test(it, w, np.x, np.y);
             }
@@ -710,11 +832,12 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 } else {
                     const float speed = P.beh_speed[bb];
                     const float vx = cn_usym(rnd.v[0], speed), vy = cn_usym(rnd.v[1], speed);
-                    const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * (idx + ww * N));
-                    if (in_contact(idx, ww, (int32_t)a.x, (int32_t)a.y)) {
-                        S.pa[4 * (idx + ww * N) + 2] = u_of(vx); S.pa[4 * (idx + ww * N) + 3] = u_of(vy);
-                        const uint32_t pos = atomicAdd(&S.cnt[C_NCON], 1u);
-                        slowlist[pos] = (uint16_t)idx;
+                    const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * idx);
+                    uint32_t m0, m1;
+                    contact_masks(ww, nn, (int32_t)a.x, (int32_t)a.y, m0, m1);
+                    if ((m0 | m1) != 0u || near_robot(ww, (int32_t)a.x, (int32_t)a.y)) {
+                        S.pa[4 * idx + 2] = u_of(vx); S.pa[4 * idx + 3] = u_of(vy);
+                        to_slow_list(idx, m0, m1);
                     } else {
                         const int2 np = finish_ped(idx, ww, (int32_t)a.x, (int32_t)a.y, vx, vy, vx, vy);
                         cand_test(idx, ww, np.x, np.y);
@@ -731,7 +854,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 const int it = (int)slowlist[q];
                 const int w = world_of(it, N, L.magic_n);
                 const uint32_t* rob = S.robot + w * CN_ROBOT_WORDS;
-                const uint4 a = spa4[it + w * N];
+                const uint4 a = spa4[it];
                 const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y;
                 float vex = f_of(a.z), vey = f_of(a.w);
                 const int32_t rxi = (int32_t)rob[CN_R_X], ryi = (int32_t)rob[CN_R_Y];
@@ -743,7 +866,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                     if (p0 | p1) {
                         int m;
                         if (p0) { m = __ffs(p0) - 1; p0 &= p0 - 1; } else { m = __ffs(p1) + 31; p1 &= p1 - 1; }
-                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (2 * w * N + m));
+                        const uint2 o = *reinterpret_cast<const uint2*>(S.pa + 4 * (w * N + m));
                         ox = (int32_t)o.x; oy = (int32_t)o.y; rsum = rr2;
                     } else {
                         robot_pending = false;
@@ -784,12 +907,11 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             rec[Q_SPB] = (uint32_t)sp.b0 | ((uint32_t)sp.b1 << 16);
             rec[Q_CNT] = 0u;
             rec[Q_CKEY] = 0xFFFFFFFFu;
-            uint32_t misc = 0u;
+            rec[Q_MISC] = 0u;
             if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
-                misc |= MISC_OVF;
+                S.mark[slot] = MARK_OVF;                                    // walked directly in phase 3 (mark is dead by now)
                 S.cnt[C_OVF] = 1u;
             }
-            rec[Q_MISC] = misc;
         }
     }
     FSTAMP(9);
@@ -815,11 +937,18 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
         }
 #pragma unroll 1
-        for (int g = tid >> 3; g < n_groups; g += T / 8) {
-            int q = src, i;
-            if (src < 0) { const uint32_t ent = S.wg[g]; i = group_ray(ent, lane8); q = (int)(ent >> 14); }
-            else i = span_ray(sp, g * 8 + lane8);
-            if (i >= 0) cast_wall(P, S, e0, q, i);
+        for (int g0 = warp * 4; g0 < n_groups; g0 += (T / 32) * 4) {        // warp-uniform trip count: shuffles inside
+            const int g = g0 + (lane >> 3);
+            int q = src;
+            uint32_t rbits = 0xFFFFFFFFu;
+            if (g < n_groups) {
+                int i;
+                if (src < 0) { const uint32_t ent = S.wg[g]; i = group_ray(ent, lane8); q = (int)(ent >> 14); }
+                else i = span_ray(sp, g * 8 + lane8);
+                if (i >= 0) rbits = cast_wall(P, S, e0, q, i);
+            }
+            rbits = group_min8(rbits);                                      // ENV:1012: min over the scan, one atomic per group
+            if (lane8 == 0 && rbits != 0xFFFFFFFFu) atomicMin(S.sc + (q >> 2) * F_WORDS + F_MINBITS, rbits);
         }
     }
 #pragma unroll 1
@@ -828,25 +957,38 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
         if (src >= 0) {
             slot_src = (int)S.clist[src];
+            if (S.mark[slot_src] != MARK_OVF) continue;
             const uint32_t* rec = S.rec + slot_src * 8;
-            if (!(rec[Q_MISC] & MISC_OVF)) continue;
             unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
             n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
         }
 #pragma unroll 1
-        for (int g0 = warp * 4; g0 < n_groups; g0 += (T / 32) * 4) {        // warp-uniform trip count: ballots inside
+        for (int g0 = warp * 4; g0 < n_groups; g0 += (T / 32) * 4) {        // warp-uniform trip count: shuffles inside
             const int g = g0 + (lane >> 3);
-            bool owned = false;
-            int slot = slot_src;
+            bool owned = false, counted = false;
+            int slot = slot_src, w = 0;
+            uint32_t rbits = 0xFFFFFFFFu, ckey = 0xFFFFFFFFu;
             if (g < n_groups) {
                 int i;
-                if (src < 0) { const uint32_t ent = S.pg[g]; i = group_ray(ent, lane8); slot = (int)(ent >> 14); }
-                else i = span_ray(sp, g * 8 + lane8);
-                if (i >= 0) owned = cast_ped(P, S, L.magic_n, e0, slot, i);
+                if (src < 0) { const uint32_t ent = S.pg[g]; i = group_ray(ent, lane8); slot = (int)(ent >> 14); counted = ent != GRP_NONE; }
+                else { i = span_ray(sp, g * 8 + lane8); counted = true; }
+                if (counted) {
+                    w = world_of(slot, N, L.magic_n);
+                    if (i >= 0) owned = cast_ped(P, S, e0, w, slot - w * N, slot, i, rbits, ckey);
+                }
             }
             const uint32_t bm = __ballot_sync(FULL, owned);
             const int c = __popc((bm >> (lane & 24)) & 0xFFu);
-            if (lane8 == 0 && c) atomicAdd(&S.rec[slot * 8 + Q_CNT], (uint32_t)c);
+            rbits = group_min8(rbits);
+            ckey = group_min8(ckey);
+            if (lane8 == 0 && c) {
+                // one thread per group folds the group's results into the candidate record: three shared-memory
+                // atomics per group of 8 rays instead of two per ray
+                uint32_t* rec = S.rec + slot * 8;
+                atomicAdd(&rec[Q_CNT], (uint32_t)c);
+                atomicMin(&rec[Q_CKEY], ckey);
+                atomicMin(S.sc + w * F_WORDS + F_MINBITS, rbits);
+            }
         }
     }
     FSTAMP(10);
@@ -854,78 +996,10 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     FSTAMP(5);
 
     // ---------------------------------------------------------------- phase 5: E-J per candidate (ENV:568-860)
-    for (int q = tid; q < n_cand; q += T) {
-        const int slot = (int)S.clist[q];
-        uint32_t* rec = S.rec + slot * 8;
-        if (rec[Q_CNT] < 4u) continue;                                      // ENV:573: fewer than 4 rays is no object
-        const int w = world_of(slot, N, L.magic_n), n = slot - w * N;
-        uint32_t* sc = S.sc + w * F_WORDS;
-        const uint32_t th = sc[S_TH];
-        // decode the centre ray from its key: ray angle = bearing +- |delta|, scan index = angle / inc (exact to rounding)
-        const uint32_t ckey = rec[Q_CKEY];
-        const uint32_t adk = ckey & ~1u;
-        const uint32_t rel2 = (rec[Q_BEAR] - th) + ((ckey & 1u) ? (0u - adk) : adk);
-        const int istar = (int)fmaf((float)rel2, P.d.inv_inc_bin, 0.5f);
-        const int jstar = NR - istar;
-        float t_raw;
-        {
-            float sn, co; cn_sincos_bin(th + (uint32_t)istar * P.d.inc_bin, &sn, &co);
-            t_raw = ped_t(P, f_of(rec[Q_QX]), f_of(rec[Q_QY]), sn, co);     // the same arithmetic as in phase 3
-        }
-        const float xf = f_of(sc[S_XF]), yf = f_of(sc[S_YF]);
-        const float d_raw = (t_raw < P.sensor_min_range) ? P.sensor_min_range : t_raw;
-        const float d3 = cn_py_round3(d_raw);                               // ENV:324,384
-        float sa, ca; cn_sincos_bin((uint32_t)jstar * P.d.hit_inc_bin - th, &sa, &ca);     // C2: UTL:110-126
-        const float hx = cn_py_round3(xf + d_raw * ca);
-        const float hy = cn_py_round3(yf + (d_raw * sa) * -1.0f);
-        // H/I: tracker with ideal association (ENV:656-760)
-        float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
-        if (S.pb[4 * slot + 3] & CN_PF_TRACKED) {
-            chx = f_of(S.pb[4 * slot + 0]) - hx; chy = f_of(S.pb[4 * slot + 1]) - hy;      // last - curr (sic), ENV:806-807
-            speed = sqrtf(fmaf(chy, chy, chx * chx)) * P.d.inv_dt;
-            ovx = chx * P.d.inv_dt; ovy = chy * P.d.inv_dt;
-        }
-        S.pb[4 * slot + 0] = u_of(hx); S.pb[4 * slot + 1] = u_of(hy);
-        atomicOr(&sc[F_CONF0 + (n >> 5)], 1u << (n & 31));
-        if (d3 < 0.140f) atomicOr(&sc[F_XFLAGS], XF_EGO);                   // ENV:1000
-        if (sc[F_XFLAGS] & XF_RESET) continue;                              // ENV:769: no previous pose at step 0
-        // J: collision cone (ENV:765-860, UTL:251-293 as a true ray-circle test)
-        const float pcx = f_of(sc[S_PCX]), pcy = f_of(sc[S_PCY]);
-        const float ppx = f_of(sc[S_PPX]), ppy = f_of(sc[S_PPY]);
-        const float agent_vel = f_of(sc[S_AVEL]);
-        const float tx = pcx + chx, ty = pcy + chy;
-        float ux = tx - ppx, uy = ty - ppy;
-        const float Ln = sqrtf(fmaf(ux, ux, uy * uy));
-        bool have_dtc = false; float dtc = 0.0f;
-        if (Ln > 0.0f) {
-            const float invL = 1.0f / Ln;
-            ux = ux * invL; uy = uy * invL;
-            const float wx_ = hx - ppx, wy_ = hy - ppy;
-            const float b = fmaf(wx_, ux, wy_ * uy);
-            const float h = fmaf(wx_, uy, -(wy_ * ux));
-            const float disc = fmaf(-h, h, P.d.cp_r2);
-            if (disc > 0.0f) {
-                const float t = b - sqrtf(disc);
-                if (t > 0.0f) { have_dtc = true; dtc = t; }
-            }
-        }
-        const float resultant = agent_vel - speed;
-        float cp_ttc = 0.0f, cp;
-        const float dto = cp_dto(P, d3);
-        if (have_dtc && resultant == 0.0f) {
-            cp = dto;
-        } else {
-            if (have_dtc) {
-                const float qq = (0.15f * resultant) / dtc;
-                cp_ttc = (qq < 1.0f) ? qq : 1.0f;
-            }
-            cp = 0.5f * cp_ttc + 0.5f * dto;
-        }
-        rec[O_CP] = u_of(cp); rec[O_VX] = u_of(ovx); rec[O_VY] = u_of(ovy); rec[O_TTC] = u_of(cp_ttc);   // x, y: ped_b
-        const uint32_t k = atomicAdd(&sc[F_NOBJ], 1u);                      // the world's object list (any order)
-        S.olist[w * N + k] = (uint16_t)slot;
-        S.rlist[atomicAdd(&S.cnt[C_NOBJ], 1u)] = (uint16_t)slot;            // ... and the tile's (the draw list is long gone)
-    }
+    // (compacted: item = candidate.  Tried: the thread that casts a candidate's last ray group goes straight on with
+    //  E-J and barrier #F goes away -- the chain then runs once per candidate with ONE active lane instead of once per
+    //  tile with one lane per candidate: c3 29.7 -> 33.6 us, c2 no better; profiles/r02/bench_*_v10.json)
+    for (int q = tid; q < n_cand; q += T) risk_candidate(P, S, L.magic_n, (int)S.clist[q]);
     __syncthreads();            // #F
     FSTAMP(6);
 
@@ -1122,17 +1196,19 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->cap_pg = (uint32_t)W * 24u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
-    /* the old-position plane is loaded twice per world (2 x 16 B per pedestrian); the candidate records (32 B per
-     * pedestrian, phases 2-6) reuse exactly that memory, dead by then */
+    /* 32 B per pedestrian: the old-position plane (16 B each) in the first half, the contact masks of the slow list
+     * (8 B each) in the second; the candidate records (32 B per pedestrian, phases 2-6) reuse all of it, dead by then */
     L->off_rec = (uint32_t)o;
     L->off_pk = 0;
+    L->off_peers = (uint32_t)(o + (size_t)W * N * 16);
     o += (size_t)W * N * 32;                        L->off_pb = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_pa2 = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
     o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
     o = up16(o + (size_t)W * D * 4);                L->off_sc = (uint32_t)o;
-    o += (size_t)W * F_WORDS * 4;                   L->off_peers = (uint32_t)o;
-    o += (size_t)W * N * 8;                         L->off_clist = (uint32_t)o;
+    L->strip_words = (N > 32) ? 2u : 1u;
+    o = up16(o + (size_t)W * F_WORDS * 4);          L->off_strips = (uint32_t)o;
+    o += (size_t)W * 64 * L->strip_words * 4;       L->off_clist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
     o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
@@ -1152,7 +1228,7 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
     // 256-thread CTAs, four per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk store) that
     // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
     // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
-    const int threads = 256, ctas = 4;
+    const int threads = 256, ctas = CN_FLAT_CTAS_PER_SM;
     const size_t budget = smem_per_sm / ctas - 1024;
     const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
     int best = 0; double best_score = -1.0;

@@ -76,6 +76,8 @@ struct cn_flat_layout {
     uint32_t off_pa, off_pb, off_pa2, off_act, off_obs, off_sc, off_rec, off_pk, off_peers,
              off_clist, off_clw, off_rlist, off_olist, off_mark, off_wg, off_pg, off_cnt, off_bar;
     int gather_debug;           /* diagnostics (CN_GATHER_DEBUG): 1 no guard wait, 2 no arrival signal, 4 no row transfer */
+    uint32_t off_strips;        /* contact prefilter: per world 2 axes x 32 strips x (1 or 2) words of pedestrian bits */
+    uint32_t strip_words;       /* words per strip mask: 1 (N <= 32) or 2 */
     uint32_t off_stage;         /* CN_FLAG_GATHER_STAGE: [W, D] floats for the previous step's rows on their way to the peers; else 0 */
     uint32_t total;             /* dynamic shared memory per CTA */
 };

@@ -83,6 +83,12 @@ typedef struct cn_derived {
     float    wheel_step;     /* wheel_accel * dt_sub: largest wheel-speed change per sub-step (0 = unlimited) */
     int32_t  obs_dim;
     int32_t  pair_cell_shift; /* log2 (grid units) of the contact-prefilter cell: cell / 2 >= contact range */
+    int32_t  robot_contact;   /* 1 when collision_range < robot_radius: the LiDAR threshold no longer ends an episode before
+                                 the body touches something, so the robot's centre is kept robot_radius off the walls and
+                                 a sub-step that would move it INTO a pedestrian's disc is not taken */
+    int32_t  rob_xmin, rob_xmax, rob_ymin, rob_ymax; /* robot centre clamp, grid units */
+    float    rob_ped_r2;      /* (robot_radius + ped_radius)^2 */
+    int32_t  strip_shift;     /* log2 (grid units) of the contact-prefilter STRIP width (cn_flat.cu): >= the contact box */
     uint32_t seed_lo, seed_hi;
 } cn_derived;
 
@@ -106,6 +112,12 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
     d->ped_xmax = (int32_t)llrint(((double)c->room_xmax - c->ped_radius) * 16777216.0);
     d->ped_ymin = (int32_t)llrint(((double)c->room_ymin + c->ped_radius) * 16777216.0);
     d->ped_ymax = (int32_t)llrint(((double)c->room_ymax - c->ped_radius) * 16777216.0);
+    d->robot_contact = (c->collision_range < c->robot_radius) ? 1 : 0;
+    d->rob_xmin = (int32_t)llrint(((double)c->room_xmin + c->robot_radius) * 16777216.0);
+    d->rob_xmax = (int32_t)llrint(((double)c->room_xmax - c->robot_radius) * 16777216.0);
+    d->rob_ymin = (int32_t)llrint(((double)c->room_ymin + c->robot_radius) * 16777216.0);
+    d->rob_ymax = (int32_t)llrint(((double)c->room_ymax - c->robot_radius) * 16777216.0);
+    { float rr = c->robot_radius + c->ped_radius; d->rob_ped_r2 = rr * rr; }
     d->ped_r2 = c->ped_radius * c->ped_radius;
     d->cp_r2 = c->cp_radius * c->cp_radius;
     d->apothem = (float)((double)c->waypoint_radius * cos(two_pi / 128.0));
@@ -132,6 +144,7 @@ static inline int cn_derive(const cn_config* c, cn_derived* d) {
         int sh = 1;
         while (sh < 29 && ldexp(1.0, sh - 1 - 24) < lim) ++sh;
         d->pair_cell_shift = sh;
+        d->strip_shift = sh - 1;             /* 2^(sh-1) grid units >= lim + 1e-4 m > the kernel's contact box half-width */
     }
     d->seed_lo = (uint32_t)(c->seed & 0xFFFFFFFFu);
     d->seed_hi = (uint32_t)(c->seed >> 32);

@@ -488,7 +488,8 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
                     pose_scalars(P, p, part, P.goal_x, P.goal_y, pd, ph, 0.0f, 0.0f, 0, false, false, 0, scl, rowl);
                 } else {
                     int bad;
-                    const PoseIn p = advance_robot(P, rob, act_smem ? s_act + 2 * lane : P.action + 2 * (size_t)(e0 + lane), bad);
+                    const PoseIn p = advance_robot(P, rob, act_smem ? s_act + 2 * lane : P.action + 2 * (size_t)(e0 + lane), bad,
+                                                   s_pa + (size_t)lane * N * 4, N);
                     pose_scalars(P, p, part, f_of(rob[CN_R_WPX]), f_of(rob[CN_R_WPY]), f_of(rob[CN_R_PDIST]),
                                  f_of(rob[CN_R_PHEAD]), f_of(rob[CN_R_PPX]), f_of(rob[CN_R_PPY]), (int)rob[CN_R_STEP] + 1,
                                  true, true, bad, scl, rowl);

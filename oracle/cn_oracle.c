@@ -585,8 +585,28 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
             int32_t dth_bin = cn_f2i(dth * CN_RAD2BIN);
             uint32_t mid = th + (uint32_t)(dth_bin >> 1);
             float sm, cm; cn_sincos_bin(mid, &sm, &cm);
-            xi += cn_f2i((ds * cm) * CN_INV_GRID);
-            yi += cn_f2i((ds * sm) * CN_INV_GRID);
+            int32_t nx = xi + cn_f2i((ds * cm) * CN_INV_GRID);
+            int32_t ny = yi + cn_f2i((ds * sm) * CN_INV_GRID);
+            if (c->d.robot_contact) {
+                /* Body contact, only when the LiDAR threshold cannot end the episode first (collision_range <
+                 * robot_radius: README.md:60-62 `min_scan_range 0.0`).  Gazebo blocks the body; here the centre stays
+                 * robot_radius off the wall faces and a sub-step INTO a pedestrian's disc (old positions) is dropped. */
+                if (nx < c->d.rob_xmin) nx = c->d.rob_xmin;
+                if (nx > c->d.rob_xmax) nx = c->d.rob_xmax;
+                if (ny < c->d.rob_ymin) ny = c->d.rob_ymin;
+                if (ny > c->d.rob_ymax) ny = c->d.rob_ymax;
+                int blocked = 0;
+                for (int n = 0; n < N; ++n) {
+                    float dxn = (float)(nx - ox[n]) * CN_GRID, dyn = (float)(ny - oy[n]) * CN_GRID;
+                    float d2n = fmaf(dxn, dxn, dyn * dyn);
+                    if (d2n < c->d.rob_ped_r2) {
+                        float dxo = (float)(xi - ox[n]) * CN_GRID, dyo = (float)(yi - oy[n]) * CN_GRID;
+                        if (d2n < fmaf(dxo, dxo, dyo * dyo)) blocked = 1;
+                    }
+                }
+                if (blocked) { nx = xi; ny = yi; }
+            }
+            xi = nx; yi = ny;
             th += (uint32_t)dth_bin;
         }
         rob[CN_R_X] = (uint32_t)xi; rob[CN_R_Y] = (uint32_t)yi; rob[CN_R_TH] = th;

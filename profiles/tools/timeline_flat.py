@@ -41,6 +41,17 @@ for it in range(4):
     span = (t.max() - t0) / 1000.0
     print("iter %d: event %.1f us; kernel span by globaltimer %.1f us; warps stamped %d" % (it, s0.elapsed_time(s1) * 1e3, span, len(t)))
     if it < 3: continue
+    # who finishes phase 1 (+ 2) when: pose warp 0 (waypoint chain + reward), pose warp 1 (velocities, wall spans, padding),
+    # pedestrian warps; and how long each warp spends waiting at the CTA barriers that follow
+    wpc = tl.shape[0] and (len(t) // n_cta)
+    role = np.arange(len(t)) % wpc if len(t) == n_cta * wpc else None
+    if role is not None:
+        for nm, sel in (("pose warp 0", role == 0), ("pose warp 1", role == 1), ("pedestrian warps", role >= 2)):
+            for k, kn in ((1, "tma landed"), (9, "phase 1+2 done"), (10, "phase 3 done"), (12, "phase 6 done")):
+                m = sel & (t[:, k] > 0)
+                if m.any():
+                    d = (t[m, k] - t[m, 14]) / 1000.0
+                    print("   [%-16s] %-16s since CTA start: min %5.2f med %5.2f p90 %5.2f max %5.2f" % (nm, kn, d.min(), np.median(d), np.percentile(d, 90), d.max()))
     for k in order:
         m = t[:, k] > 0
         if not m.any(): continue

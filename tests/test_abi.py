@@ -91,8 +91,9 @@ def test_product_never_imports_the_oracle():
 
 
 def test_tile_plan_for_the_baseline_configs(L):
-    """Host-side launch planning of the default (flat) kernel: the tile must fit a quarter of a B200 SM's shared
-    memory, keep the row block 16-byte aligned for the bulk store, and give one wave when the batch allows it."""
+    """Host-side launch planning of the default (flat) kernel: the tile must fit a fifth of a B200 SM's shared
+    memory (5 resident CTAs per SM), keep the row block 16-byte aligned for the bulk store, and give one wave when the
+    batch allows it."""
     from crowdnav_b200.config import baseline_config
     n_sms, smem_sm = 148, 233472            # B200
     plans = {}
@@ -104,13 +105,19 @@ def test_tile_plan_for_the_baseline_configs(L):
         assert L.cn_plan_tile(C.byref(cfg), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == 0
         plans[name] = (tile.value, threads.value, smem.value)
         assert threads.value == 256 and 1 <= tile.value <= 16
-        assert smem.value <= smem_sm // 4 - 1024
+        assert smem.value <= smem_sm // 5 - 1024
         assert (tile.value * cfg.obs_dim) % 4 == 0 and tile.value % 2 == 0, "row block must be able to leave by bulk store"
         assert tile.value * cfg.n_peds <= 0x3FFF
-    # c2 fits one wave of 4 CTAs/SM with 8-world tiles; c3 fills two waves best with 14-world tiles
-    assert plans["c2"][0] == 8 and (4096 + 7) // 8 <= 4 * n_sms
-    assert plans["c3"][0] == 14
-    assert (8192 + plans["c4"][0] - 1) // plans["c4"][0] <= 4 * n_sms
+    # c2 fits one wave of 5 CTAs/SM with 6-world tiles; c3 fills two waves best with 12-world tiles
+    assert plans["c2"][0] == 6 and (4096 + 5) // 6 <= 5 * n_sms
+    assert plans["c3"][0] == 12
+    assert (8192 + plans["c4"][0] - 1) // plans["c4"][0] <= 2 * 5 * n_sms
+    # the staging tile of the pipelined gather (CN_FLAG_GATHER_STAGE) still fits
+    staged = baseline_config(1)
+    staged.flags |= 16
+    tile, threads, smem = C.c_int(), C.c_int(), C.c_size_t()
+    assert L.cn_plan_tile(C.byref(staged), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == 0
+    assert smem.value <= smem_sm // 5 - 1024 and (4096 + tile.value - 1) // tile.value <= 5 * n_sms
     bad = make_config()
     bad.n_peds = 1000
     assert L.cn_plan_tile(C.byref(bad), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == -1

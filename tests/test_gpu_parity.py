@@ -126,6 +126,26 @@ def test_drive_at_pedestrians_and_walls():
     assert n_done > 20
 
 
+@pytest.mark.parametrize("kernel", ["flat", "warp"])
+def test_eval_protocol_body_contact(kernel, monkeypatch):
+    """README test protocol (`min_scan_range 0.0`): the robot's body is stopped by walls and pedestrians instead of
+    the LiDAR threshold ending the episode (robot_contact_step); wheel ramp + 15 sub-steps so that a control period is
+    partly blocked.  Both kernels, bit for bit against the oracle."""
+    from crowdnav_b200.evaluate import scenario_config
+    monkeypatch.setenv("CN_KERNEL", kernel)
+    cfg = scenario_config("towards", 20, n_envs=200, max_steps=150, wheel_accel=1.0, n_substeps=15, layout_jitter=0.3,
+                          start=(0.9, 0.0, 3.14))
+
+    def act(rng, t):
+        a = np.zeros((200, 2), dtype=np.float32)
+        a[:, 0] = 0.22
+        a[:, 1] = rng.uniform(-0.4, 0.4, 200)
+        return a
+    _rollout(cfg, 220, seed=31, action_fn=act)
+    cfg = make_config(n_envs=64, collision_range=0.0, auto_reset=True, layout_jitter=0.05, max_steps=120)   # 3 m room: walls
+    _rollout(cfg, 150, seed=32, action_fn=lambda rng, t: np.stack([np.full(64, 0.22), rng.uniform(-0.2, 0.2, 64)], 1).astype(np.float32))
+
+
 def test_nonfinite_and_out_of_range_actions():
     cfg = baseline_config(0, n_envs=32, auto_reset=True)
 

@@ -157,3 +157,44 @@ def test_config_from_the_reference_rosparam_yaml(tmp_path):
     ref = "/root/reference/turtlebot3_rl_sim/src/configs/turtlebot3_world.yaml"
     if os.path.exists(ref):
         assert bytes(config_from_rosparams(ref)) == bytes(b)
+
+
+def test_robot_body_contact_under_the_eval_protocol():
+    """README test protocol (`min_scan_range 0.0`): the LiDAR threshold no longer ends an episode, so the robot's body
+    has to be stopped by walls and pedestrians (Gazebo does; advisor finding of round 1).  With the training threshold
+    (0.12 >= robot_radius) nothing changes: the pose is integrated freely, as in the reference-in-the-loop traces."""
+    from crowdnav_b200.config import behavior_table
+    R, r = 0.105, 0.0505
+    # (a) straight at the -x wall of the 3 m room for 300 steps: the centre stops robot_radius off the wall face
+    cfg = make_config(n_envs=4, n_peds=1, layout=[(0.9, 0.9)], behaviors=[behavior_table([(0.0, 0.0)], 0.0, 0.5)],
+                      collision_range=0.0, max_steps=1000, start=(0.0, -0.5, 3.14))
+    env = OracleEnv(cfg)
+    env.reset()
+    a = np.tile(np.array([[0.22, 0.0]], dtype=np.float32), (4, 1))
+    for _ in range(300):
+        o, rew, d = env.step(a)
+        assert not d.any()
+    NR = cfg.n_samples - 1
+    x = o[:, NR + 2]
+    assert np.all(x >= cfg.room_xmin + R - 2e-3) and np.all(x <= cfg.room_xmin + R + 2e-3), x
+    # (b) straight at a standing pedestrian: never closer than robot_radius + ped_radius to where it stood when the
+    # step began (the contact stand-in pushes the pedestrian away meanwhile, so the robot keeps creeping forward)
+    cfg = make_config(n_envs=1, n_peds=1, layout=[(0.0, -0.5)], behaviors=[behavior_table([(0.0, 0.0)], 0.0, 0.5)],
+                      collision_range=0.0, max_steps=1000, start=(0.6, -0.5, 3.14))
+    env = OracleEnv(cfg)
+    env.reset()
+    a = np.array([[0.22, 0.0]], dtype=np.float32)
+    for _ in range(80):
+        pa_before = env.blob[16 + 16: 16 + 16 + 2].view(np.int32).astype(np.float64) / 2 ** 24   # pedestrian 0, x, y
+        env.step(a)
+        rob = env.blob[16:18].view(np.int32).astype(np.float64) / 2 ** 24
+        assert np.hypot(*(rob - pa_before)) >= R + r - 1e-6
+    assert rob[0] < 0.45                                   # it did drive up to the pedestrian
+    # (c) the training threshold: same action sequence, free integration (the robot ends up past the wall face)
+    cfg = make_config(n_envs=1, n_peds=1, layout=[(0.9, 0.9)], behaviors=[behavior_table([(0.0, 0.0)], 0.0, 0.5)],
+                      collision_range=0.12, max_steps=1000, start=(0.0, -0.5, 3.14))
+    env = OracleEnv(cfg)
+    env.reset()
+    for _ in range(300):
+        o, rew, d = env.step(a)
+    assert o[0, NR + 2] < cfg.room_xmin
