@@ -378,7 +378,18 @@ class Bench:
         self.env.step_n(acts, rew, done)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        stepn_ms = e0.elapsed_time(e1)
+        # the same K steps as a CUDA graph owned by the LIBRARY (cn_graph_create / cn_graph_launch: no torch capture)
+        g = self.env.make_graph(acts)
+        g.launch()
+        torch.cuda.synchronize()
+        e0.record()
+        g.launch()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1)
+        g.close()
+        return stepn_ms, graph_ms
 
     def max_over_ranks(self, vals):
         torch = self.torch
@@ -457,7 +468,7 @@ def measure(args, wl, per_gpu, gather_mode, K, warmup, full=True):
         ev_tot, ev_kern = B.events_timed(K, warmup, do_flush=True)
         out["ev_tot"], out["ev_kern"] = B.max_over_ranks([ev_tot, ev_kern])
         if world == 1:
-            out["stepn_ms"] = B.step_n_timed(K, warmup)
+            out["stepn_ms"], out["libgraph_ms"] = B.step_n_timed(K, warmup)
     return out
 
 
@@ -650,6 +661,11 @@ def main():
         if "stepn_ms" in M:
             sn = M["stepn_ms"] / K
             line["value_l2_warm"] = E_total / (sn * 1e-3)
+            lg = M["libgraph_ms"] / K
+            line["value_l2_warm_lib_graph"] = E_total / (lg * 1e-3)
+            line["roofline"]["l2_warm_lib_graph"] = {"kernel_us": lg * 1e3, "frac": E_local * B.bytes_per_env / (lg * 1e-3) / 1e9 / peak,
+                                                     "how": "the same K launches as ONE graph built by cn_graph_create and replayed by "
+                                                            "cn_graph_launch (C ABI, no torch capture), one batch, no flush"}
             line["roofline"]["l2_warm"] = {"kernel_us": sn * 1e3, "achieved": E_local * B.bytes_per_env / (sn * 1e-3) / 1e9,
                                            "frac": E_local * B.bytes_per_env / (sn * 1e-3) / 1e9 / peak,
                                            "how": "K launches enqueued by one cn_step_n call (C loop, no graph), one batch, no flush"}

@@ -444,7 +444,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     uint8_t* s_hid = reinterpret_cast<uint8_t*>(s_obs + (((size_t)CN_TILE * D + 3) & ~(size_t)3));  // [TILE][hid_stride]
     uint32_t* s_sc = reinterpret_cast<uint32_t*>(s_hid + (size_t)CN_TILE * hid_stride);              // [TILE][S_WORDS]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sc + CN_TILE * S_WORDS);
-    uint64_t* s_barA = s_bar + 1;       // phase A done: one arrival per phase-A warp
+    uint64_t* s_barA = s_bar + 1;       // phase A done: one arrival per THREAD of the phase-A warps (every writer releases its own stores)
     float* s_act = reinterpret_cast<float*>(s_bar + 2);                                              // [TILE][2]
 
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
@@ -452,7 +452,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
     const bool act_smem = (MODE == 0) && P.act_bulk_ok && (nE % 2) == 0;
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
-        mbar_init(s_barA, CN_POSE_WARPS);
+        mbar_init(s_barA, 32 * CN_POSE_WARPS);
         fence_mbar_init();
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
         mbar_expect_tx(s_bar, rob_bytes + 2u * ped_bytes + act_bytes);
@@ -497,7 +497,7 @@ cn_env_kernel(const __grid_constant__ cn_kparams P) {
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_barA);
+        mbar_arrive(s_barA);
     }
     STAMP(2);
 

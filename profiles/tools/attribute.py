@@ -2,6 +2,9 @@
 """Attribute executed warp-instructions of an ncu capture to CUDA source lines.
 
 usage: attribute.py <report.ncu-rep> <lib.so> <kernel-substring> [top_n]
+The substring must select ONE instantiation when the kernel is a template (e.g. cn_flat_kernelILi0ELi256E: the line
+tables of the instantiations are keyed by code offset and would overwrite each other), and <lib.so> must be the binary
+the capture was taken from.
 Joins `ncu --page source --print-source=sass --csv` (per-SASS-address executed
 counts, first captured launch) with `nvdisasm -g` line info of the same cubin.
 """
