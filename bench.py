@@ -234,7 +234,7 @@ class Bench:
         except Exception as exc:                       # symmetric memory / multicast unavailable: say so, fall back
             if not self.gather_mode.startswith("fused"):
                 raise
-            nxt = "fused" if self.gather_mode in ("fused_mc", "fused_async") else "collective"
+            nxt = "fused" if self.gather_mode in ("fused_mc", "fused_async", "fused_async16") else "collective"
             self.fallback = "%s unavailable (%s); using %s" % (self.gather_mode, str(exc).splitlines()[0][:160], nxt)
             if self.rank == 0:
                 print(self.fallback, file=sys.stderr)
@@ -426,23 +426,26 @@ class Bench:
             senv.wait_gathered()
             fobs, _, _ = other.step(act[flo:fhi].contiguous())
             torch.cuda.synchronize()
-            ok = ok and bool(torch.equal(senv.obs_all[flo:fhi], fobs)) and bool(torch.equal(senv.obs_all[senv.lo:senv.hi], mine.obs))
+            ok = ok and bool(torch.equal(senv.obs_all[flo:fhi].view(torch.int32), fobs.view(torch.int32))) \
+                and bool(torch.equal(senv.obs_all[senv.lo:senv.hi], mine.obs))
             self.barrier()                                      # nobody runs ahead while a peer still compares
-        if senv.gather_mode == "fused_async":
-            # ... and the pipelined path proper: rows forwarded by the NEXT step's kernel, no flush in between
-            prev_f = None
-            for s in range(steps):
+        if senv.async_mode:
+            # ... and the pipelined path proper: rows forwarded by the NEXT step's kernel (and, in the 16-bit format, rebuilt
+            # by the one after), no flush in between
+            hist = []
+            for s in range(steps + senv.lag):
                 u = torch.rand((self.E_total, 2), device=self.dev, generator=gen)
                 act = torch.stack([u[:, 0] * 0.22, u[:, 1] * 4.0 - 2.0], 1).contiguous()
                 senv.step_local(act[senv.lo:senv.hi].contiguous(), env=mine)
-                got_prev = senv.wait_pushed()
+                got = senv.wait_pushed()
                 fobs, _, _ = other.step(act[flo:fhi].contiguous())
                 torch.cuda.synchronize()
-                if prev_f is not None:
-                    ok = ok and bool(torch.equal(got_prev[flo:fhi], prev_f))
-                prev_f = fobs.clone()
+                hist.append(fobs.clone())
+                k = len(hist) - 1 - senv.lag
+                if k >= 0:
+                    ok = ok and got is not None and bool(torch.equal(got[flo:fhi].view(torch.int32), hist[k].view(torch.int32)))
                 self.barrier()
-            ok = ok and bool(torch.equal(senv.wait_gathered()[flo:fhi], prev_f))
+            ok = ok and bool(torch.equal(senv.wait_gathered()[flo:fhi].view(torch.int32), hist[-1].view(torch.int32)))
             self.barrier()
         timeouts = (mine.gather_timeouts + senv.env.gather_timeouts) if senv.fused else 0
         flag = torch.tensor([1 if (ok and timeouts == 0) else 0], dtype=torch.int64, device=self.dev)
@@ -450,7 +453,8 @@ class Bench:
         mine.close()
         other.close()
         return bool(flag.item()), {"steps": steps, "rows_compared_per_rank": 2 * self.E_local * steps,
-                                   "foreign_shard": "rank + 1", "gather_timeouts": int(timeouts)}
+                                   "foreign_shard": "rank + 1", "compared": "bit patterns",
+                                   "gather_timeouts": int(timeouts)}
 
 
 def measure(args, wl, per_gpu, gather_mode, K, warmup, full=True):
@@ -460,7 +464,9 @@ def measure(args, wl, per_gpu, gather_mode, K, warmup, full=True):
     out = {"bench": B}
     graph_ms, ginfo = B.graph_timed(K, warmup, gather=True)
     out["graph_ms"], out["ginfo"] = B.max_over_ranks([graph_ms])[0], ginfo
-    out["launches_per_rank"] = K + {"fused": 1, "fused_mc": 1, "fused_async": 2}.get(B.gather_mode if world > 1 else "", 0)
+    # step kernels + (fused: the final wait) / (async: flush + wait) / (async16: flush + wait + decode of the last two steps)
+    out["launches_per_rank"] = K + {"fused": 1, "fused_mc": 1, "fused_async": 2, "fused_async16": 4}.get(
+        B.gather_mode if world > 1 else "", 0)
     if world > 1:
         none_ms, _ = B.graph_timed(K, warmup, gather=False)
         out["none_ms"] = B.max_over_ranks([none_ms])[0]
@@ -482,8 +488,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused_async", choices=["fused_async", "fused", "fused_mc", "nccl"],
-                    help="N>1: 'fused_async' = pipelined fused gather: the kernel of step t+1 forwards the rows of step t to "
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused_async16", "fused_async", "fused", "fused_mc", "nccl"],
+                    help="N>1: 'auto' = 'fused_async' at 2 GPUs (6.5 MB of rows per rank fit under the step's compute as they are), "
+                         "'fused_async16' from 3 GPUs on (the step is NVLink-bound: halve the bytes); 'fused_async16' = 'fused_async' with the rows travelling as int16 thousandths (half the NVLink "
+                         "bytes, rebuilt bit for bit by a decode kernel behind the arrival wait); 'fused_async' = pipelined fused gather: the kernel of step t+1 forwards the rows of step t to "
                          "every peer (bulk TMA through a staging tile) under its own compute and signals the peers' arrival "
                          "counters; one push-only launch flushes the last step; 'fused' = the step kernel stores its OWN rows "
                          "into every peer at its end and signals -- no other launch per step; 'fused_mc' = the same with "
@@ -520,7 +528,7 @@ def main():
     per_gpu = args.envs_per_gpu or PER_GPU_ENVS[wl]
     gather_mode = "none"
     if world > 1:
-        gather_mode = {"nccl": "collective"}.get(args.gather, args.gather)
+        gather_mode = {"nccl": "collective", "auto": "fused_async" if world <= 2 else "fused_async16"}.get(args.gather, args.gather)
         if args.risk_faithful:
             gather_mode = "collective"
 
@@ -592,7 +600,14 @@ def main():
                                  "with_td3_update": rollout_throughput(env, B.actor, n_r, learn=True),
                                  "what": "torch policy forward + exploration noise -> cn_step -> device replay append "
                                          "(-> one TD3 update on a 256-row mini-batch per env step, TD3DRV:128-133); "
-                                         "eager PyTorch around the library call, no host synchronisation in the loop"}
+                                         "PyTorch around the library call, no host synchronisation in the loop; the "
+                                         "*_graph entries replay the same loop as one CUDA graph (GraphedCollector)"}
+            for key, learn in (("policy_only_graph", False), ("with_td3_update_graph", True)):
+                try:
+                    extras["rollout"][key] = rollout_throughput(env, B.actor, n_r, learn=learn, graph=True)
+                except Exception as exc:                       # a capture problem must not cost the bench line
+                    extras["rollout"][key] = {"error": str(exc).splitlines()[0][:200]}
+                    torch.cuda.synchronize()
 
     # keep the GPU busy long enough for the clock sampler to see it under load; every rank must run the SAME
     # number of extra steps (each step holds a cross-rank signal / collective), so rank 0 decides
@@ -631,6 +646,14 @@ def main():
                            "symmetric-memory buffer, peer order rotated per rank and per CTA) under its own compute and signals "
                            "the peers' arrival counters; the timed graph ends with one push-only launch for the last step and "
                            "the arrival wait, so all K steps' rows have landed on every rank inside the timed region" % world,
+            "fused_async16": "env-id sharding x%d; obs all-gather fused into the step kernels, PIPELINED, 16-bit wire format: the step "
+                             "kernel also writes its rows as int16 thousandths (every row value is a whole number of thousandths), "
+                             "the kernel of step t+1 forwards step t's int16 rows (bulk TMA through a staging tile into every peer's "
+                             "symmetric-memory wire buffer, peer order rotated per rank and per CTA) under its own compute and "
+                             "signals the peers' arrival counters, and the kernel of step t+2 rebuilds the peers' fp32 rows of "
+                             "step t bit for bit while its state tile loads -- one launch per step; the timed graph ends with the "
+                             "push-only launch, the arrival wait and the decode of the last two steps, so every rank holds all K "
+                             "steps' fp32 rows inside the timed region" % world,
             "collective": "env-id sharding x%d; one in-place ncclAllGather per step" % world}[B.gather_mode]
         line = {
             "metric": "env-steps/s", "value": E_total / (ms_per_step * 1e-3), "unit": "env-steps/s",

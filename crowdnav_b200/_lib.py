@@ -80,8 +80,9 @@ def load() -> C.CDLL:
     L.cn_step_gather.argtypes = [vp, vp, vp, C.POINTER(vp), i32, vp, vp, vp]
     u64 = C.c_uint64
     L.cn_step_gather_signal.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, vp, vp, vp, i32, i32, i32, vp, vp, vp]
-    L.cn_step_gather_async.argtypes = [vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, vp, i32, i32, i32, vp, vp, vp]
-    L.cn_gather_flush.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), i32, vp, i32, i32, i32, vp]
+    L.cn_step_gather_async.argtypes = [vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.cn_gather_flush.argtypes = [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), i32, vp, i32, i32, i32, vp]
+    L.cn_gather_decode16.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_longlong, vp]
     L.cn_gather_wait.argtypes = [vp, vp, i32, i32, vp]
     L.cn_gather_timeouts.argtypes = [vp, C.POINTER(C.c_uint32), vp]
     L.cn_kernel_ctas.argtypes = [vp]
@@ -107,7 +108,7 @@ def check(rc: int, what: str) -> None:
 
 
 ABI_SYMBOLS = [
-    "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_n", "cn_graph_create", "cn_graph_launch", "cn_graph_destroy", "cn_step_gather", "cn_step_gather_signal", "cn_step_gather_async", "cn_gather_flush", "cn_gather_wait", "cn_gather_timeouts", "cn_kernel_ctas",
+    "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_n", "cn_graph_create", "cn_graph_launch", "cn_graph_destroy", "cn_step_gather", "cn_step_gather_signal", "cn_step_gather_async", "cn_gather_flush", "cn_gather_decode16", "cn_gather_wait", "cn_gather_timeouts", "cn_kernel_ctas",
     "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile", "cn_plan_tile",
     "cn_last_error", "cn_abi_version",
 ]

@@ -24,6 +24,7 @@ CN_MAX_BEHAVIORS = 8
 CN_FLAG_AUTO_RESET = 1
 CN_FLAG_TOPK_HIGHEST = 2
 CN_FLAG_ENV_ORIGINAL = 4     # environment_stage_1_original.py: 363-wide row, goal-relative, its own reward
+CN_FLAG_GATHER_WIRE16 = 32   # ... with the 16-bit wire format (tile sized for bulk copies of int16 rows)
 CN_FLAG_GATHER_STAGE = 16    # staging tile for the pipelined fused all-gather (cn_step_gather_async)
 CN_FLAG_RISK_FAITHFUL = 8    # K block + safety counters from the reference's own segmentation / tracker (ENV:270-1005), float64
 CN_BEHAVIOR_RANDOM = 0

@@ -89,6 +89,11 @@ static int fail(int code, const char* fmt, const char* detail) {
     } while (0)
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+/* staging tile of the pipelined gather: 0 none, 1 fp32 rows, 2 int16 rows (tile sized for 16-byte units of int16) */
+static int stage_mode(const cn_config* cfg) {
+    if (!(cfg->flags & CN_FLAG_GATHER_STAGE)) return 0;
+    return (cfg->flags & CN_FLAG_GATHER_WIRE16) ? 2 : 1;
+}
 
 extern "C" {
 
@@ -163,12 +168,11 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             int tw = atoi(tile), tt = 256;
             const char* comma = strchr(tile, ',');
             if (comma) tt = atoi(comma + 1);
-            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &flat);
+            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, stage_mode(cfg), &flat);
         } else {
             int n_sms = 0;
             CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
-            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm,
-                                   (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &flat);
+            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, stage_mode(cfg), &flat);
         }
         { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
         /* programmatic dependent launch is opt-in (CN_PDL=1): measured on B200 it helps back-to-back stream launches
@@ -358,41 +362,50 @@ int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev,
 }
 
 /* common argument checks + parameter block of the two pipelined-gather entry points */
-static int pack_push(cn_handle* h, const char* who, cn_kparams* P, const float* push_src_dev, float* const* push_peer_dev,
+static int pack_push(cn_handle* h, const char* who, cn_kparams* P, int wire16, const void* push_src_dev, void* const* push_peer_dev,
                      unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
                      int n_ranks, int rank, int wait_back) {
     if (!h->use_flat) return fail(CN_ERR_UNSUPPORTED, "%s: default (flat) kernel only", who);
     if (h->trk) return fail(CN_ERR_UNSUPPORTED, "%s: not with CN_FLAG_RISK_FAITHFUL (gather with ncclAllGather instead)", who);
-    if (!push_src_dev || !push_peer_dev || !peer_arrive_dev || !arrive_local_dev || n_peers < 1 || n_peers > 8 || wait_back < 0)
-        return fail(CN_ERR_INVALID, "%s: null argument / 1..8 peers", who);
-    if (n_ranks < 2 || n_ranks > 32 || rank < 0 || rank >= n_ranks) return fail(CN_ERR_INVALID, "%s: 2..32 ranks, 0 <= rank < n_ranks", who);
+    if (n_peers < 0 || n_peers > 8 || wait_back < 0) return fail(CN_ERR_INVALID, "%s: 0..8 peers", who);
     *P = h->base;
+    if (n_peers == 0) return CN_OK;                                     /* nothing to forward (first step after a reset) */
+    if (!push_src_dev || !push_peer_dev || !peer_arrive_dev || !arrive_local_dev) return fail(CN_ERR_INVALID, "%s: null argument", who);
+    if (n_ranks < 2 || n_ranks > 32 || rank < 0 || rank >= n_ranks) return fail(CN_ERR_INVALID, "%s: 2..32 ranks, 0 <= rank < n_ranks", who);
     bool aligned = (((uintptr_t)push_src_dev) & 15u) == 0;
     for (int p = 0; p < n_peers; ++p) {
         if (!push_peer_dev[p] || !peer_arrive_dev[p]) return fail(CN_ERR_INVALID, "%s: null peer pointer", who);
         P->push_peers[p] = push_peer_dev[p]; P->arrive_peers[p] = peer_arrive_dev[p];
         aligned = aligned && (((uintptr_t)push_peer_dev[p]) & 15u) == 0;
     }
-    P->push_src = push_src_dev; P->n_push_peers = n_peers; P->push_bulk_ok = aligned ? 1 : 0;
+    P->push_src = push_src_dev; P->n_push_peers = n_peers; P->push_bulk_ok = aligned ? 1 : 0; P->push_wire16 = wire16 ? 1 : 0;
     P->arrive_local = arrive_local_dev; P->arrive_back = wait_back; P->arrive_slots = n_ranks; P->arrive_self = rank;
     P->ctas_per_step = (unsigned int)cn_kernel_ctas(h);
     return CN_OK;
 }
 
-int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, const float* push_src_dev,
-                         float* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
+int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, int16_t* wire_out_dev, const void* push_src_dev,
+                         void* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
                          unsigned long long* arrive_local_dev, int n_ranks, int rank, int wait_back,
+                         const int16_t* dec_wire_dev, float* dec_obs_dev,
                          float* reward_dev, uint8_t* done_dev, void* stream) {
     if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev)
         return fail(CN_ERR_INVALID, "cn_step_gather_async: null argument%s", NULL);
     if (!(h->cfg.flags & CN_FLAG_GATHER_STAGE))
         return fail(CN_ERR_INVALID, "cn_step_gather_async: create the handle with CN_FLAG_GATHER_STAGE%s", NULL);
+    if (wire_out_dev && (((uintptr_t)wire_out_dev) & 3u)) return fail(CN_ERR_INVALID, "cn_step_gather_async: wire_out_dev must be 4-byte aligned%s", NULL);
     cn_kparams P;
-    int rc = pack_push(h, "cn_step_gather_async", &P, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers, arrive_local_dev,
-                       n_ranks, rank, wait_back);
+    int rc = pack_push(h, "cn_step_gather_async", &P, wire_out_dev != NULL, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers,
+                       arrive_local_dev, n_ranks, rank, wait_back);
     if (rc != CN_OK) return rc;
     cn_device_guard guard(h->device);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
+    P.wire_out = wire_out_dev;
+    if ((dec_wire_dev != NULL) != (dec_obs_dev != NULL)) return fail(CN_ERR_INVALID, "cn_step_gather_async: dec_wire_dev and dec_obs_dev go together%s", NULL);
+    if (dec_wire_dev && (n_peers < 1 || wait_back != 1))
+        return fail(CN_ERR_INVALID, "cn_step_gather_async: decoding inside the kernel needs a pushing launch with wait_back = 1 "
+                                    "(the guard is what certifies the delivery)%s", NULL);
+    P.dec_wire = dec_wire_dev; P.dec_obs = dec_obs_dev;
     P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
     CN_CUDA(launch_env(h, P, 0, (cudaStream_t)stream));
@@ -400,16 +413,27 @@ int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, 
     return CN_OK;
 }
 
-int cn_gather_flush(cn_handle* h, const float* push_src_dev, float* const* push_peer_dev,
+int cn_gather_flush(cn_handle* h, int wire16, const void* push_src_dev, void* const* push_peer_dev,
                     unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
                     int n_ranks, int rank, int wait_back, void* stream) {
     if (!h) return fail(CN_ERR_INVALID, "cn_gather_flush: null handle%s", NULL);
+    if (n_peers < 1) return fail(CN_ERR_INVALID, "cn_gather_flush: 1..8 peers%s", NULL);
     cn_kparams P;
-    int rc = pack_push(h, "cn_gather_flush", &P, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers, arrive_local_dev,
+    int rc = pack_push(h, "cn_gather_flush", &P, wire16, push_src_dev, push_peer_dev, peer_arrive_dev, n_peers, arrive_local_dev,
                        n_ranks, rank, wait_back);
     if (rc != CN_OK) return rc;
     cn_device_guard guard(h->device);
     CN_CUDA(cn_launch_push_kernel(P, h->flat, (cudaStream_t)stream));
+    h->launches += 1;
+    return CN_OK;
+}
+
+int cn_gather_decode16(cn_handle* h, const int16_t* wire_dev, float* obs_all_dev, long long row_lo, long long row_hi,
+                       long long rows_total, void* stream) {
+    if (!h || !wire_dev || !obs_all_dev) return fail(CN_ERR_INVALID, "cn_gather_decode16: null argument%s", NULL);
+    if (row_lo < 0 || row_hi < row_lo || rows_total < row_hi) return fail(CN_ERR_INVALID, "cn_gather_decode16: 0 <= row_lo <= row_hi <= rows_total%s", NULL);
+    cn_device_guard guard(h->device);
+    CN_CUDA(cn_launch_wire_decode(wire_dev, obs_all_dev, row_lo, row_hi, rows_total, h->d.obs_dim, (cudaStream_t)stream));
     h->launches += 1;
     return CN_OK;
 }
@@ -426,8 +450,10 @@ int cn_gather_wait(cn_handle* h, const unsigned long long* arrive_local_dev, int
 int cn_gather_timeouts(cn_handle* h, unsigned int* out_host, void* stream) {
     if (!h || !out_host) return fail(CN_ERR_INVALID, "cn_gather_timeouts: null argument%s", NULL);
     cn_device_guard guard(h->device);
-    CN_CUDA(cudaMemcpyAsync(out_host, h->gather_timeouts, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    unsigned int w[3] = {0u, 0u, 0u};                 /* [0] waits given up, [1] CTA counter of the running launch, [2] wire saturations */
+    CN_CUDA(cudaMemcpyAsync(w, h->gather_timeouts, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *out_host = w[0] + w[2];
     return CN_OK;
 }
 
@@ -571,8 +597,7 @@ int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile,
     cn_derived d;
     if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_plan_tile: config out of range%s", NULL);
     cn_flat_layout L; memset(&L, 0, sizeof(L));
-    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm,
-                          (cfg->flags & CN_FLAG_GATHER_STAGE) ? 1 : 0, &L) != 0)
+    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, stage_mode(cfg), &L) != 0)
         return fail(CN_ERR_UNSUPPORTED, "cn_plan_tile: no tile fits%s", NULL);
     *tile = L.W; *threads = L.threads; *smem_bytes = L.total;
     return CN_OK;

@@ -373,6 +373,20 @@ __device__ __forceinline__ void signal_peers(const cn_kparams& P, int n_peers, i
     red_relaxed_sys_add(P.arrive_local + P.arrive_self, (unsigned long long)ctas);
 }
 
+// 16-bit wire format of an observation value: thousandths as int16 (every row entry is a whole number of thousandths
+// or hundredths by construction: cn_np_round3 / cn_py_round3 / cn_py_round2), -0.0 as -32768.  |k| <= 32767 survives
+// fl(fl(k / 1000) * 1000) with an error far below 1/2, and cn_div1000 rebuilds the correctly rounded quotient, i.e. the
+// original bits.
+__device__ __forceinline__ uint32_t wire16_encode(float v, bool& saturated) {
+    if (u_of(v) == 0x80000000u) return 0x8000u;
+    float k = rintf(v * 1000.0f);
+    if (!(fabsf(k) <= 32767.0f)) { saturated = true; k = (k < 0.0f) ? -32767.0f : 32767.0f; }
+    return (uint32_t)(int32_t)k & 0xFFFFu;
+}
+__device__ __forceinline__ float wire16_decode(int32_t k) {
+    return (k == -32768) ? f_of(0x80000000u) : cn_div1000((float)k);
+}
+
 // n 16-byte elements from shared memory to a multicast address: ONE store instruction per element, the switch
 // replicates it into every rank's buffer
 __device__ __forceinline__ void copy16_out_mc(void* mcdst, const void* ssrc, int n, int t, int nthreads) {
@@ -531,12 +545,15 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // pipelined fused gather: the rows of the PREVIOUS step (in this rank's gather buffer) go to the peers under this
     // step's compute -- bulk load into the staging tile now, bulk stores to every peer as soon as it has landed
     const bool push = (MODE == 0) && P.n_push_peers > 0;
-    const bool push_bulk = push && L.off_stage != 0u && P.push_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
+    const uint32_t push_elem = P.push_wire16 ? 2u : 4u;                 // int16 thousandths or fp32
+    const uint32_t push_bytes = (uint32_t)nE * (uint32_t)D * push_elem;
+    const size_t push_off = (size_t)e0 * D * push_elem;                 // byte offset of the tile in a row block
+    const bool push_bulk = push && L.off_stage != 0u && P.push_bulk_ok && (((size_t)W * D * push_elem) % 16 == 0) && (push_bytes % 16u == 0u);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         if (push_bulk) {
-            mbar_expect_tx(S.bar + 1, (uint32_t)((size_t)nE * D * 4));
-            tma_load(S.stage, P.push_src + (size_t)e0 * D, (uint32_t)((size_t)nE * D * 4), S.bar + 1);
+            mbar_expect_tx(S.bar + 1, push_bytes);
+            tma_load(S.stage, reinterpret_cast<const uint8_t*>(P.push_src) + push_off, push_bytes, S.bar + 1);
         }
         const uint32_t act_bytes = act_smem ? (uint32_t)nE * 8u : 0u;
         mbar_expect_tx(S.bar, rob_bytes + 2u * ped_bytes + act_bytes);
@@ -583,20 +600,52 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
     }
+    // fused gather, pipelined: before anything of the peers is touched -- their buffers by our pushes, their deliveries
+    // by our decode -- lane s of warp 0 checks source rank s's progress (normally one L2 hit, under the fills)
+    if (push && warp == 0 && !(L.gather_debug & 1)) guard_peer_buffers(P, lane);
     FSTAMP(3);
-    __syncthreads();            // fills done, barrier init visible
+    __syncthreads();            // fills done, barrier init visible, guard passed
     FSTAMP(11);
+    if (MODE == 0 && P.dec_wire != nullptr && push) {
+        // 16-bit wire format, receiving side: the peers' previous kernels delivered a step's rows as int16 thousandths
+        // into our wire buffer; this CTA rebuilds its tile's rows of every other rank's block in the fp32 gather buffer
+        // (8 values per 16-byte load) while its own state tile is still on its way
+        const int n = nE * D, n8 = n >> 3;
+#pragma unroll 1
+        for (int r = 0; r < P.arrive_slots; ++r) {
+            if (r == P.arrive_self) continue;
+            const size_t base = ((size_t)r * (size_t)P.n_envs + (size_t)e0) * (size_t)D;
+            if ((base & 7u) != 0u || (n & 7) != 0 || ((((uintptr_t)P.dec_wire) | ((uintptr_t)P.dec_obs)) & 15u) != 0u) {
+#pragma unroll 1
+                for (int i = tid; i < n; i += T) P.dec_obs[base + i] = wire16_decode((int32_t)P.dec_wire[base + i]);   // ragged tile
+                continue;
+            }
+            const uint4* src = reinterpret_cast<const uint4*>(P.dec_wire + base);
+            float4* dst = reinterpret_cast<float4*>(P.dec_obs + base);
+#pragma unroll 2
+            for (int c = tid; c < n8; c += T) {
+                const uint4 wv = src[c];
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[2 * k] = wire16_decode((int32_t)(int16_t)(ww[k] & 0xFFFFu));
+                    o[2 * k + 1] = wire16_decode((int32_t)(int16_t)(ww[k] >> 16));
+                }
+                dst[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
     if (push_bulk && warp == 0) {
-        if (!(L.gather_debug & 1)) guard_peer_buffers(P, lane);     // lane s polls source rank s (normally one L2 hit)
-        __syncwarp();
         if (tid == 0 && !(L.gather_debug & 4)) {
             mbar_wait(S.bar + 1, 0);
             int p = (P.n_push_peers > 1) ? (int)(blockIdx.x % (unsigned)P.n_push_peers) : 0;   // CTAs start at different peers
 #pragma unroll 1
             for (int k = 0; k < P.n_push_peers; ++k) {
-                tma_store(P.push_peers[p] + (size_t)e0 * D, S.stage, (uint32_t)((size_t)nE * D * 4));
+                tma_store(reinterpret_cast<uint8_t*>(P.push_peers[p]) + push_off, S.stage, push_bytes);
                 p = (p + 1 == P.n_push_peers) ? 0 : p + 1;
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1096,11 +1145,30 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // ---------------------------------------------------------------- phase 7: write-back
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
     const bool gather = (MODE == 0) && (P.n_obs_peers > 0 || P.obs_mc != nullptr);
-    if ((gather || (push && !push_bulk)) && tid < 32 && !(L.gather_debug & 1)) guard_peer_buffers(P, tid);
+    if (gather && tid < 32 && !(L.gather_debug & 1)) guard_peer_buffers(P, tid);       // (a pushing launch checked at its start)
     FSTAMP(12);
     __syncthreads();             // #G
     FSTAMP(7);
     const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
+    if (MODE == 0 && P.wire_out != nullptr) {
+        // 16-bit wire copy of the tile's finished rows into this rank's own wire buffer (the next step's kernel forwards
+        // it to the peers): two values per 4-byte store, fire and forget
+        const int n = nE * D;
+        int16_t* wout = P.wire_out + (size_t)e0 * D;
+        bool sat = false;
+        if (((n | (e0 * D)) & 1) == 0) {
+            uint32_t* w32 = reinterpret_cast<uint32_t*>(wout);
+#pragma unroll 2
+            for (int i = tid; i < (n >> 1); i += T) {
+                const float2 v = *reinterpret_cast<const float2*>(S.obs + 2 * i);
+                w32[i] = wire16_encode(v.x, sat) | (wire16_encode(v.y, sat) << 16);
+            }
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < n; i += T) wout[i] = (int16_t)wire16_encode(S.obs[i], sat);
+        }
+        if (sat && P.gather_timeouts) atomicAdd(P.gather_timeouts + 2, 1u);
+    }
     if (L.plain_store) {
         // cooperative 16-byte stores: nothing to wait for, the CTA's slot is free as soon as they are issued
         if (bulk_obs && gather && !(L.gather_debug & 4)) push_rows_to_peers(P, S.obs, (size_t)e0 * D, (nE * D) >> 2, tid, T);   // NVLink first
@@ -1166,10 +1234,10 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             // ragged or unaligned tile: forward the old rows with plain loads / stores from all threads
 #pragma unroll 1
             for (int p = 0; p < P.n_push_peers; ++p) {
-                const float* src = P.push_src + (size_t)e0 * D;
-                float* dst = P.push_peers[p] + (size_t)e0 * D;
+                const uint16_t* src = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(P.push_src) + push_off);
+                uint16_t* dst = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(P.push_peers[p]) + push_off);
 #pragma unroll 1
-                for (int k = tid; k < nE * D; k += T) dst[k] = src[k];
+                for (int k = tid; k < (int)(push_bytes >> 1); k += T) dst[k] = src[k];
             }
         }
         __syncthreads();
@@ -1219,7 +1287,7 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
     o += 16;
     L->off_stage = 0;
-    if (stage) { o = up16(o); L->off_stage = (uint32_t)o; o = up16(o + (size_t)W * D * 4); }
+    if (stage) { o = up16(o); L->off_stage = (uint32_t)o; o = up16(o + (size_t)W * D * (stage == 2 ? 2 : 4)); }   /* int16 or fp32 rows */
     L->total = (uint32_t)o;
     return 0;
 }
@@ -1235,12 +1303,13 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
     for (int W = 16; W >= 1; --W) {
         cn_flat_layout t;
         if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, &t) != 0 || t.total > budget) continue;
-        const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0;
+        const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0 && (stage < 2 || ((size_t)W * obs_dim) % 8 == 0);
         const long n_cta = ((long)n_envs + W - 1) / W;
         const long waves = (n_cta + slots - 1) / slots;
         double score;
         if (waves == 1) score = 100.0 - W;                      /* one wave: the smaller the tile the better ... */
-        else score = (double)n_cta / (double)(waves * slots) + 0.002 * W;   /* ... else wave fill, then amortisation */
+        else score = (double)n_cta / (double)(waves * slots) * ((double)W / (double)(W + 4));   /* ... else wave fill x the
+                                                                   share of a CTA's life that is not per-CTA fixed cost */
         if (W < 4) score -= 50.0;                               /* tiny tiles waste the lane = world warps */
         if (!bulk) score -= 10.0;
         if (score > best_score) { best_score = score; best = W; }
@@ -1300,25 +1369,66 @@ __global__ void __launch_bounds__(256) cn_push_kernel(const __grid_constant__ cn
     const int e0 = (int)blockIdx.x * W, nE = min(W, P.n_envs - e0);
     if (tid < 32) guard_peer_buffers(P, tid);
     __syncthreads();
-    const size_t row0 = (size_t)e0 * D;
-    const bool vec = P.push_bulk_ok && (row0 % 4 == 0) && (((size_t)nE * D) % 4 == 0);
+    const size_t elem = P.push_wire16 ? 2u : 4u;
+    const size_t off = (size_t)e0 * D * elem, bytes = (size_t)nE * D * elem;
+    const bool vec = P.push_bulk_ok && (off % 16 == 0) && (bytes % 16 == 0);
     int p = (P.n_push_peers > 1) ? (int)(blockIdx.x % (unsigned)P.n_push_peers) : 0;
 #pragma unroll 1
     for (int k = 0; k < P.n_push_peers; ++k) {
-        const float* src = P.push_src + row0;
-        float* dst = P.push_peers[p] + row0;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(P.push_src) + off;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(P.push_peers[p]) + off;
         if (vec) {
-            const int n4 = (nE * D) >> 2;
+            const int n16 = (int)(bytes >> 4);
 #pragma unroll 4
-            for (int i = tid; i < n4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+            for (int i = tid; i < n16; i += 256) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
         } else {
 #pragma unroll 1
-            for (int i = tid; i < nE * D; i += 256) dst[i] = src[i];
+            for (int i = tid; i < (int)(bytes >> 1); i += 256) reinterpret_cast<uint16_t*>(dst)[i] = reinterpret_cast<const uint16_t*>(src)[i];
         }
         p = (p + 1 == P.n_push_peers) ? 0 : p + 1;
     }
     __syncthreads();
     signal_peers(P, P.n_push_peers, tid);
+}
+// The receiving side of the 16-bit wire format: rebuild the fp32 rows of every OTHER rank ([0, rows_total) without this
+// rank's own [row_lo, row_hi), which its step kernel wrote in fp32) from the int16 thousandths the peers delivered.
+// Pure streaming: 2 bytes in, 4 bytes out per value, 8 values per thread and trip where the chunk lies outside the gap.
+__global__ void __launch_bounds__(256) cn_wire_decode_kernel(const int16_t* __restrict__ wire, float* __restrict__ obs_all,
+                                                             long long skip_lo, long long skip_hi, long long total) {
+    const long long n8 = total >> 3;
+    const bool aligned = ((((uintptr_t)wire) & 15u) == 0) && ((((uintptr_t)obs_all) & 15u) == 0);
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n8; c += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = c << 3;
+        if (i0 >= skip_lo && i0 + 8 <= skip_hi) continue;                      // wholly inside this rank's own rows
+        if (aligned && (i0 + 8 <= skip_lo || i0 >= skip_hi)) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wire + i0);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[2 * k] = wire16_decode((int32_t)(int16_t)(ww[k] & 0xFFFFu));
+                o[2 * k + 1] = wire16_decode((int32_t)(int16_t)(ww[k] >> 16));
+            }
+            reinterpret_cast<float4*>(obs_all + i0)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(obs_all + i0)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            for (long long i = i0; i < i0 + 8; ++i)
+                if (i < skip_lo || i >= skip_hi) obs_all[i] = wire16_decode((int32_t)wire[i]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (total & 7)) {
+        const long long i = (n8 << 3) + threadIdx.x;
+        if (i < skip_lo || i >= skip_hi) obs_all[i] = wire16_decode((int32_t)wire[i]);
+    }
+}
+cudaError_t cn_launch_wire_decode(const int16_t* wire, float* obs_all, long long row_lo, long long row_hi,
+                                  long long rows_total, int obs_dim, cudaStream_t stream) {
+    const long long total = rows_total * obs_dim;
+    long long blocks = ((total >> 3) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    cn_wire_decode_kernel<<<(unsigned)blocks, 256, 0, stream>>>(wire, obs_all, row_lo * obs_dim, row_hi * obs_dim, total);
+    return cudaGetLastError();
 }
 cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream) {
     const int grid = (P.n_envs + L.W - 1) / L.W;

@@ -41,10 +41,24 @@ struct cn_kparams {
      * rank's row block of the previous gather buffer -- to the peers (push_peers) at its START: thread 0 of every CTA
      * bulk-loads its tile of old rows into a staging tile and bulk-stores it into every peer, so the transfer runs
      * under the step's compute; arrivals are signalled at the end of the kernel.  Needs CN_FLAG_GATHER_STAGE. */
-    const float* push_src;
-    float* push_peers[8];
+    const void* push_src;
+    void* push_peers[8];
     int n_push_peers;
     int push_bulk_ok;               /* push_src and every push peer are 16-B aligned */
+    /* 16-bit wire format of the pipelined gather: every observation value is a whole number of thousandths (that is
+     * how the row is rounded), so a row travels as int16 thousandths -- half the NVLink bytes -- and the receiver
+     * rebuilds the identical fp32 row (cn_gather_decode16).  wire_out: this rank's row block of its OWN wire buffer
+     * for the step being computed (the kernel encodes its finished rows into it; the next step's kernel forwards it);
+     * push_src / push_peers then address int16 rows.  -0.0 travels as -32768; a value outside +-32.767 saturates and
+     * is counted in gather_timeouts[2]. */
+    int16_t* wire_out;
+    int push_wire16;
+    /* ... and the receiving side inside the SAME kernel: dec_wire / dec_obs are this rank's whole [E_total, D] int16 wire
+     * buffer and fp32 gather buffer of the step whose rows the peers' PREVIOUS kernels delivered (certified by the guard,
+     * which therefore runs with wait_back = 1 before anything else); CTA b rebuilds rows [b W, b W + nE) of every other
+     * rank's block.  NULL: nothing to decode in this launch. */
+    const int16_t* dec_wire;
+    float* dec_obs;
     unsigned int* gather_done;      /* device word: CTAs of the running launch whose rows have reached the peers (the last one signals) */
     unsigned int* gather_timeouts;  /* device counter: waits given up after CN_GATHER_WAIT_NS (diagnostics, never hangs the GPU) */
     const cn_config* cfg;       /* device copy */
@@ -85,6 +99,10 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
 int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, cn_flat_layout* L);
 /* push-only launch of the pipelined gather (the rows of the LAST step, which no later step kernel will forward) */
 cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream);
+/* int16 thousandths -> fp32 rows for every row of [0, rows_total) outside [row_lo, row_hi) (this rank's own rows are
+ * already there in fp32) */
+cudaError_t cn_launch_wire_decode(const int16_t* wire, float* obs_all, long long row_lo, long long row_hi,
+                                  long long rows_total, int obs_dim, cudaStream_t stream);
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream);
 
 /* cn_abi.cu: raise cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the CURRENT device to at least `smem`

@@ -16,7 +16,8 @@ batch-wise, everything resident on the GPU:
                                  device-side cursor, no host synchronisation.
   * `TD3Learner`              -- twin critics, target smoothing, delayed policy update (TD3:225-285).
   * `collect`                 -- batched rollout loop over CrowdNavVecEnv, statistics accumulated on the device.
-  * `rollout_throughput`      -- env-steps/s of policy + env + replay (+ learner) for bench.py.
+  * `GraphedCollector`        -- the same loop (optionally with the TD3 update) captured once as a CUDA graph.
+  * `rollout_throughput`      -- env-steps/s of policy + env + replay (+ learner) for bench.py, eager or graphed.
 
 PyTorch only; the env step underneath is the CUDA library.
 """
@@ -177,13 +178,14 @@ class TD3Learner:
 
     def __init__(self, obs_dim: int, device: torch.device, hidden: int = 256, actor_lr: float = 3e-4,
                  critic_lr: float = 3e-4, gamma: float = 0.99, tau: float = 0.005, noise_std: float = 0.2,
-                 noise_clip: float = 0.5, policy_update: int = 2):
+                 noise_clip: float = 0.5, policy_update: int = 2, capturable: bool = False):
         self.actor = TD3Actor(obs_dim, 2, hidden).to(device)
         self.critic1, self.critic2 = TD3Critic(obs_dim, 2, hidden).to(device), TD3Critic(obs_dim, 2, hidden).to(device)
         self.t_actor, self.t_critic1, self.t_critic2 = (copy.deepcopy(m) for m in (self.actor, self.critic1, self.critic2))
-        self.opt_actor = torch.optim.Adam(self.actor.parameters(), lr=actor_lr)
-        self.opt_c1 = torch.optim.Adam(self.critic1.parameters(), lr=critic_lr)
-        self.opt_c2 = torch.optim.Adam(self.critic2.parameters(), lr=critic_lr)
+        # capturable=True keeps Adam's step counters on the device so that a whole update can live in a CUDA graph
+        self.opt_actor = torch.optim.Adam(self.actor.parameters(), lr=actor_lr, capturable=capturable)
+        self.opt_c1 = torch.optim.Adam(self.critic1.parameters(), lr=critic_lr, capturable=capturable)
+        self.opt_c2 = torch.optim.Adam(self.critic2.parameters(), lr=critic_lr, capturable=capturable)
         self.gamma, self.tau, self.noise_std, self.noise_clip, self.policy_update = gamma, tau, noise_std, noise_clip, policy_update
         self.updates = 0
 
@@ -265,24 +267,99 @@ def collect(env, actor: nn.Module, steps: int, sigma: float = 0.0, replay: Repla
             "censored_mean_length": c_len / max(n_cens, 1.0)}
 
 
+class GraphedCollector:
+    """The rollout loop -- policy forward + exploration noise -> env step -> replay append -> episode statistics (->
+    TD3 update) -- captured ONCE as a CUDA graph and replayed: possible because nothing in the loop reads anything
+    back to the host (ReplayRing keeps its cursor on the device, the env step is a plain kernel launch on the capture
+    stream, Adam runs `capturable`).  One replay = `policy_update` env steps, so that the delayed actor update
+    (TD3:271) is baked in at the right cadence.  Statistics as in collect()."""
+
+    def __init__(self, env, actor: nn.Module, sigma: float = 1.0, replay: ReplayRing | None = None,
+                 learner: "TD3Learner | None" = None, batch_size: int = 256):
+        self.env, self.actor, self.sigma, self.replay, self.learner, self.batch = env, actor, sigma, replay, learner, batch_size
+        dev = env.device
+        self.obs = env.obs.clone()
+        self.ret = torch.zeros(env.E, device=dev)
+        self.length = torch.zeros(env.E, device=dev)
+        self.acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.steps_per_replay = learner.policy_update if learner is not None else 1
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                           # warm-up outside the capture (allocator, cuBLAS, Adam state)
+            for _ in range(3 * self.steps_per_replay):
+                self._iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for _ in range(self.steps_per_replay):
+                self._iteration()
+
+    def _iteration(self):
+        env = self.env
+        with torch.no_grad():
+            a = self.actor(self.obs)
+            a = explore(a, self.sigma) if self.sigma > 0 else a.contiguous()
+            nobs, r, d = env.step(a)
+            if self.replay is not None:
+                self.replay.add_batch(self.obs, a, r, nobs, d)
+            live = d != 2
+            self.ret += torch.where(live, r, torch.zeros_like(r))
+            self.length += live.float()
+            ended = d == 1
+            succ = env.counters()[:, 0] == 1
+            e64 = ended.to(torch.float64)
+            self.acc += torch.stack([e64.sum(), (ended & succ).to(torch.float64).sum(), (self.ret.double() * e64).sum(),
+                                     (self.length.double() * e64).sum()])
+            self.ret.masked_fill_(ended, 0.0)
+            self.length.masked_fill_(ended, 0.0)
+            self.obs.copy_(nobs)
+        if self.learner is not None:
+            self.learner.learn(self.replay.sample(self.batch))
+
+    def run(self, steps: int) -> int:
+        """Replay the graph until at least `steps` env steps have been taken; returns the number taken."""
+        n = -(-steps // self.steps_per_replay)
+        for _ in range(n):
+            self.graph.replay()
+        if self.learner is not None:
+            self.learner.updates += n * self.steps_per_replay     # (learn() ran inside the graph, not in Python)
+        return n * self.steps_per_replay
+
+    def stats(self) -> Dict[str, float]:
+        n_eps, n_succ, sum_ret, sum_len = (float(x) for x in self.acc.cpu())
+        return {"episodes": int(n_eps), "successes": int(n_succ), "success_rate": n_succ / max(n_eps, 1.0),
+                "mean_return": sum_ret / max(n_eps, 1.0), "mean_length": sum_len / max(n_eps, 1.0)}
+
+
 def rollout_throughput(env, policy: nn.Module, steps: int, warmup: int = 5, learn: bool = False, sigma: float = 1.0,
-                       capacity: int = 1 << 18, batch_size: int = 256) -> Dict[str, float]:
+                       capacity: int = 1 << 18, batch_size: int = 256, graph: bool = False) -> Dict[str, float]:
     """env-steps/s of the whole rollout loop -- policy forward (torch) -> env step (CUDA library) -> replay append
     (-> one TD3 update per env step, TD3DRV:128-133) -- timed on the device with one event pair around `steps`
-    iterations; no host synchronisation inside the loop."""
+    iterations; no host synchronisation inside the loop.  graph=True replays the loop as a CUDA graph
+    (GraphedCollector) instead of issuing it eagerly."""
     dev = env.device
     replay = ReplayRing(capacity, env.D, dev)
-    learner = TD3Learner(env.D, dev) if learn else None
+    learner = TD3Learner(env.D, dev, capturable=graph) if learn else None
     if learner is not None:
         policy = learner.actor
-    kw = dict(sigma=sigma, replay=replay, learner=learner, learn_every=1 if learn else 0, batch_size=batch_size)
-    collect(env, policy, warmup, **kw)
-    torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    collect(env, policy, steps, **kw)
-    e1.record()
+    if graph:
+        gc = GraphedCollector(env, policy, sigma, replay, learner, batch_size)
+        gc.run(warmup)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        steps = gc.run(steps)
+        e1.record()
+    else:
+        kw = dict(sigma=sigma, replay=replay, learner=learner, learn_every=1 if learn else 0, batch_size=batch_size)
+        collect(env, policy, warmup, **kw)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        collect(env, policy, steps, **kw)
+        e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     return {"value": env.E * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps, "steps": steps,
-            "learn": bool(learn), "updates": learner.updates if learner else 0, "replay_rows": len(replay)}
+            "learn": bool(learn), "updates": learner.updates if learner else 0, "replay_rows": len(replay),
+            "how": "CUDA graph of the loop, replayed" if graph else "eager PyTorch"}

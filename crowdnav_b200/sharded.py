@@ -39,7 +39,7 @@ def local_config(cfg_global: CnConfig, rank: int, world: int) -> CnConfig:
     return cfg
 
 
-GATHER_MODES = ("collective", "fused", "fused_mc", "fused_async", "none")
+GATHER_MODES = ("collective", "fused", "fused_mc", "fused_async", "fused_async16", "none")
 
 
 class ShardedVecEnv:
@@ -76,6 +76,16 @@ class ShardedVecEnv:
                         waits, ``wait_pushed()`` only waits for what the step kernels have forwarded so far (all rows
                         of the step BEFORE the latest one, in ``obs_all_prev``).  Rows of step t must be consumed
                         before step t+2 is launched.  Local handles are created with CN_FLAG_GATHER_STAGE.
+    ``"fused_async16"`` the same pipeline with a 16-bit wire format: every value of a row is a whole number of thousandths
+                        (that is how the reference rounds the row, ENV:1042), so the step kernel also writes its rows as
+                        int16 thousandths, the next step's kernel forwards THOSE (half the NVLink bytes), and the kernel
+                        after that rebuilds the identical fp32 rows on the receiver while its state tile is loading: ONE
+                        launch per step computes step t+1, forwards step t and completes the gather of step t-1
+                        (``lag`` = 2; the guard runs with wait_back = 1, i.e. a kernel first checks that the peers have
+                        finished their previous one -- which is what certifies the delivery it decodes).
+                        ``wait_gathered()`` = flush + wait + cn_gather_decode16 of whatever is still on the wire.  Values
+                        must stay below 32.768 in magnitude (rooms within +-30 m); a value that does not fit is counted
+                        (``env.gather_timeouts``).
     """
 
     def __init__(self, cfg_global: CnConfig, make_local: Callable, device: torch.device,
@@ -91,8 +101,10 @@ class ShardedVecEnv:
         self.gather_mode = gather if self.world > 1 else "none"
         self.fused = self.gather_mode.startswith("fused")
         self.cfg_local = local_config(cfg_global, self.rank, self.world)
-        if self.gather_mode == "fused_async":
-            self.cfg_local.flags |= 16            # CN_FLAG_GATHER_STAGE
+        self.async_mode = self.gather_mode in ("fused_async", "fused_async16")
+        self.wire16 = self.gather_mode == "fused_async16"
+        if self.async_mode:
+            self.cfg_local.flags |= 16 | (32 if self.wire16 else 0)      # CN_FLAG_GATHER_STAGE (| CN_FLAG_GATHER_WIRE16)
         self.lo, self.hi = shard_range(cfg_global.n_envs, self.rank, self.world)
         self.E, self.D = cfg_global.n_envs, cfg_global.obs_dim
         if self.fused and (cfg_global.flags & 8):
@@ -100,7 +112,10 @@ class ShardedVecEnv:
             # its rows to the peers, so the fused entry points refuse that mode
             raise ValueError("risk_faithful worlds gather with gather='collective' (ncclAllGather), not 'fused'")
         self._symm = None
-        self._pending = False                    # fused_async: the latest step's rows have not been forwarded yet
+        self._pending = False                    # pipelined modes: the latest step's rows have not been forwarded yet
+        self._inflight = None                    # fused_async16: buffer forwarded by the last kernel, not yet rebuilt
+        self._complete = None                    # newest buffer whose rows are complete on this rank
+        self._to_decode = []
         if self.fused:
             import ctypes as C
             import torch.distributed._symmetric_memory as symm_mem
@@ -110,13 +125,27 @@ class ShardedVecEnv:
             # GPUs (ascending order from 0 would aim every rank at GPU 0 first, then GPU 1, ...)
             order = [(self.rank + 1 + k) % self.world for k in range(self.world - 1)]
             off = self.lo * self.D * 4
-            for _ in range(3):
+            self._wire, self._wsymm = [], []
+            # gather buffers in rotation: three cover a lag of one step; the 16-bit pipeline completes a step two launches
+            # later, and the buffer must not be reused (this rank's own rows!) before that step has been consumed: four
+            self._R = 4 if self.wire16 else 3
+            for _ in range(self._R):
                 buf = symm_mem.empty((self.E, self.D), dtype=torch.float32, device=device)
                 buf.zero_()
                 hdl = symm_mem.rendezvous(buf, grp)
                 self._bufs.append(buf)
                 self._symm.append(hdl)
-                ptrs = [int(hdl.buffer_ptrs[r]) + off for r in order]
+                if self.wire16:
+                    # the peers write int16 rows into the wire buffers; the fp32 buffers stay local (decode target)
+                    wbuf = symm_mem.empty((self.E, self.D), dtype=torch.int16, device=device)
+                    wbuf.zero_()
+                    whdl = symm_mem.rendezvous(wbuf, grp)
+                    self._wire.append(wbuf)
+                    self._wsymm.append(whdl)
+                    ptrs = [int(whdl.buffer_ptrs[r]) + off // 2 for r in order]
+                    hdl = whdl
+                else:
+                    ptrs = [int(hdl.buffer_ptrs[r]) + off for r in order]
                 self._peers.append((C.c_void_p * len(ptrs))(*ptrs))
                 mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
                 self._mc.append(mc + off if mc else 0)
@@ -149,17 +178,35 @@ class ShardedVecEnv:
         env = self.env if env is None else env
         if self.fused:
             prev = self._cur
-            self._cur = (self._cur + 1) % 3
+            self._cur = (self._cur + 1) % self._R
             self.obs_all_prev = self._bufs[prev]
             self.obs_all = self._bufs[self._cur]
             self.obs_local = self.obs_all[self.lo:self.hi]
             env.obs = self.obs_local
-            if self.gather_mode == "fused_async":
+            if self.wire16:
+                # one launch: compute this step (fp32 rows + int16 copy into wire[cur]), forward the previous step's int16
+                # rows, rebuild the fp32 rows the peers' previous kernels delivered (the step before that)
+                wire_out = self._wire[self._cur][self.lo:self.hi].data_ptr()
+                if self._pending:
+                    dec = self._inflight
+                    env.step_gather_async(actions_local, self._wire[prev][self.lo:self.hi].data_ptr(), self._peers[prev],
+                                          self._arrive_peers, self.world - 1, self._arrive.data_ptr(), self.world, self.rank, 1,
+                                          wire_out=wire_out,
+                                          dec_wire=self._wire[dec].data_ptr() if dec is not None else 0,
+                                          dec_obs=self._bufs[dec].data_ptr() if dec is not None else 0)
+                    if dec is not None:
+                        self._complete = dec
+                    self._inflight = prev
+                else:                            # nothing to forward (first step, or the rows were flushed): encode only
+                    env.step_gather_async(actions_local, 0, None, None, 0, 0, self.world, self.rank, 1, wire_out=wire_out)
+                self._pending = True
+            elif self.async_mode:
                 if self._pending:
                     env.step_gather_async(actions_local, self._bufs[prev][self.lo:self.hi].data_ptr(), self._peers[prev],
                                           self._arrive_peers, self.world - 1, self._arrive.data_ptr(), self.world, self.rank, 2)
                 else:
                     env.step(actions_local)      # nothing to forward (first step, or the rows were flushed)
+                self._complete = prev if self._pending else self._complete
                 self._pending = True
             else:
                 mc = self.gather_mode == "fused_mc"
@@ -180,25 +227,44 @@ class ShardedVecEnv:
         return self.obs_all
 
     def flush_gather(self) -> None:
-        """fused_async: forward the rows of the latest step now (push-only launch) instead of with the next step."""
-        if self.gather_mode == "fused_async" and self._pending:
-            self.env.gather_flush(self.obs_local.data_ptr(), self._peers[self._cur], self._arrive_peers, self.world - 1,
-                                  self._arrive.data_ptr(), self.world, self.rank, 2)
+        """Pipelined modes: forward the rows of the latest step now (push-only launch) instead of with the next step."""
+        if self.async_mode and self._pending:
+            src = self._wire[self._cur][self.lo:self.hi].data_ptr() if self.wire16 else self.obs_local.data_ptr()
+            self.env.gather_flush(src, self._peers[self._cur], self._arrive_peers, self.world - 1,
+                                  self._arrive.data_ptr(), self.world, self.rank, 1 if self.wire16 else 2, wire16=self.wire16)
             self._pending = False
+            if self.wire16:
+                self._to_decode = [b for b in (self._inflight, self._cur) if b is not None]
+                self._inflight = None
 
-    def wait_pushed(self) -> torch.Tensor:
-        """Order the current stream behind the arrival of everything the peers' kernels have forwarded so far: with
-        'fused_async' that is every row of the step before the latest one (obs_all_prev); in the other fused modes the
-        latest step itself."""
-        if self.fused:
-            self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
-        return self.obs_all_prev if (self.gather_mode == "fused_async" and self._pending) else self.obs_all
+    def wait_pushed(self) -> torch.Tensor | None:
+        """The newest gather buffer that is COMPLETE on this rank without flushing anything: 'fused_async' waits for what
+        the step kernels have forwarded and returns the step before the latest one; 'fused_async16' returns the step
+        two before the latest (rebuilt inside the latest step's kernel, nothing to wait for); the non-pipelined fused
+        modes wait for the latest step itself.  None while the pipeline is still filling."""
+        if not self.fused:
+            return self.obs_all
+        if self.wire16:
+            return self._bufs[self._complete] if self._complete is not None else None
+        self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
+        if self.async_mode:
+            return self._bufs[self._complete] if self._complete is not None else None
+        return self.obs_all
+
+    @property
+    def lag(self) -> int:
+        """Steps between a step's launch and the launch whose completion makes its rows complete on every rank."""
+        return {"fused_async": 1, "fused_async16": 2}.get(self.gather_mode, 0)
 
     def wait_gathered(self) -> torch.Tensor:
         """Order the current stream behind the arrival of every rank's rows of the LATEST step."""
         if self.fused:
             self.flush_gather()
             self.env.gather_wait(self._arrive.data_ptr(), self.world, self.rank)
+            for b in getattr(self, "_to_decode", []):
+                self.env.gather_decode16(self._wire[b].data_ptr(), self._bufs[b].data_ptr(), self.lo, self.hi, self.E)
+            self._to_decode = []
+            self._complete = self._cur
         return self.obs_all
 
     def reset(self) -> torch.Tensor:
@@ -209,7 +275,8 @@ class ShardedVecEnv:
             self._symm[self._cur].barrier(channel=0)
             dist.all_gather_into_tensor(self.obs_all, self.obs_local, group=self.group)
             self._symm[self._cur].barrier(channel=0)
-            self._pending = False
+            self._pending, self._inflight, self._to_decode = False, None, []
+            self._complete = self._cur
             return self.obs_all
         return self.gather()
 

@@ -145,23 +145,31 @@ class CrowdNavVecEnv:
         return self.obs, self.reward, self.done
 
     def step_gather_async(self, actions: torch.Tensor, push_src: int, push_peers, peer_arrive, n_peers: int,
-                          arrive_local: int, n_ranks: int, rank: int, wait_back: int = 2):
+                          arrive_local: int, n_ranks: int, rank: int, wait_back: int = 2, wire_out: int = 0,
+                          dec_wire: int = 0, dec_obs: int = 0):
         """cn_step_gather_async (see include/crowdnav.h): this step's kernel forwards the PREVIOUS step's rows
-        (push_src) to the peers under its own compute.  Handle created with CN_FLAG_GATHER_STAGE."""
+        (push_src) to the peers under its own compute; with wire_out (this rank's row block of its own int16 wire
+        buffer) the rows travel as int16 thousandths; with dec_wire / dec_obs (wait_back = 1) the same kernel also rebuilds
+        the fp32 rows the peers' previous kernels delivered.  Handle created with CN_FLAG_GATHER_STAGE."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
                 or actions.numel() != 2 * self.E:
             raise ValueError("actions must be a contiguous float32 [E, 2] tensor on %s" % self.device)
-        rc = self._L.cn_step_gather_async(self._h, actions.data_ptr(), self.obs.data_ptr(), push_src, push_peers, peer_arrive,
-                                          n_peers, arrive_local, n_ranks, rank, wait_back, self.reward.data_ptr(),
-                                          self.done.data_ptr(), self._stream())
+        rc = self._L.cn_step_gather_async(self._h, actions.data_ptr(), self.obs.data_ptr(), wire_out or None, push_src or None,
+                                          push_peers, peer_arrive, n_peers, arrive_local or None, n_ranks, rank, wait_back,
+                                          dec_wire or None, dec_obs or None,
+                                          self.reward.data_ptr(), self.done.data_ptr(), self._stream())
         if rc != 0:
             _lib.check(rc, "cn_step_gather_async")
         return self.obs, self.reward, self.done
 
     def gather_flush(self, push_src: int, push_peers, peer_arrive, n_peers: int, arrive_local: int, n_ranks: int,
-                     rank: int, wait_back: int = 2) -> None:
-        _lib.check(self._L.cn_gather_flush(self._h, push_src, push_peers, peer_arrive, n_peers, arrive_local, n_ranks, rank,
-                                           wait_back, self._stream()), "cn_gather_flush")
+                     rank: int, wait_back: int = 2, wire16: bool = False) -> None:
+        _lib.check(self._L.cn_gather_flush(self._h, 1 if wire16 else 0, push_src, push_peers, peer_arrive, n_peers, arrive_local,
+                                           n_ranks, rank, wait_back, self._stream()), "cn_gather_flush")
+
+    def gather_decode16(self, wire: int, obs_all: int, row_lo: int, row_hi: int, rows_total: int) -> None:
+        _lib.check(self._L.cn_gather_decode16(self._h, wire, obs_all, row_lo, row_hi, rows_total, self._stream()),
+                   "cn_gather_decode16")
 
     def gather_wait(self, arrive_local: int, n_ranks: int, rank: int) -> None:
         _lib.check(self._L.cn_gather_wait(self._h, arrive_local, n_ranks, rank, self._stream()), "cn_gather_wait")

@@ -72,6 +72,10 @@ typedef enum cn_status {
 #define CN_FLAG_GATHER_STAGE    16u /* reserve a staging tile per CTA for cn_step_gather_async (the pipelined fused
                                        all-gather).  Costs [tile, D] floats of shared memory per CTA; no effect on results. */
 
+#define CN_FLAG_GATHER_WIRE16   32u /* with CN_FLAG_GATHER_STAGE: the pipelined gather will use the 16-bit wire format; the
+                                       tile size is then chosen so that a tile of int16 rows is a whole number of 16-byte
+                                       units (bulk copies).  No effect on results. */
+
 /* behaviour kinds (crowd_behaviors/simulate_*.py, SURVEY table P') */
 #define CN_BEHAVIOR_RANDOM 0   /* U(-speed, speed)^2 redrawn every period */
 #define CN_BEHAVIOR_TABLE  1   /* fixed per-pedestrian direction table * speed */
@@ -217,20 +221,37 @@ int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev,
  * buffer), so the NVLink transfer runs under the step's compute instead of behind it; the arrival counters (as in
  * cn_step_gather_signal, slot per source rank, device-side step counting, wait_back) are signalled at the end of the
  * kernel.  Every rank therefore holds all rows of step t once the kernel of step t+1 -- or cn_gather_flush, the
- * push-only launch for the rows of the last step -- has run on every rank (cn_gather_wait).  The first step after a
- * reset has nothing to forward: use cn_step.  Handle created with CN_FLAG_GATHER_STAGE; default kernel only; not with
- * CN_FLAG_RISK_FAITHFUL. */
-int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, const float* push_src_dev,
-                         float* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
+ * push-only launch for the rows of the last step -- has run on every rank (cn_gather_wait).  n_peers = 0: nothing is
+ * forwarded (the first step after a reset).  Handle created with CN_FLAG_GATHER_STAGE; default kernel only; not with
+ * CN_FLAG_RISK_FAITHFUL.
+ *
+ * 16-bit wire format (wire_out_dev != NULL / wire16 != 0): every value of an observation row is a whole number of
+ * thousandths -- that is how the row is rounded (ENV:1042) -- so the rows can travel as int16 thousandths, HALF the
+ * NVLink bytes, and be rebuilt bit for bit (-0.0 travels as -32768; |value| must stay below 32.768: a value that does
+ * not fit saturates and is counted, see cn_gather_timeouts).  The step kernel then ALSO writes its finished rows as
+ * int16 into wire_out_dev (this rank's row block of its own [E_total, D] int16 wire buffer of the step), and
+ * push_src_dev / push_peer_dev address int16 row blocks of the previous step's wire buffers.  The receiver turns the
+ * peers' rows back into fp32 either with cn_gather_decode16 (all rows of [0, rows_total) outside its own [row_lo,
+ * row_hi); behind cn_gather_wait) or INSIDE the next step kernel: dec_wire_dev / dec_obs_dev = this rank's whole int16
+ * wire buffer and fp32 gather buffer of the step the peers' PREVIOUS kernels delivered; with wait_back = 1 the guard at
+ * the start of the kernel certifies that delivery, and CTA b rebuilds the rows of its tile in every other rank's block
+ * while its own state tile is loading.  One launch per step then computes step t+1, forwards step t and finishes the
+ * gather of step t-1. */
+int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, int16_t* wire_out_dev, const void* push_src_dev,
+                         void* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
                          unsigned long long* arrive_local_dev, int n_ranks, int rank, int wait_back,
+                         const int16_t* dec_wire_dev, float* dec_obs_dev,
                          float* reward_dev, uint8_t* done_dev, void* stream);
-int cn_gather_flush(cn_handle* h, const float* push_src_dev, float* const* push_peer_dev,
+int cn_gather_flush(cn_handle* h, int wire16, const void* push_src_dev, void* const* push_peer_dev,
                     unsigned long long* const* peer_arrive_dev, int n_peers, unsigned long long* arrive_local_dev,
                     int n_ranks, int rank, int wait_back, void* stream);
+int cn_gather_decode16(cn_handle* h, const int16_t* wire_dev, float* obs_all_dev, long long row_lo, long long row_hi,
+                       long long rows_total, void* stream);
 /* Hold `stream` until every other rank's slot of arrive_local_dev[n_ranks] has caught up with this rank's own slot
  * (one small kernel; bounded like the in-kernel wait). */
 int cn_gather_wait(cn_handle* h, const unsigned long long* arrive_local_dev, int n_ranks, int rank, void* stream);
-/* Number of bounded gather waits that gave up since cn_create (0 in a healthy run).  Synchronous on `stream`. */
+/* Number of bounded gather waits that gave up + of observation values that did not fit the 16-bit wire format since
+ * cn_create (0 in a healthy run).  Synchronous on `stream`. */
 int cn_gather_timeouts(cn_handle* h, unsigned int* out_host, void* stream);
 /* CTAs one step launch of this handle consists of (= arrivals per peer per step). */
 int cn_kernel_ctas(const cn_handle* h);

@@ -19,7 +19,7 @@ def L():
 
 def test_every_declared_symbol_is_exported(L):
     hdr = open(os.path.join(ROOT, "include", "crowdnav.h")).read()
-    declared = set(re.findall(r"\b(cn_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(cn_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(_lib.ABI_SYMBOLS), "include/crowdnav.h and _lib.ABI_SYMBOLS disagree"
     for sym in sorted(declared):
         assert hasattr(L, sym), "libcrowdnav.so does not export %s" % sym

@@ -64,3 +64,34 @@ def test_shipped_actor_rollout_on_gpu_and_td3_update():
     # exploration (TD3:67-78) keeps actions inside the box
     noisy = collect(env, actor, 20, sigma=1.0)
     assert noisy["episodes"] >= 0
+
+
+@pytest.mark.gpu
+def test_graphed_collector_equals_the_eager_loop():
+    """The rollout loop captured as a CUDA graph (GraphedCollector) does what the eager loop does: same worlds, greedy
+    actor, 3 warm-up iterations + 40 replays vs 43 eager steps -> identical state, replay rows and episode statistics;
+    and a graph with the TD3 update inside runs."""
+    from crowdnav_b200.rollout import GraphedCollector
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    dev = torch.device("cuda", 0)
+    actor = load_reference_actor(ACTOR, dev)
+    cfg = shipped_actor_world(n_envs=512, max_steps=60, auto_reset=True)
+    e1, e2 = CrowdNavVecEnv(cfg, device=0), CrowdNavVecEnv(cfg, device=0)
+    e1.reset(); e2.reset()
+    r1, r2 = ReplayRing(50_000, e1.D, dev), ReplayRing(50_000, e2.D, dev)
+    eager = collect(e1, actor, 43, sigma=0.0, replay=r1)
+    gc = GraphedCollector(e2, actor, sigma=0.0, replay=r2)
+    assert gc.run(40) == 40
+    torch.cuda.synchronize()
+    got = gc.stats()
+    assert np.array_equal(e1.get_state_blob(), e2.get_state_blob())
+    assert len(r1) == len(r2) and torch.equal(r1.state[:len(r1)], r2.state[:len(r2)]) and torch.equal(r1.reward, r2.reward)
+    for k in ("episodes", "successes", "mean_return", "mean_length"):
+        assert eager[k] == got[k], (k, eager[k], got[k])
+    learner = TD3Learner(e2.D, dev, capturable=True)
+    gl = GraphedCollector(e2, learner.actor, sigma=1.0, replay=r2, learner=learner, batch_size=128)
+    before = [p.detach().clone() for p in learner.critic1.parameters()]
+    assert gl.run(10) == 10
+    torch.cuda.synchronize()
+    assert any(not torch.equal(a, b) for a, b in zip(before, learner.critic1.parameters()))
+    assert all(torch.isfinite(p).all() for p in learner.actor.parameters())

@@ -50,26 +50,29 @@ def _worker(rank, world, port, mode, E, steps, q):
             fo, fr, fd = full.step(a)
             torch.cuda.synchronize()
             dist.barrier()
-            if not (torch.equal(obs_all, fo) and torch.equal(r, fr[senv.lo:senv.hi]) and torch.equal(d, fd[senv.lo:senv.hi])):
+            if not (torch.equal(obs_all.view(torch.int32), fo.view(torch.int32)) and torch.equal(r, fr[senv.lo:senv.hi])
+                    and torch.equal(d, fd[senv.lo:senv.hi])):
                 bad += 1
-        if mode == "fused_async":
-            # pipelined semantics: after the kernel of step t+1 (no flush) every rank holds all rows of step t
-            prev_full = None
-            for t in range(9):
+        if mode in ("fused_async", "fused_async16"):
+            # pipelined semantics: after the kernel of step t + lag (no flush, nothing else launched) every rank holds all
+            # rows of step t -- forwarded by the next step's kernel and, in the 16-bit format, rebuilt by the one after
+            hist = []
+            for t in range(10):
                 a = torch.from_numpy(random_actions(rng, E)).to(dev)
                 senv.step_local(a[senv.lo:senv.hi].contiguous())
-                got_prev = senv.wait_pushed()
+                got = senv.wait_pushed()
                 fo, _, _ = full.step(a)
                 torch.cuda.synchronize()
                 dist.barrier()
-                if prev_full is not None and not torch.equal(got_prev, prev_full):
+                hist.append(fo.clone())
+                k = len(hist) - 1 - senv.lag
+                if k >= 0 and (got is None or not torch.equal(got.view(torch.int32), hist[k].view(torch.int32))):
                     bad += 1
-                prev_full = fo.clone()
-            if not torch.equal(senv.wait_gathered(), prev_full):        # flush: the latest step
+            if not torch.equal(senv.wait_gathered().view(torch.int32), hist[-1].view(torch.int32)):   # flush: the latest step
                 bad += 1
             torch.cuda.synchronize()
             dist.barrier()
-        if mode in ("fused", "fused_mc", "fused_async"):
+        if mode in ("fused", "fused_mc", "fused_async", "fused_async16"):
             # the same steps as ONE CUDA graph, replayed twice: the step counting of the fused gather lives on the
             # device, so every replay must wait for / signal the right steps (6 steps = two turns of the 3 buffers)
             acts = [torch.from_numpy(random_actions(rng, E)).to(dev) for _ in range(6)]
@@ -87,7 +90,7 @@ def _worker(rank, world, port, mode, E, steps, q):
                     fo, fr, fd = full.step(a)
                 torch.cuda.synchronize()
                 dist.barrier()
-                if not torch.equal(senv.obs_all, fo):
+                if not torch.equal(senv.obs_all.view(torch.int32), fo.view(torch.int32)):
                     bad += 1
             bad += senv.env.gather_timeouts
         q.put((rank, bad))
@@ -95,7 +98,7 @@ def _worker(rank, world, port, mode, E, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_mc", "fused_async", "collective"])
+@pytest.mark.parametrize("mode", ["fused", "fused_mc", "fused_async", "fused_async16", "collective"])
 def test_two_gpu_gather_equals_single_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
