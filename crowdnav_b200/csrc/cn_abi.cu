@@ -402,9 +402,9 @@ int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, 
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
     P.wire_out = wire_out_dev;
     if ((dec_wire_dev != NULL) != (dec_obs_dev != NULL)) return fail(CN_ERR_INVALID, "cn_step_gather_async: dec_wire_dev and dec_obs_dev go together%s", NULL);
-    if (dec_wire_dev && (n_peers < 1 || wait_back != 1))
-        return fail(CN_ERR_INVALID, "cn_step_gather_async: decoding inside the kernel needs a pushing launch with wait_back = 1 "
-                                    "(the guard is what certifies the delivery)%s", NULL);
+    if (dec_wire_dev && n_peers < 1)
+        return fail(CN_ERR_INVALID, "cn_step_gather_async: decoding inside the kernel needs a pushing launch (its arrival "
+                                    "counters are what certify the delivery)%s", NULL);
     P.dec_wire = dec_wire_dev; P.dec_obs = dec_obs_dev;
     P.obs_bulk_ok = (((uintptr_t)obs_dev) & 15u) == 0;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;

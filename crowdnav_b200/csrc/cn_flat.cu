@@ -600,43 +600,12 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
     }
-    // fused gather, pipelined: before anything of the peers is touched -- their buffers by our pushes, their deliveries
-    // by our decode -- lane s of warp 0 checks source rank s's progress (normally one L2 hit, under the fills)
+    // fused gather, pipelined: before the peers' buffers are touched by our pushes lane s of warp 0 checks source rank
+    // s's progress (normally one L2 hit, under the fills)
     if (push && warp == 0 && !(L.gather_debug & 1)) guard_peer_buffers(P, lane);
     FSTAMP(3);
-    __syncthreads();            // fills done, barrier init visible, guard passed
+    __syncthreads();            // fills done, barrier init visible
     FSTAMP(11);
-    if (MODE == 0 && P.dec_wire != nullptr && push) {
-        // 16-bit wire format, receiving side: the peers' previous kernels delivered a step's rows as int16 thousandths
-        // into our wire buffer; this CTA rebuilds its tile's rows of every other rank's block in the fp32 gather buffer
-        // (8 values per 16-byte load) while its own state tile is still on its way
-        const int n = nE * D, n8 = n >> 3;
-#pragma unroll 1
-        for (int r = 0; r < P.arrive_slots; ++r) {
-            if (r == P.arrive_self) continue;
-            const size_t base = ((size_t)r * (size_t)P.n_envs + (size_t)e0) * (size_t)D;
-            if ((base & 7u) != 0u || (n & 7) != 0 || ((((uintptr_t)P.dec_wire) | ((uintptr_t)P.dec_obs)) & 15u) != 0u) {
-#pragma unroll 1
-                for (int i = tid; i < n; i += T) P.dec_obs[base + i] = wire16_decode((int32_t)P.dec_wire[base + i]);   // ragged tile
-                continue;
-            }
-            const uint4* src = reinterpret_cast<const uint4*>(P.dec_wire + base);
-            float4* dst = reinterpret_cast<float4*>(P.dec_obs + base);
-#pragma unroll 2
-            for (int c = tid; c < n8; c += T) {
-                const uint4 wv = src[c];
-                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    o[2 * k] = wire16_decode((int32_t)(int16_t)(ww[k] & 0xFFFFu));
-                    o[2 * k + 1] = wire16_decode((int32_t)(int16_t)(ww[k] >> 16));
-                }
-                dst[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
-            }
-        }
-    }
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
     if (push_bulk && warp == 0) {
@@ -1221,6 +1190,44 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         // system-scope release; the peer's acquire load of its counter then sees the rows (the pattern of a grid sync)
         __syncthreads();
         if (!(L.gather_debug & 2)) signal_peers(P, P.n_obs_peers, tid);
+    }
+    if (MODE == 0 && P.dec_wire != nullptr && push) {
+        // 16-bit wire format, receiving side: the peers' PREVIOUS kernels delivered a step's rows as int16 thousandths
+        // into our wire buffer -- certified here, at the end of our own step, when they have long finished: lane s checks
+        // that source rank s has completed as many pushing launches as this rank had before this one -- and this CTA
+        // rebuilds its tile's rows of every other rank's block in the fp32 gather buffer (8 values per 16-byte load)
+        // while its own pushes drain
+        if (warp == 0 && lane < P.arrive_slots && lane != P.arrive_self && !(L.gather_debug & 1)) {
+            const unsigned long long own = ld_acquire_sys(P.arrive_local + P.arrive_self);
+            if (!wait_arrivals(P.arrive_local + lane, own) && P.gather_timeouts) atomicAdd(P.gather_timeouts, 1u);
+        }
+        __syncthreads();
+        const int n = nE * D, n8 = n >> 3;
+#pragma unroll 1
+        for (int r = 0; r < P.arrive_slots; ++r) {
+            if (r == P.arrive_self) continue;
+            const size_t base = ((size_t)r * (size_t)P.n_envs + (size_t)e0) * (size_t)D;
+            if ((base & 7u) != 0u || (n & 7) != 0 || ((((uintptr_t)P.dec_wire) | ((uintptr_t)P.dec_obs)) & 15u) != 0u) {
+#pragma unroll 1
+                for (int i = tid; i < n; i += T) P.dec_obs[base + i] = wire16_decode((int32_t)P.dec_wire[base + i]);   // ragged tile
+                continue;
+            }
+            const uint4* src = reinterpret_cast<const uint4*>(P.dec_wire + base);
+            float4* dst = reinterpret_cast<float4*>(P.dec_obs + base);
+#pragma unroll 2
+            for (int c = tid; c < n8; c += T) {
+                const uint4 wv = src[c];
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[2 * k] = wire16_decode((int32_t)(int16_t)(ww[k] & 0xFFFFu));
+                    o[2 * k + 1] = wire16_decode((int32_t)(int16_t)(ww[k] >> 16));
+                }
+                dst[2 * c] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[2 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
     }
     if (push) {
         if (push_bulk) {

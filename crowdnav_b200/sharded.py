@@ -81,8 +81,9 @@ class ShardedVecEnv:
                         int16 thousandths, the next step's kernel forwards THOSE (half the NVLink bytes), and the kernel
                         after that rebuilds the identical fp32 rows on the receiver while its state tile is loading: ONE
                         launch per step computes step t+1, forwards step t and completes the gather of step t-1
-                        (``lag`` = 2; the guard runs with wait_back = 1, i.e. a kernel first checks that the peers have
-                        finished their previous one -- which is what certifies the delivery it decodes).
+                        (``lag`` = 2; four buffers rotate; at the end of its step a CTA checks that the peers have
+                        finished their previous kernel -- which certifies the delivery -- and rebuilds its share of rows
+                        while its own pushes drain).
                         ``wait_gathered()`` = flush + wait + cn_gather_decode16 of whatever is still on the wire.  Values
                         must stay below 32.768 in magnitude (rooms within +-30 m); a value that does not fit is counted
                         (``env.gather_timeouts``).
@@ -190,7 +191,7 @@ class ShardedVecEnv:
                 if self._pending:
                     dec = self._inflight
                     env.step_gather_async(actions_local, self._wire[prev][self.lo:self.hi].data_ptr(), self._peers[prev],
-                                          self._arrive_peers, self.world - 1, self._arrive.data_ptr(), self.world, self.rank, 1,
+                                          self._arrive_peers, self.world - 1, self._arrive.data_ptr(), self.world, self.rank, 2,
                                           wire_out=wire_out,
                                           dec_wire=self._wire[dec].data_ptr() if dec is not None else 0,
                                           dec_obs=self._bufs[dec].data_ptr() if dec is not None else 0)
@@ -198,7 +199,7 @@ class ShardedVecEnv:
                         self._complete = dec
                     self._inflight = prev
                 else:                            # nothing to forward (first step, or the rows were flushed): encode only
-                    env.step_gather_async(actions_local, 0, None, None, 0, 0, self.world, self.rank, 1, wire_out=wire_out)
+                    env.step_gather_async(actions_local, 0, None, None, 0, 0, self.world, self.rank, 2, wire_out=wire_out)
                 self._pending = True
             elif self.async_mode:
                 if self._pending:
@@ -231,7 +232,7 @@ class ShardedVecEnv:
         if self.async_mode and self._pending:
             src = self._wire[self._cur][self.lo:self.hi].data_ptr() if self.wire16 else self.obs_local.data_ptr()
             self.env.gather_flush(src, self._peers[self._cur], self._arrive_peers, self.world - 1,
-                                  self._arrive.data_ptr(), self.world, self.rank, 1 if self.wire16 else 2, wire16=self.wire16)
+                                  self._arrive.data_ptr(), self.world, self.rank, 2, wire16=self.wire16)
             self._pending = False
             if self.wire16:
                 self._to_decode = [b for b in (self._inflight, self._cur) if b is not None]

@@ -233,10 +233,11 @@ int cn_step_gather_signal(cn_handle* h, const float* action_dev, float* obs_dev,
  * push_src_dev / push_peer_dev address int16 row blocks of the previous step's wire buffers.  The receiver turns the
  * peers' rows back into fp32 either with cn_gather_decode16 (all rows of [0, rows_total) outside its own [row_lo,
  * row_hi); behind cn_gather_wait) or INSIDE the next step kernel: dec_wire_dev / dec_obs_dev = this rank's whole int16
- * wire buffer and fp32 gather buffer of the step the peers' PREVIOUS kernels delivered; with wait_back = 1 the guard at
- * the start of the kernel certifies that delivery, and CTA b rebuilds the rows of its tile in every other rank's block
- * while its own state tile is loading.  One launch per step then computes step t+1, forwards step t and finishes the
- * gather of step t-1. */
+ * wire buffer and fp32 gather buffer of the step the peers' PREVIOUS kernels delivered; at the END of its own step every
+ * CTA checks that each peer has completed as many pushing launches as this rank had before this one (that certifies
+ * the delivery; by then it is long true) and rebuilds the rows of its tile in every other rank's block while its own
+ * pushes drain.  One launch per step then computes step t+1, forwards step t and finishes the gather of step t-1;
+ * rotate FOUR buffers (a step's buffer must survive until two launches later). */
 int cn_step_gather_async(cn_handle* h, const float* action_dev, float* obs_dev, int16_t* wire_out_dev, const void* push_src_dev,
                          void* const* push_peer_dev, unsigned long long* const* peer_arrive_dev, int n_peers,
                          unsigned long long* arrive_local_dev, int n_ranks, int rank, int wait_back,

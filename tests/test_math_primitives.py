@@ -88,3 +88,34 @@ def test_philox2x32_known_answers():
                             (0x243f6a88, 0x85a308d3, 0x13198a2e, (0xdd7ce038, 0xf62a4c12))):
         L.orc_philox2x32(C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(k), out)
         assert (out[0], out[1]) == want
+
+
+def test_16_bit_wire_format_is_lossless_on_the_reference_rows():
+    """The fused gather's 16-bit wire format (cn_flat.cu wire16_encode / wire16_decode): every value of an observation
+    row is a whole number of thousandths, so int16 thousandths + the correctly rounded quotient k / 1000 (cn_div1000,
+    exhaustively equal to IEEE division above) give the fp32 bits back.  Checked here on (a) every k the format can
+    carry, with the arithmetic the kernel uses, and (b) the rows the REFERENCE's own get_state returned in the golden
+    traces (float32, as the agent sees them) and the oracle's rows next to them."""
+    import glob
+    import os
+    k = np.arange(-32767, 32768, dtype=np.int32)
+    v = (k.astype(np.float64) / 1000.0).astype(np.float32)                    # what a row holds: fl32(k / 1000)
+    back = np.rint(v * np.float32(1000.0)).astype(np.int32)                   # wire16_encode: rintf(v * 1000.0f) in fp32
+    assert np.array_equal(back, k)
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    n_rows = 0
+    for f in sorted(glob.glob(os.path.join(here, "trace_*.npz"))):
+        z = np.load(f)
+        for name in ("ref_state", "oracle_obs"):
+            if name not in z.files:
+                continue
+            rows = z[name].astype(np.float32)
+            if name == "ref_state" and "original" not in f:
+                rows = rows[:, :rows.shape[1] - 4 * ((rows.shape[1] - 366) // 4)]   # K block: order / clock dependent, same format
+            kk = np.rint(rows.astype(np.float64) * 1000.0)
+            assert np.abs(kk).max() <= 32767
+            rebuilt = (kk / 1000.0).astype(np.float32)
+            zero = rows == 0
+            assert np.array_equal(rebuilt[~zero].view(np.uint32), rows[~zero].view(np.uint32)), (f, name)
+            n_rows += len(rows)
+    assert n_rows > 5000
