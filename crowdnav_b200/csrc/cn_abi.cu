@@ -27,7 +27,11 @@ struct cn_handle {
     unsigned int* gather_timeouts;  /* device word: bounded waits of the fused gather that gave up */
     int64_t launches;
     int use_flat;           /* 1: cn_flat.cu (compacted work lists, default), 0: cn_step.cu (warp per world; CN_KERNEL=warp) */
-    cn_flat_layout flat;
+    cn_flat_layout flat;    /* rows staged in shared memory: reset launches, every fused-gather entry point, host-mapped rows */
+    cn_flat_layout flat_direct;   /* "direct rows" layout of plain steps into device memory (cn_flat.cu, DIRECT = 1) */
+    int have_direct;
+    const void* obs_seen;   /* last obs pointer classified by cudaPointerGetAttributes ... */
+    int obs_seen_device;    /* ... 1: device (or managed) memory, 0: host-mapped or unknown */
     cn_kparams base;        /* everything of cn_kparams that does not change between calls, packed once (repack()) */
 };
 
@@ -59,8 +63,8 @@ cudaError_t cn_ensure_smem_attr(const void* func, int slot, size_t smem) {
     return e;
 }
 
-static cudaError_t launch_env(const cn_handle* h, cn_kparams& P, int mode, cudaStream_t s) {
-    if (h->use_flat) return cn_launch_flat_kernel(P, h->flat, mode, s);
+static cudaError_t launch_env(const cn_handle* h, cn_kparams& P, int mode, cudaStream_t s, bool direct = false) {
+    if (h->use_flat) return cn_launch_flat_kernel(P, direct ? h->flat_direct : h->flat, mode, s);
     P.obs_bulk_ok = P.obs_bulk_ok && ((size_t)CN_TILE * h->d.obs_dim) % 4 == 0;   /* every tile starts 16-B aligned */
     return cn_launch_env_kernel(P, mode, s);
 }
@@ -156,6 +160,8 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     const char* kern = getenv("CN_KERNEL");
     const int use_flat = !(kern && strcmp(kern, "warp") == 0);
     cn_flat_layout flat; memset(&flat, 0, sizeof(flat));
+    cn_flat_layout flat_direct; memset(&flat_direct, 0, sizeof(flat_direct));
+    int have_direct = 0;
     if (!use_flat && (cfg->flags & CN_FLAG_ENV_ORIGINAL))
         return fail(CN_ERR_UNSUPPORTED, "cn_create: CN_FLAG_ENV_ORIGINAL needs the default kernel (unset CN_KERNEL)%s", NULL);
     if (use_flat) {
@@ -168,11 +174,11 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
             int tw = atoi(tile), tt = 256;
             const char* comma = strchr(tile, ',');
             if (comma) tt = atoi(comma + 1);
-            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, stage_mode(cfg), &flat);
+            rc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, stage_mode(cfg), 0, &flat);
         } else {
             int n_sms = 0;
             CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
-            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, stage_mode(cfg), &flat);
+            rc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, stage_mode(cfg), 0, &flat);
         }
         { const char* st = getenv("CN_FLAT_STORE"); flat.plain_store = (st && strcmp(st, "plain") == 0) ? 1 : 0; }
         /* programmatic dependent launch is opt-in (CN_PDL=1): measured on B200 it helps back-to-back stream launches
@@ -181,6 +187,23 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
         { const char* gd = getenv("CN_GATHER_DEBUG"); flat.gather_debug = gd ? atoi(gd) : 0; }   /* timing diagnostics only */
         if (rc != 0 || flat.total > (size_t)max_smem)
             return fail(CN_ERR_UNSUPPORTED, "cn_create: tile does not fit shared memory (reduce n_samples / n_peds)%s", NULL);
+        /* the direct-rows layout of plain steps (CN_FLAT_DIRECT=0 turns it off; CN_FLAT_TILE applies to it too) */
+        const char* dr = getenv("CN_FLAT_DIRECT");
+        if (!(dr && strcmp(dr, "0") == 0)) {
+            int drc;
+            if (tile) {
+                int tw = atoi(tile), tt = 256;
+                const char* comma = strchr(tile, ',');
+                if (comma) tt = atoi(comma + 1);
+                drc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, 0, 1, &flat_direct);
+            } else {
+                int n_sms = 0;
+                CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+                drc = cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, (size_t)max_sm, 0, 1, &flat_direct);
+            }
+            have_direct = (drc == 0 && flat_direct.total <= (size_t)max_smem) ? 1 : 0;
+            flat_direct.plain_store = flat.plain_store; flat_direct.pdl = flat.pdl; flat_direct.gather_debug = 0;
+        }
     } else {
         const size_t smem = cn_kernel_smem_bytes(cfg->n_peds, cfg->n_samples, d.obs_dim);
         if (smem > (size_t)max_smem)
@@ -193,6 +216,7 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     if (!h) return fail(CN_ERR_NOMEM, "cn_create: host allocation failed%s", NULL);
     h->cfg = *cfg; h->d = d; h->device = device; h->launches = 0;
     h->use_flat = use_flat; h->flat = flat;
+    h->flat_direct = flat_direct; h->have_direct = have_direct; h->obs_seen = NULL; h->obs_seen_device = 0;
     h->dbg_ranges = NULL; h->dbg_hid = NULL;
     const size_t cfg_b = align_up(sizeof(cn_config), 256);
     const size_t rob_b = align_up(cn_robot_words(cfg) * 4, 256);
@@ -268,9 +292,24 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
 }
 
 /* one step launch (+ the risk_faithful kernel) with the handle's device already current */
+/* Direct rows only into device memory: into a host-mapped buffer (CrowdNavVecEnv.step_host(mode="mapped")) the fill and
+ * the scattered stores would cross PCIe one by one, where the staged tile leaves as one bulk store.  The pointer is
+ * classified once (no stream operation: fine under graph capture) and remembered. */
+static bool rows_in_device_memory(cn_handle* h, const void* obs_dev) {
+    if (h->obs_seen != obs_dev) {
+        cudaPointerAttributes a;
+        const cudaError_t e = cudaPointerGetAttributes(&a, obs_dev);
+        if (e != cudaSuccess) cudaGetLastError();
+        h->obs_seen = obs_dev;
+        h->obs_seen_device = (e == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) ? 1 : 0;
+    }
+    return h->obs_seen_device != 0;
+}
+
 static int step_once(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peers, int n_peers,
                      float* reward_dev, uint8_t* done_dev, cudaStream_t stream) {
     cn_kparams P = h->base;
+    const bool direct = h->use_flat && h->have_direct && n_peers == 0 && rows_in_device_memory(h, obs_dev);
     P.action = action_dev; P.obs = obs_dev; P.reward = reward_dev; P.done = done_dev;
     bool aligned = (((uintptr_t)obs_dev) & 15u) == 0;
     for (int p = 0; p < n_peers; ++p) {
@@ -280,7 +319,7 @@ static int step_once(cn_handle* h, const float* action_dev, float* obs_dev, floa
     P.n_obs_peers = n_peers;
     P.obs_bulk_ok = aligned;
     P.act_bulk_ok = (((uintptr_t)action_dev) & 15u) == 0;
-    CN_CUDA(launch_env(h, P, 0, stream));
+    CN_CUDA(launch_env(h, P, 0, stream, direct));
     h->launches += 1;
     CN_CUDA(launch_faithful(h, obs_dev, NULL, stream));
     return CN_OK;
@@ -585,7 +624,9 @@ int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev) {
 
 int64_t cn_launch_count(const cn_handle* h) { return h ? h->launches : 0; }
 const char* cn_kernel_name(const cn_handle* h) { return (h && !h->use_flat) ? "cn_env_kernel" : "cn_flat_kernel"; }
-int cn_kernel_tile(const cn_handle* h) { return !h ? 0 : (h->use_flat ? h->flat.W : CN_TILE); }
+/* worlds per CTA of a plain cn_step (the direct-rows layout when the handle has one; the fused-gather entry points use
+ * the staged layout, whose CTA count cn_kernel_ctas reports) */
+int cn_kernel_tile(const cn_handle* h) { return !h ? 0 : (h->use_flat ? (h->have_direct ? h->flat_direct.W : h->flat.W) : CN_TILE); }
 int cn_kernel_ctas(const cn_handle* h) {
     if (!h) return 0;
     const int W = h->use_flat ? h->flat.W : CN_TILE;
@@ -597,7 +638,7 @@ int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile,
     cn_derived d;
     if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_plan_tile: config out of range%s", NULL);
     cn_flat_layout L; memset(&L, 0, sizeof(L));
-    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, stage_mode(cfg), &L) != 0)
+    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, stage_mode(cfg), 0, &L) != 0)
         return fail(CN_ERR_UNSUPPORTED, "cn_plan_tile: no tile fits%s", NULL);
     *tile = L.W; *threads = L.threads; *smem_bytes = L.total;
     return CN_OK;

@@ -489,9 +489,15 @@ __device__ __forceinline__ void risk_candidate(const cn_kparams& P, const Ptrs& 
 }
 
 // ------------------------------------------------------------------- kernel
-template <int MODE, int T>
-__global__ void __launch_bounds__(T, (T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? CN_FLAT_CTAS_PER_SM : (T >= 192 ? 6 : 8))))
+// DIRECT = 1: the "direct rows" instance for plain single-GPU steps (cn_step / cn_step_n / library graphs).  The rows are
+// not staged in shared memory: S.obs points at the caller's buffer, the no-return fill and the owned rays / pose columns /
+// K slots are ordinary global stores (ordered by the CTA barriers between the phases; L2 merges them, DRAM sees each
+// line once), nothing of the fused gather is compiled in, and the tile needs 4 D fewer bytes per world.
+template <int MODE, int T, int DIRECT>
+__global__ void __launch_bounds__(T, DIRECT ? ((T >= 512) ? 3 : (T >= 384 ? 4 : (T >= 256 ? 6 : (T >= 192 ? 8 : 12))))
+                                            : ((T >= 512) ? 2 : (T >= 384 ? 3 : (T >= 256 ? CN_FLAT_CTAS_PER_SM : (T >= 192 ? 6 : 8)))))
 cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_flat_layout L) {
+    static_assert(!(DIRECT && MODE != 0), "direct rows: step launches only");
     constexpr int PED_THREADS = T - 32 * CF_POSE_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
     FSTAMP(14);
@@ -512,7 +518,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.pb = reinterpret_cast<uint32_t*>(smem + L.off_pb);
     S.pa2 = reinterpret_cast<uint32_t*>(smem + L.off_pa2);
     S.act = reinterpret_cast<float*>(smem + L.off_act);
-    S.obs = reinterpret_cast<float*>(smem + L.off_obs);
+    S.obs = DIRECT ? (P.obs + (size_t)e0 * D) : reinterpret_cast<float*>(smem + L.off_obs);
     S.sc = reinterpret_cast<uint32_t*>(smem + L.off_sc);
     S.rec = reinterpret_cast<uint32_t*>(smem + L.off_rec);
     S.pk = reinterpret_cast<uint32_t*>(smem + L.off_pk);
@@ -544,7 +550,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // pipelined fused gather: the rows of the PREVIOUS step (in this rank's gather buffer) go to the peers under this
     // step's compute -- bulk load into the staging tile now, bulk stores to every peer as soon as it has landed
-    const bool push = (MODE == 0) && P.n_push_peers > 0;
+    const bool push = (MODE == 0) && !DIRECT && P.n_push_peers > 0;
     const uint32_t push_elem = P.push_wire16 ? 2u : 4u;                 // int16 thousandths or fp32
     const uint32_t push_bytes = (uint32_t)nE * (uint32_t)D * push_elem;
     const size_t push_off = (size_t)e0 * D * push_elem;                 // byte offset of the tile in a row block
@@ -571,12 +577,28 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             // (Tried: a bulk copy of a constant tile instead -- 15 % fewer instructions at c2 but the tile lands 0.3 us
             //  later and the step is latency-bound: 11.5 vs 11.2 us.)
             const float fill = P.d.max_range_r3;
-            const int tot = nE * D, n4 = tot >> 2;
-            fill16<T>(S.obs, n4, u_of(fill), tid);
-            if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+            const int tot = nE * D;
+            if (DIRECT) {
+                // straight into the caller's rows: scalar stores up to the first 16-byte boundary, 16-byte stores, tail
+                float* g = S.obs;
+                int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u) >> 2);
+                head = min(head, tot);
+                if (tid < head) g[tid] = fill;
+                float4* g4 = reinterpret_cast<float4*>(g + head);
+                const int n4 = (tot - head) >> 2;
+                const float4 f4 = make_float4(fill, fill, fill, fill);
+#pragma unroll 4
+                for (int i = tid; i < n4; i += T) g4[i] = f4;
+                const int t0 = head + (n4 << 2);
+                if (tid < tot - t0) g[t0 + tid] = fill;
+            } else {
+                const int n4 = tot >> 2;
+                fill16<T>(S.obs, n4, u_of(fill), tid);
+                if (tid < (tot & 3)) S.obs[(n4 << 2) + tid] = fill;
+            }
         }
         {                                                                   // contact-prefilter strips: all empty
-            const int n16 = (nE * 64 * (int)L.strip_words) >> 2;
+            const int n16 = (nE * 2 * ((int)L.strip_mask + 1) * (int)L.strip_words) >> 2;
             uint4* z = reinterpret_cast<uint4*>(S.strips);
 #pragma unroll 1
             for (int i = tid; i < n16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -733,13 +755,14 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         // outside the cut-off adds exactly nothing), and the masks come out symmetric like the pairwise test's.
         const int sw = (int)L.strip_words;                                  // words per strip mask: 1 (N <= 32) or 2
         const int sshift = P.d.strip_shift;
-        auto strip_of = [&](int32_t c, int32_t origin) { return (int)(((uint32_t)(c - origin)) >> sshift) & 31; };
+        const int smask = (int)L.strip_mask, nstrip = smask + 1;               // strips per axis (a power of two)
+        auto strip_of = [&](int32_t c, int32_t origin) { return (int)(((uint32_t)(c - origin)) >> sshift) & smask; };
         auto contact_masks = [&](int w, int n, int32_t x0, int32_t y0, uint32_t& m0, uint32_t& m1) {
-            const uint32_t* xm = S.strips + (size_t)w * 64 * sw;
-            const uint32_t* ym = xm + 32 * sw;
+            const uint32_t* xm = S.strips + (size_t)w * 2 * nstrip * sw;
+            const uint32_t* ym = xm + nstrip * sw;
             const int sx = strip_of(x0, P.d.ped_xmin), sy = strip_of(y0, P.d.ped_ymin);
-            const int xa = ((sx + 31) & 31) * sw, xb = sx * sw, xc = ((sx + 1) & 31) * sw;
-            const int ya = ((sy + 31) & 31) * sw, yb = sy * sw, yc = ((sy + 1) & 31) * sw;
+            const int xa = ((sx + smask) & smask) * sw, xb = sx * sw, xc = ((sx + 1) & smask) * sw;
+            const int ya = ((sy + smask) & smask) * sw, yb = sy * sw, yc = ((sy + 1) & smask) * sw;
             uint32_t c0 = (xm[xa] | xm[xb] | xm[xc]) & (ym[ya] | ym[yb] | ym[yc]);
             uint32_t c1 = 0u;
             if (sw == 2) c1 = (xm[xa + 1] | xm[xb + 1] | xm[xc + 1]) & (ym[ya + 1] | ym[yb + 1] | ym[yc + 1]);
@@ -798,10 +821,10 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             S.mark[it] = mk;
             if (MODE == 0) {
                 const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
-                uint32_t* xm = S.strips + (size_t)w * 64 * sw;
+                uint32_t* xm = S.strips + (size_t)w * 2 * nstrip * sw;
                 const uint32_t bit = 1u << (n & 31);
                 atomicOr(xm + strip_of((int32_t)a.x, P.d.ped_xmin) * sw + (n >> 5), bit);
-                atomicOr(xm + 32 * sw + strip_of((int32_t)a.y, P.d.ped_ymin) * sw + (n >> 5), bit);
+                atomicOr(xm + nstrip * sw + strip_of((int32_t)a.y, P.d.ped_ymin) * sw + (n >> 5), bit);
             }
         }
         // contact masks and the draw list are complete; pose warp 1 has published the robot's new pose
@@ -1113,13 +1136,14 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 
     // ---------------------------------------------------------------- phase 7: write-back
     fence_async_smem();          // generic-proxy writes -> visible to the async proxy
-    const bool gather = (MODE == 0) && (P.n_obs_peers > 0 || P.obs_mc != nullptr);
+    const bool gather = (MODE == 0) && !DIRECT && (P.n_obs_peers > 0 || P.obs_mc != nullptr);
     if (gather && tid < 32 && !(L.gather_debug & 1)) guard_peer_buffers(P, tid);       // (a pushing launch checked at its start)
     FSTAMP(12);
     __syncthreads();             // #G
     FSTAMP(7);
-    const bool bulk_obs = (MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0);
-    if (MODE == 0 && P.wire_out != nullptr) {
+    // (direct rows: the rows are already where they belong -- "bulk_obs" only switches the row copies below off)
+    const bool bulk_obs = DIRECT || ((MODE == 0) && P.obs_bulk_ok && (((size_t)W * D) % 4 == 0) && (((size_t)nE * D) % 4 == 0));
+    if (MODE == 0 && !DIRECT && P.wire_out != nullptr) {
         // 16-bit wire copy of the tile's finished rows into this rank's own wire buffer (the next step's kernel forwards
         // it to the peers): two values per 4-byte store, fire and forget
         const int n = nE * D;
@@ -1146,7 +1170,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             copy16_out(P.ped_a + (size_t)e0 * N * 4, S.pa2, n_items, tid, T);
             copy16_out(P.ped_b + (size_t)e0 * N * 4, S.pb, n_items, tid, T);
         }
-        if (bulk_obs) copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
+        if (bulk_obs && !DIRECT) copy16_out(P.obs + (size_t)e0 * D, S.obs, (nE * D) >> 2, tid, T);
     } else {
         if (tid == 0) {
             tma_store(P.robot + (size_t)e0 * CN_ROBOT_WORDS, S.robot, rob_bytes);
@@ -1154,7 +1178,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 tma_store(P.ped_a + (size_t)e0 * N * 4, S.pa2, ped_bytes);
                 tma_store(P.ped_b + (size_t)e0 * N * 4, S.pb, ped_bytes);
             }
-            if (bulk_obs) tma_store(P.obs + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
+            if (bulk_obs && !DIRECT) tma_store(P.obs + (size_t)e0 * D, S.obs, (uint32_t)((size_t)nE * D * 4));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         // fused all-gather: the same block of rows goes straight into every peer's gather buffer over NVLink, as plain
@@ -1191,7 +1215,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         __syncthreads();
         if (!(L.gather_debug & 2)) signal_peers(P, P.n_obs_peers, tid);
     }
-    if (MODE == 0 && P.dec_wire != nullptr && push) {
+    if (MODE == 0 && !DIRECT && P.dec_wire != nullptr && push) {
         // 16-bit wire format, receiving side: the peers' PREVIOUS kernels delivered a step's rows as int16 thousandths
         // into our wire buffer -- certified here, at the end of our own step, when they have long finished: lane s checks
         // that source rank s has completed as many pushing launches as this rank had before this one -- and this CTA
@@ -1257,8 +1281,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 // ------------------------------------------------------------- host side
 static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, cn_flat_layout* L) {
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, int direct, cn_flat_layout* L) {
     const int N = n_peds, D = obs_dim, W = tile;
+    if (direct && stage) return -1;
     if (threads != 128 && threads != 192 && threads != 256 && threads != 384 && threads != 512) return -1;
     if (W < 1 || W > 32) return -1;
     if ((size_t)W * N > 0x3FFF) return -1;                                  // group-entry / list-entry fields
@@ -1267,8 +1292,12 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->threads = threads;
     L->plain_store = 0;
     L->magic_n = (N > 1) ? (uint32_t)(((1ull << 32) + (uint64_t)N - 1) / (uint64_t)N) : 0u;
-    L->cap_wg = (uint32_t)W * 32u;
-    L->cap_pg = (uint32_t)W * 24u;
+    L->obs_direct = direct ? 1 : 0;
+    /* ray-group lists: a primitive whose groups do not fit is walked directly (same results), so the capacity is a
+     * matter of speed only; the direct layout, which is after the smallest tile, sizes them for the average world */
+    L->cap_wg = (uint32_t)W * (direct ? 20u : 32u);
+    L->cap_pg = (uint32_t)W * (direct ? 12u : 24u);
+    L->strip_mask = direct ? 15u : 31u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
     /* 32 B per pedestrian: the old-position plane (16 B each) in the first half, the contact masks of the slow list
@@ -1280,10 +1309,10 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o += (size_t)W * N * 16;                        L->off_pa2 = (uint32_t)o;
     o += (size_t)W * N * 16;                        L->off_act = (uint32_t)o;
     o = up16(o + (size_t)W * 8);                    L->off_obs = (uint32_t)o;
-    o = up16(o + (size_t)W * D * 4);                L->off_sc = (uint32_t)o;
+    o = up16(o + (direct ? 0 : (size_t)W * D * 4)); L->off_sc = (uint32_t)o;
     L->strip_words = (N > 32) ? 2u : 1u;
     o = up16(o + (size_t)W * F_WORDS * 4);          L->off_strips = (uint32_t)o;
-    o += (size_t)W * 64 * L->strip_words * 4;       L->off_clist = (uint32_t)o;
+    o += (size_t)W * 2 * (L->strip_mask + 1) * L->strip_words * 4;   L->off_clist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
     o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
@@ -1299,18 +1328,19 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     return 0;
 }
 
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, cn_flat_layout* L) {
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, int direct, cn_flat_layout* L) {
     // 256-thread CTAs, four per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk store) that
     // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
     // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
-    const int threads = 256, ctas = CN_FLAT_CTAS_PER_SM;
+    // Direct rows: six resident CTAs per SM (40 registers), tiles up to 32 worlds (the lane = world warps), any width.
+    const int threads = 256, ctas = direct ? 6 : CN_FLAT_CTAS_PER_SM;
     const size_t budget = smem_per_sm / ctas - 1024;
     const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
     int best = 0; double best_score = -1.0;
-    for (int W = 16; W >= 1; --W) {
+    for (int W = direct ? 32 : 16; W >= 1; --W) {
         cn_flat_layout t;
-        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, &t) != 0 || t.total > budget) continue;
-        const bool bulk = ((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0 && (stage < 2 || ((size_t)W * obs_dim) % 8 == 0);
+        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, direct, &t) != 0 || t.total > budget) continue;
+        const bool bulk = direct || (((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0 && (stage < 2 || ((size_t)W * obs_dim) % 8 == 0));
         const long n_cta = ((long)n_envs + W - 1) / W;
         const long waves = (n_cta + slots - 1) / slots;
         double score;
@@ -1322,15 +1352,15 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
         if (score > best_score) { best_score = score; best = W; }
     }
     if (!best) return -1;
-    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, L);
+    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, direct, L);
 }
 
-template <int MODE, int T>
+template <int MODE, int T, int DIRECT>
 static cudaError_t launch_flat_t(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream) {
-    auto k = cn_flat_kernel<MODE, T>;
+    auto k = cn_flat_kernel<MODE, T, DIRECT>;
     {
         constexpr int ti = (T == 128) ? 0 : (T == 192) ? 1 : (T == 256) ? 2 : (T == 384) ? 3 : 4;
-        cudaError_t e = cn_ensure_smem_attr(reinterpret_cast<const void*>(k), MODE * 5 + ti, L.total);
+        cudaError_t e = cn_ensure_smem_attr(reinterpret_cast<const void*>(k), DIRECT ? 16 + ti : MODE * 5 + ti, L.total);
         if (e != cudaSuccess) return e;
     }
     const int grid = (P.n_envs + L.W - 1) / L.W;
@@ -1444,9 +1474,17 @@ cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, 
 }
 
 cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, int mode, cudaStream_t stream) {
-    if (L.threads == 128) return mode == 0 ? launch_flat_t<0, 128>(P, L, stream) : launch_flat_t<1, 128>(P, L, stream);
-    if (L.threads == 192) return mode == 0 ? launch_flat_t<0, 192>(P, L, stream) : launch_flat_t<1, 192>(P, L, stream);
-    if (L.threads == 384) return mode == 0 ? launch_flat_t<0, 384>(P, L, stream) : launch_flat_t<1, 384>(P, L, stream);
-    if (L.threads == 256) return mode == 0 ? launch_flat_t<0, 256>(P, L, stream) : launch_flat_t<1, 256>(P, L, stream);
-    return mode == 0 ? launch_flat_t<0, 512>(P, L, stream) : launch_flat_t<1, 512>(P, L, stream);
+    if (L.obs_direct) {
+        if (mode != 0) return cudaErrorInvalidValue;                        // the direct-rows layout serves step launches only
+        if (L.threads == 128) return launch_flat_t<0, 128, 1>(P, L, stream);
+        if (L.threads == 192) return launch_flat_t<0, 192, 1>(P, L, stream);
+        if (L.threads == 384) return launch_flat_t<0, 384, 1>(P, L, stream);
+        if (L.threads == 256) return launch_flat_t<0, 256, 1>(P, L, stream);
+        return launch_flat_t<0, 512, 1>(P, L, stream);
+    }
+    if (L.threads == 128) return mode == 0 ? launch_flat_t<0, 128, 0>(P, L, stream) : launch_flat_t<1, 128, 0>(P, L, stream);
+    if (L.threads == 192) return mode == 0 ? launch_flat_t<0, 192, 0>(P, L, stream) : launch_flat_t<1, 192, 0>(P, L, stream);
+    if (L.threads == 384) return mode == 0 ? launch_flat_t<0, 384, 0>(P, L, stream) : launch_flat_t<1, 384, 0>(P, L, stream);
+    if (L.threads == 256) return mode == 0 ? launch_flat_t<0, 256, 0>(P, L, stream) : launch_flat_t<1, 256, 0>(P, L, stream);
+    return mode == 0 ? launch_flat_t<0, 512, 0>(P, L, stream) : launch_flat_t<1, 512, 0>(P, L, stream);
 }

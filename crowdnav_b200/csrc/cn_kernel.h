@@ -94,9 +94,15 @@ struct cn_flat_layout {
     uint32_t strip_words;       /* words per strip mask: 1 (N <= 32) or 2 */
     uint32_t off_stage;         /* CN_FLAG_GATHER_STAGE: [W, D] floats for the previous step's rows on their way to the peers; else 0 */
     uint32_t total;             /* dynamic shared memory per CTA */
+    /* "direct rows" variant (plain single-GPU steps): the observation rows are not staged in shared memory -- the
+     * no-return fill and the few owned rays / pose columns / K slots go straight to the caller's [E, D] buffer (L2
+     * absorbs them) -- which takes 4 D bytes per world out of the tile and lets an SM hold all its worlds at once */
+    int obs_direct;
+    uint32_t strip_mask;        /* strips per axis - 1 (31, or 15 in the direct layout) */
 };
-int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, cn_flat_layout* L);
-int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, cn_flat_layout* L);
+/* stage: 0 none, 1 fp32 staging tile, 2 int16 staging tile; direct: 1 = rows straight to global memory (no stage) */
+int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, int direct, cn_flat_layout* L);
+int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, int direct, cn_flat_layout* L);
 /* push-only launch of the pipelined gather (the rows of the LAST step, which no later step kernel will forward) */
 cudaError_t cn_launch_push_kernel(const cn_kparams& P, const cn_flat_layout& L, cudaStream_t stream);
 /* int16 thousandths -> fp32 rows for every row of [0, rows_total) outside [row_lo, row_hi) (this rank's own rows are
@@ -107,8 +113,9 @@ cudaError_t cn_launch_flat_kernel(const cn_kparams& P, const cn_flat_layout& L, 
 
 /* cn_abi.cu: raise cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the CURRENT device to at least `smem`
  * (the attribute is per device; the table is keyed by (slot, device) and guarded by a mutex).  Slots: 0-9 flat
- * kernel (mode * 5 + CTA-size index), 10-13 warp kernel (NPL, mode), 14 risk_faithful kernel. */
-#define CN_ATTR_SLOTS 16
+ * kernel (mode * 5 + CTA-size index), 10-13 warp kernel (NPL, mode), 14 risk_faithful kernel, 16-20 flat kernel
+ * with direct rows (CTA-size index). */
+#define CN_ATTR_SLOTS 24
 #define CN_ATTR_MAX_DEVICES 64
 cudaError_t cn_ensure_smem_attr(const void* func, int slot, size_t smem);
 

@@ -275,13 +275,18 @@ def test_both_step_kernels_against_the_oracle(kernel, monkeypatch):
     n_done = _rollout(baseline_config(4, n_envs=96, auto_reset=True), 40, seed=52)     # 50 pedestrians, 720 rays, K = 16
 
 
-@pytest.mark.parametrize("tile", ["2,256", "5,256", "16,256", "6,128", "20,512"])
-def test_flat_kernel_tile_shapes(tile, monkeypatch):
+@pytest.mark.parametrize("direct", ["1", "0"])
+@pytest.mark.parametrize("tile", ["2,256", "5,256", "16,256", "6,128", "20,512", "19,256", "28,384", "32,512"])
+def test_flat_kernel_tile_shapes(tile, direct, monkeypatch):
     """Tile size / CTA size are launch parameters of the flat kernel, not part of the result: odd tiles (rows leave by
     plain stores), ragged last tiles, several pedestrian passes per thread, group-list overflow (all worlds start next
-    to two walls in the 3 m room) -- all bit-exact."""
+    to two walls in the 3 m room) -- all bit-exact.  direct = 1: plain steps write their rows straight to global memory
+    (the default, DIRECT instance of cn_flat_kernel); 0: the staged instance every fused-gather entry point uses."""
+    if direct == "0" and int(tile.split(",")[0]) > 20:
+        pytest.skip("the staged layout of this tile does not fit shared memory")
     monkeypatch.setenv("CN_KERNEL", "flat")
     monkeypatch.setenv("CN_FLAT_TILE", tile)
+    monkeypatch.setenv("CN_FLAT_DIRECT", direct)
     cfg = make_config(n_envs=77, auto_reset=True, layout_jitter=0.05)
     torch, g, o = _mk(cfg)
     assert g.kernel_tile == int(tile.split(",")[0])
@@ -289,6 +294,34 @@ def test_flat_kernel_tile_shapes(tile, monkeypatch):
     _rollout(cfg, 60, seed=53)
     monkeypatch.setenv("CN_FLAT_STORE", "plain")
     _rollout(baseline_config(1, n_envs=130, auto_reset=True), 30, seed=54)
+
+
+@pytest.mark.parametrize("off", [1, 2, 3])
+def test_direct_rows_into_an_unaligned_buffer(off):
+    """The direct-rows step kernel writes the no-return fill and the owned rays straight into the caller's buffer:
+    a row block that starts 4 / 8 / 12 bytes off a 16-byte boundary (a slice of a larger tensor), with an odd number
+    of worlds, must come out the same as the oracle's, and the bytes around the block must stay untouched."""
+    import torch
+    from crowdnav_b200.vec_env import CrowdNavVecEnv
+    from oracle.oracle import OracleEnv
+    cfg = make_config(n_envs=53, auto_reset=True, layout_jitter=0.05)
+    E, D = cfg.n_envs, cfg.obs_dim
+    big = torch.full((E * D + 64,), -7.0, dtype=torch.float32, device="cuda")
+    view = big[off:off + E * D].view(E, D)
+    g, o = CrowdNavVecEnv(cfg, device=0, obs_out=view), OracleEnv(cfg)
+    g.reset(); o.reset()
+    rng = np.random.default_rng(81 + off)
+    for t in range(25):
+        a = random_actions(rng, E)
+        obs, rew, done = g.step(torch.from_numpy(a).cuda())
+        o_obs, o_rew, o_done = o.step(a)
+        assert obs.data_ptr() == view.data_ptr()
+        got = view.cpu().numpy()
+        assert bits_equal(got, o_obs), describe_obs_diff(cfg, got, o_obs)
+        assert np.array_equal(rew.cpu().numpy(), o_rew) and np.array_equal(done.cpu().numpy(), o_done)
+    assert float(big[:off].min()) == -7.0 and float(big[off + E * D:].max()) == -7.0 and float(big[off + E * D:].min()) == -7.0
+    assert bits_equal(g.get_state_blob(), o.blob)
+    g.close()
 
 
 def test_original_env_variant():
