@@ -108,7 +108,9 @@ struct Ptrs {
     uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
     uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
     uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar; float* stage; uint32_t* strips;
+    float* fillc;
 };
+#define CF_FILLC_BYTES 512u     // direct rows: constant tile of "no return" values the bulk fill stores read
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -534,6 +536,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     S.stage = reinterpret_cast<float*>(smem + L.off_stage);
     S.strips = reinterpret_cast<uint32_t*>(smem + L.off_strips);
+    S.fillc = reinterpret_cast<float*>(smem + L.off_fillc);
 
     FSTAMP(0);
     const int n_items = nE * N;                       // pedestrians of the tile
@@ -579,18 +582,15 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             const float fill = P.d.max_range_r3;
             const int tot = nE * D;
             if (DIRECT) {
-                // straight into the caller's rows: scalar stores up to the first 16-byte boundary, 16-byte stores, tail
-                float* g = S.obs;
-                int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u)) & 15u) >> 2);
-                head = min(head, tot);
-                if (tid < head) g[tid] = fill;
-                float4* g4 = reinterpret_cast<float4*>(g + head);
-                const int n4 = (tot - head) >> 2;
-                const float4 f4 = make_float4(fill, fill, fill, fill);
-#pragma unroll 4
-                for (int i = tid; i < n4; i += T) g4[i] = f4;
-                const int t0 = head + (n4 << 2);
-                if (tid < tot - t0) g[t0 + tid] = fill;
+                // Direct rows: the "no return" fill of the ray columns is left to the TMA engine -- bulk stores from a
+                // 512-byte constant tile, issued by warp 0 (lane = row) once the state tile has landed, draining under
+                // the pedestrian phase.  (Measured at c3, one wave: the fill as plain stores from every thread here
+                // saturates the L2 write path, the tile's bulk loads queue behind 26 MB of stores and land after 5.8 us
+                // instead of 1.7; streamed by one warp it takes that warp 11 us -- per-warp store issue, not bandwidth.)
+                if (warp == 0) {
+                    reinterpret_cast<float4*>(S.fillc)[lane] = make_float4(fill, fill, fill, fill);
+                    fence_async_smem();
+                }
             } else {
                 const int n4 = tot >> 2;
                 fill16<T>(S.obs, n4, u_of(fill), tid);
@@ -630,6 +630,25 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     FSTAMP(11);
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
+    if (DIRECT && warp == 0) {
+        // lane = row: the 16-byte-aligned interior of the row's ray columns by bulk stores from the constant tile, the
+        // (at most three + three) floats in front of and behind it by plain stores; the pose columns and the K block
+        // are not touched (the pose warps write them, in any order with this)
+        if (lane < nE) {
+            const float fill = P.d.max_range_r3;
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(S.obs + (size_t)lane * D), a1 = a0 + (uintptr_t)NR * 4u;
+            uintptr_t b0 = (a0 + 15u) & ~(uintptr_t)15u, b1 = a1 & ~(uintptr_t)15u;
+            if (b1 < b0) { b0 = a1; b1 = a1; }
+#pragma unroll 1
+            for (uintptr_t q = a0; q < b0; q += 4u) *reinterpret_cast<float*>(q) = fill;
+#pragma unroll 1
+            for (uintptr_t q = b1; q < a1; q += 4u) *reinterpret_cast<float*>(q) = fill;
+#pragma unroll 1
+            for (uintptr_t q = b0; q < b1; q += CF_FILLC_BYTES)
+                tma_store(reinterpret_cast<void*>(q), S.fillc, (uint32_t)min((uintptr_t)CF_FILLC_BYTES, b1 - q));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
     if (push_bulk && warp == 0) {
         if (tid == 0 && !(L.gather_debug & 4)) {
             mbar_wait(S.bar + 1, 0);
@@ -693,6 +712,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             pose_scalars(P, p, part, wpx, wpy, pd, ph, ppx, ppy, stepc, !reset_now, !reset_now, bad, scl, rowl);
             if (part == 1) scl[S_WDIRTY] = 0u;
         }
+
         if (part == 1) {
             // the walls in range of the sensor, one lane per (world, face) instead of four faces in a row per world:
             // the rays that can see the face (span), the chunks of the row they touch, the span's ray groups
@@ -714,6 +734,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 }
             }
         }
+        // direct rows: the fill stores have long completed; make that formal before #A, behind which the owned rays
+        // are written over them
+        if (DIRECT && part == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // item = pedestrian of the tile (P: CROWD:98-144 + contact stand-in, Jacobi: old positions in pa, new in pa2)
         const int ptid = tid - 32 * CF_POSE_WARPS;
@@ -1295,7 +1318,7 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->obs_direct = direct ? 1 : 0;
     /* ray-group lists: a primitive whose groups do not fit is walked directly (same results), so the capacity is a
      * matter of speed only; the direct layout, which is after the smallest tile, sizes them for the average world */
-    L->cap_wg = (uint32_t)W * (direct ? 20u : 32u);
+    L->cap_wg = (uint32_t)W * (direct ? 16u : 32u);
     L->cap_pg = (uint32_t)W * (direct ? 12u : 24u);
     L->strip_mask = direct ? 15u : 31u;
     size_t o = 0;
@@ -1322,6 +1345,8 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o = up16(o + (size_t)L->cap_pg * 4);            L->off_cnt = (uint32_t)o;
     o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
     o += 16;
+    L->off_fillc = 0;
+    if (direct) { o = up16(o); L->off_fillc = (uint32_t)o; o += CF_FILLC_BYTES; }
     L->off_stage = 0;
     if (stage) { o = up16(o); L->off_stage = (uint32_t)o; o = up16(o + (size_t)W * D * (stage == 2 ? 2 : 4)); }   /* int16 or fp32 rows */
     L->total = (uint32_t)o;
@@ -1333,6 +1358,8 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
     // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
     // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
     // Direct rows: six resident CTAs per SM (40 registers), tiles up to 32 worlds (the lane = world warps), any width.
+    // Measured (profiles/r02/direct_rows_ab.txt): c3 fits ONE wave with 19 worlds per CTA (24.5 us against 30.1 us
+    // staged, two residency rounds); 28 worlds x 384 threads x 4 CTAs per SM is the same within 1 %.
     const int threads = 256, ctas = direct ? 6 : CN_FLAT_CTAS_PER_SM;
     const size_t budget = smem_per_sm / ctas - 1024;
     const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
@@ -1349,6 +1376,7 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
                                                                    share of a CTA's life that is not per-CTA fixed cost */
         if (W < 4) score -= 50.0;                               /* tiny tiles waste the lane = world warps */
         if (!bulk) score -= 10.0;
+        if (direct && (W & 1)) score -= (waves == 1) ? 1.5 : 0.1;   /* odd tiles: actions by plain loads (measured c2: W = 5 11.95 us, 6 11.45) */
         if (score > best_score) { best_score = score; best = W; }
     }
     if (!best) return -1;
