@@ -196,6 +196,14 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
                 const char* comma = strchr(tile, ',');
                 if (comma) tt = atoi(comma + 1);
                 drc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, 0, 1, &flat_direct);
+                if (drc == 0) {     /* what the CTA's share of shared memory leaves goes to the fill tile (as cn_flat_pick_tile does) */
+                    const int ctas = tt >= 512 ? 3 : tt >= 384 ? 4 : tt >= 256 ? 6 : tt >= 192 ? 8 : 12;
+                    const size_t budget = (size_t)max_sm / ctas - 1024, want = (((size_t)cfg->n_samples - 1) * 4 + 15) & ~(size_t)15;
+                    size_t fc = 512 + (budget > flat_direct.total ? budget - flat_direct.total : 0);
+                    if (fc > want) fc = want;
+                    fc &= ~(size_t)15;
+                    if (fc > 512) drc = cn_flat_make_layout(cfg->n_peds, cfg->n_samples, d.obs_dim, tw, tt, 0, (int)fc, &flat_direct);
+                }
             } else {
                 int n_sms = 0;
                 CN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));

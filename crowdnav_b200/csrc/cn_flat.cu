@@ -84,7 +84,8 @@ enum {
     F_OVF_FACES,        // wall faces whose ray groups did not fit the group list
     F_NOBJ,             // objects of this world in the K block (entries of its object list)
     F_NCAND,            // LiDAR candidates of this world (entries of its candidate list)
-    F_EXI, F_EYI, F_ETH, F_EOFFX, F_EOFFY,      // new robot pose + sensor offset, published early by warp 2 (= S_XI ... S_OFFY)
+    F_ETH,                                      // new robot pose + sensor offset, published early by pose warp 1 (= S_TH,
+    F_EXI, F_EYI, F_EOFFX, F_EOFFY,             //  S_XI, S_YI, S_OFFX, S_OFFY); the last four are one aligned 16-byte quad
     F_WORDS = 52
 };
 #define XF_ACTIVE 1u    // the world is processed by this launch
@@ -92,6 +93,7 @@ enum {
 #define XF_EGO    4u    // an object's centre range < 0.140 (ENV:1000)
 
 enum { C_NCAND = 0, C_NRES, C_NWG, C_NPG, C_OVF, C_NCON, C_NOBJ, C_WORDS = 8 };
+static_assert((F_EXI % 4) == 0 && (F_WORDS % 4) == 0, "the published-pose quad must be 16-byte aligned");
 
 // candidate record (8 words per pedestrian slot).  Phases 2-3: q (sensor-relative centre), bearing, span,
 // owned-ray count, centre ray.  Phase 5 puts the object's CP row for phase 6 into the words nobody else reads
@@ -108,9 +110,9 @@ struct Ptrs {
     uint32_t* robot; uint32_t* pa; uint32_t* pb; uint32_t* pa2; float* act; float* obs;
     uint32_t* sc; uint32_t* rec; uint32_t* pk; uint32_t* peers; uint16_t* clist; uint8_t* clw; uint16_t* rlist;
     uint16_t* olist; uint8_t* mark; uint32_t* wg; uint32_t* pg; uint32_t* cnt; uint64_t* bar; float* stage; uint32_t* strips;
-    float* fillc;
+    float* fillc; uint32_t* strips_y;
 };
-#define CF_FILLC_BYTES 512u     // direct rows: constant tile of "no return" values the bulk fill stores read
+#define CF_FILLC_MIN 512u       // direct rows: smallest constant tile of "no return" values the bulk fill stores read
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -536,9 +538,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     S.bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     S.stage = reinterpret_cast<float*>(smem + L.off_stage);
     S.strips = reinterpret_cast<uint32_t*>(smem + L.off_strips);
+    S.strips_y = reinterpret_cast<uint32_t*>(smem + L.off_strips_y);
     S.fillc = reinterpret_cast<float*>(smem + L.off_fillc);
 
-    FSTAMP(0);
     const int n_items = nE * N;                       // pedestrians of the tile
     const uint32_t rob_bytes = (uint32_t)nE * CN_ROBOT_WORDS * 4u;
     const uint32_t ped_bytes = (uint32_t)n_items * 16u;
@@ -588,7 +590,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 // saturates the L2 write path, the tile's bulk loads queue behind 26 MB of stores and land after 5.8 us
                 // instead of 1.7; streamed by one warp it takes that warp 11 us -- per-warp store issue, not bandwidth.)
                 if (warp == 0) {
-                    reinterpret_cast<float4*>(S.fillc)[lane] = make_float4(fill, fill, fill, fill);
+#pragma unroll 1
+                    for (int i = lane; i < (int)(L.fillc_bytes >> 4); i += 32)
+                        reinterpret_cast<float4*>(S.fillc)[i] = make_float4(fill, fill, fill, fill);
                     fence_async_smem();
                 }
             } else {
@@ -598,10 +602,13 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             }
         }
         {                                                                   // contact-prefilter strips: all empty
-            const int n16 = (nE * 2 * ((int)L.strip_mask + 1) * (int)L.strip_words) >> 2;
-            uint4* z = reinterpret_cast<uint4*>(S.strips);
+            const int n16 = (nE * ((int)L.strip_mask + 1) * (int)L.strip_words) >> 2;     // per axis
+            uint4* zx = reinterpret_cast<uint4*>(S.strips);
+            uint4* zy = reinterpret_cast<uint4*>(S.strips_y);
 #pragma unroll 1
-            for (int i = tid; i < n16; i += T) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < 2 * n16; i += T) {
+                if (i < n16) zx[i] = make_uint4(0u, 0u, 0u, 0u); else zy[i - n16] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         if (tid < C_WORDS) S.cnt[tid] = 0u;
         if (tid < nE) {
@@ -625,9 +632,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // fused gather, pipelined: before the peers' buffers are touched by our pushes lane s of warp 0 checks source rank
     // s's progress (normally one L2 hit, under the fills)
     if (push && warp == 0 && !(L.gather_debug & 1)) guard_peer_buffers(P, lane);
-    FSTAMP(3);
     __syncthreads();            // fills done, barrier init visible
-    FSTAMP(11);
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
     if (DIRECT && warp == 0) {
@@ -644,8 +649,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
 #pragma unroll 1
             for (uintptr_t q = b1; q < a1; q += 4u) *reinterpret_cast<float*>(q) = fill;
 #pragma unroll 1
-            for (uintptr_t q = b0; q < b1; q += CF_FILLC_BYTES)
-                tma_store(reinterpret_cast<void*>(q), S.fillc, (uint32_t)min((uintptr_t)CF_FILLC_BYTES, b1 - q));
+            for (uintptr_t q = b0; q < b1; q += L.fillc_bytes)
+                tma_store(reinterpret_cast<void*>(q), S.fillc, (uint32_t)min((uintptr_t)L.fillc_bytes, b1 - q));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
@@ -762,8 +767,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         };
         auto cand_test = [&](int it, int w, int32_t nx, int32_t ny) {
             uint32_t* sc = S.sc + w * F_WORDS;
-            const float qx = (float)(nx - (int32_t)sc[F_EXI]) * CN_GRID - f_of(sc[F_EOFFX]);
-            const float qy = (float)(ny - (int32_t)sc[F_EYI]) * CN_GRID - f_of(sc[F_EOFFY]);
+            const uint4 ep = *reinterpret_cast<const uint4*>(sc + F_EXI);   // EXI, EYI, EOFFX, EOFFY in one load
+            const float qx = (float)(nx - (int32_t)ep.x) * CN_GRID - f_of(ep.z);
+            const float qy = (float)(ny - (int32_t)ep.y) * CN_GRID - f_of(ep.w);
             if (fmaf(qx, qx, qy * qy) < P.d.cand_d2) {
                 const uint32_t pos = atomicAdd(&S.cnt[C_NCAND], 1u);
                 S.clist[pos] = (uint16_t)it;
@@ -781,8 +787,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         const int smask = (int)L.strip_mask, nstrip = smask + 1;               // strips per axis (a power of two)
         auto strip_of = [&](int32_t c, int32_t origin) { return (int)(((uint32_t)(c - origin)) >> sshift) & smask; };
         auto contact_masks = [&](int w, int n, int32_t x0, int32_t y0, uint32_t& m0, uint32_t& m1) {
-            const uint32_t* xm = S.strips + (size_t)w * 2 * nstrip * sw;
-            const uint32_t* ym = xm + nstrip * sw;
+            const uint32_t* xm = S.strips + (size_t)w * nstrip * sw;
+            const uint32_t* ym = S.strips_y + (size_t)w * nstrip * sw;
             const int sx = strip_of(x0, P.d.ped_xmin), sy = strip_of(y0, P.d.ped_ymin);
             const int xa = ((sx + smask) & smask) * sw, xb = sx * sw, xc = ((sx + 1) & smask) * sw;
             const int ya = ((sy + smask) & smask) * sw, yb = sy * sw, yc = ((sy + 1) & smask) * sw;
@@ -844,15 +850,19 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             S.mark[it] = mk;
             if (MODE == 0) {
                 const uint2 a = *reinterpret_cast<const uint2*>(S.pa + 4 * it);
-                uint32_t* xm = S.strips + (size_t)w * 2 * nstrip * sw;
                 const uint32_t bit = 1u << (n & 31);
-                atomicOr(xm + strip_of((int32_t)a.x, P.d.ped_xmin) * sw + (n >> 5), bit);
-                atomicOr(xm + nstrip * sw + strip_of((int32_t)a.y, P.d.ped_ymin) * sw + (n >> 5), bit);
+                atomicOr(S.strips + (size_t)w * nstrip * sw + strip_of((int32_t)a.x, P.d.ped_xmin) * sw + (n >> 5), bit);
+                atomicOr(S.strips_y + (size_t)w * nstrip * sw + strip_of((int32_t)a.y, P.d.ped_ymin) * sw + (n >> 5), bit);
             }
         }
-        // contact masks and the draw list are complete; pose warp 1 has published the robot's new pose
+        // contact masks and the draw list are complete; pose warp 1 has published the robot's new pose.
+        // (Tried: a pedestrian-only barrier here and the candidate tests as a separate pass after the second barrier,
+        //  so that nobody waits for pose warp 1 -- 0.9 us per warp at c3: slower, c2 11.04 -> 11.58 us, c3 24.44 ->
+        //  24.94 us.  The phase is bound by the instructions issued per SM, not by a warp's critical path: a waiting warp
+        //  costs nothing, the extra pass does.)
         FSTAMP(4);
         named_bar_sync(2, 32 + PED_THREADS);
+        FSTAMP(0);
 
         // -- B: pedestrians with nothing special: integrate, candidate test.  Contacts go to the slow list.
         if (MODE == 0) {
@@ -867,10 +877,11 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 cand_test(it, w, np.x, np.y);
             }
         }
+        FSTAMP(3);
         //    ... and the compacted list of pedestrians that draw this step: Philox, then the same
+        //    (entry q goes to thread PED_THREADS - 1 - q: the high threads have no pedestrian of their own when the
+        //     tile has fewer pedestrians than threads, so the draws start at once instead of after a plain item)
         {
-            // (entry q goes to thread PED_THREADS - 1 - q: the high threads have no pedestrian of their own when the
-            //  tile has fewer pedestrians than threads, so the draws start at once instead of after a plain item)
             const int n_res = (int)S.cnt[C_NRES];
             for (int q = PED_THREADS - 1 - ptid; q < n_res; q += PED_THREADS) {
                 const uint32_t ent = S.rlist[q];
@@ -909,6 +920,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 }
             }
         }
+        FSTAMP(11);
         named_bar_sync(1, PED_THREADS);
 
         // -- C: the few pedestrians with somebody inside the contact box: repulsion (index order, like the oracle)
@@ -954,8 +966,9 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             const uint32_t* sc = S.sc + w * F_WORDS;
             uint32_t* rec = S.rec + slot * 8;
             const uint2 a = *reinterpret_cast<const uint2*>(S.pa2 + 4 * slot);
-            const float qx = (float)((int32_t)a.x - (int32_t)sc[F_EXI]) * CN_GRID - f_of(sc[F_EOFFX]);
-            const float qy = (float)((int32_t)a.y - (int32_t)sc[F_EYI]) * CN_GRID - f_of(sc[F_EOFFY]);
+            const uint4 ep = *reinterpret_cast<const uint4*>(sc + F_EXI);
+            const float qx = (float)((int32_t)a.x - (int32_t)ep.x) * CN_GRID - f_of(ep.z);
+            const float qy = (float)((int32_t)a.y - (int32_t)ep.y) * CN_GRID - f_of(ep.w);
             const float d2 = fmaf(qx, qx, qy * qy);
             const uint32_t bearing = cn_rad2bin(cn_atan2(qy, qx));
             float alpha = 4.0f;                                    // sensor inside / touching the disc: all rays
@@ -1310,7 +1323,6 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     if (threads != 128 && threads != 192 && threads != 256 && threads != 384 && threads != 512) return -1;
     if (W < 1 || W > 32) return -1;
     if ((size_t)W * N > 0x3FFF) return -1;                                  // group-entry / list-entry fields
-    (void)n_samples;
     L->W = W;
     L->threads = threads;
     L->plain_store = 0;
@@ -1318,9 +1330,18 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->obs_direct = direct ? 1 : 0;
     /* ray-group lists: a primitive whose groups do not fit is walked directly (same results), so the capacity is a
      * matter of speed only; the direct layout, which is after the smallest tile, sizes them for the average world */
-    L->cap_wg = (uint32_t)W * (direct ? 16u : 32u);
-    L->cap_pg = (uint32_t)W * (direct ? 12u : 24u);
-    L->strip_mask = direct ? 15u : 31u;
+    if (direct) {
+        /* 14 wall groups and 10 pedestrian groups of 8 rays per world at 359 rays, in proportion for other scans
+         * (measured at c5, 719 rays: the 359-ray capacities overflow all the time, 95 -> 102 us) */
+        const uint32_t nr = (uint32_t)(n_samples > 1 ? n_samples - 1 : 1);
+        const uint32_t gw = (14u * nr + 358u) / 359u, gp = (10u * nr + 358u) / 359u;
+        L->cap_wg = (uint32_t)W * (gw < 8u ? 8u : gw);
+        L->cap_pg = (uint32_t)W * (gp < 8u ? 8u : gp);
+    } else {
+        L->cap_wg = (uint32_t)W * 32u;
+        L->cap_pg = (uint32_t)W * 24u;
+    }
+    L->strip_mask = 31u;
     size_t o = 0;
     o += (size_t)W * CN_ROBOT_WORDS * 4;            L->off_pa = (uint32_t)o;
     /* 32 B per pedestrian: the old-position plane (16 B each) in the first half, the contact masks of the slow list
@@ -1335,7 +1356,18 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o = up16(o + (direct ? 0 : (size_t)W * D * 4)); L->off_sc = (uint32_t)o;
     L->strip_words = (N > 32) ? 2u : 1u;
     o = up16(o + (size_t)W * F_WORDS * 4);          L->off_strips = (uint32_t)o;
-    o += (size_t)W * 2 * (L->strip_mask + 1) * L->strip_words * 4;   L->off_clist = (uint32_t)o;
+    {
+        /* contact-prefilter strip masks: [W][32][strip_words] per axis.  The staged layout keeps both axes here; the
+         * direct layout puts the y masks into the quarter of the pa / peers / rec region nobody uses while they are
+         * alive (32 B per pedestrian: 16 B old position, 8 B contact masks, 8 B free until the candidate records take
+         * the region over in phase 2b) when they fit there */
+        const size_t axis = (size_t)W * (L->strip_mask + 1) * L->strip_words * 4;
+        const size_t free_lo = up16((size_t)L->off_peers + (size_t)W * N * 8), free_hi = (size_t)L->off_pb;
+        o += axis;
+        if (direct && free_lo + axis <= free_hi) L->off_strips_y = (uint32_t)free_lo;
+        else { L->off_strips_y = (uint32_t)o; o += axis; }
+    }
+    L->off_clist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_clw = (uint32_t)o;
     o = up16(o + (size_t)W * N);                    L->off_rlist = (uint32_t)o;
     o = up16(o + (size_t)W * N * 2);                L->off_olist = (uint32_t)o;
@@ -1346,7 +1378,12 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     o += C_WORDS * 4;                               L->off_bar = (uint32_t)o;
     o += 16;
     L->off_fillc = 0;
-    if (direct) { o = up16(o); L->off_fillc = (uint32_t)o; o += CF_FILLC_BYTES; }
+    L->fillc_bytes = 0;
+    if (direct) {
+        /* direct > 1: the size of the constant tile in bytes (one bulk store covers that much of a row's ray columns) */
+        L->fillc_bytes = (direct > 1) ? (uint32_t)(direct & ~15) : CF_FILLC_MIN;
+        o = up16(o); L->off_fillc = (uint32_t)o; o += L->fillc_bytes;
+    }
     L->off_stage = 0;
     if (stage) { o = up16(o); L->off_stage = (uint32_t)o; o = up16(o + (size_t)W * D * (stage == 2 ? 2 : 4)); }   /* int16 or fp32 rows */
     L->total = (uint32_t)o;
@@ -1380,6 +1417,17 @@ int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_
         if (score > best_score) { best_score = score; best = W; }
     }
     if (!best) return -1;
+    if (direct) {
+        /* whatever the tile leaves of the CTA's share of shared memory goes to the constant tile of the bulk fill,
+         * up to one whole row of ray columns (one bulk store per row instead of three) */
+        cn_flat_layout t;
+        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, 1, &t) != 0) return -1;
+        const size_t want = up16((size_t)(n_samples - 1) * 4);
+        size_t fc = CF_FILLC_MIN + (budget > t.total ? budget - t.total : 0);
+        if (fc > want) fc = want;
+        direct = (int)(fc & ~(size_t)15);
+        if (direct < (int)CF_FILLC_MIN) direct = (int)CF_FILLC_MIN;
+    }
     return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, direct, L);
 }
 

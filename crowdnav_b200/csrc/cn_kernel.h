@@ -98,8 +98,10 @@ struct cn_flat_layout {
      * no-return fill and the few owned rays / pose columns / K slots go straight to the caller's [E, D] buffer (L2
      * absorbs them) -- which takes 4 D bytes per world out of the tile and lets an SM hold all its worlds at once */
     int obs_direct;
-    uint32_t strip_mask;        /* strips per axis - 1 (31, or 15 in the direct layout) */
-    uint32_t off_fillc;         /* direct layout: 512-byte constant tile the bulk fill stores read */
+    uint32_t strip_mask;        /* strips per axis - 1 */
+    uint32_t off_strips_y;      /* the y-axis strip masks (off_strips: the x-axis ones) */
+    uint32_t off_fillc;         /* direct layout: constant tile the bulk fill stores read ... */
+    uint32_t fillc_bytes;       /* ... and its size (512 bytes up to one row of ray columns, as the tile leaves room) */
 };
 /* stage: 0 none, 1 fp32 staging tile, 2 int16 staging tile; direct: 1 = rows straight to global memory (no stage) */
 int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int threads, int stage, int direct, cn_flat_layout* L);

@@ -25,10 +25,10 @@ for _ in range(30):
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 L.cn_debug_set_timeline_flat.argtypes = [C.c_void_p]
 assert L.cn_debug_set_timeline_flat(C.c_void_p(tl.data_ptr())) == 0
-names = {14: "kernel entry", 15: "tma issued (thread 0)", 3: "fills done (per warp)", 4: "ped A done (ped warps)", 0: "pointers set up", 11: "fills done (bar #0)", 1: "tma landed", 13: "peds integrated (ped warps)", 9: "phase 1+2 done (per warp)",
+names = {14: "kernel entry", 15: "tma issued (thread 0)", 3: "draws done (ped warps)", 4: "ped A done (ped warps)", 0: "after ped barrier A (ped warps)", 11: "B done, before barrier (ped warps)", 1: "tma landed", 13: "peds integrated (ped warps)", 9: "phase 1+2 done (per warp)",
          2: "after #A", 10: "phase 3 done (per warp)", 5: "after #E", 6: "after #F (5)", 12: "phase 6 done (per warp)",
          7: "after #G", 8: "stores drained (thread 0)"}
-order = [14, 0, 15, 3, 11, 1, 4, 13, 9, 2, 10, 5, 6, 12, 7, 8]
+order = [14, 15, 1, 4, 0, 3, 11, 13, 9, 2, 10, 5, 6, 12, 7, 8]
 for it in range(4):
     tl.zero_()
     (flush.fill_(it) if os.environ.get("CN_NOFLUSH") is None else None); torch.cuda.synchronize()
@@ -59,3 +59,14 @@ for it in range(4):
         d = (t[m, k] - t[m, 14]) / 1000.0    # since this warp's kernel entry
         print("   %-28s abs: med %6.2f max %6.2f | since CTA start: min %5.2f med %5.2f p90 %5.2f max %5.2f" % (
             names[k], np.median(c), c.max(), d.min(), np.median(d), np.percentile(d, 90), d.max()))
+    # per-warp durations between consecutive stamps (only warps that have both), by role
+    print("   -- per-warp durations (us): median / p90 / max, by role")
+    for nm, sel in (("pose warp 0", role == 0), ("pose warp 1", role == 1), ("pedestrian warps", role >= 2)) if role is not None else ():
+        prev = 14
+        for k in order[1:]:
+            m = sel & (t[:, k] > 0) & (t[:, prev] > 0)
+            if not m.any():
+                continue
+            d = (t[m, k] - t[m, prev]) / 1000.0
+            print("   [%-16s] %-36s -> %-36s med %5.2f p90 %5.2f max %5.2f (n=%d)" % (nm, names[prev], names[k], np.median(d), np.percentile(d, 90), d.max(), m.sum()))
+            prev = k
