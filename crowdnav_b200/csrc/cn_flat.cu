@@ -58,6 +58,8 @@
 #define CN_COMPACT_CODE 1
 #define CN_WALLS_BY_LANE 1      // pose_scalars leaves the wall faces to the kernel: one lane per (world, face)
 #include "cn_dev.h"
+#include <stdlib.h>
+#include <string.h>
 
 #define CF_POSE_WARPS 2
 #ifndef CN_FLAT_CTAS_PER_SM
@@ -101,6 +103,8 @@ static_assert((F_EXI % 4) == 0 && (F_WORDS % 4) == 0, "the published-pose quad m
 enum { Q_QX = 0, Q_QY, Q_BEAR, Q_SPA, Q_SPB, Q_CNT, Q_MISC, Q_CKEY };
 enum { O_CP = Q_BEAR, O_VX = Q_CNT, O_VY = Q_MISC, O_TTC = Q_CKEY };   // Q_CKEY: min centre-ray key over the owned rays
 #define MARK_OVF 3           // S.mark[slot] of a candidate whose ray groups did not fit the group list
+#define MARK_KIND 0x7Fu      // S.mark: low bits = what the pedestrian is this step (0 plain, 1 on the draw list, 2 untouched, MARK_OVF)
+#define MARK_WAS_TRACKED 0x80u   // ... bit 7 = it was a tracked object when the step began (phase A moves the flag here)
 
 // ray-group entry: up to 8 consecutive scan indices of one primitive
 //   bits 0-2 count - 1, bits 3-13 first index, bits 14-31 primitive (pedestrian slot, or world * 4 + face)
@@ -445,13 +449,14 @@ __device__ __forceinline__ void risk_candidate(const cn_kparams& P, const Ptrs& 
     const float hy = cn_py_round3(yf + (d_raw * sa) * -1.0f);
     // H/I: tracker with ideal association (ENV:656-760)
     float chx = 0.0f, chy = 0.0f, speed = -1.0f, ovx = 0.0f, ovy = 0.0f;
-    if (S.pb[4 * slot + 3] & CN_PF_TRACKED) {
+    if (S.mark[slot] & MARK_WAS_TRACKED) {                             // (the flag word itself was cleared by phase A)
         chx = f_of(S.pb[4 * slot + 0]) - hx; chy = f_of(S.pb[4 * slot + 1]) - hy;      // last - curr (sic), ENV:806-807
         speed = sqrtf(fmaf(chy, chy, chx * chx)) * P.d.inv_dt;
         ovx = chx * P.d.inv_dt; ovy = chy * P.d.inv_dt;
     }
     S.pb[4 * slot + 0] = u_of(hx); S.pb[4 * slot + 1] = u_of(hy);
     atomicOr(&sc[F_CONF0 + (n >> 5)], 1u << (n & 31));
+    S.pb[4 * slot + 3] |= CN_PF_TRACKED;                                // tracked next step iff confirmed now (ENV:656-743, ideal association)
     if (d3 < 0.140f) atomicOr(&sc[F_XFLAGS], XF_EGO);                   // ENV:1000
     if (sc[F_XFLAGS] & XF_RESET) return;                              // ENV:769: no previous pose at step 0
     // J: collision cone (ENV:765-860, UTL:251-293 as a true ray-circle test)
@@ -831,7 +836,12 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 continue;
             }
             uint8_t mk = 0;
-            int32_t tm = (int32_t)S.pb[4 * it + 2] - CN_TICKS_PER_STEP;
+            // (timer, flags) in one load.  A pedestrian is tracked next step iff it is confirmed as an object in THIS one:
+            // the flag moves into the mark byte here, where phase 5 reads it, and phase 5 sets it again for what it
+            // confirms -- instead of a pass over every pedestrian at the end that rewrites a flag which almost never changes
+            const uint2 tf = *reinterpret_cast<const uint2*>(S.pb + 4 * it + 2);
+            if (tf.y & CN_PF_TRACKED) { S.pb[4 * it + 3] = tf.y & ~CN_PF_TRACKED; mk = MARK_WAS_TRACKED; }
+            int32_t tm = (int32_t)tf.x - CN_TICKS_PER_STEP;
             if (tm <= 0) {
                 const uint32_t gid = (uint32_t)(P.env_id_offset + e0 + w);
                 const int b = (P.n_behaviors == 1) ? 0 : (int)(gid % (uint32_t)P.n_behaviors);
@@ -839,7 +849,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                 if (P.beh_kind[b] == CN_BEHAVIOR_RANDOM) {
                     const uint32_t pos = atomicAdd(&S.cnt[C_NRES], 1u);
                     S.rlist[pos] = (uint16_t)it;
-                    mk = 1;
+                    mk |= 1;
                 } else {
                     const float speed = P.beh_speed[b];
                     S.pa[4 * it + 2] = u_of(__ldg(&P.cfg->behavior_table[b][n][0]) * speed);
@@ -867,7 +877,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         // -- B: pedestrians with nothing special: integrate, candidate test.  Contacts go to the slow list.
         if (MODE == 0) {
             for (int it = ptid; it < n_items; it += PED_THREADS) {
-                if (S.mark[it] != 0) continue;
+                if ((S.mark[it] & MARK_KIND) != 0) continue;
                 const int w = world_of(it, N, L.magic_n);
                 const uint4 a = spa4[it];
                 uint32_t m0, m1;
@@ -986,7 +996,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
             rec[Q_CKEY] = 0xFFFFFFFFu;
             rec[Q_MISC] = 0u;
             if (!push_groups(S.pg, &S.cnt[C_NPG], (int)L.cap_pg, (uint32_t)slot, sp)) {
-                S.mark[slot] = MARK_OVF;                                    // walked directly in phase 3 (mark is dead by now)
+                S.mark[slot] = (uint8_t)((S.mark[slot] & MARK_WAS_TRACKED) | MARK_OVF);   // walked directly in phase 3
                 S.cnt[C_OVF] = 1u;
             }
         }
@@ -1034,7 +1044,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
         if (src >= 0) {
             slot_src = (int)S.clist[src];
-            if (S.mark[slot_src] != MARK_OVF) continue;
+            if ((S.mark[slot_src] & MARK_KIND) != MARK_OVF) continue;
             const uint32_t* rec = S.rec + slot_src * 8;
             unpack_span(rec[Q_SPA], rec[Q_SPB], sp);
             n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
@@ -1105,15 +1115,8 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
         blk[0] = f_of(S.pb[4 * slot + 0]); blk[1] = f_of(S.pb[4 * slot + 1]);      // hit point: already multiples of 0.001
         blk[2] = cn_np_round3(f_of(rec[O_VX])); blk[3] = cn_np_round3(f_of(rec[O_VY]));
     }
-    // 6b  tracker flags: a pedestrian is tracked next step iff it was confirmed now (ENV:656-743, ideal association)
-    for (int it = tid; it < n_items && tid < T6; it += T6) {
-        const int w = world_of(it, N, L.magic_n), n = it - w * N;
-        const uint32_t* sc = S.sc + w * F_WORDS;
-        if (sc[F_XFLAGS] & XF_ACTIVE) {
-            const uint32_t bit = (sc[F_CONF0 + (n >> 5)] >> (n & 31)) & 1u;
-            S.pb[4 * it + 3] = (S.pb[4 * it + 3] & ~CN_PF_TRACKED) | (bit ? CN_PF_TRACKED : 0u);
-        }
-    }
+    // (6b, the tracker flags of every pedestrian, is gone: phase A clears the flag of what was tracked, phase 5 sets it for
+    //  what it confirms)
     // 6c  lane = world (last warp): M counters, N done, W terminal reward, robot record
     if (warp == T / 32 - 1) {
         for (int w = lane; w < nE; w += 32) {
@@ -1330,16 +1333,20 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
     L->obs_direct = direct ? 1 : 0;
     /* ray-group lists: a primitive whose groups do not fit is walked directly (same results), so the capacity is a
      * matter of speed only; the direct layout, which is after the smallest tile, sizes them for the average world */
-    if (direct) {
-        /* 14 wall groups and 10 pedestrian groups of 8 rays per world at 359 rays, in proportion for other scans
-         * (measured at c5, 719 rays: the 359-ray capacities overflow all the time, 95 -> 102 us) */
+    {
+        /* Ray-group lists: 14 wall groups and 10 pedestrian groups of 8 rays per world at 359 rays in the direct layout
+         * (which is after the smallest tile), 32 and 24 in the staged one -- in proportion for other scans.  Measured at c5
+         * (719 rays): with the 359-ray capacities the lists overflow all the time and the primitives are walked on the
+         * slow path, 95 us per step; in proportion 67 us.  CN_FLAT_CAPS="gw,gp" overrides the per-world figures (experiments). */
         const uint32_t nr = (uint32_t)(n_samples > 1 ? n_samples - 1 : 1);
-        const uint32_t gw = (14u * nr + 358u) / 359u, gp = (10u * nr + 358u) / 359u;
+        uint32_t gw = ((direct ? 14u : 32u) * nr + 358u) / 359u, gp = ((direct ? 10u : 24u) * nr + 358u) / 359u;
+        if (const char* caps = getenv("CN_FLAT_CAPS")) {
+            const int a = atoi(caps); const char* comma = strchr(caps, ',');
+            if (a > 0) gw = (uint32_t)a;
+            if (comma && atoi(comma + 1) > 0) gp = (uint32_t)atoi(comma + 1);
+        }
         L->cap_wg = (uint32_t)W * (gw < 8u ? 8u : gw);
         L->cap_pg = (uint32_t)W * (gp < 8u ? 8u : gp);
-    } else {
-        L->cap_wg = (uint32_t)W * 32u;
-        L->cap_pg = (uint32_t)W * 24u;
     }
     L->strip_mask = 31u;
     size_t o = 0;
@@ -1391,44 +1398,52 @@ int cn_flat_make_layout(int n_peds, int n_samples, int obs_dim, int tile, int th
 }
 
 int cn_flat_pick_tile(int n_peds, int n_samples, int obs_dim, int n_envs, int n_sms, size_t smem_per_sm, int stage, int direct, cn_flat_layout* L) {
-    // 256-thread CTAs, four per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk store) that
-    // fit a quarter of the SM's shared memory: a batch that fits one wave gets the smallest tile that still does
-    // (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
-    // Direct rows: six resident CTAs per SM (40 registers), tiles up to 32 worlds (the lane = world warps), any width.
-    // Measured (profiles/r02/direct_rows_ab.txt): c3 fits ONE wave with 19 worlds per CTA (24.5 us against 30.1 us
-    // staged, two residency rounds); 28 worlds x 384 threads x 4 CTAs per SM is the same within 1 %.
-    const int threads = 256, ctas = direct ? 6 : CN_FLAT_CTAS_PER_SM;
-    const size_t budget = smem_per_sm / ctas - 1024;
-    const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
-    int best = 0; double best_score = -1.0;
-    for (int W = direct ? 32 : 16; W >= 1; --W) {
-        cn_flat_layout t;
-        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, direct, &t) != 0 || t.total > budget) continue;
-        const bool bulk = direct || (((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0 && (stage < 2 || ((size_t)W * obs_dim) % 8 == 0));
-        const long n_cta = ((long)n_envs + W - 1) / W;
-        const long waves = (n_cta + slots - 1) / slots;
-        double score;
-        if (waves == 1) score = 100.0 - W;                      /* one wave: the smaller the tile the better ... */
-        else score = (double)n_cta / (double)(waves * slots) * ((double)W / (double)(W + 4));   /* ... else wave fill x the
-                                                                   share of a CTA's life that is not per-CTA fixed cost */
-        if (W < 4) score -= 50.0;                               /* tiny tiles waste the lane = world warps */
-        if (!bulk) score -= 10.0;
-        if (direct && (W & 1)) score -= (waves == 1) ? 1.5 : 0.1;   /* odd tiles: actions by plain loads (measured c2: W = 5 11.95 us, 6 11.45) */
-        if (score > best_score) { best_score = score; best = W; }
+    // Staged rows: 256-thread CTAs, five per SM.  Among the tiles (even, <= 16 worlds, row block able to leave by bulk
+    // store) that fit the CTA's share of the SM's shared memory: a batch that fits one wave gets the smallest tile that
+    // still does (most CTAs in flight, shortest critical path); a larger batch the tile that fills its waves best.
+    // Direct rows: tiles up to 32 worlds (the lane = world warps), any width; 256 threads x 6 CTAs per SM (40 registers)
+    // or 384 threads x 4.  Measured on B200 (profiles/r02b/direct_rows_ab.txt): c3 fits ONE wave with 19 worlds x 256
+    // threads (24.0 us against 30.1 us staged, two residency rounds; 28 worlds x 384 threads is the same within 1 %);
+    // c5, which needs three waves either way, is 5 % faster with 12 worlds x 384 threads than with 8 x 256 -- the
+    // per-CTA fixed cost is shared by more worlds.  So: the smallest one-wave tile at 256 threads if there is one, else
+    // the best-scoring of both CTA sizes.
+    const int n_opt = direct ? 2 : 1;
+    const int opt_threads[2] = {256, 384};
+    const int opt_ctas[2] = {direct ? 6 : CN_FLAT_CTAS_PER_SM, 4};
+    int best = 0, best_threads = 256; double best_score = -1.0; size_t best_budget = 0;
+    for (int k = 0; k < n_opt; ++k) {
+        const int threads = opt_threads[k], ctas = opt_ctas[k];
+        const size_t budget = smem_per_sm / ctas - 1024;
+        const long slots = (long)ctas * (n_sms > 0 ? n_sms : 148);
+        for (int W = direct ? 32 : 16; W >= 1; --W) {
+            cn_flat_layout t;
+            if (cn_flat_make_layout(n_peds, n_samples, obs_dim, W, threads, stage, direct, &t) != 0 || t.total > budget) continue;
+            const bool bulk = direct || (((size_t)W * obs_dim) % 4 == 0 && W % 2 == 0 && (stage < 2 || ((size_t)W * obs_dim) % 8 == 0));
+            const long n_cta = ((long)n_envs + W - 1) / W;
+            const long waves = (n_cta + slots - 1) / slots;
+            double score;
+            if (waves == 1) score = 100.0 - W - (k ? 50.0 : 0.0);   /* one wave: the smaller the tile the better, 256 threads first ... */
+            else score = (double)n_cta / (double)(waves * slots) * ((double)W / (double)(W + 4));   /* ... else wave fill x the
+                                                                       share of a CTA's life that is not per-CTA fixed cost */
+            if (W < 4) score -= 50.0;                               /* tiny tiles waste the lane = world warps */
+            if (!bulk) score -= 10.0;
+            if (direct && (W & 1)) score -= (waves == 1) ? 1.5 : 0.1;   /* odd tiles: actions by plain loads (measured c2: W = 5 11.95 us, 6 11.45) */
+            if (score > best_score) { best_score = score; best = W; best_threads = threads; best_budget = budget; }
+        }
     }
     if (!best) return -1;
     if (direct) {
         /* whatever the tile leaves of the CTA's share of shared memory goes to the constant tile of the bulk fill,
          * up to one whole row of ray columns (one bulk store per row instead of three) */
         cn_flat_layout t;
-        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, 1, &t) != 0) return -1;
+        if (cn_flat_make_layout(n_peds, n_samples, obs_dim, best, best_threads, stage, 1, &t) != 0) return -1;
         const size_t want = up16((size_t)(n_samples - 1) * 4);
-        size_t fc = CF_FILLC_MIN + (budget > t.total ? budget - t.total : 0);
+        size_t fc = CF_FILLC_MIN + (best_budget > t.total ? best_budget - t.total : 0);
         if (fc > want) fc = want;
         direct = (int)(fc & ~(size_t)15);
         if (direct < (int)CF_FILLC_MIN) direct = (int)CF_FILLC_MIN;
     }
-    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, threads, stage, direct, L);
+    return cn_flat_make_layout(n_peds, n_samples, obs_dim, best, best_threads, stage, direct, L);
 }
 
 template <int MODE, int T, int DIRECT>
