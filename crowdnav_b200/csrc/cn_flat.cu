@@ -62,6 +62,7 @@
 #include <string.h>
 
 #define CF_POSE_WARPS 2
+#define CF_RISK_WARPS 2      // warps that run E-J (phase 5) while the others cast the wall faces
 #ifndef CN_FLAT_CTAS_PER_SM
 // resident 256-thread CTAs per SM the kernel is compiled (register cap: 45 registers, no spills) and tiled for.
 // Measured on B200 (profiles/r02/ctas_per_sm_ab.txt): 4 -> 5 is neutral at c2 / c3 and 10 % faster at c5; 6 (40 registers)
@@ -1013,31 +1014,11 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // ---------------------------------------------------------------- phase 3: cast + ownership (L, C: XACRO:148-179, UTL:375-392)
     // source -1 is the group list; a source >= 0 is a primitive whose groups did not fit and is walked directly
     // (one call site for both keeps the code small)
-#pragma unroll 1
-    for (int src = -1; src < (overflow ? nE * 4 : 0); ++src) {
-        int n_groups = n_wg;
-        Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
-        if (src >= 0) {
-            const uint32_t* sc = S.sc + (src >> 2) * F_WORDS;
-            if (!((sc[F_OVF_FACES] >> (src & 3)) & 1u)) continue;
-            wall_span(sc, src & 3, sp);
-            n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
-        }
-#pragma unroll 1
-        for (int g0 = warp * 4; g0 < n_groups; g0 += (T / 32) * 4) {        // warp-uniform trip count: shuffles inside
-            const int g = g0 + (lane >> 3);
-            int q = src;
-            uint32_t rbits = 0xFFFFFFFFu;
-            if (g < n_groups) {
-                int i;
-                if (src < 0) { const uint32_t ent = S.wg[g]; i = group_ray(ent, lane8); q = (int)(ent >> 14); }
-                else i = span_ray(sp, g * 8 + lane8);
-                if (i >= 0) rbits = cast_wall(P, S, e0, q, i);
-            }
-            rbits = group_min8(rbits);                                      // ENV:1012: min over the scan, one atomic per group
-            if (lane8 == 0 && rbits != 0xFFFFFFFFu) atomicMin(S.sc + (q >> 2) * F_WORDS + F_MINBITS, rbits);
-        }
-    }
+    // The pedestrians' ray groups first, by everybody; then, behind barrier #E, the first CF_RISK_WARPS warps run E-J for
+    // the candidates (one short list, one long dependent chain) WHILE the other warps cast the wall faces' groups: the
+    // chain of phase 5 -- 1.4 us with one busy warp per CTA -- disappears under the wall rays.  (Walls do not need the
+    // candidates' E-J results and E-J does not need the walls' rays: ownership tests intersect the other primitives on
+    // the spot, and phase 5 leaves q and the spans of the candidate records alone.)
 #pragma unroll 1
     for (int src = -1; src < (overflow ? n_cand : 0); ++src) {
         int n_groups = n_pg, slot_src = 0;
@@ -1086,7 +1067,35 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     // (compacted: item = candidate.  Tried: the thread that casts a candidate's last ray group goes straight on with
     //  E-J and barrier #F goes away -- the chain then runs once per candidate with ONE active lane instead of once per
     //  tile with one lane per candidate: c3 29.7 -> 33.6 us, c2 no better; profiles/r02/bench_*_v10.json)
-    for (int q = tid; q < n_cand; q += T) risk_candidate(P, S, L.magic_n, (int)S.clist[q]);
+    if (warp < CF_RISK_WARPS) {
+        for (int q = tid; q < n_cand; q += 32 * CF_RISK_WARPS) risk_candidate(P, S, L.magic_n, (int)S.clist[q]);
+    } else {
+#pragma unroll 1
+        for (int src = -1; src < (overflow ? nE * 4 : 0); ++src) {
+            int n_groups = n_wg;
+            Span sp; sp.a0 = 1; sp.a1 = 0; sp.b0 = 1; sp.b1 = 0;
+            if (src >= 0) {
+                const uint32_t* sc = S.sc + (src >> 2) * F_WORDS;
+                if (!((sc[F_OVF_FACES] >> (src & 3)) & 1u)) continue;
+                wall_span(sc, src & 3, sp);
+                n_groups = (span_len_a(sp) + span_len_b(sp) + 7) >> 3;
+            }
+#pragma unroll 1
+            for (int g0 = (warp - CF_RISK_WARPS) * 4; g0 < n_groups; g0 += (T / 32 - CF_RISK_WARPS) * 4) {   // warp-uniform trip count: shuffles inside
+                const int g = g0 + (lane >> 3);
+                int q = src;
+                uint32_t rbits = 0xFFFFFFFFu;
+                if (g < n_groups) {
+                    int i;
+                    if (src < 0) { const uint32_t ent = S.wg[g]; i = group_ray(ent, lane8); q = (int)(ent >> 14); }
+                    else i = span_ray(sp, g * 8 + lane8);
+                    if (i >= 0) rbits = cast_wall(P, S, e0, q, i);
+                }
+                rbits = group_min8(rbits);                                      // ENV:1012: min over the scan, one atomic per group
+                if (lane8 == 0 && rbits != 0xFFFFFFFFu) atomicMin(S.sc + (q >> 2) * F_WORDS + F_MINBITS, rbits);
+            }
+        }
+    }
     __syncthreads();            // #F
     FSTAMP(6);
 
