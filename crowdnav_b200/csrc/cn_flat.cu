@@ -62,6 +62,12 @@
 #include <string.h>
 
 #define CF_POSE_WARPS 2
+#ifndef CF_FILL_LATE
+// 0: pose warp 0 issues the bulk fill of the ray columns as soon as the state tile has landed.  1: after it has advanced
+// the robots (about 1 us later, so that the first CTAs' fill traffic does not compete with the bulk loads of the CTAs whose
+// tile has not landed yet) -- measured slower at c3 (24.86 vs 23.87 us, same box), equal at c2 / c5.
+#define CF_FILL_LATE 0
+#endif
 #define CF_RISK_WARPS 2      // warps that run E-J (phase 5) while the others cast the wall faces
 #ifndef CN_FLAT_CTAS_PER_SM
 // resident 256-thread CTAs per SM the kernel is compiled (register cap: 45 registers, no spills) and tiled for.
@@ -312,6 +318,24 @@ __device__ __forceinline__ void fill16(void* base, int n, uint32_t word, int tid
         if (i + 2 * T < n) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 32u * T), "r"(word) : "memory");
         if (i + 3 * T < n) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 48u * T), "r"(word) : "memory");
     }
+}
+
+// Direct rows, lane = row: "no return" into the row's ray columns [0, NR) -- the 16-byte-aligned interior by bulk stores
+// from the constant tile (the TMA engine streams it, no thread waits), the at most three + three floats in front of and
+// behind it by plain stores.  The pose columns and the K block are not touched (the pose warps write them, in any order
+// with this).  The caller waits for the group (cp.async.bulk.wait_group 0) before barrier #A.
+__device__ __forceinline__ void bulk_fill_row(float* row, int NR, float fill, const float* fillc, uint32_t fillc_bytes) {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(row), a1 = a0 + (uintptr_t)NR * 4u;
+    uintptr_t b0 = (a0 + 15u) & ~(uintptr_t)15u, b1 = a1 & ~(uintptr_t)15u;
+    if (b1 < b0) { b0 = a1; b1 = a1; }
+#pragma unroll 1
+    for (uintptr_t q = a0; q < b0; q += 4u) *reinterpret_cast<float*>(q) = fill;
+#pragma unroll 1
+    for (uintptr_t q = b1; q < a1; q += 4u) *reinterpret_cast<float*>(q) = fill;
+#pragma unroll 1
+    for (uintptr_t q = b0; q < b1; q += fillc_bytes)
+        tma_store(reinterpret_cast<void*>(q), fillc, (uint32_t)min((uintptr_t)fillc_bytes, b1 - q));
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 // n 16-byte elements from shared to global memory, strided over `nthreads` threads (fire-and-forget stores)
@@ -641,25 +665,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
     __syncthreads();            // fills done, barrier init visible
     mbar_wait(S.bar, 0);        // state tile + actions have landed
     FSTAMP(1);
-    if (DIRECT && warp == 0) {
-        // lane = row: the 16-byte-aligned interior of the row's ray columns by bulk stores from the constant tile, the
-        // (at most three + three) floats in front of and behind it by plain stores; the pose columns and the K block
-        // are not touched (the pose warps write them, in any order with this)
-        if (lane < nE) {
-            const float fill = P.d.max_range_r3;
-            const uintptr_t a0 = reinterpret_cast<uintptr_t>(S.obs + (size_t)lane * D), a1 = a0 + (uintptr_t)NR * 4u;
-            uintptr_t b0 = (a0 + 15u) & ~(uintptr_t)15u, b1 = a1 & ~(uintptr_t)15u;
-            if (b1 < b0) { b0 = a1; b1 = a1; }
-#pragma unroll 1
-            for (uintptr_t q = a0; q < b0; q += 4u) *reinterpret_cast<float*>(q) = fill;
-#pragma unroll 1
-            for (uintptr_t q = b1; q < a1; q += 4u) *reinterpret_cast<float*>(q) = fill;
-#pragma unroll 1
-            for (uintptr_t q = b0; q < b1; q += L.fillc_bytes)
-                tma_store(reinterpret_cast<void*>(q), S.fillc, (uint32_t)min((uintptr_t)L.fillc_bytes, b1 - q));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
+    if (DIRECT && warp == 0 && !CF_FILL_LATE && lane < nE) bulk_fill_row(S.obs + (size_t)lane * D, NR, P.d.max_range_r3, S.fillc, L.fillc_bytes);
     if (push_bulk && warp == 0) {
         if (tid == 0 && !(L.gather_debug & 4)) {
             mbar_wait(S.bar + 1, 0);
@@ -696,6 +702,7 @@ cn_flat_kernel(const __grid_constant__ cn_kparams P, const __grid_constant__ cn_
                                        S.pa + (size_t)w * N * 4, N);
             }
         }
+        if (DIRECT && part == 0 && CF_FILL_LATE && lane < nE) bulk_fill_row(rowl, NR, P.d.max_range_r3, S.fillc, L.fillc_bytes);
         if (part == 1) {
             if (run) {
                 float sy, cy; cn_sincos_bin(p.th, &sy, &cy);
