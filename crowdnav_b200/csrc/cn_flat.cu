@@ -18,21 +18,21 @@
  * gathered across the whole tile, so rare work is compacted into full warps:
  *
  *   phase 0   thread 0 issues the bulk TMA loads of the tile's three state
- *             planes + actions; meanwhile all threads pre-fill the observation
- *             rows with the no-return value (16-byte stores).
- *   phase 1   warps 0-2: lane = WORLD, the pose-only part of get_state /
+ *             planes + actions; meanwhile the threads clear the contact strips and
+ *             (staged rows) pre-fill the observation rows with the no-return value.
+ *   phase 1   warps 0-1: lane = WORLD, the pose-only part of get_state /
  *             compute_reward (unicycle, waypoint, heading, distance, reward
- *             shaping, wall spans; warp 2 only the new pose, early, for the
- *             pedestrian side).  Other warps, concurrently: item = PEDESTRIAN
- *             of the tile: timers; contact prefilter over packed coordinates;
- *             Philox only for the compacted list of pedestrians that resample
- *             (or are re-spawned) this step; integrate + wall clamp into a
- *             second copy of the position plane (Jacobi on the old one), the
- *             few pedestrians in contact again as a compacted list; then
- *   phase 2   (same warps) item = pedestrian: LiDAR candidate test -> compact
- *             candidate lists (per tile and per world); item = candidate:
- *             bearing, angular span; every span (wall faces too) is cut into
- *             groups of <= 8 consecutive rays appended to a group list.
+ *             shaping; warp 1 publishes the new pose early for the pedestrian
+ *             side and then takes the wall faces, one lane per (world, face)).
+ *             Other warps, concurrently: item = PEDESTRIAN of the tile: timers;
+ *             strip-mask contact prefilter; Philox only for the compacted list
+ *             of pedestrians that resample (or are re-spawned) this step;
+ *             integrate + wall clamp into a second copy of the position plane
+ *             (Jacobi on the old one), the few pedestrians in contact again as
+ *             a compacted list; LiDAR candidate test on the spot; then
+ *   phase 2   (same warps) item = candidate: bearing, angular span; every span
+ *             (wall faces too) is cut into groups of <= 8 consecutive rays
+ *             appended to a group list.
  *   phase 3   8 lanes per ray group: ray-disc / ray-face intersection with the
  *             oracle's per-ray arithmetic.  Whether the primitive OWNS the ray
  *             (oracle: walls first, then pedestrians in index order, strict <)
@@ -40,13 +40,28 @@
  *             other primitives of that world whose span contains it -- no
  *             per-ray key array, no atomics on rays.  An owned ray gets its
  *             final cleaned, rounded value in the observation row; min(scan)
- *             and rays owned per pedestrian are accumulated.
- *   phase 5   item = candidate: centre ray, hit point, tracker, collision
- *             cone, CP (ENV:656-860).
- *   phase 6   item = object: top-K rank + slot write; item = pedestrian:
- *             tracker flags; lane = world: counters, done, reward, robot record.
- *   phase 7   bulk TMA stores of the state planes and the [W, D] block of rows
- *             (and, for cn_step_gather, of the same block into every peer GPU).
+ *             and rays owned per pedestrian are accumulated.  The pedestrians'
+ *             groups go first; the wall faces' groups are cast by warps 2.. while
+ *   phase 5   warps 0-1, item = candidate: centre ray, hit point, tracker,
+ *             collision cone, CP (ENV:656-860), tracker flag for the next step.
+ *   phase 6   item = object: top-K rank + slot write; lane = world: counters,
+ *             done, reward, robot record.
+ *   phase 7   bulk TMA stores of the state planes and (staged rows) the [W, D]
+ *             block of rows (and, for cn_step_gather, of the same block into
+ *             every peer GPU).
+ *
+ * Two instances.  STAGED rows (DIRECT = 0): the tile's rows are assembled in
+ * shared memory and leave by one bulk store -- reset launches, every fused-gather
+ * entry point (the rows are pushed / encoded from shared memory), rows in
+ * host-mapped memory.  DIRECT rows (DIRECT = 1, plain steps into device memory):
+ * S.obs points at the caller's buffer; the no-return fill of the ray columns is
+ * a few bulk stores per row from a small constant tile (warp 0, lane = row, as
+ * soon as the state tile has landed; the TMA engine drains it under the
+ * pedestrian phase), the owned rays / pose columns / K slots are ordinary global
+ * stores ordered by the CTA barriers between the phases.  Without the row block
+ * a world needs 2.0 instead of 3.8 KB of shared memory, so BASELINE configs[2]
+ * (16 384 worlds) runs as ONE wave of 19-world CTAs instead of two residency
+ * rounds: 23.8 instead of 30.1 us per step on a B200 (profiles/r02b).
  *
  * Numerics: everything that reaches an output goes through cn_math.h
  * primitives in the oracle's operation order; -fmad=false.  Approximate

@@ -159,7 +159,12 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
  * and compute_reward (ENV:1046-1162).
  *   action_dev [E, 2] (v, w); obs_dev [E, D] row-major; reward_dev [E];
  *   done_dev [E]: 0 running, 1 = episode ended on this step (obs row is the terminal observation),
- *   2 = this step was an auto-reset (CN_FLAG_AUTO_RESET only; transition to be skipped). */
+ *   2 = this step was an auto-reset (CN_FLAG_AUTO_RESET only; transition to be skipped).
+ * When obs_dev is device memory the kernel writes the rows in place while it runs ("direct rows": the no-return fill
+ * first, then the rays that hit something, the pose columns and the K block): the rows are complete when the launch
+ * has completed, as stream order guarantees for any consumer; nothing else about the call changes.  Rows in
+ * host-mapped memory (a pinned buffer passed as obs_dev) are staged in shared memory and leave by one bulk store
+ * per tile, as they do for cn_reset and for every fused-gather entry point below. */
 int cn_step(cn_handle* h, const float* action_dev, float* obs_dev,
             float* reward_dev, uint8_t* done_dev, void* stream);
 
@@ -279,7 +284,8 @@ int cn_set_debug_taps(cn_handle* h, float* ranges_dev, uint8_t* hit_ids_dev);
 int64_t cn_launch_count(const cn_handle* h);
 /* Name of the step-kernel variant this handle launches ("cn_flat_kernel": compacted work lists, the default;
  * "cn_env_kernel": one warp per world, selected with the environment variable CN_KERNEL=warp at cn_create) and
- * the number of worlds per CTA it uses.  For benchmarks and profiles; results are bit-identical. */
+ * the number of worlds per CTA a plain cn_step uses (the fused-gather entry points use the staged layout, whose CTA count
+ * cn_kernel_ctas reports).  For benchmarks and profiles; results are bit-identical. */
 const char* cn_kernel_name(const cn_handle* h);
 int cn_kernel_tile(const cn_handle* h);
 /* Host-only planning query (no GPU needed): the tile (worlds per CTA), CTA size and dynamic shared memory the default
