@@ -520,6 +520,7 @@ int cn_graph_create(cn_handle* h, int n_steps, const float* action_dev, size_t a
     *out = NULL;
     if (n_steps < 1) return fail(CN_ERR_INVALID, "cn_graph_create: n_steps < 1%s", NULL);
     cn_device_guard guard(h->device);
+    (void)rows_in_device_memory(h, obs_dev);            /* classify the row buffer before the capture starts */
     cudaStream_t cap;
     CN_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     const int64_t before = h->launches;

@@ -28,7 +28,10 @@ cn_faithful_kernel(cnf_params P, const uint32_t* __restrict__ robot, uint32_t* _
     cnf_scratch_carve(cnf_smem + (size_t)wi * scratch_bytes, P.n_rays, &S);
     const uint32_t* rob = robot + (size_t)e * CN_ROBOT_WORDS;
     uint32_t* g = trk + (size_t)e * CNF_WORLD_WORDS;
-    for (int k = lane; k < CNF_WORLD_WORDS; k += CNF_LANES) S.trk[k] = g[k];
+    static_assert(CNF_WORLD_WORDS % 4 == 0, "the tracker record moves as 16-byte words");
+    // (16-byte words: 99 per world, two trips per lane instead of seven; the plane and the scratch are 16-byte aligned)
+    for (int k = lane; k < CNF_WORLD_WORDS / 4; k += CNF_LANES)
+        reinterpret_cast<uint4*>(S.trk)[k] = reinterpret_cast<const uint4*>(g)[k];
     CNF_SYNC();
     const double x = (double)((float)(int32_t)rob[CN_R_X] * CN_GRID);
     const double y = (double)((float)(int32_t)rob[CN_R_Y] * CN_GRID);
@@ -36,7 +39,8 @@ cn_faithful_kernel(cnf_params P, const uint32_t* __restrict__ robot, uint32_t* _
     const int step_counter = (int)rob[CN_R_STEP];
     cnf_world(&P, S, x, y, yaw, ranges + (size_t)e * P.n_rays, no_return32, step_counter,
               obs + (size_t)e * obs_dim + P.n_rays + 7, lane, CNF_LANES, bar);
-    for (int k = lane; k < CNF_WORLD_WORDS; k += CNF_LANES) g[k] = S.trk[k];
+    for (int k = lane; k < CNF_WORLD_WORDS / 4; k += CNF_LANES)
+        reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(S.trk)[k];
 }
 
 /* [E, 4] int32: success (robot record), ego / social violations, obstacle-present steps (tracker record) */

@@ -149,6 +149,96 @@ CNF_FN_BIG cnf_pt cnf_hit_point(double inc_deg, double x, double y, double yaw, 
     return o;
 }
 
+/* ---- collectives over the world's lanes.  Every lane of the world calls them from converged code.  On the device
+ * (CNF_LANES = 64 = two warps) they are shuffle scans / reductions plus ONE exchange between the two warps through
+ * S.red[slot ...] and one CNF_SYNC(); on the host (nl lanes as threads, or nl = 1) they are the plain loops over
+ * per-lane partials in S.red the kernel itself used before (9.7 + 6.4 + 10.4 % of its executed instructions were those
+ * loops: profiles/r02/ncu_c2_faithful_v12.txt).  Call sites use distinct slots, so a lane that is still reading the
+ * previous exchange cannot meet the next one's writes. ---- */
+#if defined(__CUDACC__)
+#define CNF_COLL_ARGS const cnf_scratch& S, int lane, int nl, int bar
+#define CNF_COLL_PASS S, lane, nl, bar
+CNF_FN int cnf_warp_incl(int v, int l32) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (l32 >= d) v += y; }
+    return v;
+}
+/* exclusive prefix sum of v in lane order; *total = the sum over all lanes */
+CNF_FN int cnf_scan_excl(CNF_COLL_ARGS, int slot, int v, int* total) {
+    (void)nl;
+    const int l32 = lane & 31;
+    const int x = cnf_warp_incl(v, l32);
+    if (l32 == 31) S.red[slot + (lane >> 5)] = x;
+    CNF_SYNC();
+    const int t0 = S.red[slot], t1 = S.red[slot + 1];
+    *total = t0 + t1;
+    return x - v + (lane >= 32 ? t0 : 0);
+}
+/* three exclusive prefix sums at once (a | b << 10 | c << 20 would overflow: counts go up to n each), one exchange */
+CNF_FN void cnf_scan_excl3(CNF_COLL_ARGS, int slot, int* a, int* b, int* c, int* total_a) {
+    (void)nl;
+    const int l32 = lane & 31;
+    const int xa = cnf_warp_incl(*a, l32), xb = cnf_warp_incl(*b, l32), xc = cnf_warp_incl(*c, l32);
+    if (l32 == 31) { int32_t* r = S.red + slot + 3 * (lane >> 5); r[0] = xa; r[1] = xb; r[2] = xc; }
+    CNF_SYNC();
+    const int hi = lane >= 32;
+    *total_a = S.red[slot] + S.red[slot + 3];
+    *a = xa - *a + (hi ? S.red[slot] : 0);
+    *b = xb - *b + (hi ? S.red[slot + 1] : 0);
+    *c = xc - *c + (hi ? S.red[slot + 2] : 0);
+}
+/* min of mn, max of mx, sum of sm over all lanes, to every lane */
+CNF_FN void cnf_min_max_sum(CNF_COLL_ARGS, int slot, int* mn, int* mx, int* sm) {
+    (void)nl;
+    int a = *mn, b = *mx, c = *sm;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d), c2 = __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        a = a2 < a ? a2 : a; b = b2 > b ? b2 : b; c += c2;
+    }
+    if ((lane & 31) == 0) { int32_t* r = S.red + slot + 3 * (lane >> 5); r[0] = a; r[1] = b; r[2] = c; }
+    CNF_SYNC();
+    const int32_t* r = S.red + slot;
+    *mn = r[0] < r[3] ? r[0] : r[3]; *mx = r[1] > r[4] ? r[1] : r[4]; *sm = r[2] + r[5];
+}
+#else
+#define CNF_COLL_ARGS const cnf_scratch& S, int lane, int nl, int bar
+#define CNF_COLL_PASS S, lane, nl, bar
+CNF_FN int cnf_scan_excl(CNF_COLL_ARGS, int slot, int v, int* total) {
+    (void)bar;
+    CNF_SYNC();                 /* the partials of the previous collective (same words) have been read by everybody */
+    S.red[slot + lane] = v;
+    CNF_SYNC();
+    int base = 0, t = 0;
+    for (int l = 0; l < nl; ++l) { if (l < lane) base += S.red[slot + l]; t += S.red[slot + l]; }
+    *total = t;
+    return base;
+}
+CNF_FN void cnf_scan_excl3(CNF_COLL_ARGS, int slot, int* a, int* b, int* c, int* total_a) {
+    (void)bar;
+    CNF_SYNC();                 /* the partials of the previous collective (same words) have been read by everybody */
+    int32_t* r = S.red + slot;
+    r[3 * lane] = *a; r[3 * lane + 1] = *b; r[3 * lane + 2] = *c;
+    CNF_SYNC();
+    int ba = 0, bb = 0, bc = 0, t = 0;
+    for (int l = 0; l < nl; ++l) {
+        if (l < lane) { ba += r[3 * l]; bb += r[3 * l + 1]; bc += r[3 * l + 2]; }
+        t += r[3 * l];
+    }
+    *a = ba; *b = bb; *c = bc; *total_a = t;
+}
+CNF_FN void cnf_min_max_sum(CNF_COLL_ARGS, int slot, int* mn, int* mx, int* sm) {
+    (void)bar;
+    CNF_SYNC();                 /* the partials of the previous collective (same words) have been read by everybody */
+    int32_t* r = S.red + slot;
+    r[3 * lane] = *mn; r[3 * lane + 1] = *mx; r[3 * lane + 2] = *sm;
+    CNF_SYNC();
+    int a = r[0], b = r[1], c = 0;
+    for (int l = 0; l < nl; ++l) { if (r[3 * l] < a) a = r[3 * l]; if (r[3 * l + 1] > b) b = r[3 * l + 1]; c += r[3 * l + 2]; }
+    *mn = a; *mx = b; *sm = c;
+}
+#endif
+
 /*
  * One get_state of the perception block for one world.
  *   scan32 : cleaned ranges in observation order (UTL:375-392), fp32, `no_return32` where nothing was hit
@@ -214,24 +304,22 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     const int c_lo = (lane * chunk < n) ? lane * chunk : n;
     const int c_hi = (c_lo + chunk < n) ? c_lo + chunk : n;
     int16_t* cand = S.sub;                                      /* free until the sub-segment offsets are built */
+    int my_cand = 0;
     {
         int cnt = 0;
         CNF_ROLLED for (int i = c_lo; i < c_hi; ++i) {
             S.type[i] = (uint8_t)CNF_T_NONE; S.src[i] = (int16_t)i;
             cnt += (i != n - 1 && CNF_CHG_OK(i));
         }
-        S.red[lane] = cnt;
+        my_cand = cnt;
     }
-    CNF_SYNC();
     CNF_STAMP(3);
     {
-        int base = 0;
-        CNF_ROLLED for (int l = 0; l < lane; ++l) base += S.red[l];
+        int total = 0;
+        int base = cnf_scan_excl(CNF_COLL_PASS, 0, my_cand, &total);
         CNF_ROLLED for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && CNF_CHG_OK(i)) cand[base++] = (int16_t)i;
-        if (lane == nl - 1) S.misc[3] = base;                   /* the last lane ends at the total */
         CNF_SYNC();
         if (lane == 0) {
-            const int total = S.misc[3];
             /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
             int last_ok = 0; double last_val = 0.0;
             if (S.gok[n - 1]) {
@@ -270,6 +358,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     CNF_STAMP(4);
     /* neighbour association on the records' poses (ENV:443-486); does the record carry a hit? */
     uint8_t* hflag = S.gok;                                     /* gradients are consumed */
+    int seg_first = n, seg_last = -1, seg_cnt = 0;
     {
         int first = n, last = -1, cnt = 0;
         CNF_ROLLED for (int i = lane; i < n; i += nl) {
@@ -282,21 +371,12 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
             if (cl) { ++cnt; if (i < first) first = i; if (i != n - 1 && i > last) last = i; }
         }
-        S.red[lane] = first; S.red[64 + lane] = last; S.red[128 + lane] = cnt;
+        seg_first = first; seg_last = last; seg_cnt = cnt;
     }
-    CNF_SYNC();
     CNF_STAMP(5);
-    CNF_ROLLED for (int q = lane; q < 3; q += nl) {                        /* min / max / sum of the partials, one lane each */
-        int v = (q == 0) ? n : (q == 1 ? -1 : 0);
-        CNF_ROLLED for (int l = 0; l < nl; ++l) {
-            const int c = S.red[64 * q + l];
-            if (q == 0) { if (c < v) v = c; } else if (q == 1) { if (c > v) v = c; } else v += c;
-        }
-        S.misc[4 + q] = v;
-    }
-    CNF_SYNC();
+    cnf_min_max_sum(CNF_COLL_PASS, 16, &seg_first, &seg_last, &seg_cnt);   /* (its barrier also publishes close[] / hflag[]) */
     CNF_STAMP(6);
-    const int e0 = S.misc[4], zb = S.misc[5] + 1, nseg = S.misc[6];
+    const int e0 = seg_first, zb = seg_last + 1, nseg = seg_cnt;
     int merged = 0;
     if (nseg > 1) {
         const int a = S.src[0], b = S.src[n - 1];
@@ -309,6 +389,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     int16_t* cum_o = (int16_t*)S.gk;                             /* [n + 1] each; the gradients are consumed */
     int16_t* cum_w = cum_o + (n + 1);
     uint8_t* subend = S.subend;
+    int p_end = 0, p_o = 0, p_w = 0;
     {
         int n_end = 0, n_o = 0, n_w = 0;
         CNF_ROLLED for (int k = c_lo; k < c_hi; ++k) {
@@ -320,13 +401,13 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             subend[k] = (uint8_t)end;
             n_end += end; n_o += (S.type[r] == CNF_T_O); n_w += (S.type[r] == CNF_T_W);
         }
-        S.red[3 * lane] = n_end; S.red[3 * lane + 1] = n_o; S.red[3 * lane + 2] = n_w;
+        p_end = n_end; p_o = n_o; p_w = n_w;
     }
-    CNF_SYNC();
     CNF_STAMP(7);
+    int nsub_total = 0;
     {
-        int b_end = 0, b_o = 0, b_w = 0;
-        CNF_ROLLED for (int l = 0; l < lane; ++l) { b_end += S.red[3 * l]; b_o += S.red[3 * l + 1]; b_w += S.red[3 * l + 2]; }
+        int b_end = p_end, b_o = p_o, b_w = p_w;
+        cnf_scan_excl3(CNF_COLL_PASS, 32, &b_end, &b_o, &b_w, &nsub_total);   /* (its barrier also publishes subend[]) */
         if (lane == 0) { S.sub[0] = 0; cum_o[0] = 0; cum_w[0] = 0; }
         CNF_ROLLED for (int k = c_lo; k < c_hi; ++k) {
             const int r = CNF_FLAT_OF(k);
@@ -334,11 +415,10 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             cum_o[k + 1] = (int16_t)b_o; cum_w[k + 1] = (int16_t)b_w;
             if (subend[k]) S.sub[++b_end] = (int16_t)(k + 1);
         }
-        if (lane == nl - 1) S.misc[3] = b_end;                  /* the last lane ends at the total */
     }
     CNF_SYNC();
     CNF_STAMP(8);
-    const int nsub = S.misc[3];
+    const int nsub = nsub_total;
     /* confirmation (ENV:573-620, UTL:395-402), one lane per sub-segment; every record of a sub-segment is a hit or
      * none is, so its first one decides */
     int16_t* verdict = (int16_t*)S.subend;                       /* [nsub] <= n over subend[] + type[], both consumed */
