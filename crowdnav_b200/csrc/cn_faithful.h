@@ -318,34 +318,54 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         int total = 0;
         int base = cnf_scan_excl(CNF_COLL_PASS, 0, my_cand, &total);
         CNF_ROLLED for (int i = c_lo; i < c_hi; ++i) if (i != n - 1 && CNF_CHG_OK(i)) cand[base++] = (int16_t)i;
-        CNF_SYNC();
+        /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient (lane 0 finds it) */
         if (lane == 0) {
-            /* the last ray inherits `last_grad`: the change of the latest earlier ray that has a gradient */
-            int last_ok = 0; double last_val = 0.0;
+            int last_ok = 0, last_j = 0;
             if (S.gok[n - 1]) {
                 CNF_ROLLED for (int i = n - 2; i >= 0; --i)
-                    if (S.gok[i]) { last_ok = CNF_CHG_OK(i); if (last_ok) last_val = CNF_CHG(i); break; }
+                    if (S.gok[i]) { last_ok = CNF_CHG_OK(i); last_j = i; break; }
             }
+            S.misc[3] = last_ok; S.misc[4] = last_j;
+        }
+        CNF_SYNC();
+        /* What the state machine asks of a candidate are four yes / no questions about float64 values -- is its change of
+         * gradient zero, has the next ray a change, is that one zero, are the two equal -- and each depends on the
+         * candidate alone: the lanes answer them side by side (the same doubles, the same comparisons), and lane 0
+         * then walks the candidates over one byte each instead of evaluating ~50 dependent float64 instructions per step
+         * of a serial walk (9 us of a 44 us world lifetime at c2: profiles/r02b/timeline_faithful_v20.txt). */
+        uint8_t* cflag = S.close;                               /* free until the association stage writes it */
+        {
+            const int last_ok = S.misc[3], last_j = S.misc[4];
+            CNF_ROLLED for (int q = lane; q < total; q += nl) {
+                const int i = cand[q];
+                const double ci = CNF_CHG(i);
+                const int nok = (i + 1 == n - 1) ? last_ok : CNF_CHG_OK(i + 1);
+                double cn = 0.0;
+                if (nok) cn = (i + 1 == n - 1) ? CNF_CHG(last_j) : CNF_CHG(i + 1);
+                cflag[q] = (uint8_t)((ci == 0.0 ? 1 : 0) | (nok ? 2 : 0) | ((nok && cn == 0.0) ? 4 : 0) |
+                                     ((nok && fabs(ci - cn) == 0.0) ? 8 : 0));
+            }
+        }
+        CNF_SYNC();
+        if (lane == 0) {
             /* a record is (type, source ray): `_scans_object_type[i] = last_type` hands ray i an EARLIER ray's range and pose */
             int last_type = CNF_T_NONE, last_src = 0, du = 0;
             CNF_ROLLED for (int q = 0; q < total; ++q) {
                 const int i = cand[q];
+                const int f = cflag[q];
+                const int ci_zero = f & 1, nok = f & 2, cn_zero = f & 4, same = f & 8;
                 int t, s = i;
-                const double ci = CNF_CHG(i);
-                const int nok = (i + 1 == n - 1) ? last_ok : CNF_CHG_OK(i + 1);
-                double cn = 0.0;
-                if (nok) cn = (i + 1 == n - 1) ? last_val : CNF_CHG(i + 1);
-                if (ci == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; }
+                if (ci_zero) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; }
                 else if (du != 1) {
                     t = CNF_T_O;
-                    if (nok && cn == 0.0) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; du = 0; }
+                    if (cn_zero) { t = CNF_T_W; last_type = CNF_T_W; last_src = i; du = 0; }
                     if (nok) {
-                        if (fabs(ci - cn) == 0.0) { t = CNF_T_W; s = i; last_type = CNF_T_W; last_src = i; du = 0; }
+                        if (same) { t = CNF_T_W; s = i; last_type = CNF_T_W; last_src = i; du = 0; }
                         else { t = last_type; s = (last_type == CNF_T_NONE) ? i : last_src; du += 1; }
                     }
                 } else {
                     t = CNF_T_O; last_type = CNF_T_O; last_src = i;
-                    if (nok && cn == 0.0) du = 0;
+                    if (cn_zero) du = 0;
                 }
                 S.type[i] = (uint8_t)t; S.src[i] = (int16_t)s;
             }
@@ -538,7 +558,9 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             }
         S.trk[CNF_H_N] = (uint32_t)n_ent;
         /* speed (ENV:745-760), obstacle velocity and the probe target of the collision cone (ENV:799-815) */
-        const double curx = cn_milli64(cnf_round3k(x)), cury = cn_milli64(cnf_round3k(y));
+        const long long pose_kx = cnf_round3k(x), pose_ky = cnf_round3k(y);   /* round(x, 3), round(y, 3) in thousandths ... */
+        S.misc[5] = (int32_t)pose_kx; S.misc[6] = (int32_t)pose_ky;           /* ... needed again by the last stage (lane 0) */
+        const double curx = cn_milli64(pose_kx), cury = cn_milli64(pose_ky);
         double vox = curx, voy = cury;
         CNF_ROLLED for (int i = 0; i < n_ent; ++i) {
             uint32_t* q = E + i * CNF_ENTRY_WORDS;
@@ -647,9 +669,11 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     if (lane == 0) {
         uint32_t* E = S.trk + CNF_HDR_WORDS;
         double ego_score = cnf_ld64(S.trk + CNF_H_EGOSCORE);
-        const double curx = cn_milli64(cnf_round3k(x)), cury = cn_milli64(cnf_round3k(y));
+        const long long kx = S.misc[5], ky = S.misc[6];
+        const double curx = cn_milli64(kx), cury = cn_milli64(ky);
+        const float padx = (float)cnf_np_round3(x), pady = (float)cnf_np_round3(y);     /* once, not once per slot */
         CNF_ROLLED for (int s = 0; s < K; ++s) {
-            kblock[4 * s] = (float)cnf_np_round3(x); kblock[4 * s + 1] = (float)cnf_np_round3(y);
+            kblock[4 * s] = padx; kblock[4 * s + 1] = pady;
             kblock[4 * s + 2] = 0.0f; kblock[4 * s + 3] = 0.0f;
         }
         if (have_prev) {
@@ -692,8 +716,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
         }
         cnf_st64(S.trk + CNF_H_EGOSCORE, ego_score);
         S.trk[CNF_H_HAVE_PREV] = 1u;
-        S.trk[CNF_H_PPX] = (uint32_t)(int32_t)cnf_round3k(x);
-        S.trk[CNF_H_PPY] = (uint32_t)(int32_t)cnf_round3k(y);
+        S.trk[CNF_H_PPX] = (uint32_t)(int32_t)kx;
+        S.trk[CNF_H_PPY] = (uint32_t)(int32_t)ky;
         if (S.misc[1]) S.trk[CNF_H_EGO] += 1;
         if (ego_score > 0.4) S.trk[CNF_H_SOCIAL] += 1;
         if (step_counter == 0) { S.trk[CNF_H_EGO] = 0; S.trk[CNF_H_SOCIAL] = 0; S.trk[CNF_H_PRESENT] = 0; }   /* ENV:1258-1262 */
