@@ -133,9 +133,27 @@ CNF_FN_BIG double cnf_iou(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, do
     const double w = (ax1 < bx1 ? ax1 : bx1) - (ax0 > bx0 ? ax0 : bx0);
     const double hh = (ay1 < by1 ? ay1 : by1) - (ay0 > by0 ? ay0 : by0);
     const double inter = (w > 0.0 && hh > 0.0) ? w * hh : 0.0;
+    if (inter == 0.0) return 0.0;                               /* 0 / union = +0.0, round(+0.0, 3) = 0.0: the same bits, no division */
     const double area_a = (ax1 - ax0) * (ay1 - ay0), area_b = (bx1 - bx0) * (by1 - by0);
     const double uni = area_a + area_b - inter;
     return cn_milli64(cn_py_round3_k64(cnf_div(inter, uni)));
+}
+/* round(IoU, 3) > 0 -- all the association stage asks -- i.e. IoU >= 0.0005 after the division's and the rounding's own
+ * round-off.  Far from that threshold the answer needs neither: inter > union / 1000 is a certain yes (ratio > 0.000999),
+ * inter < union / 4000 a certain no; only what lies between goes through the division and the exact rounding. */
+CNF_FN_BIG int cnf_iou_pos(int32_t axk, int32_t ayk, int32_t bxk, int32_t byk, double h) {
+    const double ax = CNF_MILLI(axk), ay = CNF_MILLI(ayk), bx = CNF_MILLI(bxk), by = CNF_MILLI(byk);
+    const double ax0 = ax - h, ax1 = ax + h, ay0 = ay - h, ay1 = ay + h;
+    const double bx0 = bx - h, bx1 = bx + h, by0 = by - h, by1 = by + h;
+    const double w = (ax1 < bx1 ? ax1 : bx1) - (ax0 > bx0 ? ax0 : bx0);
+    const double hh = (ay1 < by1 ? ay1 : by1) - (ay0 > by0 ? ay0 : by0);
+    if (!(w > 0.0 && hh > 0.0)) return 0;
+    const double inter = w * hh;
+    const double area_a = (ax1 - ax0) * (ay1 - ay0), area_b = (bx1 - bx0) * (by1 - by0);
+    const double uni = area_a + area_b - inter;
+    if (inter * 1000.0 > uni) return 1;
+    if (inter * 4000.0 < uni) return 0;
+    return cn_py_round3_k64(cnf_div(inter, uni)) > 0;
 }
 
 /* UTL:110-126 for observation ray i: both coordinates in thousandths */
@@ -385,7 +403,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             int cl = 1;
             if (i != n - 1) {
                 const int a = S.src[i], b = S.src[i + 1];
-                cl = !(cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox) > 0.0);
+                cl = !cnf_iou_pos(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox);
             }
             S.close[i] = (uint8_t)cl;
             hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
@@ -400,7 +418,7 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     int merged = 0;
     if (nseg > 1) {
         const int a = S.src[0], b = S.src[n - 1];
-        merged = cnf_iou(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox * 2.0) > 0.0;
+        merged = cnf_iou_pos(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox * 2.0);
     }
     const int len_a = e0 + 1, len_z = merged ? n - zb : 0;
 #define CNF_FLAT_OF(k) ((k) < len_a ? (k) : ((k) < len_a + len_z ? zb + ((k) - len_a) : (k) - len_z))
@@ -622,9 +640,17 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
                     const double den = rx * sy - ry * sx;
                     int f = 0;
                     if (den != 0.0) {
-                        const double t = cnf_div((ax - a0x) * sy - (ay - a0y) * sx, den);
-                        const double u = cnf_div((ax - a0x) * ry - (ay - a0y) * rx, den);
-                        if (0.0 <= t && t <= 1.0 && 0.0 <= u && u <= 1.0) { f = 1; S.hit[2 * k] = a0x + t * rx; S.hit[2 * k + 1] = a0y + t * ry; }
+                        const double nt = (ax - a0x) * sy - (ay - a0y) * sx, nu = (ax - a0x) * ry - (ay - a0y) * rx;
+                        /* t = nt / den and u = nu / den must both lie in [0, 1].  62 of the 64 edges miss by a wide margin:
+                         * a numerator outside [0, |den|] by more than 1e-9 |den| (the quotient's round-off is 1e-16) is a
+                         * certain miss and needs no division */
+                        const double ad = fabs(den), st = den > 0.0 ? nt : -nt, su = den > 0.0 ? nu : -nu;
+                        const double lo = -1.0e-9 * ad, hi = ad * (1.0 + 1.0e-9);
+                        if (!(st < lo || st > hi || su < lo || su > hi)) {
+                            const double t = cnf_div(nt, den);
+                            const double u = cnf_div(nu, den);
+                            if (0.0 <= t && t <= 1.0 && 0.0 <= u && u <= 1.0) { f = 1; S.hit[2 * k] = a0x + t * rx; S.hit[2 * k + 1] = a0y + t * ry; }
+                        }
                     }
                     S.hitf[k] = (uint8_t)f;
                 }
