@@ -30,8 +30,9 @@ struct cn_handle {
     cn_flat_layout flat;    /* rows staged in shared memory: reset launches, every fused-gather entry point, host-mapped rows */
     cn_flat_layout flat_direct;   /* "direct rows" layout of plain steps into device memory (cn_flat.cu, DIRECT = 1) */
     int have_direct;
-    const void* obs_seen;   /* last obs pointer classified by cudaPointerGetAttributes ... */
-    int obs_seen_device;    /* ... 1: device (or managed) memory, 0: host-mapped or unknown */
+    const void* obs_seen[4];   /* the last few obs pointers classified by cudaPointerGetAttributes (rollouts alternate buffers) ... */
+    int obs_seen_device[4];    /* ... 1: device (or managed) memory, 0: host-mapped or unknown */
+    int obs_seen_next;
     cn_kparams base;        /* everything of cn_kparams that does not change between calls, packed once (repack()) */
 };
 
@@ -224,7 +225,8 @@ int cn_create(const cn_config* cfg, int device, cn_handle** out) {
     if (!h) return fail(CN_ERR_NOMEM, "cn_create: host allocation failed%s", NULL);
     h->cfg = *cfg; h->d = d; h->device = device; h->launches = 0;
     h->use_flat = use_flat; h->flat = flat;
-    h->flat_direct = flat_direct; h->have_direct = have_direct; h->obs_seen = NULL; h->obs_seen_device = 0;
+    h->flat_direct = flat_direct; h->have_direct = have_direct; h->obs_seen_next = 0;
+    for (int i = 0; i < 4; ++i) { h->obs_seen[i] = NULL; h->obs_seen_device[i] = 0; }
     h->dbg_ranges = NULL; h->dbg_hid = NULL;
     const size_t cfg_b = align_up(sizeof(cn_config), 256);
     const size_t rob_b = align_up(cn_robot_words(cfg) * 4, 256);
@@ -304,14 +306,16 @@ int cn_reset(cn_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream
  * the scattered stores would cross PCIe one by one, where the staged tile leaves as one bulk store.  The pointer is
  * classified once (no stream operation: fine under graph capture) and remembered. */
 static bool rows_in_device_memory(cn_handle* h, const void* obs_dev) {
-    if (h->obs_seen != obs_dev) {
-        cudaPointerAttributes a;
-        const cudaError_t e = cudaPointerGetAttributes(&a, obs_dev);
-        if (e != cudaSuccess) cudaGetLastError();
-        h->obs_seen = obs_dev;
-        h->obs_seen_device = (e == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) ? 1 : 0;
-    }
-    return h->obs_seen_device != 0;
+    for (int i = 0; i < 4; ++i)
+        if (h->obs_seen[i] == obs_dev) return h->obs_seen_device[i] != 0;
+    cudaPointerAttributes a;
+    const cudaError_t e = cudaPointerGetAttributes(&a, obs_dev);
+    if (e != cudaSuccess) cudaGetLastError();
+    const int k = h->obs_seen_next;
+    h->obs_seen_next = (k + 1) & 3;
+    h->obs_seen[k] = obs_dev;
+    h->obs_seen_device[k] = (e == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) ? 1 : 0;
+    return h->obs_seen_device[k] != 0;
 }
 
 static int step_once(cn_handle* h, const float* action_dev, float* obs_dev, float* const* peers, int n_peers,
