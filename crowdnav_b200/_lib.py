@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     L.cn_kernel_name.argtypes = [vp]
     L.cn_kernel_tile.argtypes = [vp]
     L.cn_plan_tile.argtypes = [C.POINTER(CnConfig), i32, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]
+    L.cn_plan_tile_direct.argtypes = [C.POINTER(CnConfig), i32, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]
     _lib = L
     return L
 
@@ -109,6 +110,6 @@ def check(rc: int, what: str) -> None:
 
 ABI_SYMBOLS = [
     "cn_config_default", "cn_obs_dim", "cn_blob_bytes", "cn_create", "cn_destroy", "cn_reset", "cn_step", "cn_step_n", "cn_graph_create", "cn_graph_launch", "cn_graph_destroy", "cn_step_gather", "cn_step_gather_signal", "cn_step_gather_async", "cn_gather_flush", "cn_gather_decode16", "cn_gather_wait", "cn_gather_timeouts", "cn_kernel_ctas",
-    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile", "cn_plan_tile",
+    "cn_get_counters", "cn_clear_done", "cn_get_blob", "cn_set_blob", "cn_set_debug_taps", "cn_launch_count", "cn_kernel_name", "cn_kernel_tile", "cn_plan_tile", "cn_plan_tile_direct",
     "cn_last_error", "cn_abi_version",
 ]

@@ -657,4 +657,15 @@ int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile,
     return CN_OK;
 }
 
+int cn_plan_tile_direct(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes) {
+    if (!cfg || !tile || !threads || !smem_bytes) return fail(CN_ERR_INVALID, "cn_plan_tile_direct: null argument%s", NULL);
+    cn_derived d;
+    if (cn_derive(cfg, &d) != 0) return fail(CN_ERR_INVALID, "cn_plan_tile_direct: config out of range%s", NULL);
+    cn_flat_layout L; memset(&L, 0, sizeof(L));
+    if (cn_flat_pick_tile(cfg->n_peds, cfg->n_samples, d.obs_dim, cfg->n_envs, n_sms, smem_per_sm, 0, 1, &L) != 0)
+        return fail(CN_ERR_UNSUPPORTED, "cn_plan_tile_direct: no tile fits%s", NULL);
+    *tile = L.W; *threads = L.threads; *smem_bytes = L.total;
+    return CN_OK;
+}
+
 }  /* extern "C" */

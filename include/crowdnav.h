@@ -288,9 +288,12 @@ int64_t cn_launch_count(const cn_handle* h);
  * cn_kernel_ctas reports).  For benchmarks and profiles; results are bit-identical. */
 const char* cn_kernel_name(const cn_handle* h);
 int cn_kernel_tile(const cn_handle* h);
-/* Host-only planning query (no GPU needed): the tile (worlds per CTA), CTA size and dynamic shared memory the default
- * step kernel would use for this config on a device with n_sms SMs and smem_per_sm bytes of shared memory per SM. */
+/* Host-only planning query (no GPU needed): the tile (worlds per CTA), CTA size and dynamic shared memory the staged
+ * instance of the step kernel (reset, fused gather, rows in host-mapped memory) would use for this config on a device with n_sms SMs and smem_per_sm bytes of shared memory per SM. */
 int cn_plan_tile(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes);
+/* The same for the direct-rows instance a plain cn_step into device memory launches (rows written in place, no staging
+ * tile): 256 threads x 6 resident CTAs per SM, or 384 x 4 for batches that need several waves anyway. */
+int cn_plan_tile_direct(const cn_config* cfg, int n_sms, size_t smem_per_sm, int* tile, int* threads, size_t* smem_bytes);
 
 const char* cn_last_error(void);
 int cn_abi_version(void);

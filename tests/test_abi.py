@@ -123,6 +123,34 @@ def test_tile_plan_for_the_baseline_configs(L):
     assert L.cn_plan_tile(C.byref(bad), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == -1
 
 
+def test_tile_plan_of_the_direct_rows_instance(L):
+    """Plain steps into device memory run the direct-rows instance (no staging tile: ~2.0 instead of ~3.8 KB of shared
+    memory per world).  Its planner must give BASELINE configs[2] ONE wave (that is the point of the layout: 863 CTAs of
+    19 worlds on 6 x 148 slots), keep one wave for c2 / the c4 shard, use 384-thread CTAs for the 50-pedestrian config,
+    and never exceed the CTA's share of a B200 SM."""
+    from crowdnav_b200.config import baseline_config
+    n_sms, smem_sm = 148, 233472
+    plans = {}
+    for idx, name in ((1, "c2"), (2, "c3"), (3, "c4"), (4, "c5"), (0, "c1")):
+        cfg = baseline_config(idx)
+        if name == "c4":
+            cfg.n_envs = 8192
+        tile, threads, smem = C.c_int(), C.c_int(), C.c_size_t()
+        assert L.cn_plan_tile_direct(C.byref(cfg), n_sms, smem_sm, C.byref(tile), C.byref(threads), C.byref(smem)) == 0
+        plans[name] = (tile.value, threads.value, smem.value)
+        ctas = {256: 6, 384: 4}[threads.value]
+        assert 1 <= tile.value <= 32 and smem.value <= smem_sm // ctas - 1024
+        assert ctas * (smem.value + 1024) <= smem_sm, "the resident CTAs (+ 1 KB each reserved by the driver) must fit the SM"
+        staged_tile, st, ss = C.c_int(), C.c_int(), C.c_size_t()
+        assert L.cn_plan_tile(C.byref(cfg), n_sms, smem_sm, C.byref(staged_tile), C.byref(st), C.byref(ss)) == 0
+        if name != "c1":        # (36-ray rows are too small to matter)
+            assert smem.value / tile.value < 0.62 * ss.value / staged_tile.value, "no row block in the direct layout"
+    assert plans["c2"][:2] == (6, 256)
+    assert plans["c3"][:2] == (19, 256) and (16384 + 18) // 19 <= 6 * n_sms          # one wave
+    assert plans["c4"][1] == 256 and (8192 + plans["c4"][0] - 1) // plans["c4"][0] <= 6 * n_sms
+    assert plans["c5"][1] == 384
+
+
 def test_original_env_flag_row_width(L):
     """CN_FLAG_ENV_ORIGINAL: (R-1) + 4 columns, K must be 0 (library and ctypes mirror agree)."""
     cfg = make_config(env_original=True)
