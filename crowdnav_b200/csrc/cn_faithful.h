@@ -290,13 +290,27 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
     }
     const double bbox = cnf_ld64(S.trk + CNF_H_BBOX);
 
-    /* ---- per-ray maps ---- */
+    /* ---- per-ray maps ----
+     * Nine rays in ten return nothing, and nothing downstream ever looks at such a ray's hit point unless a ray that
+     * did return something is its neighbour: gradients (ENV:329-347) are taken at returning rays and reach one ray
+     * ahead, segments without a return are dropped before their poses are read (ENV:573), the first / last merge reads
+     * rays 0 and n - 1 -- and the association of two CONSECUTIVE no-return rays (UTL:435-448) is known without their
+     * points: both lie on the max-range circle one ray spacing apart, the squares around them have half-size
+     * bounding_box_size = that spacing (ENV:286-290), so after rounding to millimetres they still overlap by a third
+     * of their area (IoU 0.13 ... 0.33 against the 0.0005 that decides) as long as the spacing is well above the
+     * millimetre -- `lean` below.  So the float64 sin / cos / roundings of a hit point run only for the rays that
+     * returned something, their two neighbours and rays 0 and n - 1. */
+    const int lean = bbox >= 0.003;
     CNF_ROLLED for (int i = lane; i < n; i += nl) {
         const float r32 = scan32[i];
-        const double r = (r32 >= no_return32) ? P->max_range : (double)r32;
-        const cnf_pt h = cnf_hit_point(P->inc_deg, x, y, yaw, i, r);
+        const int ret = !(r32 >= no_return32);
+        const double r = ret ? (double)r32 : P->max_range;
+        int need = !lean || ret || i == 0 || i == n - 1;
+        if (!need) need = !(scan32[i - 1] >= no_return32) || !(scan32[i + 1] >= no_return32);
+        cnf_pt h; h.x = 0; h.y = 0;
+        if (need) h = cnf_hit_point(P->inc_deg, x, y, yaw, i, r);
         S.hx[i] = h.x; S.hy[i] = h.y;
-        S.rmm[i] = (int32_t)cnf_round3k(r);
+        S.rmm[i] = ret ? (int32_t)cnf_round3k(r) : max_mm;
     }
     CNF_SYNC();
     CNF_STAMP(1);
@@ -403,7 +417,8 @@ CNF_FN void cnf_world(const cnf_params* P, const cnf_scratch S, double x, double
             int cl = 1;
             if (i != n - 1) {
                 const int a = S.src[i], b = S.src[i + 1];
-                cl = !cnf_iou_pos(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox);
+                if (lean && S.rmm[a] == max_mm && S.rmm[b] == max_mm) cl = 0;       /* two no-return neighbours: see the per-ray maps */
+                else cl = !cnf_iou_pos(S.hx[a], S.hy[a], S.hx[b], S.hy[b], bbox);
             }
             S.close[i] = (uint8_t)cl;
             hflag[i] = (uint8_t)(S.rmm[S.src[i]] != max_mm);
