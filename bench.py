@@ -128,13 +128,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- the CPU arm
-def _oracle_rate(wl: str, risk_faithful: bool, min_seconds: float, min_steps: int, n_envs_cap: int = 4096):
+def _oracle_rate(wl: str, risk_faithful: bool, min_seconds: float, min_steps: int, n_envs_cap: int = 4096, threads: int = 0):
     """env-steps/s of the oracle port (oracle/cn_oracle.c, OpenMP over worlds, all host threads) on a bounded sample
     of workload `wl`: the OpenMP pool is warmed first, then at least `min_steps` steps and at least `min_seconds`."""
     import numpy as np
     from crowdnav_b200.config import baseline_config
     from oracle.oracle import OracleEnv
-    cores = os.cpu_count() or 1
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
     n = min(PER_GPU_ENVS[wl], n_envs_cap)
     cfg = baseline_config(WORKLOADS[wl], n_envs=n)
     if risk_faithful:
@@ -186,8 +186,14 @@ def run_reference(args):
 def cpu_baseline(wl: str, risk_faithful: bool = False):
     """The oracle port on the box's host cores: bounded sample of the same workload (about 10 s)."""
     value, cores, n, steps, dt = _oracle_rate(wl, risk_faithful, 10.0, 20)
+    # ... and the same port on ONE core (BASELINE.md section 4: a single-core figure next to the all-cores one)
+    v1, _, n1, s1, dt1 = _oracle_rate(wl, risk_faithful, 2.0, 4, n_envs_cap=1024, threads=1)
+    from oracle.oracle import lib as _oracle_lib
+    _oracle_lib().orc_set_threads(os.cpu_count() or 1)      # whoever uses the oracle after this gets all cores back
     return {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d steps x %d worlds (%.1f s), oracle/cn_oracle.c with OpenMP over worlds, pool warmed" % (steps, n, dt)}
+            "sample": "%d steps x %d worlds (%.1f s), oracle/cn_oracle.c with OpenMP over worlds, pool warmed" % (steps, n, dt),
+            "one_core": {"value": v1, "unit": "env-steps/s", "cores": 1,
+                         "sample": "%d steps x %d worlds (%.1f s), the same port on one thread" % (s1, n1, dt1)}}
 
 
 _REAL_STDOUT = None

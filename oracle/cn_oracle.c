@@ -652,6 +652,18 @@ static void step_env(const orc_ctx* c, int e, uint32_t* rob, uint32_t* pa, uint3
 }
 
 /* ---- batch entry points -------------------------------------------------- */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* threads of the batch loops below (bench.py: the same sample on all host cores and on ONE core); <= 0: leave as is */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void orc_reset(const orc_ctx* c, uint32_t* blob, const uint8_t* mask, float* obs,
                float* dbg_ranges, uint8_t* dbg_hid) {
     const int E = c->cfg.n_envs, N = c->cfg.n_peds, D = c->d.obs_dim, NR = c->cfg.n_samples - 1;

@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.POINTER(CnConfig)]
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_int]
         L.orc_blob_bytes.restype = C.c_size_t
         L.orc_blob_bytes.argtypes = [C.c_void_p]
         L.orc_obs_dim.argtypes = [C.c_void_p]
@@ -72,6 +73,8 @@ class OracleEnv:
         if threads is not None:
             os.environ["OMP_NUM_THREADS"] = str(threads)
         self._L = lib()
+        if threads is not None:
+            self._L.orc_set_threads(int(threads))   # (the environment variable only counts before the first parallel region)
         self._ctx = self._L.orc_create(C.byref(self.cfg))
         if not self._ctx:
             raise ValueError("oracle rejected the config")
